@@ -1,0 +1,18 @@
+"""acvae_b200 -- B200-native AC-VAE latent word-decoding step.
+
+The public surface mirrors the reference's `models` package for this path
+(`Hybrid_VAEModel`, `VAEModel`, `VAERNNBahdanauAttnDecoder`, `PosteriorRNN_hybrid`,
+`PosteriorRNN`, `PriorRNN`, `Seq2SeqAttention`, `CaptionModel`) plus the two loss
+callables of the runner boundary.  Importing this package does not need a GPU;
+running it does, and needs `libacvae_b200.so` (there is no fallback).
+"""
+from . import synthetic  # noqa: F401
+from .models import (CaptionModel, Hybrid_VAEModel, PosteriorRNN, PosteriorRNN_hybrid, PrecomputedEncoder,  # noqa: F401
+                     PriorRNN, Seq2SeqAttention, VAEModel, VAERNNBahdanauAttnDecoder)
+from .train_util import CrossEntropyLoss, LabelSmoothingLoss, Normal_kl_loss  # noqa: F401
+from .lazy import LazyLogits  # noqa: F401
+
+# the reference resolves decoders as getattr(models.decoder, name) and posteriors/priors as
+# getattr(text_encoder, name) (pytorch_runner_vae.py:44, vae_model.py:678-691): same attribute paths
+from . import models as decoder  # noqa: F401,E402
+from . import models as text_encoder  # noqa: F401,E402

@@ -1,0 +1,224 @@
+// C ABI of libacvae_b200.so (see include/acvae_b200.h).  Thin: argument checks,
+// workspace carve-up and kernel enqueueing; no torch types, no exceptions.
+#include "../../include/acvae_b200.h"
+#include "sample.cuh"
+#include "train.cuh"
+
+namespace acvae {
+thread_local char g_err[512] = {0};
+std::atomic<unsigned long long> g_launches{0};
+
+struct VocabWs {
+  float *pmax, *pexp, *psum, *pbest; int* parg;
+  float *row_loss, *row_cnt, *scal, *dlogits;
+  size_t bytes;
+};
+static VocabWs carve_vocab_ws(int M, int V, void* base, bool with_dlogits) {
+  Arena ar(base);
+  VocabWs w{};
+  const size_t nt = (V + kVocabTile - 1) / kVocabTile;
+  w.pmax = ar.take<float>((size_t)M * nt); w.pexp = ar.take<float>((size_t)M * nt); w.psum = ar.take<float>((size_t)M * nt);
+  w.pbest = ar.take<float>((size_t)M * nt * 2); w.parg = ar.take<int>((size_t)M * nt);
+  w.row_loss = ar.take<float>(M); w.row_cnt = ar.take<float>(M); w.scal = ar.take<float>(8);
+  if (with_dlogits) w.dlogits = ar.take<float>((size_t)M * V);
+  w.bytes = ar.off;
+  return w;
+}
+
+__global__ void __launch_bounds__(1024) kl_fwd_kernel(long long n_elem, float inv_rows, const float* __restrict__ mq,
+                                                       const float* __restrict__ lq, const float* __restrict__ mp,
+                                                       const float* __restrict__ lp, float* __restrict__ out) {
+  __shared__ float red[33];
+  float s = 0.0f;
+  for (long long i = threadIdx.x; i < n_elem; i += blockDim.x) {
+    const float d = mq[i] - mp[i];
+    s += 0.5f * lp[i] - 0.5f * lq[i] + (expf(lq[i]) + d * d) / (2.0f * expf(lp[i])) - 0.5f;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[0] = s * inv_rows;
+}
+}  // namespace acvae
+
+using namespace acvae;
+
+extern "C" {
+
+const char* acvae_last_error(void) { return g_err; }
+int acvae_abi_version(void) { return ACVAE_ABI_VERSION; }
+uint64_t acvae_launch_count(void) { return g_launches.load(); }
+
+size_t acvae_train_workspace_bytes(const acvae_dims* d) {
+  if (check_dims(d) != 0) return 0;
+  return carve_train_ws(*d, nullptr).bytes;
+}
+
+int acvae_memory_prepare(const acvae_dims* d, const acvae_weights* w, const float* audio_embeds, float* mem, float* Pp,
+                         float* Pd, void* stream) {
+  ACVAE_TRY(check_dims(d));
+  ACVAE_REQUIRE(w && audio_embeds && mem && Pp && Pd, "NULL pointer");
+  return memory_prepare(*d, *w, audio_embeds, mem, Pp, Pd, (cudaStream_t)stream);
+}
+
+int acvae_train_fwd(const acvae_dims* d, const acvae_weights* w, const acvae_train_io* io, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  ACVAE_TRY(check_dims(d));
+  ACVAE_REQUIRE(w && io && workspace, "NULL pointer");
+  ACVAE_REQUIRE(d->mem_rep == 1, "training requires mem_rep == 1");
+  ACVAE_REQUIRE(d->T <= 64, "T > 64 decode steps not supported");
+  ACVAE_REQUIRE(d->L >= d->T + 1, "caps row stride L must be >= T + 1");
+  ACVAE_REQUIRE(workspace_bytes >= carve_train_ws(*d, nullptr).bytes, "workspace too small");
+  ACVAE_REQUIRE(io->tf_flags && io->dis_flags, "tf_flags / dis_flags are required (host arrays of T bytes)");
+  ACVAE_REQUIRE(io->audio_embeds && io->mem_lens && io->caps_ids && io->cap_lens && io->eps_q && io->eps_p, "NULL input");
+  ACVAE_REQUIRE(io->q_means && io->q_logs && io->q_z && io->p_means && io->p_logs && io->p_z && io->outputs &&
+                    io->seqs && io->sampled_logprobs && io->logit_lse && io->logit_sum,
+                "NULL output");
+  ACVAE_REQUIRE(d->variant == 1 || (io->q_means_utt && io->p_means_utt), "hybrid variant needs *_means_utt outputs");
+  return train_fwd(*d, *w, *io, workspace, (cudaStream_t)stream);
+}
+
+int acvae_train_bwd(const acvae_dims* d, const acvae_weights* w, const acvae_train_io* io,
+                    const acvae_train_grads_in* gin, acvae_weight_grads* gw, float* d_audio_embeds, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  ACVAE_TRY(check_dims(d));
+  ACVAE_REQUIRE(w && io && gin && gw && workspace, "NULL pointer");
+  ACVAE_REQUIRE(workspace_bytes >= carve_train_ws(*d, nullptr).bytes, "workspace too small");
+  return train_bwd(*d, *w, *io, *gin, *gw, d_audio_embeds, workspace, (cudaStream_t)stream);
+}
+
+size_t acvae_vocab_workspace_bytes(int32_t M, int32_t V, int32_t E) {
+  (void)E;
+  if (M <= 0 || V <= 0) return 0;
+  return carve_vocab_ws(M, V, nullptr, true).bytes;
+}
+
+int acvae_vocab_logits(int32_t M, int32_t V, int32_t E, const float* hidden, const float* cls_w, const float* cls_b,
+                       float* logits, void* stream) {
+  ACVAE_REQUIRE(M > 0 && V > 0 && E > 0 && hidden && cls_w && logits, "bad argument");
+  return linear_fwd(M, V, E, hidden, E, cls_w, E, cls_b, logits, V, (cudaStream_t)stream);
+}
+
+int acvae_vocab_logits_bwd(int32_t M, int32_t V, int32_t E, const float* hidden, const float* cls_w,
+                           const float* d_logits, float* d_hidden, float* d_cls_w, float* d_cls_b, void* stream) {
+  ACVAE_REQUIRE(M > 0 && V > 0 && E > 0 && hidden && cls_w && d_logits, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d_hidden) ACVAE_TRY(linear_bwd_data(M, E, V, d_logits, V, cls_w, E, d_hidden, E, st));
+  if (d_cls_w) ACVAE_TRY(linear_bwd_weight(V, E, M, d_logits, V, hidden, E, d_cls_w, E, st));
+  if (d_cls_b) ACVAE_TRY(colsum(M, V, d_logits, V, d_cls_b, st));
+  return 0;
+}
+
+int acvae_vocab_stats(int32_t M, int32_t V, int32_t E, const float* hidden, const float* cls_w, const float* cls_b,
+                      float* row_lse, float* row_sum, int64_t* row_argmax, float* row_logprob, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  ACVAE_REQUIRE(M > 0 && V > 0 && E > 0 && hidden && cls_w && workspace, "bad argument");
+  ACVAE_REQUIRE(workspace_bytes >= carve_vocab_ws(M, V, nullptr, false).bytes, "workspace too small");
+  VocabWs ws = carve_vocab_ws(M, V, workspace, false);
+  VocabStatsArgs v{};
+  v.M = M; v.V = V; v.E = E; v.hidden = hidden; v.ld_h = E; v.cls_w = cls_w; v.cls_b = cls_b;
+  v.pmax = ws.pmax; v.pexp = ws.pexp; v.psum = ws.psum; v.pbest = ws.pbest; v.parg = ws.parg;
+  v.red.lse = row_lse; v.red.lsum = row_sum; v.red.logprob = row_logprob; v.red.ld_row = 1;
+  v.red.seqs = (long long*)row_argmax; v.red.ld_seqs = 1;
+  return vocab_stats(v, (cudaStream_t)stream);
+}
+
+int acvae_vocab_ce_fwd(int32_t M, int32_t V, int32_t E, const float* hidden, const float* cls_w, const float* cls_b,
+                       const int32_t* targets, const float* row_w, float smoothing, int32_t have_stats, float* row_lse,
+                       float* row_sum, float* loss_out, void* workspace, size_t workspace_bytes, void* stream) {
+  ACVAE_REQUIRE(M > 0 && V > 1 && E > 0 && hidden && cls_w && cls_b && targets && row_lse && row_sum && loss_out && workspace,
+                "bad argument");
+  ACVAE_REQUIRE(workspace_bytes >= carve_vocab_ws(M, V, nullptr, false).bytes, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  VocabWs ws = carve_vocab_ws(M, V, workspace, false);
+  if (!have_stats) {
+    VocabStatsArgs v{};
+    v.M = M; v.V = V; v.E = E; v.hidden = hidden; v.ld_h = E; v.cls_w = cls_w; v.cls_b = cls_b;
+    v.pmax = ws.pmax; v.pexp = ws.pexp; v.psum = ws.psum; v.pbest = ws.pbest; v.parg = ws.parg;
+    v.red.lse = row_lse; v.red.lsum = row_sum; v.red.ld_row = 1;
+    ACVAE_TRY(vocab_stats(v, st));
+  }
+  CeRowsParams c{};
+  c.M = M; c.V = V; c.E = E; c.hidden = hidden; c.ld_h = E; c.cls_w = cls_w; c.cls_b = cls_b; c.targets = targets;
+  c.row_w = row_w; c.lse = row_lse; c.lsum = row_sum;
+  c.on = 1.0f - smoothing; c.off = smoothing / (float)(V - 1);   // utils/train_util.py:237,249-250
+  c.row_loss = ws.row_loss; c.row_cnt = ws.row_cnt;
+  ACVAE_LAUNCH(ce_rows_kernel, (M + 7) / 8, 256, 0, st, c);
+  ACVAE_LAUNCH(final_sum_kernel, 1, 256, 0, st, M, (const float*)ws.row_cnt, 1.0f, (const float*)nullptr, ws.scal);
+  ACVAE_LAUNCH(final_sum_kernel, 1, 256, 0, st, M, (const float*)ws.row_loss, 1.0f, (const float*)ws.scal, loss_out);
+  return 0;
+}
+
+int acvae_vocab_ce_bwd(int32_t M, int32_t V, int32_t E, const float* hidden, const float* cls_w, const float* cls_b,
+                       const int32_t* targets, const float* row_w, float smoothing, const float* row_lse,
+                       const float* d_loss, float* d_hidden, float* d_cls_w, float* d_cls_b, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  ACVAE_REQUIRE(M > 0 && V > 1 && E > 0 && hidden && cls_w && cls_b && targets && row_lse && d_loss && workspace, "bad argument");
+  ACVAE_REQUIRE(workspace_bytes >= carve_vocab_ws(M, V, nullptr, true).bytes, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  VocabWs ws = carve_vocab_ws(M, V, workspace, true);
+  ACVAE_LAUNCH(ce_gscale_kernel, 1, 256, 0, st, M, row_w, d_loss, ws.scal);
+  GemmParams p{};
+  p.M = M; p.U = V; p.G = 1; p.nseg = 1;
+  p.seg[0] = seg_plain(hidden, E, cls_w, E, E);
+  p.epi.bias[0] = cls_b; p.epi.c[0] = ws.dlogits; p.epi.ldc = V;
+  p.epi.lse = row_lse; p.epi.targets = targets; p.epi.row_w = row_w; p.epi.gscale = ws.scal;
+  p.epi.smooth_on = 1.0f - smoothing; p.epi.smooth_off = smoothing / (float)(V - 1);
+  ACVAE_TRY(launch_gemm<EPI_DLOGITS>(p, st));
+  if (d_hidden) ACVAE_TRY(linear_bwd_data(M, E, V, ws.dlogits, V, cls_w, E, d_hidden, E, st));
+  if (d_cls_w) ACVAE_TRY(linear_bwd_weight(V, E, M, ws.dlogits, V, hidden, E, d_cls_w, E, st));
+  if (d_cls_b) ACVAE_TRY(colsum(M, V, ws.dlogits, V, d_cls_b, st));
+  return 0;
+}
+
+int acvae_kl_fwd(int64_t rows, int32_t E, const float* q_mean, const float* q_log, const float* p_mean,
+                 const float* p_log, float* kl_out, void* stream) {
+  ACVAE_REQUIRE(rows > 0 && E > 0 && q_mean && q_log && p_mean && p_log && kl_out, "bad argument");
+  ACVAE_LAUNCH(kl_fwd_kernel, 1, 1024, 0, (cudaStream_t)stream, (long long)rows * E, 1.0f / (float)rows, q_mean, q_log,
+               p_mean, p_log, kl_out);
+  return 0;
+}
+
+int acvae_kl_bwd(int64_t rows, int32_t E, const float* q_mean, const float* q_log, const float* p_mean,
+                 const float* p_log, const float* d_kl, float* d_q_mean, float* d_q_log, float* d_p_mean,
+                 float* d_p_log, void* stream) {
+  ACVAE_REQUIRE(rows > 0 && E > 0 && q_mean && q_log && p_mean && p_log && d_kl && d_q_mean && d_q_log && d_p_mean && d_p_log,
+                "bad argument");
+  const long long n = (long long)rows * E;
+  ACVAE_LAUNCH(kl_bwd_kernel, grid1d(n), 256, 0, (cudaStream_t)stream, n, 1.0f / (float)rows, q_mean, q_log, p_mean,
+               p_log, d_kl, d_q_mean, d_q_log, d_p_mean, d_p_log);
+  return 0;
+}
+
+size_t acvae_sample_workspace_bytes(const acvae_dims* d) {
+  if (check_dims(d) != 0) return 0;
+  return carve_sample_ws(*d, nullptr).bytes;
+}
+
+int acvae_decode_sample(const acvae_dims* d, const acvae_weights* w, const acvae_sample_io* io, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  ACVAE_TRY(check_dims(d));
+  ACVAE_REQUIRE(w && io && workspace, "NULL pointer");
+  ACVAE_REQUIRE(io->audio_embeds && io->mem_lens && io->eps_p && io->seqs && io->sampled_logprobs, "NULL pointer in io");
+  ACVAE_REQUIRE(io->method == 0 || io->u, "method sample/gumbel needs uniform noise u");
+  ACVAE_REQUIRE(io->method >= 0 && io->method <= 2, "unknown sampling method");
+  ACVAE_REQUIRE(io->temp > 0.0f, "temp must be positive");
+  ACVAE_REQUIRE(workspace_bytes >= carve_sample_ws(*d, nullptr).bytes, "workspace too small");
+  return decode_sample(*d, *w, *io, workspace, (cudaStream_t)stream);
+}
+
+size_t acvae_beam_workspace_bytes(const acvae_dims* d, int32_t beam) {
+  if (check_dims(d) != 0 || beam <= 0) return 0;
+  return carve_beam_ws(*d, beam, nullptr).bytes;
+}
+
+int acvae_beam_search(const acvae_dims* d, const acvae_weights* w, const float* audio_embeds, const int32_t* mem_lens,
+                      const float* eps_b, int32_t beam, int32_t start_idx, int64_t* seqs, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  ACVAE_TRY(check_dims(d));
+  ACVAE_REQUIRE(w && audio_embeds && mem_lens && eps_b && seqs && workspace, "NULL pointer");
+  ACVAE_REQUIRE(beam >= 1 && beam <= 32, "beam must be in [1, 32]");
+  ACVAE_REQUIRE(d->mem_rep == 1, "beam search takes one row per clip (mem_rep == 1)");
+  ACVAE_REQUIRE(workspace_bytes >= carve_beam_ws(*d, beam, nullptr).bytes, "workspace too small");
+  return beam_search(*d, *w, audio_embeds, mem_lens, eps_b, beam, start_idx, seqs, workspace, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,247 @@
+// Inference loops with latents drawn from the autoregressive prior:
+//   - decode_sample: greedy / multinomial / gumbel stepwise decoding
+//     (reference models/vae_model.py:700-720, 880-894; models/word_model.py:173-207)
+//   - beam_search:   per-clip beam search with per-beam prior noise
+//     (reference models/vae_model.py:896-995)
+// State lives in a 2-slot ring [N,2,*]; nothing is kept per step.  `mem_rep`
+// consecutive sequences share one clip's memory and projected memory, so K
+// captions per clip read the clip's frames from L2 once per step instead of
+// K tiled copies (the reference tiles the clip K times through the encoder,
+// runners/pytorch_runner_vae.py:101-104).
+#pragma once
+#include "train.cuh"
+
+namespace acvae {
+
+struct SampleWs {
+  float *mem, *Pp, *Pd;
+  int *words, *unfinished, *active;
+  float *qp_p, *w_p, *ctx_p, *gates_p, *c_p, *h_p, *pm, *pl, *pz, *qp_d, *w_d, *ctx_d, *gates_d, *hd;
+  float *pmax, *pexp, *psum, *pbest; int* parg;
+  size_t bytes;
+};
+
+inline SampleWs carve_sample_ws(const acvae_dims& d, void* base) {
+  Arena ar(base);
+  SampleWs w{};
+  const size_t N = d.N, Te = d.Te, E = d.E, A = d.A, clips = d.N / d.mem_rep;
+  const size_t nt = (d.V + kVocabTile - 1) / kVocabTile;
+  w.mem = ar.take<float>(clips * Te * E); w.Pp = ar.take<float>(clips * Te * E); w.Pd = ar.take<float>(clips * Te * A);
+  w.words = ar.take<int>(N * 2); w.unfinished = ar.take<int>(N); w.active = ar.take<int>((size_t)d.T + 1);
+  w.qp_p = ar.take<float>(N * 2 * E); w.w_p = ar.take<float>(N * 2 * Te); w.ctx_p = ar.take<float>(N * 2 * E);
+  w.gates_p = ar.take<float>(N * 2 * 4 * E); w.c_p = ar.take<float>(N * 2 * E); w.h_p = ar.take<float>(N * 2 * E);
+  w.pm = ar.take<float>(N * 2 * E); w.pl = ar.take<float>(N * 2 * E); w.pz = ar.take<float>(N * 2 * E);
+  w.qp_d = ar.take<float>(N * 2 * A); w.w_d = ar.take<float>(N * 2 * Te); w.ctx_d = ar.take<float>(N * 2 * E);
+  w.gates_d = ar.take<float>(N * 2 * 4 * E); w.hd = ar.take<float>(N * 2 * E);
+  w.pmax = ar.take<float>(N * nt); w.pexp = ar.take<float>(N * nt); w.psum = ar.take<float>(N * nt);
+  w.pbest = ar.take<float>(N * nt * 2); w.parg = ar.take<int>(N * nt);
+  w.bytes = ar.off;
+  return w;
+}
+
+__global__ void sample_init_kernel(int N, int T, int start_idx, int end_idx, int* __restrict__ words,
+                                   int* __restrict__ unfinished, int* __restrict__ active, long long* __restrict__ seqs,
+                                   float* __restrict__ logprobs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) { words[i * 2] = start_idx; words[i * 2 + 1] = start_idx; unfinished[i] = 1; }
+  if (i <= T) active[i] = 0;
+  if (i < N * T) { seqs[i] = end_idx; logprobs[i] = 0.0f; }   // vae_model.py:764,767
+}
+
+__global__ void sample_nsteps_kernel(int T, const int* __restrict__ active, int* __restrict__ n_steps) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int n = T;
+    for (int t = 0; t < T; ++t)
+      if (active[t] == 0) { n = t + 1; break; }   // vae_model.py:719-720
+    *n_steps = n;
+  }
+}
+
+inline int decode_sample(const acvae_dims& d, const acvae_weights& w, const acvae_sample_io& io, void* workspace,
+                         cudaStream_t st) {
+  SampleWs ws = carve_sample_ws(d, workspace);
+  const int N = d.N, T = d.T, E = d.E;
+  ACVAE_TRY(memory_prepare(d, w, io.audio_embeds, ws.mem, ws.Pp, ws.Pd, st));
+  ACVAE_LAUNCH(sample_init_kernel, grid1d((long long)N * T + T + 1), 256, 0, st, N, T, io.start_idx, io.end_idx, ws.words,
+               ws.unfinished, ws.active, (long long*)io.seqs, io.sampled_logprobs);
+  StepBufs b{2, ws.qp_p, ws.w_p, ws.ctx_p, ws.gates_p, ws.c_p, ws.h_p, ws.pm, ws.pl, ws.pz,
+             ws.qp_d, ws.w_d, ws.ctx_d, ws.gates_d, ws.hd};
+  for (int t = 0; t < T; ++t) {
+    const int slot = t & 1, prev = t > 0 ? (t - 1) & 1 : -1;
+    const int* live = t > 0 ? ws.active + (t - 1) : nullptr;
+    StepCtx c{d, w, st, io.mem_lens, ws.mem, ws.Pp, ws.Pd, live};
+    ACVAE_TRY(prior_step(c, b, slot, prev, ws.words + slot, 2, io.eps_p + (long long)t * N * E));
+    // inference: the decoder consumes the prior's sample (vae_model.py:808)
+    ACVAE_TRY(decoder_step(c, b, slot, prev, ws.words + slot, 2, ws.pz + (long long)slot * E, 2LL * E, nullptr, 0, 0));
+    VocabStatsArgs v{};
+    v.M = N; v.V = d.V; v.E = E; v.hidden = ws.hd + (long long)slot * E; v.ld_h = 2LL * E;
+    v.cls_w = w.cls_w; v.cls_b = w.cls_b; v.live = live;
+    v.pmax = ws.pmax; v.pexp = ws.pexp; v.psum = ws.psum; v.pbest = ws.pbest; v.parg = ws.parg;
+    if (io.method != 0) {
+      v.noise = io.u + (long long)t * N * d.V; v.ld_noise = d.V;
+      v.inv_temp = io.method == 1 ? 1.0f / io.temp : 1.0f;   // word_model.py:187-198
+    }
+    v.red.logprob = io.sampled_logprobs + t; v.red.ld_row = T;
+    v.red.seqs = (long long*)io.seqs + t; v.red.ld_seqs = T;
+    v.red.next_word = ws.words + (slot ^ 1); v.red.ld_next = 2;
+    v.red.unfinished = ws.unfinished; v.red.end_idx = io.end_idx; v.red.active_count = ws.active + t;
+    ACVAE_TRY(vocab_stats(v, st));
+    auto keep = [&](float* dst, const float* ring) -> int {
+      if (!dst) return 0;
+      ACVAE_LAUNCH(copy2d_kernel, grid1d((long long)N * E), 256, 0, st, (long long)N, E, ring + (long long)slot * E,
+                   2LL * E, dst + (long long)t * E, (long long)T * E);
+      return 0;
+    };
+    ACVAE_TRY(keep(io.p_means, ws.pm)); ACVAE_TRY(keep(io.p_logs, ws.pl));
+    ACVAE_TRY(keep(io.p_z, ws.pz)); ACVAE_TRY(keep(io.outputs, ws.hd));
+  }
+  if (io.n_steps) ACVAE_LAUNCH(sample_nsteps_kernel, 1, 32, 0, st, T, (const int*)ws.active, io.n_steps);
+  return 0;
+}
+
+// ================================ beam search ====================================================
+struct BeamWs {
+  float *mem, *Pp, *Pd;
+  int *words, *prev, *hist[2];
+  float *top_lp, *logits;
+  float *qp_p, *w_p, *ctx_p, *gates_p, *c_p, *h_p, *pm, *pl, *pz, *qp_d, *w_d, *ctx_d, *gates_d, *hd;
+  size_t bytes;
+};
+
+inline BeamWs carve_beam_ws(const acvae_dims& d, int beam, void* base) {
+  Arena ar(base);
+  BeamWs w{};
+  const size_t clips = d.N, R = (size_t)d.N * beam, Te = d.Te, E = d.E, A = d.A, T = d.T;
+  w.mem = ar.take<float>(clips * Te * E); w.Pp = ar.take<float>(clips * Te * E); w.Pd = ar.take<float>(clips * Te * A);
+  w.words = ar.take<int>(R * 2); w.prev = ar.take<int>(R); w.hist[0] = ar.take<int>(R * T); w.hist[1] = ar.take<int>(R * T);
+  w.top_lp = ar.take<float>(R); w.logits = ar.take<float>(R * d.V);
+  w.qp_p = ar.take<float>(R * 2 * E); w.w_p = ar.take<float>(R * 2 * Te); w.ctx_p = ar.take<float>(R * 2 * E);
+  w.gates_p = ar.take<float>(R * 2 * 4 * E); w.c_p = ar.take<float>(R * 2 * E); w.h_p = ar.take<float>(R * 2 * E);
+  w.pm = ar.take<float>(R * 2 * E); w.pl = ar.take<float>(R * 2 * E); w.pz = ar.take<float>(R * 2 * E);
+  w.qp_d = ar.take<float>(R * 2 * A); w.w_d = ar.take<float>(R * 2 * Te); w.ctx_d = ar.take<float>(R * 2 * E);
+  w.gates_d = ar.take<float>(R * 2 * 4 * E); w.hd = ar.take<float>(R * 2 * E);
+  w.bytes = ar.off;
+  return w;
+}
+
+__global__ void beam_init_kernel(int R, int start_idx, int* __restrict__ words, float* __restrict__ top_lp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < R) { words[i * 2] = start_idx; words[i * 2 + 1] = start_idx; top_lp[i] = 0.0f; }   // vae_model.py:929,962
+}
+
+// One CTA per clip: log-softmax each beam row, add the running beam score, take the top `beam`
+// of the beam*V candidates (vae_model.py:909-916), extend the hypotheses (:917-921).
+__global__ void __launch_bounds__(256) beam_topk_kernel(int beam, int V, int T, int t, float* __restrict__ logits,
+                                                        float* __restrict__ top_lp, int* __restrict__ prev,
+                                                        int* __restrict__ words /*[R,2] slot 0*/,
+                                                        const int* __restrict__ hist_in, int* __restrict__ hist_out) {
+  __shared__ float red[33];
+  __shared__ float s_val[8];
+  __shared__ int s_idx[8];
+  __shared__ float s_lse[32];
+  __shared__ float s_newlp[32];
+  __shared__ int s_newidx[32];
+  const int clip = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  float* lg = logits + (long long)clip * beam * V;
+  for (int b = 0; b < beam; ++b) {
+    float mx = -INFINITY;
+    for (int v = tid; v < V; v += blockDim.x) mx = fmaxf(mx, lg[(long long)b * V + v]);
+    mx = block_max(mx, red);
+    float se = 0.0f;
+    for (int v = tid; v < V; v += blockDim.x) se += expf(lg[(long long)b * V + v] - mx);
+    se = block_sum(se, red);
+    if (tid == 0) s_lse[b] = mx + logf(se);
+  }
+  __syncthreads();
+  // candidates in place: score = top_lp[b] + logit - lse[b]
+  for (int b = 0; b < beam; ++b) {
+    const float off = top_lp[clip * beam + b] - s_lse[b];
+    for (int v = tid; v < V; v += blockDim.x) lg[(long long)b * V + v] += off;
+  }
+  __syncthreads();
+  const int total = beam * V;
+  for (int k = 0; k < beam; ++k) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < total; i += blockDim.x) {
+      const float x = lg[i];
+      if (x > best) { best = x; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { s_val[wid] = best; s_idx[wid] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      float bb = s_val[0]; int ii = s_idx[0];
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+        if (s_val[w] > bb || (s_val[w] == bb && s_idx[w] < ii)) { bb = s_val[w]; ii = s_idx[w]; }
+      s_newlp[k] = bb; s_newidx[k] = ii;
+      lg[ii] = -INFINITY;   // exclude from the next pass
+    }
+    __syncthreads();
+  }
+  for (int k = tid; k < beam; k += blockDim.x) {
+    const int idx = s_newidx[k];
+    const int r = clip * beam + k;
+    top_lp[r] = s_newlp[k];
+    prev[r] = idx / V;
+    words[r * 2] = idx % V;
+  }
+  for (int i = tid; i < beam * (t + 1); i += blockDim.x) {
+    const int k = i / (t + 1), tt = i % (t + 1);
+    const int idx = s_newidx[k];
+    const int src = clip * beam + idx / V;
+    hist_out[(long long)(clip * beam + k) * T + tt] = tt < t ? hist_in[(long long)src * T + tt] : idx % V;
+  }
+}
+
+// state[(clip,k), slot 0] = state[(clip, prev[k]), slot 1]   (vae_model.py:963-969)
+__global__ void beam_reindex_kernel(int R, int beam, int E, const int* __restrict__ prev, float* __restrict__ hd,
+                                    float* __restrict__ h_p, float* __restrict__ c_p, float* __restrict__ pz) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)R * E) return;
+  const int r = (int)(i / E), e = (int)(i % E);
+  const int src = (r / beam) * beam + prev[r];
+  const long long so = ((long long)src * 2 + 1) * E + e, dst_o = ((long long)r * 2) * E + e;
+  hd[dst_o] = hd[so]; h_p[dst_o] = h_p[so]; c_p[dst_o] = c_p[so]; pz[dst_o] = pz[so];
+}
+
+__global__ void beam_final_kernel(int N, int beam, int T, const int* __restrict__ hist, long long* __restrict__ seqs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * T) return;
+  const int n = i / T, t = i % T;
+  seqs[i] = hist[(long long)(n * beam) * T + t];   // top beam (vae_model.py:986)
+}
+
+inline int beam_search(const acvae_dims& d0, const acvae_weights& w, const float* audio, const int* mem_lens,
+                       const float* eps_b, int beam, int start_idx, int64_t* seqs, void* workspace, cudaStream_t st) {
+  BeamWs ws = carve_beam_ws(d0, beam, workspace);
+  const int clips = d0.N, T = d0.T, E = d0.E, V = d0.V, R = clips * beam;
+  acvae_dims dm = d0;                       // memory: one row per clip
+  ACVAE_TRY(memory_prepare(dm, w, audio, ws.mem, ws.Pp, ws.Pd, st));
+  acvae_dims d = d0;
+  d.N = R; d.mem_rep = beam;                // decode rows: beam hypotheses per clip share its memory
+  ACVAE_LAUNCH(beam_init_kernel, grid1d(R), 256, 0, st, R, start_idx, ws.words, ws.top_lp);
+  StepBufs b{2, ws.qp_p, ws.w_p, ws.ctx_p, ws.gates_p, ws.c_p, ws.h_p, ws.pm, ws.pl, ws.pz,
+             ws.qp_d, ws.w_d, ws.ctx_d, ws.gates_d, ws.hd};
+  StepCtx c{d, w, st, mem_lens, ws.mem, ws.Pp, ws.Pd, nullptr};
+  for (int t = 0; t < T; ++t) {
+    const int prev = t > 0 ? 0 : -1;        // slot 0 holds the re-indexed state, slot 1 the fresh step
+    ACVAE_TRY(prior_step(c, b, 1, prev, ws.words, 2, eps_b + (long long)t * R * E));
+    ACVAE_TRY(decoder_step(c, b, 1, prev, ws.words, 2, ws.pz + E, 2LL * E, nullptr, 0, 0));
+    ACVAE_TRY(linear_fwd(R, V, E, ws.hd + E, 2LL * E, w.cls_w, E, w.cls_b, ws.logits, V, st));
+    ACVAE_LAUNCH(beam_topk_kernel, clips, 256, 0, st, beam, V, T, t, ws.logits, ws.top_lp, ws.prev, ws.words,
+                 (const int*)ws.hist[t & 1], ws.hist[(t + 1) & 1]);
+    ACVAE_LAUNCH(beam_reindex_kernel, grid1d((long long)R * E), 256, 0, st, R, beam, E, (const int*)ws.prev, ws.hd,
+                 ws.h_p, ws.c_p, ws.pz);
+  }
+  ACVAE_LAUNCH(beam_final_kernel, grid1d((long long)clips * T), 256, 0, st, clips, beam, T, (const int*)ws.hist[T & 1],
+               (long long*)seqs);
+  return 0;
+}
+
+}  // namespace acvae

@@ -1,0 +1,381 @@
+"""torch.autograd bridges over the C-ABI (`include/acvae_b200.h`).
+
+PyTorch is plumbing here: it owns device memory, the current stream and the
+autograd tape.  All arithmetic of the hot path happens inside
+`libacvae_b200.so`; there is no eager/CPU fallback -- a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+# order in which weights are handed to the autograd Function
+HOT_KEYS_HYBRID = [
+    "ln.weight", "ln.bias",
+    "qnet.word_embedding.weight",
+    "qnet.network.weight_ih_l0", "qnet.network.weight_hh_l0", "qnet.network.bias_ih_l0", "qnet.network.bias_hh_l0",
+    "qnet.network.weight_ih_l0_reverse", "qnet.network.weight_hh_l0_reverse",
+    "qnet.network.bias_ih_l0_reverse", "qnet.network.bias_hh_l0_reverse",
+    "qnet.token_mean_log.weight", "qnet.token_mean_log.bias",
+    "pnet.word_embedding.weight",
+    "pnet.word_attn.h2attn.weight", "pnet.word_attn.h2attn.bias", "pnet.word_attn.v",
+    "pnet.network.weight_ih_l0", "pnet.network.weight_hh_l0", "pnet.network.bias_ih_l0", "pnet.network.bias_hh_l0",
+    "pnet.mean_log_out.weight", "pnet.mean_log_out.bias",
+    "decoder.word_embeddings.weight",
+    "decoder.attn.h2attn.weight", "decoder.attn.h2attn.bias", "decoder.attn.v",
+    "decoder.model.weight_ih_l0", "decoder.model.weight_hh_l0", "decoder.model.bias_ih_l0", "decoder.model.bias_hh_l0",
+    "decoder.classifier.weight", "decoder.classifier.bias",
+    "mean_log_out.weight", "mean_log_out.bias",
+]
+
+# state_dict key -> (C struct field, index or None)
+_FIELD = {
+    "ln.weight": ("ln_w", None), "ln.bias": ("ln_b", None),
+    "qnet.word_embedding.weight": ("q_emb", None),
+    "qnet.network.weight_ih_l0": ("q_wih", 0), "qnet.network.weight_hh_l0": ("q_whh", 0),
+    "qnet.network.bias_ih_l0": ("q_bih", 0), "qnet.network.bias_hh_l0": ("q_bhh", 0),
+    "qnet.network.weight_ih_l0_reverse": ("q_wih", 1), "qnet.network.weight_hh_l0_reverse": ("q_whh", 1),
+    "qnet.network.bias_ih_l0_reverse": ("q_bih", 1), "qnet.network.bias_hh_l0_reverse": ("q_bhh", 1),
+    "qnet.token_mean_log.weight": ("q_head_w", None), "qnet.token_mean_log.bias": ("q_head_b", None),
+    "qnet.mean_log_out.weight": ("q_head_w", None), "qnet.mean_log_out.bias": ("q_head_b", None),
+    "pnet.word_embedding.weight": ("p_emb", None),
+    "pnet.word_attn.h2attn.weight": ("p_attn_w", None), "pnet.word_attn.h2attn.bias": ("p_attn_b", None),
+    "pnet.word_attn.v": ("p_attn_v", None),
+    "pnet.network.weight_ih_l0": ("p_wih", None), "pnet.network.weight_hh_l0": ("p_whh", None),
+    "pnet.network.bias_ih_l0": ("p_bih", None), "pnet.network.bias_hh_l0": ("p_bhh", None),
+    "pnet.mean_log_out.weight": ("p_head_w", None), "pnet.mean_log_out.bias": ("p_head_b", None),
+    "decoder.word_embeddings.weight": ("d_emb", None),
+    "decoder.attn.h2attn.weight": ("d_attn_w", None), "decoder.attn.h2attn.bias": ("d_attn_b", None),
+    "decoder.attn.v": ("d_attn_v", None),
+    "decoder.model.weight_ih_l0": ("d_wih", None), "decoder.model.weight_hh_l0": ("d_whh", None),
+    "decoder.model.bias_ih_l0": ("d_bih", None), "decoder.model.bias_hh_l0": ("d_bhh", None),
+    "decoder.classifier.weight": ("cls_w", None), "decoder.classifier.bias": ("cls_b", None),
+    "mean_log_out.weight": ("g_w", None), "mean_log_out.bias": ("g_b", None),
+}
+
+
+def _dev(t: torch.Tensor, dtype=torch.float32) -> int:
+    if not t.is_cuda:
+        raise RuntimeError("acvae_b200 runs on CUDA tensors only (no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError("expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def _opt(t: Optional[torch.Tensor], dtype=torch.float32):
+    return None if t is None else _dev(t, dtype)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def pack_weights(weights: Dict[str, torch.Tensor], struct_cls=_lib.Weights):
+    s = struct_cls()
+    for k, t in weights.items():
+        if t is None:
+            continue
+        field, idx = _FIELD[k]
+        if idx is None:
+            setattr(s, field, _dev(t))
+        else:
+            getattr(s, field)[idx] = _dev(t)
+    return s
+
+
+def make_dims(N, Te, T, E, A, V, Eenc, L=0, mem_rep=1, variant=0) -> _lib.Dims:
+    return _lib.Dims(N, Te, T, E, A, V, Eenc, L, mem_rep, variant)
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def launch_count() -> int:
+    return int(_lib.lib().acvae_launch_count())
+
+
+# --------------------------------------------------------------------------------
+class TrainMeta:
+    """Non-tensor inputs of one training forward (ids, lengths, noise, decisions)."""
+
+    def __init__(self, dims, keys, caps_ids, cap_lens, mem_lens, eps_q, eps_p, tf_flags, dis_flags,
+                 want_logits=False):
+        self.dims, self.keys = dims, list(keys)
+        self.caps_ids, self.cap_lens, self.mem_lens = caps_ids, cap_lens, mem_lens
+        self.eps_q, self.eps_p = eps_q, eps_p
+        self.tf_flags = np.ascontiguousarray(np.asarray(tf_flags, dtype=np.uint8))
+        self.dis_flags = np.ascontiguousarray(np.asarray(dis_flags, dtype=np.uint8))
+        self.want_logits = want_logits
+
+
+class LatentDecodeTrainFn(torch.autograd.Function):
+    """Fused training forward/backward of the latent word-decoding step.
+
+    Replaces autograd over `Hybrid_VAEModel.forward` (reference
+    models/vae_model.py:732-750, 700-730) with `acvae_train_fwd` /
+    `acvae_train_bwd`.
+    outputs: q_means, q_logs, q_z, p_means, p_logs, p_z, outputs, q_means_utt,
+             p_means_utt, | attn_weights, seqs, sampled_logprobs, logit_lse,
+             logit_sum, rnn_input, logits (the tail is non-differentiable)
+    """
+
+    @staticmethod
+    def forward(ctx, meta: TrainMeta, audio_embeds: torch.Tensor, *weights: torch.Tensor):
+        l = _lib.lib()
+        d = meta.dims
+        dev = audio_embeds.device
+        N, T, E, Te, V = d.N, d.T, d.E, d.Te, d.V
+        audio_embeds = audio_embeds.contiguous()
+        wmap = dict(zip(meta.keys, [w.detach().contiguous() for w in weights]))
+        wstruct = pack_weights(wmap)
+        f32 = dict(dtype=torch.float32, device=dev)
+        o = {k: torch.empty(N, T, E, **f32) for k in ("q_means", "q_logs", "q_z", "p_means", "p_logs", "p_z", "outputs")}
+        hybrid = d.variant == 0
+        o["q_means_utt"] = torch.empty(N, 2 * E, **f32) if hybrid else torch.zeros(1, **f32)
+        o["p_means_utt"] = torch.empty(N, 2 * E, **f32) if hybrid else torch.zeros(1, **f32)
+        o["attn_weights"] = torch.empty(N, Te, T, **f32)
+        o["seqs"] = torch.empty(N, T, dtype=torch.int64, device=dev)
+        o["sampled_logprobs"] = torch.empty(N, T, **f32)
+        o["logit_lse"] = torch.empty(N, T, **f32)
+        o["logit_sum"] = torch.empty(N, T, **f32)
+        o["rnn_input"] = torch.empty(N, T, 3 * E, **f32) if not hybrid else torch.zeros(1, **f32)
+        o["logits"] = torch.empty(N, T, V, **f32) if meta.want_logits else torch.zeros(1, **f32)
+        io = _lib.TrainIO()
+        io.audio_embeds = _dev(audio_embeds)
+        io.mem_lens = _dev(meta.mem_lens, torch.int32)
+        io.caps_ids = _dev(meta.caps_ids, torch.int32)
+        io.cap_lens = _dev(meta.cap_lens, torch.int32)
+        io.eps_q = _dev(meta.eps_q)
+        io.eps_p = _dev(meta.eps_p)
+        io.tf_flags = meta.tf_flags.ctypes.data
+        io.dis_flags = meta.dis_flags.ctypes.data
+        for k in ("q_means", "q_logs", "q_z", "p_means", "p_logs", "p_z", "outputs", "attn_weights",
+                  "sampled_logprobs", "logit_lse", "logit_sum"):
+            setattr(io, k, _dev(o[k]))
+        io.seqs = _dev(o["seqs"], torch.int64)
+        if hybrid:
+            io.q_means_utt = _dev(o["q_means_utt"]); io.p_means_utt = _dev(o["p_means_utt"])
+        else:
+            io.rnn_input = _dev(o["rnn_input"])
+        if meta.want_logits:
+            io.logits = _dev(o["logits"])
+        nbytes = l.acvae_train_workspace_bytes(C.byref(d))
+        ws = _workspace(nbytes, dev)
+        _lib.check(l.acvae_train_fwd(C.byref(d), C.byref(wstruct), C.byref(io), ws.data_ptr(), ws.numel(), _stream()),
+                   "acvae_train_fwd")
+        ctx.meta, ctx.ws, ctx.io, ctx.wmap, ctx.audio = meta, ws, io, wmap, audio_embeds
+        ctx.need_audio_grad = audio_embeds.requires_grad
+        order = ["q_means", "q_logs", "q_z", "p_means", "p_logs", "p_z", "outputs", "q_means_utt", "p_means_utt",
+                 "attn_weights", "seqs", "sampled_logprobs", "logit_lse", "logit_sum", "rnn_input", "logits"]
+        res = tuple(o[k] for k in order)
+        ctx.mark_non_differentiable(*res[9:])
+        # `io` holds raw pointers into these outputs; saving them keeps the storage alive for backward
+        ctx.save_for_backward(*res[:9])
+        return res
+
+    @staticmethod
+    def backward(ctx, *g):
+        l = _lib.lib()
+        meta, d = ctx.meta, ctx.meta.dims
+        dev = ctx.audio.device
+        names = ["d_q_means", "d_q_logs", "d_q_z", "d_p_means", "d_p_logs", "d_p_z", "d_outputs",
+                 "d_q_means_utt", "d_p_means_utt"]
+        gin = _lib.TrainGradsIn()
+        keep = []
+        for name, gt in zip(names, g[:9]):
+            if gt is None or (d.variant == 1 and name.endswith("_utt")):
+                continue
+            gt = gt.contiguous()
+            keep.append(gt)
+            setattr(gin, name, _dev(gt))
+        # one flat gradient buffer, carved per weight (a single NCCL all-reduce can cover it)
+        sizes = [ctx.wmap[k].numel() for k in meta.keys]
+        offs = np.concatenate([[0], np.cumsum([(s + 63) // 64 * 64 for s in sizes])])
+        flat = torch.zeros(int(offs[-1]), dtype=torch.float32, device=dev)
+        gmap = {k: flat[int(offs[i]):int(offs[i]) + sizes[i]].view_as(ctx.wmap[k]) for i, k in enumerate(meta.keys)}
+        gstruct = pack_weights(gmap, _lib.WeightGrads)
+        d_audio = torch.empty_like(ctx.audio) if ctx.need_audio_grad else None
+        wstruct = pack_weights(ctx.wmap)
+        _lib.check(l.acvae_train_bwd(C.byref(d), C.byref(wstruct), C.byref(ctx.io), C.byref(gin), C.byref(gstruct),
+                                     _opt(d_audio), ctx.ws.data_ptr(), ctx.ws.numel(), _stream()), "acvae_train_bwd")
+        grads = []
+        for k in meta.keys:
+            grads.append(None if k.startswith("decoder.classifier") else gmap[k])
+        return (None, d_audio, *grads)
+
+
+# --------------------------------------------------------------------------------
+class VocabLogitsFn(torch.autograd.Function):
+    """logits = hidden @ W^T + b  (reference models/decoder.py:199), materialised."""
+
+    @staticmethod
+    def forward(ctx, hidden, cls_w, cls_b):
+        l = _lib.lib()
+        shp = hidden.shape
+        h2 = hidden.contiguous().view(-1, shp[-1])
+        M, E = h2.shape
+        V = cls_w.shape[0]
+        out = torch.empty(M, V, dtype=torch.float32, device=hidden.device)
+        w, b = cls_w.detach().contiguous(), cls_b.detach().contiguous()
+        _lib.check(l.acvae_vocab_logits(M, V, E, _dev(h2), _dev(w), _dev(b), _dev(out), _stream()), "acvae_vocab_logits")
+        ctx.save_for_backward(h2, w)
+        ctx.shp = shp
+        return out.view(*shp[:-1], V)
+
+    @staticmethod
+    def backward(ctx, g):
+        l = _lib.lib()
+        h2, w = ctx.saved_tensors
+        M, E = h2.shape
+        V = w.shape[0]
+        g2 = g.contiguous().view(M, V)
+        dh = torch.empty_like(h2); dw = torch.empty_like(w)
+        db = torch.empty(V, dtype=torch.float32, device=h2.device)
+        _lib.check(l.acvae_vocab_logits_bwd(M, V, E, _dev(h2), _dev(w), _dev(g2), _dev(dh), _dev(dw), _dev(db), _stream()),
+                   "acvae_vocab_logits_bwd")
+        return dh.view(ctx.shp), dw, db
+
+
+class VocabCEFn(torch.autograd.Function):
+    """Label-smoothed CE over packed rows without materialising logits.
+
+    Replaces `criterion(packed_logits, targets)` (reference
+    runners/pytorch_runner_vae.py:315 with utils/train_util.py:244-251).
+    """
+
+    @staticmethod
+    def forward(ctx, hidden, cls_w, cls_b, targets, smoothing, row_lse, row_sum):
+        l = _lib.lib()
+        h2 = hidden.contiguous()
+        M, E = h2.shape
+        V = cls_w.shape[0]
+        w, b = cls_w.detach().contiguous(), cls_b.detach().contiguous()
+        tg = targets.to(device=h2.device, dtype=torch.int32).contiguous()
+        have = row_lse is not None and row_sum is not None
+        if have:
+            row_lse, row_sum = row_lse.contiguous(), row_sum.contiguous()
+        else:
+            row_lse = torch.empty(M, dtype=torch.float32, device=h2.device)
+            row_sum = torch.empty(M, dtype=torch.float32, device=h2.device)
+        loss = torch.empty((), dtype=torch.float32, device=h2.device)
+        nbytes = l.acvae_vocab_workspace_bytes(M, V, E)
+        ws = _workspace(nbytes, h2.device)
+        _lib.check(l.acvae_vocab_ce_fwd(M, V, E, _dev(h2), _dev(w), _dev(b), _dev(tg, torch.int32), None,
+                                        float(smoothing), int(have), _dev(row_lse), _dev(row_sum), _dev(loss),
+                                        ws.data_ptr(), ws.numel(), _stream()), "acvae_vocab_ce_fwd")
+        ctx.save_for_backward(h2, w, b, tg, row_lse)
+        ctx.smoothing, ctx.ws = float(smoothing), ws
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        l = _lib.lib()
+        h2, w, b, tg, row_lse = ctx.saved_tensors
+        M, E = h2.shape
+        V = w.shape[0]
+        g = g.contiguous().to(torch.float32)
+        dh = torch.empty_like(h2); dw = torch.empty_like(w)
+        db = torch.empty(V, dtype=torch.float32, device=h2.device)
+        _lib.check(l.acvae_vocab_ce_bwd(M, V, E, _dev(h2), _dev(w), _dev(b), _dev(tg, torch.int32), None, ctx.smoothing,
+                                        _dev(row_lse), _dev(g), _dev(dh), _dev(dw), _dev(db),
+                                        ctx.ws.data_ptr(), ctx.ws.numel(), _stream()), "acvae_vocab_ce_bwd")
+        return dh, dw, db, None, None, None, None
+
+
+class NormalKLFn(torch.autograd.Function):
+    """KL(q||p) summed over d, mean over all positions (utils/train_util.py:259-266)."""
+
+    @staticmethod
+    def forward(ctx, mu1, lv1, mu2, lv2):
+        l = _lib.lib()
+        ts = [t.contiguous() for t in (mu1, lv1, mu2, lv2)]
+        E = ts[0].shape[-1]
+        rows = ts[0].numel() // E
+        out = torch.empty((), dtype=torch.float32, device=ts[0].device)
+        _lib.check(l.acvae_kl_fwd(rows, E, *[_dev(t) for t in ts], _dev(out), _stream()), "acvae_kl_fwd")
+        ctx.save_for_backward(*ts)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        l = _lib.lib()
+        ts = ctx.saved_tensors
+        E = ts[0].shape[-1]
+        rows = ts[0].numel() // E
+        outs = [torch.empty_like(t) for t in ts]
+        g = g.contiguous().to(torch.float32)
+        _lib.check(l.acvae_kl_bwd(rows, E, *[_dev(t) for t in ts], _dev(g), *[_dev(t) for t in outs], _stream()),
+                   "acvae_kl_bwd")
+        return tuple(outs)
+
+
+def vocab_stats(hidden, cls_w, cls_b):
+    """(lse, sum, argmax, logprob_of_argmax) per row of hidden [M,E]; no logits stored."""
+    l = _lib.lib()
+    h2 = hidden.contiguous().view(-1, hidden.shape[-1])
+    M, E = h2.shape
+    V = cls_w.shape[0]
+    dev = h2.device
+    lse = torch.empty(M, dtype=torch.float32, device=dev); ssum = torch.empty_like(lse); lp = torch.empty_like(lse)
+    arg = torch.empty(M, dtype=torch.int64, device=dev)
+    ws = _workspace(l.acvae_vocab_workspace_bytes(M, V, E), dev)
+    _lib.check(l.acvae_vocab_stats(M, V, E, _dev(h2), _dev(cls_w.detach().contiguous()), _dev(cls_b.detach().contiguous()),
+                                   _dev(lse), _dev(ssum), _dev(arg, torch.int64), _dev(lp), ws.data_ptr(), ws.numel(),
+                                   _stream()), "acvae_vocab_stats")
+    return lse, ssum, arg, lp
+
+
+def decode_sample(dims, weights: Dict[str, torch.Tensor], audio_embeds, mem_lens, eps_p, u=None, method="greedy",
+                  temp=1.0, start_idx=1, end_idx=2, keep_latents=False):
+    """Prior-latent stepwise decoding (reference vae_model.py:880-894, 700-720)."""
+    l = _lib.lib()
+    dev = audio_embeds.device
+    N, T, E = dims.N, dims.T, dims.E
+    code = {"greedy": 0, "sample": 1, "gumbel": 2}.get(method, 1)   # word_model.py:196: any other string samples
+    io = _lib.SampleIO()
+    audio_embeds = audio_embeds.contiguous()
+    io.audio_embeds = _dev(audio_embeds); io.mem_lens = _dev(mem_lens, torch.int32); io.eps_p = _dev(eps_p)
+    if code != 0:
+        if u is None:
+            raise RuntimeError("sampling methods need uniform noise `u` [T,N,V]")
+        io.u = _dev(u)
+    io.method, io.temp, io.start_idx, io.end_idx = code, float(temp), int(start_idx), int(end_idx)
+    out = {"seqs": torch.empty(N, T, dtype=torch.int64, device=dev),
+           "sampled_logprobs": torch.empty(N, T, dtype=torch.float32, device=dev),
+           "n_steps": torch.zeros((), dtype=torch.int32, device=dev)}
+    io.seqs = _dev(out["seqs"], torch.int64); io.sampled_logprobs = _dev(out["sampled_logprobs"])
+    io.n_steps = _dev(out["n_steps"], torch.int32)
+    if keep_latents:
+        for k in ("p_means", "p_logs", "p_z", "outputs"):
+            out[k] = torch.empty(N, T, E, dtype=torch.float32, device=dev)
+            setattr(io, k, _dev(out[k]))
+    wmap = {k: v.detach().contiguous() for k, v in weights.items()}
+    wstruct = pack_weights(wmap)
+    ws = _workspace(l.acvae_sample_workspace_bytes(C.byref(dims)), dev)
+    _lib.check(l.acvae_decode_sample(C.byref(dims), C.byref(wstruct), C.byref(io), ws.data_ptr(), ws.numel(), _stream()),
+               "acvae_decode_sample")
+    return out
+
+
+def beam_search(dims, weights, audio_embeds, mem_lens, eps_b, beam=3, start_idx=1):
+    """Beam search with per-beam prior noise (reference vae_model.py:896-995).
+    eps_b: [T, N*beam, E]."""
+    l = _lib.lib()
+    dev = audio_embeds.device
+    seqs = torch.empty(dims.N, dims.T, dtype=torch.int64, device=dev)
+    wmap = {k: v.detach().contiguous() for k, v in weights.items()}
+    wstruct = pack_weights(wmap)
+    audio_embeds = audio_embeds.contiguous()
+    ws = _workspace(l.acvae_beam_workspace_bytes(C.byref(dims), int(beam)), dev)
+    _lib.check(l.acvae_beam_search(C.byref(dims), C.byref(wstruct), _dev(audio_embeds), _dev(mem_lens, torch.int32),
+                                   _dev(eps_b.contiguous()), int(beam), int(start_idx), _dev(seqs, torch.int64),
+                                   ws.data_ptr(), ws.numel(), _stream()), "acvae_beam_search")
+    return {"seqs": seqs}

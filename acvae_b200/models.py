@@ -1,0 +1,369 @@
+"""Host-side mirror of the reference's model classes for the AC-VAE hot path.
+
+Same class names, constructor arguments, `forward` signatures, output-dict keys
+and `state_dict` names as the reference, so `runners/pytorch_runner_vae.py`
+(`getattr(models, config["model"])(encoder, decoder, **model_args)`,
+pytorch_runner_vae.py:32-73) can drive them unchanged -- see INTEGRATION.md.
+The sub-modules only OWN parameters (they are never called layer by layer):
+the whole step runs inside `libacvae_b200.so`.
+
+reference                                         here
+models/attn_model.py:6-46     Seq2SeqAttention    Seq2SeqAttention      (parameter container)
+models/decoder.py:164-203     VAERNNBahdanau...   VAERNNBahdanauAttnDecoder
+models/text_encoder.py:156    PosteriorRNN_hybrid PosteriorRNN_hybrid
+models/text_encoder.py:96     PosteriorRNN        PosteriorRNN          (AR posterior, VAEModel)
+models/text_encoder.py:218    PriorRNN            PriorRNN
+models/word_model.py:14       CaptionModel        CaptionModel          (ids, set_index)
+models/vae_model.py:674       Hybrid_VAEModel     Hybrid_VAEModel
+models/vae_model.py:12        VAEModel            VAEModel
+"""
+from __future__ import annotations
+
+import random
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import functional as F
+from .lazy import LazyLogits
+
+
+def _fused_only(name):
+    def forward(self, *a, **k):
+        raise NotImplementedError(
+            f"{name}.forward is fused into Hybrid_VAEModel/VAEModel.forward (libacvae_b200.so); "
+            "the sub-module only owns its parameters")
+    return forward
+
+
+def _init_linear_xavier(module: nn.Module):
+    """PosteriorBaseEncoder.init / PriorBaseEncoder.init (text_encoder.py:26-42, 66-81)."""
+    for m in module.modules():
+        if isinstance(m, nn.Linear):
+            nn.init.xavier_uniform_(m.weight)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+
+
+class Seq2SeqAttention(nn.Module):
+    """Parameters of the additive attention (attn_model.py:8-18): h2attn [A, hs_dec+hs_enc]
+    (query columns first, :31), v [A] ~ N(0,1)."""
+
+    def __init__(self, hs_enc, hs_dec, attn_size):
+        super().__init__()
+        self.h2attn = nn.Linear(hs_enc + hs_dec, attn_size)
+        self.v = nn.Parameter(torch.randn(attn_size))
+        nn.init.kaiming_uniform_(self.h2attn.weight)
+
+    forward = _fused_only("Seq2SeqAttention")
+
+
+class VAERNNBahdanauAttnDecoder(nn.Module):
+    """decoder.py:164-173 (+ RNNDecoder.__init__ :30-48, BaseDecoder :17-22)."""
+
+    def __init__(self, vocab_size, enc_mem_size, **kwargs):
+        super().__init__()
+        embed_size = kwargs.get("embed_size", 256)
+        hidden_size = kwargs.get("hidden_size", 256)
+        if kwargs.get("num_layers", 1) != 1 or kwargs.get("bidirectional", False) or kwargs.get("rnn_type", "GRU") != "GRU":
+            raise NotImplementedError("the fused step implements the reference default: 1-layer unidirectional GRU")
+        self.embed_size, self.vocab_size, self.enc_mem_size = embed_size, vocab_size, enc_mem_size * 2
+        self.word_embeddings = nn.Embedding(vocab_size, embed_size)
+        self.dropoutlayer = nn.Dropout(kwargs.get("dropout", 0.0))
+        self.model = nn.GRU(input_size=embed_size + enc_mem_size * 2, hidden_size=hidden_size, num_layers=1,
+                            batch_first=True, bidirectional=False)
+        self.classifier = nn.Linear(hidden_size, vocab_size)
+        nn.init.kaiming_uniform_(self.word_embeddings.weight)
+        nn.init.kaiming_uniform_(self.classifier.weight)
+        attn_size = kwargs.get("attn_size", hidden_size)
+        self.attn = Seq2SeqAttention(enc_mem_size, hidden_size, attn_size)
+
+    def load_word_embeddings(self, embeddings, tune=True, **kwargs):
+        """decoder.py:50-64 (projection variant not supported by the fused step)."""
+        assert embeddings.shape[0] == self.vocab_size, "vocabulary size mismatch!"
+        embeddings = torch.as_tensor(embeddings).float()
+        assert embeddings.shape[1] == self.embed_size, "embedding size mismatch!"
+        self.word_embeddings.weight = nn.Parameter(embeddings)
+        for para in self.word_embeddings.parameters():
+            para.requires_grad = tune
+
+    def init_hidden(self, bs):
+        return torch.zeros(1, bs, self.model.hidden_size)
+
+    forward = _fused_only("VAERNNBahdanauAttnDecoder")
+
+
+class _PosteriorBase(nn.Module):
+    def __init__(self, word_dim, embed_size, vocab_size, **kwargs):
+        super().__init__()
+        self.word_dim, self.embed_size, self.vocab_size = word_dim, embed_size, vocab_size
+        self.word_embedding = nn.Embedding(vocab_size, word_dim)
+        self.hidden_size = kwargs.get("hidden_size", 256)
+        if (not kwargs.get("bidirectional", True)) or kwargs.get("num_layers", 1) != 1 or kwargs.get("rnn_type", "GRU") != "GRU":
+            raise NotImplementedError("the fused step implements the reference default: 1-layer bidirectional GRU")
+        self.network = nn.GRU(word_dim, self.hidden_size, num_layers=1, bidirectional=True, batch_first=True)
+
+
+class PosteriorRNN_hybrid(_PosteriorBase):
+    """text_encoder.py:156-180: contextual posterior + utterance pooling."""
+
+    def __init__(self, word_dim, embed_size, vocab_size, **kwargs):
+        super().__init__(word_dim, embed_size, vocab_size, **kwargs)
+        self.token_mean_log = nn.Linear(2 * self.hidden_size, 2 * embed_size)
+        _init_linear_xavier(self)
+
+    forward = _fused_only("PosteriorRNN_hybrid")
+
+
+class PosteriorRNN(_PosteriorBase):
+    """text_encoder.py:96-119: autoregressive posterior (VAEModel)."""
+
+    def __init__(self, word_dim, embed_size, vocab_size, **kwargs):
+        super().__init__(word_dim, embed_size, vocab_size, **kwargs)
+        self.mean_log_out = nn.Linear(embed_size + 2 * self.hidden_size, 2 * embed_size)
+        _init_linear_xavier(self)
+
+    forward = _fused_only("PosteriorRNN")
+
+
+class PriorRNN(nn.Module):
+    """text_encoder.py:218-238: autoregressive prior (word attention + LSTM + Gaussian head)."""
+
+    def __init__(self, word_dim, audiofeats_size, embed_size, vocab_size, **kwargs):
+        super().__init__()
+        self.word_dim, self.embed_size, self.vocab_size, self.audiofeats_size = word_dim, embed_size, vocab_size, audiofeats_size
+        self.word_embedding = nn.Embedding(vocab_size, word_dim)
+        self.hidden_size = kwargs.get("hidden_size", 256)
+        if kwargs.get("bidirectional", False) or kwargs.get("num_layers", 1) != 1 or kwargs.get("rnn_type", "LSTM") != "LSTM":
+            raise NotImplementedError("the fused step implements the reference default: 1-layer unidirectional LSTM")
+        self.word_attn = Seq2SeqAttention(audiofeats_size, word_dim, audiofeats_size)
+        self.network = nn.LSTM(word_dim + audiofeats_size + embed_size, self.hidden_size, num_layers=1,
+                               bidirectional=False, batch_first=True)
+        self.mean_log_out = nn.Linear(self.hidden_size, 2 * embed_size)
+        _init_linear_xavier(self)
+
+    forward = _fused_only("PriorRNN")
+
+
+_text_encoders = {"PosteriorRNN_hybrid": PosteriorRNN_hybrid, "PosteriorRNN": PosteriorRNN, "PriorRNN": PriorRNN}
+
+
+class CaptionModel(nn.Module):
+    """word_model.py:14-44: special-token ids and the encoder/decoder pair."""
+
+    pad_idx = 0
+    start_idx = 1
+    end_idx = 2
+    max_length = 20
+
+    def __init__(self, encoder: nn.Module, decoder: nn.Module, **kwargs):
+        super().__init__()
+        self.encoder = encoder
+        self.decoder = decoder
+        self.vocab_size = decoder.vocab_size
+        if kwargs.get("freeze_encoder"):
+            for param in self.encoder.parameters():
+                param.requires_grad = False
+
+    @classmethod
+    def set_index(cls, start_idx, end_idx):
+        cls.start_idx = start_idx
+        cls.end_idx = end_idx
+
+
+class _FusedVAEBase(CaptionModel):
+    variant = 0
+    #: "device": noise from the CUDA generator (fast path); "reference_cpu": the reference's CPU
+    #: generator stream in its exact draw order, for seed-for-seed comparisons
+    noise_source = "device"
+    #: False: output["logits"] is a LazyLogits handle; True: a dense [N,T,V] tensor
+    materialize_logits = False
+
+    def __init__(self, Audioencoder, Textdecoder, **kwargs):
+        super().__init__(Audioencoder, Textdecoder, **kwargs)
+        E = Textdecoder.embed_size
+        if Textdecoder.model.hidden_size != E:
+            raise ValueError("decoder hidden_size must equal embed_size (reference vae_model.py:693,726)")
+        self.qnet = _text_encoders[kwargs["posterior_model"]](
+            word_dim=E, embed_size=E, vocab_size=Textdecoder.vocab_size, **kwargs["posterior_args"])
+        self.pnet = _text_encoders[kwargs["prior_model"]](
+            word_dim=E, audiofeats_size=E, embed_size=E, vocab_size=Textdecoder.vocab_size, **kwargs["prior_args"])
+        if self.qnet.hidden_size != E or self.pnet.hidden_size != E:
+            raise ValueError("posterior/prior hidden_size must equal embed_size (SURVEY.md section 8)")
+
+    # ---- plumbing ------------------------------------------------------------------------
+    def _hot_weights(self) -> Dict[str, torch.Tensor]:
+        sd = dict(self.named_parameters())
+        return {k: v for k, v in sd.items() if not k.startswith("encoder.")}
+
+    def _encode(self, feats, feat_lens):
+        encoded = self.encoder(feats, feat_lens)
+        return encoded["audio_embeds"], encoded["audio_embeds_lens"]
+
+    def _dims(self, N, Te, T, L=0, mem_rep=1):
+        dec = self.decoder
+        Eenc = self.encoder.embed_size if hasattr(self, "ln") else dec.embed_size
+        return F.make_dims(N, Te, T, dec.embed_size, dec.attn.h2attn.out_features, dec.vocab_size, Eenc, L,
+                           mem_rep, self.variant)
+
+    def forward(self, *input, **kwargs):
+        """vae_model.py:732-760 (same two call forms, same exception text)."""
+        if len(input) == 4:
+            feats, feat_lens, caps, cap_lens = input
+            audio_embeds, mem_lens = self._encode(feats, feat_lens)
+            return self.train_forward({"audio_embeds": audio_embeds, "audio_embeds_lens": mem_lens}, caps, cap_lens, **kwargs)
+        elif len(input) == 2:
+            feats, feat_lens = input
+            audio_embeds, mem_lens = self._encode(feats, feat_lens)
+            return self.inference_forward({"audio_embeds": audio_embeds, "audio_embeds_lens": mem_lens}, **kwargs)
+        raise Exception("Number of input should be either 4 (feats, feat_lens, caps, cap_lens) or 2 (feats, feat_lens)")
+
+    # ---- training ------------------------------------------------------------------------
+    def train_forward(self, encoded, caps, cap_lens, **kwargs):
+        """vae_model.py:871-878 -> stepwise_forward :700-730, fused.
+
+        Required kwargs as in the reference: `ss_ratio`, `dis_ratio`
+        (decode_step reads them without defaults, vae_model.py:802,826).
+        Optional injection (parity tests): `eps_q`, `eps_p`, `tf_flags`, `dis_flags`.
+        """
+        if self.training and self.decoder.dropoutlayer.p > 0:
+            raise NotImplementedError("decoder dropout > 0 is not implemented in the fused step (reference default 0.0)")
+        audio = encoded["audio_embeds"]
+        dev = audio.device
+        if not audio.is_cuda:
+            raise RuntimeError("acvae_b200 needs CUDA tensors: there is no CPU path")
+        cap_lens_np = np.asarray(cap_lens).astype(np.int64)
+        N, Te = audio.shape[0], audio.shape[1]
+        T = int(cap_lens_np.max()) - 1                                     # vae_model.py:703
+        E = self.decoder.embed_size
+        caps_ids = torch.as_tensor(caps).to(device=dev, dtype=torch.int32).contiguous()  # caps.long(), :827
+        L = caps_ids.shape[1]
+        ss_ratio, dis_ratio = kwargs["ss_ratio"], kwargs["dis_ratio"]
+        eps_q, eps_p = kwargs.get("eps_q"), kwargs.get("eps_p")
+        tf_flags, dis_flags = kwargs.get("tf_flags"), kwargs.get("dis_flags")
+        hybrid = self.variant == 0
+        if self.noise_source == "reference_cpu" and eps_q is None:
+            # exact CPU-generator draw order of the reference
+            if hybrid:
+                eps_q = torch.randn(N, T, E)
+            else:
+                eps_q = torch.stack([torch.randn(N, E) for _ in range(T)])
+            tf_l, eps_l, dis_l = [], [], []
+            for _ in range(T):
+                tf_l.append(random.random() < ss_ratio)
+                eps_l.append(torch.randn(N, E))
+                dis_l.append(bool(dis_ratio != 0 and float(torch.rand(1)) <= dis_ratio))
+            eps_p = torch.stack(eps_l)
+            tf_flags, dis_flags = tf_l, dis_l
+        if eps_q is None:
+            eps_q = torch.randn((N, T, E) if hybrid else (T, N, E), device=dev)
+        if eps_p is None:
+            eps_p = torch.randn(T, N, E, device=dev)
+        if tf_flags is None:
+            tf_flags = [random.random() < ss_ratio for _ in range(T)]      # vae_model.py:826
+        if dis_flags is None:
+            dis_flags = [bool(dis_ratio != 0 and random.random() <= dis_ratio) for _ in range(T)]  # :802-804
+        eps_q = eps_q.to(device=dev, dtype=torch.float32).contiguous()
+        eps_p = eps_p.to(device=dev, dtype=torch.float32).contiguous()
+        mem_lens = torch.as_tensor(encoded["audio_embeds_lens"]).to(device=dev, dtype=torch.int32).contiguous()
+        cap_lens_dev = torch.as_tensor(cap_lens_np).to(device=dev, dtype=torch.int32)
+        weights = self._hot_weights()
+        keys = list(weights.keys())
+        dims = self._dims(N, Te, T, L)
+        meta = F.TrainMeta(dims, keys, caps_ids, cap_lens_dev, mem_lens, eps_q, eps_p, tf_flags, dis_flags,
+                           want_logits=False)
+        (q_means, q_logs, q_z, p_means, p_logs, p_z, outputs, q_utt, p_utt, attn_w, seqs, slp, lse, lsum, rnn_input,
+         _logits) = F.LatentDecodeTrainFn.apply(meta, audio, *[weights[k] for k in keys])
+        lazy = LazyLogits(outputs, self.decoder.classifier.weight, self.decoder.classifier.bias, lse, lsum)
+        out = {
+            "seqs": seqs, "logits": lazy.materialize() if self.materialize_logits else lazy,
+            "outputs": outputs, "sampled_logprobs": slp, "attn_weights": attn_w,
+            "p_means": p_means, "p_logs": p_logs, "p_z": p_z,
+            "q_means": q_means, "q_logs": q_logs, "q_z": q_z,
+            "state": outputs[:, -1].unsqueeze(0), "last_z": p_z[:, -1],
+        }
+        if hybrid:
+            out.update({"q_means_utt": q_utt, "q_logs_utt": None, "p_means_utt": p_utt, "p_logs_utt": None})
+        else:
+            out["rnn_input"] = rnn_input
+        return out
+
+    # ---- inference -----------------------------------------------------------------------
+    def inference_forward(self, encoded, **kwargs):
+        """vae_model.py:880-894.  Extra kwargs: `n_captions` (K sequences per clip sharing the
+        clip's memory), `eps_p`, `u` (noise injection)."""
+        method = kwargs.get("method", "greedy")
+        max_length = kwargs.get("max_length", self.max_length)
+        audio = encoded["audio_embeds"]
+        dev = audio.device
+        if not audio.is_cuda:
+            raise RuntimeError("acvae_b200 needs CUDA tensors: there is no CPU path")
+        clips, Te = audio.shape[0], audio.shape[1]
+        E, V = self.decoder.embed_size, self.decoder.vocab_size
+        mem_lens = torch.as_tensor(encoded["audio_embeds_lens"]).to(device=dev, dtype=torch.int32).contiguous()
+        weights = {k: v for k, v in self._hot_weights().items()}
+        if method == "beam":
+            beam = kwargs.get("beam_size", 3)
+            dims = self._dims(clips, Te, max_length)
+            eps_b = kwargs.get("eps_b")
+            if eps_b is None:
+                eps_b = torch.randn(max_length, clips * beam, E, device=dev)
+            return F.beam_search(dims, weights, audio, mem_lens, eps_b.to(dev), beam, self.start_idx)
+        if method == "dbs":
+            raise NotImplementedError("diverse beam search (word_model.py:297-394) is not yet on the fused path")
+        K = int(kwargs.get("n_captions", 1))
+        N = clips * K
+        dims = self._dims(N, Te, max_length, mem_rep=K)
+        eps_p, u = kwargs.get("eps_p"), kwargs.get("u")
+        if eps_p is None:
+            eps_p = torch.randn(max_length, N, E, device=dev)
+        if method != "greedy" and u is None:
+            u = torch.rand(max_length, N, V, device=dev)
+        out = F.decode_sample(dims, weights, audio, mem_lens, eps_p.to(dev).contiguous(),
+                              None if u is None else u.to(dev).contiguous(), method, kwargs.get("temp", 1),
+                              self.start_idx, self.end_idx, keep_latents=kwargs.get("keep_latents", False))
+        if K > 1:
+            out["seqs"] = out["seqs"].view(clips, K, max_length)
+        return out
+
+
+class Hybrid_VAEModel(_FusedVAEBase):
+    """vae_model.py:674-698: contextual posterior + autoregressive prior + global constraint."""
+    variant = 0
+
+    def __init__(self, Audioencoder, Textdecoder, **kwargs):
+        super().__init__(Audioencoder, Textdecoder, **kwargs)
+        E = Textdecoder.embed_size
+        self.mean_log_out = nn.Linear(E, 2 * E)
+        if E != Audioencoder.embed_size:
+            self.ln = nn.Linear(Audioencoder.embed_size, E)
+            nn.init.xavier_uniform_(self.ln.weight)
+        nn.init.xavier_uniform_(self.mean_log_out.weight)
+
+
+class VAEModel(_FusedVAEBase):
+    """vae_model.py:12-38: same step, AR posterior, no global head, extra `rnn_input` output."""
+    variant = 1
+
+    def __init__(self, Audioencoder, Textdecoder, **kwargs):
+        super().__init__(Audioencoder, Textdecoder, **kwargs)
+        E = Textdecoder.embed_size
+        if E != Audioencoder.embed_size:
+            self.ln = nn.Linear(Audioencoder.embed_size, E)
+            nn.init.xavier_uniform_(self.ln.weight)
+
+
+class PrecomputedEncoder(nn.Module):
+    """Stands in for an audio encoder when its output is already available
+    (hot-path-only form): returns the contract of
+    models/encoder.py:672-707 for `feats = audio_embeds`."""
+
+    def __init__(self, embed_size):
+        super().__init__()
+        self.embed_size = embed_size
+
+    def forward(self, feats, feat_lens):
+        return {"audio_embeds": feats, "audio_embeds_pooled": None,
+                "audio_embeds_lens": feat_lens, "state": None}

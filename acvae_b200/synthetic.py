@@ -82,9 +82,10 @@ def make_params(d: Dims, seed: int = 1, variant: str = "hybrid") -> Dict[str, np
         p["qnet.mean_log_out.bias"] = _uniform(rs, (2 * E,), 0.05)
     # prior
     p["pnet.word_embedding.weight"] = rs.standard_normal((V, E)).astype(np.float32)
-    p["pnet.word_attn.h2attn.weight"] = _xavier(rs, A, 2 * E)
-    p["pnet.word_attn.h2attn.bias"] = _uniform(rs, (A,), 0.05)
-    p["pnet.word_attn.v"] = rs.standard_normal((A,)).astype(np.float32)
+    # the prior's attention width is E, not attn_size (text_encoder.py:225)
+    p["pnet.word_attn.h2attn.weight"] = _xavier(rs, E, 2 * E)
+    p["pnet.word_attn.h2attn.bias"] = _uniform(rs, (E,), 0.05)
+    p["pnet.word_attn.v"] = rs.standard_normal((E,)).astype(np.float32)
     k = 1.0 / math.sqrt(E)
     p["pnet.network.weight_ih_l0"] = _uniform(rs, (4 * E, 3 * E), k)
     p["pnet.network.weight_hh_l0"] = _uniform(rs, (4 * E, E), k)

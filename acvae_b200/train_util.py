@@ -1,0 +1,59 @@
+"""Drop-in loss callables of the reference runner's boundary
+(`utils/train_util.py:234-266`; used at `runners/pytorch_runner_vae.py:222-227, 315-320`),
+backed by the fused CUDA kernels.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import functional as F
+from .lazy import LazyLogits
+
+
+class LabelSmoothingLoss(torch.nn.Module):
+    """utils/train_util.py:234-251.  `forward(logit, target)`:
+    a packed `LazyLogits` runs the fused vocabulary-projection + CE kernels and
+    never materialises `[M,V]`; a dense tensor follows the reference arithmetic."""
+
+    def __init__(self, classes, smoothing=0.0, device=0, dim=-1):
+        super().__init__()
+        self.confidence = 1.0 - smoothing
+        self.smoothing = smoothing
+        self.cls = classes
+        self.dim = dim
+        self.device = device
+
+    def forward(self, logit, target):
+        if isinstance(logit, LazyLogits):
+            if logit.dim() != 2:
+                raise ValueError("fused CE expects packed rows [M,V] (pack_padded_sequence(...).data)")
+            return F.VocabCEFn.apply(logit.hidden, logit.cls_w, logit.cls_b, target, self.smoothing,
+                                     logit.row_lse, logit.row_sum)
+        pred = logit.log_softmax(dim=self.dim)
+        with torch.no_grad():
+            true_dist = torch.zeros_like(pred)
+            true_dist.fill_(self.smoothing / (self.cls - 1))
+            true_dist.scatter_(1, target.unsqueeze(1).long().to(pred.device), self.confidence)
+        return torch.mean(torch.sum(-true_dist * pred, dim=self.dim))
+
+
+class CrossEntropyLoss(torch.nn.Module):
+    """`torch.nn.CrossEntropyLoss()` replacement for the `label_smoothing: False`
+    branch (pytorch_runner_vae.py:226): smoothing 0 on the fused path."""
+
+    def forward(self, logit, target):
+        if isinstance(logit, LazyLogits):
+            return F.VocabCEFn.apply(logit.hidden, logit.cls_w, logit.cls_b, target, 0.0, logit.row_lse, logit.row_sum)
+        return torch.nn.functional.cross_entropy(logit, target.long().to(logit.device))
+
+
+class Normal_kl_loss(torch.nn.Module):
+    """utils/train_util.py:253-266: sum over d, mean over ALL positions (padding included)."""
+
+    def __init__(self, device=0, dim=-1):
+        super().__init__()
+        self.dim = dim
+        self.device = device
+
+    def forward(self, mu1, lv1, mu2, lv2):
+        return F.NormalKLFn.apply(mu1, lv1, mu2, lv2)

@@ -1,0 +1,213 @@
+/*
+ * acvae_b200.h -- C ABI of the B200-native AC-VAE latent word-decoding step.
+ *
+ * The reference (XinMing0411/AC-VAE) is pure Python/PyTorch and has no FFI or
+ * operator registry; its boundary for this path is the Python class contract
+ * of `models/vae_model.py`.  This header is the C-ABI
+ * that our Python mirror of that contract (`acvae_b200/`) binds with ctypes.
+ * Every entry point below names the reference code it replaces (paths are
+ * relative to the upstream repository root).
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers owned by the caller (torch tensors),
+ *     borrowed for the duration of the call.  fp32 unless the name says ids
+ *     (int32) or seqs (int64).  Row-major; the last index is contiguous.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     performs no allocation and no host synchronisation, and is re-entrant
+ *     per stream.  Scratch comes from the caller-supplied workspace whose
+ *     size `acvae_*_workspace_bytes` reports.
+ *   - Return value 0 = ok, <0 = error; `acvae_last_error()` returns a
+ *     thread-local message.  No C++ exception crosses this boundary.
+ *   - Shape constraint inherited from the reference: E == H == Hq == prior
+ *     hidden size (models/decoder.py:171, models/text_encoder.py:240-245,
+ *     models/vae_model.py:693,726); E, A, Eenc multiples of 4.
+ */
+#ifndef ACVAE_B200_H_
+#define ACVAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACVAE_ABI_VERSION 1
+
+typedef struct acvae_dims {
+  int32_t N;     /* sequences in the batch (clips x captions-per-clip)        */
+  int32_t Te;    /* padded encoder frames of the memory                        */
+  int32_t T;     /* decode steps = max(cap_lens) - 1 (train) or max_length     */
+  int32_t E;     /* embedding = latent = hidden width (E == H == Hq)           */
+  int32_t A;     /* decoder attention width (decoder.py:172); the prior's is E   */
+  int32_t V;     /* vocabulary                                                 */
+  int32_t Eenc;  /* audio-encoder width; ln is skipped when Eenc == E and ln_w == NULL */
+  int32_t L;     /* row stride (columns) of caps_ids; >= T + 1 for training    */
+  int32_t mem_rep; /* sequences per clip sharing one memory row (sampling K); 1 in training */
+  int32_t variant; /* 0 = Hybrid_VAEModel, 1 = VAEModel (AR posterior, no global head) */
+} acvae_dims;
+
+/* Weights, named after the reference state_dict. */
+typedef struct acvae_weights {
+  const float *ln_w, *ln_b;                       /* ln.weight [E,Eenc], ln.bias [E]                 vae_model.py:695-697 */
+  const float *q_emb;                             /* qnet.word_embedding.weight [V,E]                text_encoder.py:24   */
+  const float *q_wih[2], *q_whh[2];               /* qnet.network.weight_{ih,hh}_l0[_reverse] [3E,E] text_encoder.py:166  */
+  const float *q_bih[2], *q_bhh[2];               /* qnet.network.bias_{ih,hh}_l0[_reverse] [3E]                          */
+  const float *q_head_w, *q_head_b;               /* hybrid: qnet.token_mean_log [2E,2E]; vae: qnet.mean_log_out [2E,3E]  */
+  const float *p_emb;                             /* pnet.word_embedding.weight [V,E]                                     */
+  const float *p_attn_w, *p_attn_b, *p_attn_v;    /* pnet.word_attn.h2attn [E,2E],[E]; .v [E]        text_encoder.py:225  */
+  const float *p_wih, *p_whh, *p_bih, *p_bhh;     /* pnet.network LSTM [4E,3E],[4E,E],[4E],[4E]      text_encoder.py:229  */
+  const float *p_head_w, *p_head_b;               /* pnet.mean_log_out [2E,E],[2E]                   text_encoder.py:236  */
+  const float *d_emb;                             /* decoder.word_embeddings.weight [V,E]            decoder.py:22        */
+  const float *d_attn_w, *d_attn_b, *d_attn_v;    /* decoder.attn.h2attn [A,2E],[A]; .v [A]          decoder.py:173       */
+  const float *d_wih, *d_whh, *d_bih, *d_bhh;     /* decoder.model GRU [3E,3E],[3E,E],[3E],[3E]      decoder.py:39-44     */
+  const float *cls_w, *cls_b;                     /* decoder.classifier [V,E],[V]                    decoder.py:45-46     */
+  const float *g_w, *g_b;                         /* mean_log_out [2E,E],[2E] (hybrid only)          vae_model.py:693     */
+} acvae_weights;
+
+/* Gradients: same fields, writable.  Backward entry points OVERWRITE them. */
+typedef struct acvae_weight_grads {
+  float *ln_w, *ln_b, *q_emb, *q_wih[2], *q_whh[2], *q_bih[2], *q_bhh[2], *q_head_w, *q_head_b;
+  float *p_emb, *p_attn_w, *p_attn_b, *p_attn_v, *p_wih, *p_whh, *p_bih, *p_bhh, *p_head_w, *p_head_b;
+  float *d_emb, *d_attn_w, *d_attn_b, *d_attn_v, *d_wih, *d_whh, *d_bih, *d_bhh, *cls_w, *cls_b, *g_w, *g_b;
+} acvae_weight_grads;
+
+/* Inputs and user-visible outputs of one training forward
+ * (Hybrid_VAEModel.forward 4-input branch, vae_model.py:732-750, with the
+ * encoder output given; output dict of vae_model.py:762-790, 850-869). */
+typedef struct acvae_train_io {
+  /* inputs */
+  const float   *audio_embeds;   /* [N,Te,Eenc] encoder output (models/encoder.py:672-707 contract) */
+  const int32_t *mem_lens;       /* [N] valid frames per clip (audio_embeds_lens)                   */
+  const int32_t *caps_ids;       /* [N,L] caption token ids (caps.long(), <start>=1 ... <end>=2, pad 0) */
+  const int32_t *cap_lens;       /* [N] caption lengths incl. <start>/<end>, sorted descending      */
+  const float   *eps_q;          /* hybrid: [N,T,E] posterior noise (text_encoder.py:196); vae: [T,N,E] (:143) */
+  const float   *eps_p;          /* [T,N,E] prior noise, one draw per step (text_encoder.py:259)    */
+  const uint8_t *tf_flags;       /* HOST [T]: 1 = feed caps[:,t] (random.random() < ss_ratio, vae_model.py:826) */
+  const uint8_t *dis_flags;      /* HOST [T]: 1 = decoder consumes the prior's z (vae_model.py:802-806) */
+  /* outputs (all [N,T,*] unless noted) */
+  float   *q_means, *q_logs, *q_z;       /* [N,T,E]                                   */
+  float   *q_means_utt;                  /* [N,2E]  (hybrid)                          */
+  float   *p_means, *p_logs, *p_z;       /* [N,T,E]                                   */
+  float   *outputs;                      /* [N,T,E] decoder GRU hidden states         */
+  float   *p_means_utt;                  /* [N,2E]  global-constraint head (hybrid)   */
+  float   *attn_weights;                 /* [N,Te,T] decoder attention (vae_model.py:868) */
+  float   *rnn_input;                    /* [N,T,3E] (vae variant, vae_model.py:187) or NULL */
+  int64_t *seqs;                         /* [N,T] greedy argmax per step              */
+  float   *sampled_logprobs;             /* [N,T] log-prob of the argmax              */
+  float   *logit_lse;                    /* [N,T] log-sum-exp of the step's logits    */
+  float   *logit_sum;                    /* [N,T] sum_j logits (label smoothing term) */
+  float   *logits;                       /* [N,T,V] or NULL: materialise only on request */
+} acvae_train_io;
+
+/* Upstream gradients for the training backward. NULL = zero. */
+typedef struct acvae_train_grads_in {
+  const float *d_q_means, *d_q_logs, *d_q_z;     /* [N,T,E] */
+  const float *d_p_means, *d_p_logs, *d_p_z;     /* [N,T,E] */
+  const float *d_outputs;                        /* [N,T,E] */
+  const float *d_q_means_utt, *d_p_means_utt;    /* [N,2E]  */
+} acvae_train_grads_in;
+
+const char *acvae_last_error(void);
+int acvae_abi_version(void);
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+uint64_t acvae_launch_count(void);
+
+/* ---- training ---------------------------------------------------------- */
+size_t acvae_train_workspace_bytes(const acvae_dims *d);
+
+/* H1: memory projection + both attentions' memory halves, once per batch.
+ * Replaces vae_model.py:743-744 and the per-step re-projection of the whole
+ * memory in attn_model.py:29-32 (factorised).
+ * mem [Nc,Te,E], Pp [Nc,Te,E], Pd [Nc,Te,A] with Nc = N / mem_rep clips. */
+int acvae_memory_prepare(const acvae_dims *d, const acvae_weights *w, const float *audio_embeds,
+                         float *mem, float *Pp, float *Pd, void *stream);
+
+/* Full training forward: H1 + H2 (posterior) + T x {H3 prior, H4 z choice,
+ * H5 decoder, H6 greedy word, H7 bookkeeping} + H8 global head + vocab
+ * statistics (argmax / lse / sum) without storing logits.
+ * Replaces Hybrid_VAEModel.forward (vae_model.py:732-750) / VAEModel.forward. */
+int acvae_train_fwd(const acvae_dims *d, const acvae_weights *w, const acvae_train_io *io,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* Reverse-time BPTT of acvae_train_fwd given upstream gradients; writes all
+ * weight gradients except cls_w/cls_b (see acvae_vocab_ce_bwd) and
+ * d_audio_embeds [N,Te,Eenc].  Replaces autograd over vae_model.py:700-869. */
+int acvae_train_bwd(const acvae_dims *d, const acvae_weights *w, const acvae_train_io *io,
+                    const acvae_train_grads_in *gin, acvae_weight_grads *gw, float *d_audio_embeds,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- vocabulary projection + (label-smoothed) cross-entropy -------------
+ * Replaces decoder.py:199 + pack_padded_sequence (pytorch_runner_vae.py:94-95)
+ * + LabelSmoothingLoss.forward (utils/train_util.py:244-251).
+ * hidden [M,E] rows (already packed or not), targets [M] int32.
+ * loss_out[0] = mean over rows with weight row_w[m] (NULL = all rows)       */
+size_t acvae_vocab_workspace_bytes(int32_t M, int32_t V, int32_t E);
+/* Materialise logits [M,V] (compat path for callers that really want them). */
+int acvae_vocab_logits(int32_t M, int32_t V, int32_t E, const float *hidden, const float *cls_w,
+                       const float *cls_b, float *logits, void *stream);
+/* Backward of acvae_vocab_logits given d_logits [M,V]: d_hidden [M,E], d_cls_w [V,E], d_cls_b [V]
+ * (any output may be NULL). */
+int acvae_vocab_logits_bwd(int32_t M, int32_t V, int32_t E, const float *hidden, const float *cls_w,
+                           const float *d_logits, float *d_hidden, float *d_cls_w, float *d_cls_b,
+                           void *stream);
+/* Per-row log-sum-exp, sum of logits, greedy argmax (word_model.py:177-179) and its
+ * log-probability, computed tile by tile without storing logits.  Outputs may be NULL. */
+int acvae_vocab_stats(int32_t M, int32_t V, int32_t E, const float *hidden, const float *cls_w,
+                      const float *cls_b, float *row_lse, float *row_sum, int64_t *row_argmax,
+                      float *row_logprob, void *workspace, size_t workspace_bytes, void *stream);
+/* Label-smoothed CE.  have_stats != 0: row_lse/row_sum are INPUTS (e.g. from acvae_train_fwd's
+ * logit_lse/logit_sum gathered to the packed rows); otherwise they are computed here and returned. */
+int acvae_vocab_ce_fwd(int32_t M, int32_t V, int32_t E, const float *hidden, const float *cls_w,
+                       const float *cls_b, const int32_t *targets, const float *row_w, float smoothing,
+                       int32_t have_stats, float *row_lse, float *row_sum, float *loss_out,
+                       void *workspace, size_t workspace_bytes, void *stream);
+int acvae_vocab_ce_bwd(int32_t M, int32_t V, int32_t E, const float *hidden, const float *cls_w,
+                       const float *cls_b, const int32_t *targets, const float *row_w, float smoothing,
+                       const float *row_lse, const float *d_loss /* device scalar */,
+                       float *d_hidden, float *d_cls_w, float *d_cls_b,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- Gaussian KL (utils/train_util.py:259-266) ---------------------------
+ * kl_out[0] = mean over `rows` positions of sum_d KL(q || p).              */
+int acvae_kl_fwd(int64_t rows, int32_t E, const float *q_mean, const float *q_log, const float *p_mean,
+                 const float *p_log, float *kl_out, void *stream);
+int acvae_kl_bwd(int64_t rows, int32_t E, const float *q_mean, const float *q_log, const float *p_mean,
+                 const float *p_log, const float *d_kl /* device scalar */, float *d_q_mean, float *d_q_log,
+                 float *d_p_mean, float *d_p_log, void *stream);
+
+/* ---- diverse sampling loop ------------------------------------------------
+ * Replaces Hybrid_VAEModel.inference_forward -> stepwise_forward with
+ * caps=None (vae_model.py:880-894, 700-720) and sample_next_word
+ * (word_model.py:173-207).  N sequences, `mem_rep` consecutive sequences
+ * share one clip's memory (audio_embeds is [N/mem_rep,Te,Eenc]).
+ * method: 0 greedy, 1 multinomial-as-Gumbel-max (needs u), 2 gumbel (needs u). */
+typedef struct acvae_sample_io {
+  const float   *audio_embeds;   /* [N/mem_rep,Te,Eenc] */
+  const int32_t *mem_lens;       /* [N/mem_rep]         */
+  const float   *eps_p;          /* [T,N,E] prior noise */
+  const float   *u;              /* [T,N,V] uniforms in (0,1) or NULL for greedy */
+  int32_t method;
+  float   temp;
+  int32_t start_idx, end_idx;
+  int64_t *seqs;                 /* [N,T] END-filled after a row finishes */
+  float   *sampled_logprobs;     /* [N,T] */
+  float   *p_means, *p_logs, *p_z, *outputs;  /* [N,T,E] or NULL */
+  int32_t *n_steps;              /* device scalar: steps executed before every row had finished */
+} acvae_sample_io;
+size_t acvae_sample_workspace_bytes(const acvae_dims *d);
+int acvae_decode_sample(const acvae_dims *d, const acvae_weights *w, const acvae_sample_io *io,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- beam search with prior latents (vae_model.py:896-995) ---------------
+ * N clips, `beam` hypotheses each; eps_b [T, N*beam, E] (step-major: the caller permutes the
+ * reference's per-clip draw order); seqs [N,T] = top beam. */
+size_t acvae_beam_workspace_bytes(const acvae_dims *d, int32_t beam);
+int acvae_beam_search(const acvae_dims *d, const acvae_weights *w, const float *audio_embeds,
+                      const int32_t *mem_lens, const float *eps_b, int32_t beam, int32_t start_idx,
+                      int64_t *seqs, void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACVAE_B200_H_ */

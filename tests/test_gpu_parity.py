@@ -1,0 +1,240 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the public reference-shaped API and the
+C-ABI underneath, against (a) golden vectors minted from the reference itself and (b) the CPU
+oracle on the same seeded inputs and injected noise.
+
+Tolerances (BASELINE.json north_star): fp32 -- loss, KL and gradients within 1e-4 relative;
+greedy / fixed-noise token ids identical."""
+import numpy as np
+import pytest
+import torch
+
+import harness
+from harness import synthetic
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _require_cuda():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from acvae_b200 import _lib
+    _lib.lib()   # fails loudly if the extension is missing
+
+
+def _check_train_golden(name, variant="hybrid"):
+    _require_cuda()
+    g = harness.load_golden(name)
+    d = harness.dims_from_golden(g)
+    r = harness.run_cuda_train(d, int(g["meta_seed"]), float(g["meta_ss_ratio"]), float(g["meta_dis_ratio"]), variant,
+                               float(g["meta_smoothing"]), float(g["meta_kl_weight"]), float(g["meta_alpha"]))
+    keys = ("loss", "ce", "kl") + (("global",) if variant == "hybrid" else ())
+    for k in keys:
+        assert abs(float(r["terms"][k]) - float(g[k])) <= TOL * max(1.0, abs(float(g[k]))), (k, float(r["terms"][k]), float(g[k]))
+    assert np.array_equal(r["out"]["seqs"].cpu().numpy(), g["seqs"]), "greedy token ids differ"
+    for k in [k[4:] for k in g if k.startswith("out_") and not k.startswith("out_logits")]:
+        assert harness.rel_err(r["out"][k], g["out_" + k]) < TOL, k
+    lg = r["out"]["logits"].materialize().detach()
+    if "out_logits" in g:
+        assert harness.rel_err(lg, g["out_logits"]) < TOL
+        for k in [k[5:] for k in g if k.startswith("grad_")]:
+            assert k in r["grads"], f"no gradient produced for {k}"
+            assert harness.rel_err(r["grads"][k], g["grad_" + k]) < TOL, ("grad", k)
+    else:
+        assert harness.rel_err(torch.logsumexp(lg, -1), g["out_logits_lse"]) < TOL
+        assert harness.rel_err(lg[:, :, ::97], g["out_logits_sample"]) < TOL
+        for k in [k[9:] for k in g if k.startswith("gradnorm_")]:
+            gn, ref = float(r["grads"][k].norm()), float(g["gradnorm_" + k])
+            assert abs(gn - ref) <= TOL * max(ref, 1e-6), ("gradnorm", k, gn, ref)
+            flat = r["grads"][k].reshape(-1)
+            stride = max(1, flat.numel() // 4096)
+            assert harness.rel_err(flat[::stride][:4096], g["gradsample_" + k]) < TOL, ("gradsample", k)
+
+
+@pytest.mark.parametrize("name", ["tiny_train", "tiny_train_dis", "tiny_train_ss"])
+def test_train_tiny_golden(name):
+    _check_train_golden(name)
+
+
+def test_train_tiny_vae_golden():
+    _check_train_golden("tiny_train_vae", "vae")
+
+
+@pytest.mark.parametrize("name", ["cfg0_train", "cfg0_train_dis", "cfg0_train_ss"])
+def test_train_cfg0_golden(name):
+    _check_train_golden(name)
+
+
+def test_train_cfg1_vs_oracle():
+    """BASELINE configs[1] shape (N=32, Te=62, L=20, V=4400, E=256): every gradient vs oracle autograd."""
+    _require_cuda()
+    d = synthetic.CFG1
+    r = harness.run_cuda_train(d, 11)
+    o = harness.run_oracle_train(d, 11)
+    for k in ("loss", "ce", "kl", "global"):
+        assert abs(float(r["terms"][k]) - float(o["terms"][k])) <= TOL * max(1.0, abs(float(o["terms"][k]))), k
+    assert np.array_equal(r["out"]["seqs"].cpu().numpy(), o["out"]["seqs"].numpy())
+    assert harness.rel_err(r["out"]["attn_weights"], o["out"]["attn_weights"]) < TOL
+    for k, ref in o["grads"].items():
+        assert harness.rel_err(r["grads"][k], ref) < TOL, ("grad", k)
+
+
+def test_train_dense_logits_path_matches_fused():
+    """Compat mode (materialised [N,T,V] logits + dense criterion) == fused lazy path."""
+    _require_cuda()
+    d = synthetic.TINY
+    a = harness.run_cuda_train(d, 5)
+    b = harness.run_cuda_train(d, 5, dense_logits=True)
+    assert abs(float(a["terms"]["loss"]) - float(b["terms"]["loss"])) < 1e-5
+    for k in a["grads"]:
+        assert harness.rel_err(a["grads"][k], b["grads"][k]) < 1e-4, k
+
+
+def test_train_ragged_edges_vs_oracle():
+    """min-length caption (<start>,<end>), a one-frame clip, odd sizes (N=5, Te=7, V=37)."""
+    _require_cuda()
+    import acvae_oracle as oracle
+    d = synthetic.Dims(N=5, Te=7, L=6, E=16, H=16, A=24, Hq=16, V=37, Eenc=20)
+    r = harness.run_cuda_train(d, 9)
+    o = harness.run_oracle_train(d, 9)
+    for k in ("loss", "ce", "kl", "global"):
+        assert abs(float(r["terms"][k]) - float(o["terms"][k])) <= TOL * max(1.0, abs(float(o["terms"][k]))), k
+    for k, ref in o["grads"].items():
+        assert harness.rel_err(r["grads"][k], ref) < TOL, ("grad", k)
+
+
+def test_train_properties_stress_size():
+    """BASELINE configs[4] shape (N=128, Te=187, L=30, V=5000): size-independent properties."""
+    _require_cuda()
+    d = synthetic.STRESS
+    r = harness.run_cuda_train(d, 3)
+    out = r["out"]
+    b = synthetic.make_batch(d, 3)
+    aw = out["attn_weights"]                                     # [N,Te,T]
+    assert torch.allclose(aw.sum(1), torch.ones_like(aw.sum(1)), atol=1e-5)
+    for n in (0, 17, 127):
+        assert float(aw[n, int(b["mem_lens"][n]):].abs().max() if b["mem_lens"][n] < d.Te else 0.0) == 0.0
+    assert float(r["terms"]["kl"]) >= 0 and np.isfinite(float(r["terms"]["loss"]))
+    bias = r["model"].qnet.token_mean_log.bias.detach()
+    n, ln = d.N - 1, int(b["cap_lens"][-1]) - 1
+    if ln < d.T:    # padded posterior positions: head sees ho = 0 => mean = bias
+        assert torch.allclose(out["q_means"][n, ln:], bias[:d.E].expand(d.T - ln, d.E), atol=1e-6)
+    r2 = harness.run_cuda_train(d, 3, model=r["model"])
+    assert float(r2["terms"]["loss"]) == float(r["terms"]["loss"]), "forward is not deterministic"
+    # analytic identity: d loss / d classifier.bias sums to 0 (softmax minus a distribution)
+    assert abs(float(r["grads"]["decoder.classifier.bias"].sum())) < 1e-5
+
+
+# ----------------------------------------------------------------------------- sampling
+def _run_sample(d, seed, method, ml, temp=1.0, K=1):
+    m = harness.build_model(d, seed).eval()
+    b = synthetic.make_batch(d, seed, sample_steps=ml)
+    with torch.no_grad():
+        out = m(torch.from_numpy(b["audio_embeds"]).cuda(), torch.from_numpy(b["mem_lens"].copy()), method=method,
+                max_length=ml, temp=temp, eps_p=torch.from_numpy(b["eps_s"]), u=torch.from_numpy(b["u_s"]),
+                keep_latents=True)
+    torch.cuda.synchronize()
+    return out, b
+
+
+@pytest.mark.parametrize("name", ["tiny_sample_greedy", "tiny_sample_multinomial", "cfg0_sample_greedy",
+                                  "cfg0_sample_multinomial"])
+def test_sampling_golden(name):
+    _require_cuda()
+    g = harness.load_golden(name)
+    d = harness.dims_from_golden(g)
+    out, _ = _run_sample(d, int(g["meta_seed"]), str(g["meta_method"]), int(g["meta_max_length"]), float(g["meta_temp"]))
+    assert np.array_equal(out["seqs"].cpu().numpy(), g["seqs"]), "sampled token ids differ from the reference"
+    n = int(g["n_steps"])
+    assert int(out["n_steps"]) == n
+    assert harness.rel_err(out["p_z"][:, :n], g["out_p_z"]) < TOL
+    assert harness.rel_err(out["sampled_logprobs"][:, :n], g["out_sampled_logprobs"]) < 1e-3
+
+
+def test_sampling_gumbel_vs_oracle():
+    _require_cuda()
+    import acvae_oracle as oracle
+    d, seed, ml = synthetic.TINY, 4, 8
+    out, b = _run_sample(d, seed, "gumbel", ml, temp=0.7)
+    p = harness.oracle_params(d, seed)
+    with torch.no_grad():
+        o = oracle.inference_forward(p, torch.from_numpy(b["audio_embeds"]), b["mem_lens"], torch.from_numpy(b["eps_s"]),
+                                     "gumbel", ml, 0.7, torch.from_numpy(b["u_s"]))
+    assert np.array_equal(out["seqs"].cpu().numpy(), o["seqs"].numpy())
+
+
+def test_sampling_k_captions_share_clip_memory():
+    """K captions per clip (mem_rep=K) == the reference's tiling of the clip K times (aligned)."""
+    _require_cuda()
+    import acvae_oracle as oracle
+    d, seed, ml, K = synthetic.TINY, 6, 8, 3
+    m = harness.build_model(d, seed).eval()
+    b = synthetic.make_batch(d, seed)
+    rs = np.random.RandomState(0)
+    eps = torch.from_numpy(rs.standard_normal((ml, d.N * K, d.E)).astype(np.float32))
+    u = torch.from_numpy(rs.uniform(size=(ml, d.N * K, d.V)).astype(np.float32))
+    with torch.no_grad():
+        out = m(torch.from_numpy(b["audio_embeds"]).cuda(), torch.from_numpy(b["mem_lens"].copy()), method="sample",
+                max_length=ml, n_captions=K, eps_p=eps, u=u)
+        p = harness.oracle_params(d, seed)
+        o = oracle.inference_forward(p, torch.from_numpy(b["audio_embeds"]).repeat_interleave(K, 0),
+                                     np.repeat(b["mem_lens"], K), eps, "sample", ml, 1.0, u)
+    assert tuple(out["seqs"].shape) == (d.N, K, ml)
+    assert np.array_equal(out["seqs"].cpu().numpy().reshape(d.N * K, ml), o["seqs"].numpy())
+
+
+@pytest.mark.parametrize("name", ["tiny_beam", "cfg0_beam"])
+def test_beam_golden(name):
+    _require_cuda()
+    g = harness.load_golden(name)
+    d = harness.dims_from_golden(g)
+    seed, ml, beam = int(g["meta_seed"]), int(g["meta_max_length"]), int(g["meta_beam"])
+    m = harness.build_model(d, seed).eval()
+    b = synthetic.make_batch(d, seed, sample_steps=ml, beam=beam)
+    eps_b = torch.from_numpy(b["eps_b"]).permute(1, 0, 2, 3).reshape(ml, d.N * beam, d.E).contiguous()
+    with torch.no_grad():
+        out = m(torch.from_numpy(b["audio_embeds"]).cuda(), torch.from_numpy(b["mem_lens"].copy()), method="beam",
+                beam_size=beam, max_length=ml, eps_b=eps_b)
+    assert np.array_equal(out["seqs"].cpu().numpy(), g["seqs"])
+
+
+# ----------------------------------------------------------------------------- components
+def test_vocab_stats_and_ce_vs_torch():
+    _require_cuda()
+    from acvae_b200 import functional as F
+    torch.manual_seed(0)
+    M, E, V = 77, 64, 4401
+    h = torch.randn(M, E, device="cuda", requires_grad=True)
+    w = (torch.randn(V, E, device="cuda") * 0.1).requires_grad_(True)
+    b = torch.randn(V, device="cuda", requires_grad=True)
+    y = torch.randint(0, V, (M,), device="cuda")
+    lse, ssum, arg, lp = F.vocab_stats(h, w, b)
+    logits = (h @ w.t() + b).double()
+    assert harness.rel_err(lse, torch.logsumexp(logits, -1)) < 1e-6
+    assert harness.rel_err(ssum, logits.sum(-1)) < 1e-4
+    assert torch.equal(arg, logits.argmax(-1))
+    loss = F.VocabCEFn.apply(h, w, b, y, 0.1, None, None)
+    loss.backward()
+    h2, w2, b2 = (t.detach().double().requires_grad_(True) for t in (h, w, b))
+    lg = torch.log_softmax(h2 @ w2.t() + b2, -1)
+    td = torch.full_like(lg, 0.1 / (V - 1)); td.scatter_(1, y.unsqueeze(1), 0.9)
+    ref = (-(td * lg).sum(-1)).mean()
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+    assert harness.rel_err(h.grad, h2.grad) < 1e-5 and harness.rel_err(w.grad, w2.grad) < 1e-5
+    assert harness.rel_err(b.grad, b2.grad) < 1e-5
+
+
+def test_kl_vs_oracle():
+    _require_cuda()
+    import acvae_oracle as oracle
+    from acvae_b200 import Normal_kl_loss
+    torch.manual_seed(1)
+    ts = [torch.randn(6, 5, 32, device="cuda", requires_grad=True) for _ in range(4)]
+    kl = Normal_kl_loss()(*ts)
+    kl.backward()
+    ts2 = [t.detach().cpu().double().requires_grad_(True) for t in ts]
+    ref = oracle.normal_kl_loss(*ts2)
+    ref.backward()
+    assert abs(float(kl) - float(ref)) < 1e-5 * abs(float(ref))
+    for a, b in zip(ts, ts2):
+        assert harness.rel_err(a.grad, b.grad) < 1e-5

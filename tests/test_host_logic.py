@@ -1,0 +1,79 @@
+"""CPU: host-side logic -- state_dict parity with the reference keys, deterministic synthetic data,
+the LazyLogits packing protocol, loud failure without CUDA."""
+import numpy as np
+import pytest
+import torch
+
+import harness
+from harness import synthetic
+
+
+def test_state_dict_keys_match_reference_names():
+    d = synthetic.TINY
+    m = harness.build_model(d, 1, "hybrid", device="cpu")
+    want = set(synthetic.make_params(d, 1, "hybrid").keys())
+    assert set(m.state_dict().keys()) == want
+    g = harness.load_golden("tiny_train")
+    ref_keys = {k[5:] for k in g if k.startswith("grad_")} - {"audio_embeds"}
+    assert ref_keys == want          # the keys the REFERENCE's named_parameters() produced
+    mv = harness.build_model(d, 3, "vae", device="cpu")
+    gv = harness.load_golden("tiny_train_vae")
+    assert {k[5:] for k in gv if k.startswith("grad_")} - {"audio_embeds"} == set(mv.state_dict().keys())
+
+
+def test_synthetic_is_deterministic_and_sorted():
+    a = synthetic.make_batch(synthetic.CFG0, 1)
+    b = synthetic.make_batch(synthetic.CFG0, 1)
+    for k in a:
+        assert np.array_equal(a[k], b[k])
+    assert np.all(np.diff(a["cap_lens"]) <= 0) and a["cap_lens"][0] == synthetic.CFG0.L
+    assert a["caps"].dtype == np.float32 and np.all(a["caps"][:, 0] == 1)
+    for n, ln in enumerate(a["cap_lens"]):
+        assert a["caps"][n, ln - 1] == 2 and np.all(a["caps"][n, ln:] == 0)
+    assert a["mem_lens"].max() == synthetic.CFG0.Te
+
+
+def test_no_cpu_fallback():
+    d = synthetic.TINY
+    m = harness.build_model(d, 1, "hybrid", device="cpu")
+    b = synthetic.make_batch(d, 1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.from_numpy(b["audio_embeds"]), torch.from_numpy(b["mem_lens"]), torch.from_numpy(b["caps"]),
+          b["cap_lens"], ss_ratio=1.0, dis_ratio=0.0)
+    with pytest.raises(Exception, match="Number of input should be either 4"):
+        m(torch.zeros(1))
+
+
+def test_lazy_logits_pack_protocol(monkeypatch):
+    """pack_padded_sequence(lazy).data packs the hidden rows; other torch functions materialise."""
+    from acvae_b200 import lazy as lz
+    from acvae_b200 import functional as F
+
+    class FakeFn:
+        @staticmethod
+        def apply(h, w, b):
+            return h @ w.t() + b
+    monkeypatch.setattr(F, "VocabLogitsFn", FakeFn)
+    N, T, H, V = 3, 4, 8, 11
+    h = torch.randn(N, T, H); w = torch.randn(V, H); b = torch.randn(V)
+    lse = torch.randn(N, T); ssum = torch.randn(N, T)
+    lens = torch.tensor([4, 3, 1])
+    lazy = lz.LazyLogits(h, w, b, lse, ssum)
+    assert tuple(lazy.shape) == (N, T, V)
+    packed = torch.nn.utils.rnn.pack_padded_sequence(lazy, lens, batch_first=True).data
+    assert isinstance(packed, lz.LazyLogits) and tuple(packed.shape) == (8, V)
+    dense = torch.nn.utils.rnn.pack_padded_sequence(h @ w.t() + b, lens, batch_first=True).data
+    assert torch.allclose(packed.materialize(), dense, atol=1e-6)
+    assert torch.allclose(packed.row_lse, torch.nn.utils.rnn.pack_padded_sequence(lse, lens, batch_first=True).data)
+    # generic torch function -> dense
+    assert torch.allclose(torch.log_softmax(lazy, dim=-1), torch.log_softmax(h @ w.t() + b, dim=-1), atol=1e-6)
+    assert torch.allclose(lazy[:, 1], (h @ w.t() + b)[:, 1], atol=1e-6)
+
+
+def test_dense_label_smoothing_matches_oracle():
+    import acvae_oracle as oracle
+    from acvae_b200 import LabelSmoothingLoss
+    x = torch.randn(7, 13); y = torch.randint(0, 13, (7,)).float()
+    a = LabelSmoothingLoss(13, smoothing=0.1, device="cpu")(x, y)
+    b = oracle.label_smoothing_loss(x, y, 13, 0.1)
+    assert torch.allclose(a, b, atol=1e-6)
