@@ -8,7 +8,7 @@ running it does, and needs `libacvae_b200.so` (there is no fallback).
 """
 from . import synthetic  # noqa: F401
 from .models import (CaptionModel, Hybrid_VAEModel, PosteriorRNN, PosteriorRNN_hybrid, PrecomputedEncoder,  # noqa: F401
-                     PriorRNN, Seq2SeqAttention, VAEModel, VAERNNBahdanauAttnDecoder)
+                     PreparedBatch, PriorRNN, Seq2SeqAttention, VAEModel, VAERNNBahdanauAttnDecoder)
 from .train_util import CrossEntropyLoss, LabelSmoothingLoss, Normal_kl_loss  # noqa: F401
 from .lazy import LazyLogits  # noqa: F401
 

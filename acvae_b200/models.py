@@ -173,6 +173,15 @@ class CaptionModel(nn.Module):
         cls.end_idx = end_idx
 
 
+class PreparedBatch:
+    """Caption-side inputs of a training step already on the device (ids int32, lengths int32) plus
+    the host-known step count T.  Lets a step run without any host->device copy (CUDA-graph capture,
+    device-resident benchmarking); `Hybrid_VAEModel.prepare_batch` builds it."""
+
+    def __init__(self, caps_ids, cap_lens_dev, T, targets=None):
+        self.caps_ids, self.cap_lens_dev, self.T, self.targets = caps_ids, cap_lens_dev, int(T), targets
+
+
 class _FusedVAEBase(CaptionModel):
     variant = 0
     #: "device": noise from the CUDA generator (fast path); "reference_cpu": the reference's CPU
@@ -220,6 +229,18 @@ class _FusedVAEBase(CaptionModel):
             return self.inference_forward({"audio_embeds": audio_embeds, "audio_embeds_lens": mem_lens}, **kwargs)
         raise Exception("Number of input should be either 4 (feats, feat_lens, caps, cap_lens) or 2 (feats, feat_lens)")
 
+    def prepare_batch(self, caps, cap_lens, device) -> PreparedBatch:
+        """Host -> device staging of (caps, cap_lens) exactly as the step consumes them, plus the
+        packed CE targets of pytorch_runner_vae.py:89-90."""
+        cap_lens_np = np.asarray(cap_lens).astype(np.int64)
+        caps_t = torch.as_tensor(caps)
+        lens1 = torch.as_tensor(cap_lens_np) - 1
+        targets = torch.nn.utils.rnn.pack_padded_sequence(caps_t[:, 1:].cpu(), lens1, batch_first=True).data
+        return PreparedBatch(caps_t.to(device=device, dtype=torch.int32, non_blocking=True).contiguous(),
+                             torch.as_tensor(cap_lens_np).to(device=device, dtype=torch.int32, non_blocking=True),
+                             int(cap_lens_np.max()) - 1,
+                             targets.to(device=device, dtype=torch.int32, non_blocking=True))
+
     # ---- training ------------------------------------------------------------------------
     def train_forward(self, encoded, caps, cap_lens, **kwargs):
         """vae_model.py:871-878 -> stepwise_forward :700-730, fused.
@@ -234,11 +255,15 @@ class _FusedVAEBase(CaptionModel):
         dev = audio.device
         if not audio.is_cuda:
             raise RuntimeError("acvae_b200 needs CUDA tensors: there is no CPU path")
-        cap_lens_np = np.asarray(cap_lens).astype(np.int64)
         N, Te = audio.shape[0], audio.shape[1]
-        T = int(cap_lens_np.max()) - 1                                     # vae_model.py:703
         E = self.decoder.embed_size
-        caps_ids = torch.as_tensor(caps).to(device=dev, dtype=torch.int32).contiguous()  # caps.long(), :827
+        if isinstance(caps, PreparedBatch):
+            caps_ids, cap_lens_dev, T = caps.caps_ids, caps.cap_lens_dev, caps.T
+        else:
+            cap_lens_np = np.asarray(cap_lens).astype(np.int64)
+            T = int(cap_lens_np.max()) - 1                                 # vae_model.py:703
+            caps_ids = torch.as_tensor(caps).to(device=dev, dtype=torch.int32).contiguous()  # caps.long(), :827
+            cap_lens_dev = torch.as_tensor(cap_lens_np).to(device=dev, dtype=torch.int32)
         L = caps_ids.shape[1]
         ss_ratio, dis_ratio = kwargs["ss_ratio"], kwargs["dis_ratio"]
         eps_q, eps_p = kwargs.get("eps_q"), kwargs.get("eps_p")
@@ -268,7 +293,6 @@ class _FusedVAEBase(CaptionModel):
         eps_q = eps_q.to(device=dev, dtype=torch.float32).contiguous()
         eps_p = eps_p.to(device=dev, dtype=torch.float32).contiguous()
         mem_lens = torch.as_tensor(encoded["audio_embeds_lens"]).to(device=dev, dtype=torch.int32).contiguous()
-        cap_lens_dev = torch.as_tensor(cap_lens_np).to(device=dev, dtype=torch.int32)
         weights = self._hot_weights()
         keys = list(weights.keys())
         dims = self._dims(N, Te, T, L)

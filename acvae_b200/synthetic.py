@@ -112,7 +112,7 @@ def make_params(d: Dims, seed: int = 1, variant: str = "hybrid") -> Dict[str, np
 
 
 def make_batch(d: Dims, seed: int = 1, min_cap_len: Optional[int] = None,
-               sample_steps: int = 0, beam: int = 0) -> Dict[str, np.ndarray]:
+               sample_steps: int = 0, beam: int = 0, cap_lens_override: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
     """One synthetic batch in hot-path-only form plus all injected noise.
 
     Returns float32 `audio_embeds [N,Te,Eenc]`, int64 `mem_lens [N]`,
@@ -135,6 +135,8 @@ def make_batch(d: Dims, seed: int = 1, min_cap_len: Optional[int] = None,
     cap_lens = rs.randint(lo_c, L + 1, size=N).astype(np.int64)
     cap_lens[0] = L
     cap_lens = np.sort(cap_lens)[::-1].copy()
+    if cap_lens_override is not None:       # share one length profile across a pool of batches
+        cap_lens = np.asarray(cap_lens_override, dtype=np.int64).copy()
     caps = np.zeros((N, L), dtype=np.float32)
     for n in range(N):
         ln = int(cap_lens[n])

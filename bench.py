@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the AC-VAE latent word-decoding hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one complete training step of the hot path on one synthetic Clotho-shaped batch with
+the encoder output precomputed (BASELINE.json configs[1]: batch 32 per GPU, Te=62, caption length
+20, V=4400, E=256, fp32): zero-grad, fused forward, the runner's loss composition
+(CE + kl_w*KL + alpha*MSE, reference runners/pytorch_runner_vae.py:315-320), backward,
+[NCCL gradient all-reduce for N>1], global-norm clipping (:322) and the Adam update (:324).
+`value` = clips/s with inputs resident in HBM; `e2e` = the same step called through the public
+reference-shaped API with HOST inputs (pinned), H2D copies and a D2H read of the loss inside the
+timed region.  A second measurement, `sampling`, times the diverse-sampling loop (configs[3]:
+1045 clips x 10 prior-sampled captions, clips partitioned over ranks, no collective).
+
+`--impl reference` times the reference's CPU path: the oracle port of the same step
+(oracle/acvae_oracle.py, pinned to the reference's outputs) on all host cores, rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALPHA, KL_WEIGHT, SMOOTHING, MAX_GRAD_NORM, LR = 1.0, 0.5, 0.1, 1.0, 5e-4
+N_BATCH_POOL = 4
+SAMPLE_CLIPS, SAMPLE_K, SAMPLE_LEN = 1045, 10, 20
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j["bf16_tflops"], "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+def algorithmic_bytes_train(d, n_params):
+    """fp32 algorithmic bytes of one fused train step (logits not materialised)."""
+    N, Te, T, E = d.N, d.Te, d.T, d.E
+    return 3 * n_params * 4 + N * Te * d.Eenc * 4 + T * 3 * N * Te * E * 4 * 2 + N * T * 7 * E * 4
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons}
+
+
+def make_host_batches(d, n, seed0):
+    from acvae_b200 import synthetic
+    first = synthetic.make_batch(d, seed0)
+    return [first] + [synthetic.make_batch(d, seed0 + i, cap_lens_override=first["cap_lens"]) for i in range(1, n)]
+
+
+# ----------------------------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch.distributed as dist
+    import acvae_b200 as models
+    from acvae_b200 import functional as F, parallel, synthetic
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import harness
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    d = synthetic.CFG1
+    model = harness.build_model(d, seed=1, device=dev).train()
+    n_params = sum(p.numel() for p in model.parameters())
+    flat = parallel.FlatGradBuffer(model.parameters())
+    opt = torch.optim.Adam(model.parameters(), lr=LR, fused=True, capturable=True)
+    crit = models.LabelSmoothingLoss(d.V, smoothing=SMOOTHING, device=dev)
+    klf = models.Normal_kl_loss(device=dev)
+    mse = torch.nn.MSELoss()
+
+    # a pool of distinct batches that share one caption-length profile (static pack indices / graph shapes)
+    host = make_host_batches(d, N_BATCH_POOL, seed0=100 + 1000 * rank)
+    pinned = [{"audio": torch.from_numpy(b["audio_embeds"]).pin_memory(), "caps": torch.from_numpy(b["caps"]).pin_memory(),
+               "cap_lens": b["cap_lens"], "mem_lens": torch.from_numpy(b["mem_lens"].astype(np.int32)).pin_memory()} for b in host]
+    resident = [{"audio": p["audio"].to(dev), "mem_lens": p["mem_lens"].to(dev),
+                 "prep": model.prepare_batch(p["caps"], p["cap_lens"], dev)} for p in pinned]
+    # static device buffers the (graphed) step reads
+    st_audio = torch.empty_like(resident[0]["audio"])
+    st_mem_lens = torch.empty_like(resident[0]["mem_lens"])
+    prep0 = resident[0]["prep"]
+    st_prep = models.PreparedBatch(torch.empty_like(prep0.caps_ids), torch.empty_like(prep0.cap_lens_dev), prep0.T, None)
+    lens1 = torch.as_tensor(pinned[0]["cap_lens"]) - 1
+    M = int(lens1.sum())
+    st_targets = torch.empty(M, dtype=torch.int32, device=dev)
+    loss_buf = torch.zeros((), device=dev)
+
+    def load_resident(i):
+        r = resident[i % N_BATCH_POOL]
+        st_audio.copy_(r["audio"]); st_mem_lens.copy_(r["mem_lens"])
+        st_prep.caps_ids.copy_(r["prep"].caps_ids); st_prep.cap_lens_dev.copy_(r["prep"].cap_lens_dev)
+        st_targets.copy_(r["prep"].targets)
+
+    def step_body():
+        flat.zero()
+        out = model.train_forward({"audio_embeds": st_audio, "audio_embeds_lens": st_mem_lens}, st_prep, None,
+                                  ss_ratio=1.0, dis_ratio=0.0, tf_flags=[True] * st_prep.T, dis_flags=[False] * st_prep.T)
+        packed = torch.nn.utils.rnn.pack_padded_sequence(out["logits"], lens1, batch_first=True).data
+        loss = crit(packed, st_targets) + KL_WEIGHT * klf(out["q_means"], out["q_logs"], out["p_means"], out["p_logs"]) \
+            + ALPHA * mse(out["q_means_utt"], out["p_means_utt"])
+        loss.backward()
+        flat.all_reduce()
+        flat.clip_grad_norm_(MAX_GRAD_NORM)
+        opt.step()
+        loss_buf.copy_(loss.detach())
+
+    # ---- warm-up (eager) and optional whole-step CUDA graph ---------------------------------
+    load_resident(0)
+    l0 = F.launch_count()
+    step_body()
+    torch.cuda.synchronize()
+    launches_per_step = F.launch_count() - l0
+    graph = None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step_body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step_body()
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:  # keep the eager path; say so in the JSON line
+            graph = None
+            sys.stderr.write(f"[bench] CUDA-graph capture unavailable ({type(e).__name__}: {e}); running eager\n")
+            torch.cuda.synchronize()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            step_body()
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, feed):
+        """Per-step CUDA-event timing on the launching stream, L2 flushed (untimed) between steps."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        barrier()
+        for i, (a, b) in enumerate(evs):
+            flush.fill_(float(i))
+            a.record()
+            feed(i)
+            run_step()
+            b.record()
+        barrier()
+        ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / n_steps
+
+    for i in range(max(args.warmup, 3)):
+        load_resident(i); run_step()
+    clocks = ClockSampler(local); clocks.start()
+    ms_resident = timed(args.steps, load_resident)
+
+    # ---- e2e: HOST inputs through the public API, H2D + loss D2H inside the timed region -------
+    h2d_bytes = (pinned[0]["audio"].numel() * 4 + pinned[0]["caps"].numel() * 4 + pinned[0]["mem_lens"].numel() * 4 + d.N * 4 + M * 4)
+    host_losses = []
+
+    def feed_host(i):
+        p = pinned[i % N_BATCH_POOL]
+        r = resident[i % N_BATCH_POOL]
+        st_audio.copy_(p["audio"], non_blocking=True)
+        st_mem_lens.copy_(p["mem_lens"], non_blocking=True)
+        prep = model.prepare_batch(p["caps"], p["cap_lens"], dev)       # caps float32 host -> ids/lens/targets on device
+        st_prep.caps_ids.copy_(prep.caps_ids); st_prep.cap_lens_dev.copy_(prep.cap_lens_dev); st_targets.copy_(prep.targets)
+
+    def timed_e2e(n_steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        barrier()
+        wall = 0.0
+        for i, (a, b) in enumerate(evs):
+            flush.fill_(float(i))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            a.record()
+            feed_host(i)
+            run_step()
+            b.record()
+            host_losses.append(float(loss_buf))        # D2H read of the step's loss (synchronises)
+            wall += time.perf_counter() - t0
+        barrier()
+        ms = torch.tensor([wall * 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / n_steps
+
+    for i in range(3):
+        feed_host(i); run_step()
+    ms_e2e = timed_e2e(args.steps)
+    clk = clocks.stop()
+
+    # ---- diverse sampling: clips partitioned across ranks, K captions share a clip's memory --------
+    lo, hi = parallel.shard_range(SAMPLE_CLIPS, rank, world)
+    ds = synthetic.Dims(N=hi - lo, Te=d.Te, L=SAMPLE_LEN + 1)
+    sb = synthetic.make_batch(ds, 7 + rank)
+    model.eval()
+    s_audio = torch.from_numpy(sb["audio_embeds"]).to(dev)
+    s_lens = torch.from_numpy(sb["mem_lens"].astype(np.int32)).to(dev)
+
+    def sample_once():
+        with torch.no_grad():
+            return model.inference_forward({"audio_embeds": s_audio, "audio_embeds_lens": s_lens}, method="sample",
+                                           max_length=SAMPLE_LEN, n_captions=SAMPLE_K)
+    sample_once(); torch.cuda.synchronize()
+    l1 = F.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); a.record()
+    n_rep = 3
+    for _ in range(n_rep):
+        o = sample_once()
+    b.record(); barrier()
+    sample_launches = (F.launch_count() - l1) // n_rep
+    ms_s = torch.tensor([a.elapsed_time(b) / n_rep], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_s, op=dist.ReduceOp.MAX)
+    ms_sample = float(ms_s)
+
+    if rank == 0:
+        peaks = load_peaks()
+        clips = d.N * world
+        value = clips / (ms_resident * 1e-3)
+        e2e = clips / (ms_e2e * 1e-3)
+        bytes_step = algorithmic_bytes_train(d, n_params)
+        ach = bytes_step / (ms_resident * 1e-3) / 1e9
+        line = {
+            "metric": "train_clips_per_s", "value": round(value, 1), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_resident, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: AC-VAE hot-path train step, batch 32/GPU, Te=62 (1000 frames/16), "
+                                   "caption len 20, V=4400, E=H=A=256, Eenc=512, label-smoothed CE + 0.5*KL + MSE global, "
+                                   "grad clip + Adam; encoder output precomputed",
+                       "global_batch": clips, "parallelism": f"dp{world}", "l2": "flushed between timed steps (256 MiB write)",
+                       "cuda_graph": graph is not None, "noise": "device generator"},
+            "e2e": {"value": round(e2e, 1), "unit": "clips/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
+                    "ms_per_step": round(ms_e2e, 4)},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches_per_step": int(launches_per_step),
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None,
+                         "kernel": "whole fused step (launch sequence of acvae_train_fwd/bwd + vocab CE); "
+                                   "algorithmic bytes per step from SURVEY.md 8d",
+                         "algorithmic_bytes_per_step": int(bytes_step), "peak_source": peaks["src"]},
+            "sampling": {"metric": "sampled_captions_per_s", "value": round(SAMPLE_CLIPS * SAMPLE_K / (ms_sample * 1e-3), 1),
+                         "unit": "captions/s", "ms": round(ms_sample, 3), "clips": SAMPLE_CLIPS, "captions_per_clip": SAMPLE_K,
+                         "max_length": SAMPLE_LEN, "method": "sample", "launches": int(sample_launches),
+                         "n_steps_executed": int(o["n_steps"])},
+            "final_loss": host_losses[-1] if host_losses else None,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(d, budget_s=20.0)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------ CPU reference arm
+def oracle_step_factory(d, seed=1):
+    """The reference's CPU path for the same step: oracle port (pinned to the reference) + the same
+    clip/Adam tail in stock torch on the CPU."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import acvae_oracle as oracle
+    from acvae_b200 import synthetic
+    params = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in synthetic.make_params(d, seed).items()}
+    opt = torch.optim.Adam(list(params.values()), lr=LR)
+    batches = make_host_batches(d, N_BATCH_POOL, 100)
+
+    def step(i):
+        b = batches[i % N_BATCH_POOL]
+        T = int(b["cap_lens"].max()) - 1
+        opt.zero_grad(set_to_none=True)
+        caps = torch.from_numpy(b["caps"])
+        out = oracle.train_forward(params, torch.from_numpy(b["audio_embeds"]), b["mem_lens"], caps, b["cap_lens"],
+                                   torch.randn(d.N, T, d.E), torch.randn(T, d.N, d.E))
+        terms = oracle.train_loss(out, caps, b["cap_lens"], d.V, SMOOTHING, KL_WEIGHT, ALPHA, "MSE")
+        terms["loss"].backward()
+        torch.nn.utils.clip_grad_norm_(list(params.values()), MAX_GRAD_NORM)
+        opt.step()
+        return float(terms["loss"])
+    return step
+
+
+def cpu_baseline(d, budget_s=20.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = oracle_step_factory(d)
+    step(0)
+    t0 = time.perf_counter(); n = 0
+    while True:
+        step(n + 1); n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 50:
+            break
+    dt = (time.perf_counter() - t0) / n
+    return {"value": round(d.N / dt, 2), "unit": "clips/s", "cores": cores, "kind": "port",
+            "sample": f"{n} full train steps of the same workload (batch {d.N}) after 1 warm-up, oracle port of the "
+                      f"reference step on torch CPU with {cores} threads", "ms_per_step": round(dt * 1e3, 2)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from acvae_b200 import synthetic
+    d = synthetic.CFG1
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = oracle_step_factory(d)
+    for i in range(max(1, min(args.warmup, 3))):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = round(d.N / dt, 2)
+    line = {"impl": "reference", "metric": "train_clips_per_s", "value": v, "unit": "clips/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": round(dt * 1e3, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: AC-VAE hot-path train step, batch 32, Te=62, caption len 20, V=4400, "
+                                   "E=256 on the host CPU (reference algorithm, oracle port; one replica on rank 0)",
+                       "global_batch": d.N, "parallelism": "cpu"},
+            "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} full steps, batch {d.N}"},
+            "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 40:
+            args.steps = 40      # bounded: ~0.5-1 s per CPU step
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
