@@ -30,6 +30,7 @@ struct GemmSeg {
   long long ldw;
   int w_trans;
   int K;
+  int a_vec, w_vec;               // set by the launcher: 16-byte vector loads are legal for this operand
   int k_zero_period, k_zero_rem;  // if period > 0: k with k % period == rem contribute nothing (shifted operands)
 };
 
@@ -79,101 +80,17 @@ __device__ __forceinline__ float gumbel_from_u(float u) {
   return -logf(-logf(u + 1e-20f) + 1e-20f);
 }
 
-template <int BM, int BN, int EPI>
-__global__ void __launch_bounds__(256) gemm_kernel(const __grid_constant__ GemmParams p) {
-  constexpr int BK = 16;
-  constexpr int TM = BM / 16, TN = BN / 16;
-  __shared__ __align__(16) float As[BK][BM + 4];
-  __shared__ __align__(16) float Bs[BK][BN + 4];
-  __shared__ float Cs[BM][BN + 1];
 
-  if (p.live && *p.live == 0) return;
-  const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
-  const int m0 = blockIdx.y * BM;
-  const int c0 = blockIdx.x * BN;
+// ---- epilogue shared by both kernels: Cs is the staged accumulator tile [BM][ldcs] -------------
+template <int EPI, int BM, int BN>
+__device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const float* __restrict__ Cs_, int ldcs, int m0, int c0,
+                                              int tid, int tile_x, int ntiles_x) {
+  // 2-D view helper
+  struct View { const float* b; int ld; __device__ const float* operator[](int r) const { return b + r * ld; } };
+  // EPI_STATS rewrites the tile in place (adds the bias), hence the const_cast below
+  struct MView { float* b; int ld; __device__ float* operator[](int r) const { return b + r * ld; } };
+  const MView Cs{const_cast<float*>(Cs_), ldcs};
   const int G = p.G;
-  const int NC = p.U * G;
-
-  float acc[TM][TN];
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
-
-  for (int s = 0; s < p.nseg; ++s) {
-    const GemmSeg& sg = p.seg[s];
-    for (int k0 = 0; k0 < sg.K; k0 += BK) {
-      // ---- A tile -> As[k][m]
-      if (!sg.a_trans) {
-        for (int e = tid; e < BM * BK; e += 256) {
-          const int m = e / BK, k = e % BK;
-          const int gm = m0 + m, gk = k0 + k;
-          float v = 0.0f;
-          if (gm < p.M && gk < sg.K) {
-            const long long row = sg.gather ? (long long)sg.gather[gm * sg.gather_stride] : (long long)gm;
-            v = __ldg(sg.a + row * sg.lda + gk);
-          }
-          As[k][m] = v;
-        }
-      } else {
-        for (int e = tid; e < BM * BK; e += 256) {
-          const int k = e / BM, m = e % BM;
-          const int gm = m0 + m, gk = k0 + k;
-          float v = 0.0f;
-          if (gm < p.M && gk < sg.K && !(sg.k_zero_period && gk % sg.k_zero_period == sg.k_zero_rem))
-            v = __ldg(sg.a + (long long)gk * sg.lda + gm);
-          As[k][m] = v;
-        }
-      }
-      // ---- B tile -> Bs[k][c]
-      if (!sg.w_trans) {
-        for (int e = tid; e < BN * BK; e += 256) {
-          const int c = e / BK, k = e % BK;
-          const int gc = c0 + c, gk = k0 + k;
-          float v = 0.0f;
-          if (gc < NC && gk < sg.K) {
-            const int g = gc % G, u = gc / G;
-            const float* wp = sg.w[g];
-            if (wp) v = __ldg(wp + (long long)u * sg.ldw + gk);
-          }
-          Bs[k][c] = v;
-        }
-      } else {
-        for (int e = tid; e < BN * BK; e += 256) {
-          const int k = e / BN, c = e % BN;
-          const int gc = c0 + c, gk = k0 + k;
-          float v = 0.0f;
-          if (gc < NC && gk < sg.K && !(sg.k_zero_period && gk % sg.k_zero_period == sg.k_zero_rem)) {
-            const int g = gc % G, u = gc / G;
-            const float* wp = sg.w[g];
-            if (wp) v = __ldg(wp + (long long)gk * sg.ldw + u);
-          }
-          Bs[k][c] = v;
-        }
-      }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < BK; ++k) {
-        float a[TM], b[TN];
-#pragma unroll
-        for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
-#pragma unroll
-        for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
-#pragma unroll
-        for (int i = 0; i < TM; ++i)
-#pragma unroll
-          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-      }
-      __syncthreads();
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) Cs[ty * TM + i][tx * TN + j] = acc[i][j];
-  __syncthreads();
-
   const EpiParams& ep = p.epi;
   const int U = p.U;
 
@@ -260,7 +177,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const __grid_constant__ GemmP
   } else if constexpr (EPI == EPI_STATS) {
     // one warp handles rows r = warp, warp+8, ...; lanes stride the BN columns
     const int lane = tid & 31, wid = tid >> 5;
-    const int ntiles = gridDim.x;
+    const int ntiles = ntiles_x;
     for (int r = wid; r < BM; r += 8) {
       const int gm = m0 + r;
       if (gm >= p.M) continue;  // warp-uniform
@@ -293,7 +210,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const __grid_constant__ GemmP
         if (ob > best || (ob == best && oa < barg)) { best = ob; barg = oa; bestlogit = ol; }
       }
       if (lane == 0) {
-        const long long o = (long long)gm * ntiles + blockIdx.x;
+        const long long o = (long long)gm * ntiles + tile_x;
         ep.pmax[o] = wmax; ep.pexp[o] = vexp; ep.psum[o] = vsum; ep.pbest[o * 2] = best; ep.pbest[o * 2 + 1] = bestlogit;
         ep.parg[o] = barg;
       }
@@ -313,25 +230,304 @@ __global__ void __launch_bounds__(256) gemm_kernel(const __grid_constant__ GemmP
   }
 }
 
-// Host-side launch: picks a tile by M and issues the kernel.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int n = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(n));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem, bool pred) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int n = pred ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem), "r"(n));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// =================================================================================================
+// Skinny kernel: the recurrent chain's GEMMs have M = batch <= 32..64 rows.  One CTA owns all 32 rows
+// of a BN-column slab and the FULL K; K is split over the 8 warps (split-K inside the CTA, reduced
+// through shared memory), operands are staged with double-buffered cp.async in KC-wide chunks.  The
+// point is latency: a handful of L2 round trips per launch instead of K/16 synchronous tile loads.
+// =================================================================================================
+constexpr int kSkinnyKC = 64;
+constexpr int kSkinnyLD = kSkinnyKC + 4;
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(256) skinny_gemm_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int BM = 32, KC = kSkinnyKC, LD = kSkinnyLD, NJ = BN / 4;
+  __shared__ __align__(16) float As[2][BM][LD];
+  __shared__ __align__(16) float Ws[2][BN][LD];
+  __shared__ long long rowoff[kMaxSeg][BM];
+  if (p.live && *p.live == 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int m0 = blockIdx.y * BM, c0 = blockIdx.x * BN;
+  const int G = p.G, NC = p.U * G;
+
+  for (int i = tid; i < p.nseg * BM; i += 256) {
+    const int s = i / BM, r = i % BM;
+    const GemmSeg& sg = p.seg[s];
+    const int gm = m0 + r;
+    long long off = -1;
+    if (gm < p.M) off = (sg.gather ? (long long)sg.gather[gm * sg.gather_stride] : (long long)gm) * sg.lda;
+    rowoff[s][r] = off;
+  }
+  __syncthreads();
+
+  // chunk schedule: segment s contributes ceil(K_s / KC) chunks
+  int nchunk = 0;
+  for (int s = 0; s < p.nseg; ++s) nchunk += (p.seg[s].K + KC - 1) / KC;
+
+  auto issue = [&](int chunk, int buf) {
+    int s = 0, k0 = 0, c = chunk;
+    for (; s < p.nseg; ++s) {
+      const int n = (p.seg[s].K + KC - 1) / KC;
+      if (c < n) { k0 = c * KC; break; }
+      c -= n;
+    }
+    const GemmSeg& sg = p.seg[s];
+    // A: BM rows x KC/4 float4
+#pragma unroll
+    for (int i = 0; i < (BM * KC / 4) / 256; ++i) {
+      const int idx = tid + i * 256;
+      const int r = idx / (KC / 4), k4 = (idx % (KC / 4)) * 4;
+      const int gk = k0 + k4;
+      const long long off = rowoff[s][r];
+      const bool ok = off >= 0 && gk < sg.K;
+      cp_async16(&As[buf][r][k4], ok ? (const void*)(sg.a + off + gk) : (const void*)sg.a, ok);
+    }
+    if (!sg.w_trans) {
+#pragma unroll
+      for (int i = 0; i < (BN * KC / 4 + 255) / 256; ++i) {
+        const int idx = tid + i * 256;
+        if (idx < BN * KC / 4) {
+          const int c_ = idx / (KC / 4), k4 = (idx % (KC / 4)) * 4;
+          const int gc = c0 + c_, gk = k0 + k4;
+          const int g = gc % G, u = gc / G;
+          const float* wp = gc < NC ? sg.w[g] : nullptr;
+          const bool ok = wp != nullptr && gk < sg.K;
+          cp_async16(&Ws[buf][c_][k4], ok ? (const void*)(wp + (long long)u * sg.ldw + gk) : (const void*)sg.a, ok);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < (BN * KC) / 256; ++i) {
+        const int idx = tid + i * 256;
+        const int k = idx / BN, c_ = idx % BN;
+        const int gc = c0 + c_, gk = k0 + k;
+        const int g = gc % G, u = gc / G;
+        const float* wp = gc < NC ? sg.w[g] : nullptr;
+        const bool ok = wp != nullptr && gk < sg.K;
+        cp_async4(&Ws[buf][c_][k], ok ? (const void*)(wp + (long long)gk * sg.ldw + u) : (const void*)sg.a, ok);
+      }
+    }
+    cp_async_commit();
+  };
+
+  float acc[4][NJ];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[i][j] = 0.0f;
+  const int rg = lane >> 2, cg = lane & 3;
+
+  if (nchunk > 0) issue(0, 0);
+  for (int ch = 0; ch < nchunk; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nchunk) { issue(ch + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KC / 32; ++kk) {
+      const int k = wid * (KC / 8) + kk * 4;
+      float4 a[4], w[NJ];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(&As[buf][rg + 8 * i][k]);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) w[j] = *reinterpret_cast<const float4*>(&Ws[buf][cg + 4 * j][k]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          acc[i][j] = fmaf(a[i].x, w[j].x, acc[i][j]);
+          acc[i][j] = fmaf(a[i].y, w[j].y, acc[i][j]);
+          acc[i][j] = fmaf(a[i].z, w[j].z, acc[i][j]);
+          acc[i][j] = fmaf(a[i].w, w[j].w, acc[i][j]);
+        }
+    }
+    __syncthreads();
+  }
+  // cross-warp split-K reduction through shared memory (reuses the operand buffers)
+  float* part = &As[0][0][0];                 // [8][BM][BN]  (8*32*16*4 = 16 KB <= sizeof(As))
+  static_assert(8 * BM * BN <= 2 * BM * LD, "partial buffer does not fit");
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) part[(wid * BM + rg + 8 * i) * BN + cg + 4 * j] = acc[i][j];
+  __syncthreads();
+  float* Cs = &Ws[0][0][0];                    // [BM][BN+1]
+  static_assert(BM * (BN + 1) <= 2 * BN * LD, "C tile does not fit");
+  for (int e = tid; e < BM * BN; e += 256) {
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[w * BM * BN + e];
+    Cs[(e / BN) * (BN + 1) + (e % BN)] = s;
+  }
+  __syncthreads();
+  gemm_epilogue<EPI, BM, BN>(p, Cs, BN + 1, m0, c0, tid, blockIdx.x, gridDim.x);
+}
+
+// =================================================================================================
+// Tiled kernel for the batched contractions (M = N*T rows or weight-gradient shapes): 64x64x16 tiles,
+// 4x4 register blocking, next tile prefetched into registers while the current one is multiplied.
+// =================================================================================================
 template <int EPI>
-inline int launch_gemm(const GemmParams& p, cudaStream_t st) {
+__global__ void __launch_bounds__(256) tiled_gemm_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  __shared__ float Cs[BM][BN + 1];
+  if (p.live && *p.live == 0) return;
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int m0 = blockIdx.y * BM, c0 = blockIdx.x * BN;
+  const int G = p.G, NC = p.U * G;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  // per-thread load coordinates: non-transposed operand -> (row = tid/4, k4 = (tid%4)*4);
+  //                              transposed operand     -> (k = tid/16, x4 = (tid%16)*4)
+  const int nt_r = tid >> 2, nt_k = (tid & 3) * 4;
+  const int tr_k = tid >> 4, tr_x = (tid & 15) * 4;
+
+  int buf = 0;
+  for (int s = 0; s < p.nseg; ++s) {
+    const GemmSeg& sg = p.seg[s];
+    // hoisted row pointers for this segment
+    const float* a_row = nullptr;
+    if (!sg.a_trans) {
+      const int gm = m0 + nt_r;
+      if (gm < p.M) a_row = sg.a + (sg.gather ? (long long)sg.gather[gm * sg.gather_stride] : (long long)gm) * sg.lda;
+    }
+    const float* w_row = nullptr;
+    if (!sg.w_trans) {
+      const int gc = c0 + nt_r;
+      if (gc < NC) { const float* wp = sg.w[gc % G]; if (wp) w_row = wp + (long long)(gc / G) * sg.ldw; }
+    }
+    const int ntile = (sg.K + BK - 1) / BK;
+    float4 ra, rb;
+    auto kz = [&](int gk) { return sg.k_zero_period && gk % sg.k_zero_period == sg.k_zero_rem; };
+    auto fetch = [&](int kt) {
+      const int k0 = kt * BK;
+      ra = make_float4(0.f, 0.f, 0.f, 0.f); rb = ra;
+      if (!sg.a_trans) {
+        const int gk = k0 + nt_k;
+        if (a_row && gk < sg.K) {
+          if (sg.a_vec) ra = __ldg(reinterpret_cast<const float4*>(a_row + gk));
+          else { ra.x = __ldg(a_row + gk); if (gk + 1 < sg.K) ra.y = __ldg(a_row + gk + 1);
+                 if (gk + 2 < sg.K) ra.z = __ldg(a_row + gk + 2); if (gk + 3 < sg.K) ra.w = __ldg(a_row + gk + 3); }
+        }
+      } else {
+        const int gk = k0 + tr_k, gm = m0 + tr_x;
+        if (gk < sg.K && gm < p.M && !kz(gk)) {
+          const float* src = sg.a + (long long)gk * sg.lda + gm;
+          if (sg.a_vec && gm + 3 < p.M) ra = __ldg(reinterpret_cast<const float4*>(src));
+          else { ra.x = __ldg(src); if (gm + 1 < p.M) ra.y = __ldg(src + 1); if (gm + 2 < p.M) ra.z = __ldg(src + 2);
+                 if (gm + 3 < p.M) ra.w = __ldg(src + 3); }
+        }
+      }
+      if (!sg.w_trans) {
+        const int gk = k0 + nt_k;
+        if (w_row && gk < sg.K) {
+          if (sg.w_vec) rb = __ldg(reinterpret_cast<const float4*>(w_row + gk));
+          else { rb.x = __ldg(w_row + gk); if (gk + 1 < sg.K) rb.y = __ldg(w_row + gk + 1);
+                 if (gk + 2 < sg.K) rb.z = __ldg(w_row + gk + 2); if (gk + 3 < sg.K) rb.w = __ldg(w_row + gk + 3); }
+        }
+      } else {
+        const int gk = k0 + tr_k, gc = c0 + tr_x;
+        if (gk < sg.K && gc < NC && !kz(gk)) {
+          if (G == 1) {
+            const float* src = sg.w[0] + (long long)gk * sg.ldw + gc;
+            if (sg.w_vec && gc + 3 < NC) rb = __ldg(reinterpret_cast<const float4*>(src));
+            else { rb.x = __ldg(src); if (gc + 1 < NC) rb.y = __ldg(src + 1); if (gc + 2 < NC) rb.z = __ldg(src + 2);
+                   if (gc + 3 < NC) rb.w = __ldg(src + 3); }
+          } else {
+            float t4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int c_ = gc + q;
+              if (c_ < NC) { const float* wp = sg.w[c_ % G]; if (wp) t4[q] = __ldg(wp + (long long)gk * sg.ldw + c_ / G); }
+            }
+            rb = make_float4(t4[0], t4[1], t4[2], t4[3]);
+          }
+        }
+      }
+    };
+    auto stash = [&](int b) {
+      if (!sg.a_trans) { As[b][nt_k][nt_r] = ra.x; As[b][nt_k + 1][nt_r] = ra.y; As[b][nt_k + 2][nt_r] = ra.z; As[b][nt_k + 3][nt_r] = ra.w; }
+      else *reinterpret_cast<float4*>(&As[b][tr_k][tr_x]) = ra;
+      if (!sg.w_trans) { Bs[b][nt_k][nt_r] = rb.x; Bs[b][nt_k + 1][nt_r] = rb.y; Bs[b][nt_k + 2][nt_r] = rb.z; Bs[b][nt_k + 3][nt_r] = rb.w; }
+      else *reinterpret_cast<float4*>(&Bs[b][tr_k][tr_x]) = rb;
+    };
+    if (ntile > 0) { fetch(0); stash(buf); }
+    __syncthreads();
+    for (int kt = 0; kt < ntile; ++kt) {
+      if (kt + 1 < ntile) fetch(kt + 1);
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      if (kt + 1 < ntile) stash(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Cs[ty * 4 + i][tx * 4 + j] = acc[i][j];
+  __syncthreads();
+  gemm_epilogue<EPI, BM, BN>(p, &Cs[0][0], BN + 1, m0, c0, tid, blockIdx.x, gridDim.x);
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Host-side launch: annotates vector-load legality, then picks the kernel by shape.
+template <int EPI>
+inline int launch_gemm(GemmParams p, cudaStream_t st) {
   if (p.M <= 0 || p.U <= 0) return 0;
   const int NC = p.U * p.G;
-  if (EPI == EPI_STATS || p.M > 48) {
-    if (EPI != EPI_STATS && (long long)((p.M + 63) / 64) * ((NC + 63) / 64) < 96) {
-      dim3 grid((NC + 31) / 32, (p.M + 31) / 32);
-      ACVAE_LAUNCH((gemm_kernel<32, 32, EPI>), grid, 256, 0, st, p);
+  bool skinny_ok = EPI != EPI_STATS && EPI != EPI_DLOGITS && p.M <= 64;
+  for (int s = 0; s < p.nseg; ++s) {
+    GemmSeg& sg = p.seg[s];
+    bool wal = true;
+    for (int g = 0; g < p.G; ++g) wal = wal && (sg.w[g] == nullptr || aligned16(sg.w[g]));
+    if (!sg.a_trans) sg.a_vec = aligned16(sg.a) && sg.lda % 4 == 0 && sg.K % 4 == 0;
+    else sg.a_vec = aligned16(sg.a) && sg.lda % 4 == 0;
+    if (!sg.w_trans) sg.w_vec = wal && sg.ldw % 4 == 0 && sg.K % 4 == 0;
+    else sg.w_vec = wal && sg.ldw % 4 == 0 && p.G == 1;
+    skinny_ok = skinny_ok && !sg.a_trans && sg.a_vec && (sg.w_trans || sg.w_vec) && sg.k_zero_period == 0;
+  }
+  if (skinny_ok) {
+    if (NC >= 512) {
+      dim3 grid((NC + 15) / 16, (p.M + 31) / 32);
+      ACVAE_LAUNCH((skinny_gemm_kernel<16, EPI>), grid, 256, 0, st, p);
     } else {
-      dim3 grid((NC + 63) / 64, (p.M + 63) / 64);
-      ACVAE_LAUNCH((gemm_kernel<64, 64, EPI>), grid, 256, 0, st, p);
+      dim3 grid((NC + 7) / 8, (p.M + 31) / 32);
+      ACVAE_LAUNCH((skinny_gemm_kernel<8, EPI>), grid, 256, 0, st, p);
     }
-  } else if (p.M > 16) {
-    dim3 grid((NC + 31) / 32, (p.M + 31) / 32);
-    ACVAE_LAUNCH((gemm_kernel<32, 32, EPI>), grid, 256, 0, st, p);
   } else {
-    dim3 grid((NC + 31) / 32, (p.M + 15) / 16);
-    ACVAE_LAUNCH((gemm_kernel<16, 32, EPI>), grid, 256, 0, st, p);
+    dim3 grid((NC + 63) / 64, (p.M + 63) / 64);
+    ACVAE_LAUNCH((tiled_gemm_kernel<EPI>), grid, 256, 0, st, p);
   }
   return 0;
 }
