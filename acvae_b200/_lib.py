@@ -79,7 +79,7 @@ SYMBOLS = {
                                      _vp, _sz, _vp]),
     "acvae_vocab_ce_bwd": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp,
                                      _vp, _sz, _vp]),
-    "acvae_kl_fwd": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "acvae_kl_fwd": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "acvae_kl_bwd": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "acvae_sample_workspace_bytes": (_sz, [_DP]),
     "acvae_decode_sample": (C.c_int, [_DP, _WP, C.POINTER(SampleIO), _vp, _sz, _vp]),

@@ -19,11 +19,7 @@ namespace acvae {
 struct AttnFwdParams {
   int rows, Te, A, E, Dq;
   int rows_per_clip;                 // clip(r) = r / rows_per_clip
-  const float* qp_in; long long ld_qp_in;      // precomputed q·Wq^T [rows,A] or NULL
-  const float* q; long long ld_q;               // query rows (NULL => q = 0)
-  const int* q_gather; long long q_gather_stride;  // optional: q row index = q_gather[r*stride] (embedding lookup)
-  const float* wq; long long ldwq;              // Wq[a*ldwq + k]
-  float* qp_out; long long ld_qp_out;           // saved projection (backward) or NULL
+  const float* qp_in; long long ld_qp_in;      // q·Wq^T [rows,A] (skinny GEMM) or NULL => zero query
   const float* P; const float* mem; const float* v; const int* mem_lens;
   float* ctx; long long ld_ctx;                 // [rows,E]
   float* w_out; long long ld_w;                 // saved weights [rows,Te] or NULL
@@ -31,52 +27,85 @@ struct AttnFwdParams {
   const int* live;                              // optional device flag: return at once when *live == 0
 };
 
-// dynamic smem: A (qp) + Te (scores) + Dq (q) + 33 floats
+// The clip's projected memory P[clip] and memory mem[clip] are streamed through a 4-deep ring of
+// 32-frame shared-memory tiles with cp.async: all tiles of a 62-frame clip are in flight at once, so
+// a CTA pays one L2/HBM round trip, not one per frame.
+constexpr int kAttnJT = 32;      // frames per tile
+constexpr int kAttnNB = 4;       // ring depth
+
+__device__ __forceinline__ void attn_cp16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void attn_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void attn_wait_dyn(int pending) {
+  switch (pending) {
+    case 0: asm volatile("cp.async.wait_group 0;\n" ::); break;
+    case 1: asm volatile("cp.async.wait_group 1;\n" ::); break;
+    case 2: asm volatile("cp.async.wait_group 2;\n" ::); break;
+    default: asm volatile("cp.async.wait_group 3;\n" ::); break;
+  }
+}
+
+// Ring schedule shared by forward and backward: `ntile` tiles per pass, two passes over the clip
+// (src0 then src1), widths W0 / W1 floats per frame (multiples of 4, 16-byte aligned rows).
+struct AttnRing {
+  const float *src0, *src1;
+  int W0, W1, len, ntile, WMAX;
+  float* bufs;
+  __device__ __forceinline__ void issue(int c) const {
+    const bool second = c >= ntile;
+    const int t = second ? c - ntile : c;
+    const float* src = (second ? src1 : src0) + (long long)t * kAttnJT * (second ? W1 : W0);
+    const int W = second ? W1 : W0;
+    const int nf = min(kAttnJT, len - t * kAttnJT);
+    float* dst = bufs + (size_t)(c % kAttnNB) * kAttnJT * WMAX;
+    const int n4 = nf * W / 4;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) attn_cp16(dst + i * 4, src + i * 4);   // tile stored densely [nf][W]
+    attn_commit();
+  }
+  __device__ __forceinline__ const float* tile(int c) const { return bufs + (size_t)(c % kAttnNB) * kAttnJT * WMAX; }
+};
+
+// dynamic smem: A (qp) + Te (scores) + 64 (reduction scratch) + ring
 __global__ void __launch_bounds__(256) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
-  extern __shared__ float sm[];
-  float* qp = sm;
-  float* sc = qp + p.A;
-  float* qs = sc + p.Te;
-  float* red = qs + p.Dq;
+  extern __shared__ __align__(16) float sm[];
   if (p.live && *p.live == 0) return;
+  const int WMAX = max(p.A, p.E);
+  float* bufs = sm;
+  float* qp = bufs + (size_t)kAttnNB * kAttnJT * WMAX;
+  float* sc = qp + p.A;
+  float* red = sc + p.Te;
   const int r = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
   const int clip = r / p.rows_per_clip;
-  const int len = min(p.mem_lens[clip], p.Te);
+  const int len = max(1, min(p.mem_lens[clip], p.Te));
+  AttnRing ring{p.P + (long long)clip * p.Te * p.A, p.mem + (long long)clip * p.Te * p.E, p.A, p.E, len,
+                (len + kAttnJT - 1) / kAttnJT, WMAX, bufs};
+  const int nchunk = 2 * ring.ntile;
+  int issued = 0;
+  for (; issued < min(nchunk, kAttnNB); ++issued) ring.issue(issued);
 
-  // 1. query projection
-  if (p.qp_in) {
-    for (int a = tid; a < p.A; a += blockDim.x) qp[a] = p.qp_in[(long long)r * p.ld_qp_in + a];
-  } else if (p.q) {
-    const long long qrow = p.q_gather ? (long long)p.q_gather[r * p.q_gather_stride] : (long long)r;
-    for (int k = tid; k < p.Dq; k += blockDim.x) qs[k] = p.q[qrow * p.ld_q + k];
+  for (int a = tid; a < p.A; a += blockDim.x) qp[a] = p.qp_in ? p.qp_in[(long long)r * p.ld_qp_in + a] : 0.0f;
+  __syncthreads();
+
+  // pass 1: scores, one warp per frame
+  for (int c = 0; c < ring.ntile; ++c) {
+    attn_wait_dyn(issued - 1 - c);
     __syncthreads();
-    for (int a = wid; a < p.A; a += nw) {
-      const float* wr = p.wq + (long long)a * p.ldwq;
+    const float* tile = ring.tile(c);
+    const int nf = min(kAttnJT, len - c * kAttnJT);
+    for (int jj = wid; jj < nf; jj += nw) {
+      const float* pr = tile + jj * p.A;
       float s = 0.0f;
-      for (int k = lane; k < p.Dq; k += 32) s = fmaf(qs[k], __ldg(wr + k), s);
+      for (int a = lane; a < p.A; a += 32) s = fmaf(__ldg(p.v + a), tanhf(pr[a] + qp[a]), s);
       s = warp_sum(s);
-      if (lane == 0) qp[a] = s;
+      if (lane == 0) sc[c * kAttnJT + jj] = s;
     }
-  } else {
-    for (int a = tid; a < p.A; a += blockDim.x) qp[a] = 0.0f;
+    __syncthreads();
+    if (issued < nchunk) { ring.issue(issued); ++issued; }
   }
-  __syncthreads();
-  if (p.qp_out)
-    for (int a = tid; a < p.A; a += blockDim.x) p.qp_out[(long long)r * p.ld_qp_out + a] = qp[a];
-
-  // 2. scores: one warp per frame
-  const float* Pc = p.P + (long long)clip * p.Te * p.A;
-  for (int j = wid; j < len; j += nw) {
-    const float* pr = Pc + (long long)j * p.A;
-    float s = 0.0f;
-    for (int a = lane; a < p.A; a += 32) s = fmaf(__ldg(p.v + a), tanhf(pr[a] + qp[a]), s);
-    s = warp_sum(s);
-    if (lane == 0) sc[j] = s;
-  }
-  __syncthreads();
-
-  // 3. masked softmax over valid frames (masked frames get exactly 0)
+  // masked softmax over valid frames (masked frames: exp(-1e10 - max) == 0 exactly in fp32)
   float mx = -INFINITY;
   for (int j = tid; j < len; j += blockDim.x) mx = fmaxf(mx, sc[j]);
   mx = block_max(mx, red);
@@ -94,27 +123,53 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const __grid_constant__ A
     if (p.w_out) p.w_out[(long long)r * p.ld_w + j] = w;
     if (p.aw_out) p.aw_out[(long long)r * p.aw_ld_r + (long long)j * p.aw_ld_j] = w;
   }
-  __syncthreads();
-
-  // 4. context
-  const float* mc = p.mem + (long long)clip * p.Te * p.E;
-  for (int e = tid; e < p.E; e += blockDim.x) {
-    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-    int j = 0;
-    for (; j + 4 <= len; j += 4) {
-      a0 = fmaf(sc[j], mc[(long long)j * p.E + e], a0);
-      a1 = fmaf(sc[j + 1], mc[(long long)(j + 1) * p.E + e], a1);
-      a2 = fmaf(sc[j + 2], mc[(long long)(j + 2) * p.E + e], a2);
-      a3 = fmaf(sc[j + 3], mc[(long long)(j + 3) * p.E + e], a3);
+  // pass 2: context, one thread per feature
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};   // supports E <= 4 * blockDim.x
+  for (int c = ring.ntile; c < nchunk; ++c) {
+    attn_wait_dyn(issued - 1 - c);
+    __syncthreads();
+    const float* tile = ring.tile(c);
+    const int j0 = (c - ring.ntile) * kAttnJT;
+    const int nf = min(kAttnJT, len - j0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = tid + q * blockDim.x;
+      if (e < p.E) {
+        float a0 = 0.f, a1 = 0.f;
+        int jj = 0;
+        for (; jj + 2 <= nf; jj += 2) {
+          a0 = fmaf(sc[j0 + jj], tile[jj * p.E + e], a0);
+          a1 = fmaf(sc[j0 + jj + 1], tile[(jj + 1) * p.E + e], a1);
+        }
+        if (jj < nf) a0 = fmaf(sc[j0 + jj], tile[jj * p.E + e], a0);
+        acc[q] += a0 + a1;
+      }
     }
-    for (; j < len; ++j) a0 = fmaf(sc[j], mc[(long long)j * p.E + e], a0);
-    p.ctx[(long long)r * p.ld_ctx + e] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (issued < nchunk) { ring.issue(issued); ++issued; }
   }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int e = tid + q * blockDim.x;
+    if (e < p.E) p.ctx[(long long)r * p.ld_ctx + e] = acc[q];
+  }
+}
+
+inline size_t attn_smem_bytes(int A, int E, int Te, int extra) {
+  const int WMAX = A > E ? A : E;
+  return ((size_t)kAttnNB * kAttnJT * WMAX + A + Te + 64 + extra) * sizeof(float);
 }
 
 inline int launch_attn_fwd(const AttnFwdParams& p, cudaStream_t st) {
   if (p.rows <= 0) return 0;
-  const size_t smem = (size_t)(p.A + p.Te + p.Dq + 33) * sizeof(float);
+  ACVAE_REQUIRE(p.E <= 1024 && p.A % 4 == 0 && p.E % 4 == 0, "attention: E <= 1024 and A, E multiples of 4");
+  const size_t smem = attn_smem_bytes(p.A, p.E, p.Te, 0);
+  ACVAE_REQUIRE(smem <= 227 * 1024, "attention tile ring exceeds shared memory");
+  static size_t configured = 0;
+  if (smem > configured) {
+    ACVAE_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
   ACVAE_LAUNCH(attn_fwd_kernel, p.rows, 256, smem, st, p);
   return 0;
 }
@@ -130,25 +185,42 @@ struct AttnBwdQParams {
   float* dqp; long long ld_dqp;             // out: d(q·Wq^T) [rows,A]
 };
 
+// dynamic smem: ring + A (qp) + Te (dw/ds) + 64 + E (dctx)
 __global__ void __launch_bounds__(256) attn_bwd_q_kernel(const __grid_constant__ AttnBwdQParams p) {
-  extern __shared__ float sm[];
-  float* dw = sm;            // Te
-  float* dc = dw + p.Te;     // E
-  float* red = dc + p.E;     // 33
+  extern __shared__ __align__(16) float sm[];
+  const int WMAX = max(p.A, p.E);
+  float* bufs = sm;
+  float* qp = bufs + (size_t)kAttnNB * kAttnJT * WMAX;
+  float* dw = qp + p.A;
+  float* red = dw + p.Te;
+  float* dc = red + 64;
   const int r = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
   const int clip = r / p.rows_per_clip;
-  const int len = min(p.mem_lens[clip], p.Te);
+  const int len = max(1, min(p.mem_lens[clip], p.Te));
+  // pass 1 streams mem (dw_j = dctx . mem_j), pass 2 streams P (tanh derivative)
+  AttnRing ring{p.mem + (long long)clip * p.Te * p.E, p.P + (long long)clip * p.Te * p.A, p.E, p.A, len,
+                (len + kAttnJT - 1) / kAttnJT, WMAX, bufs};
+  const int nchunk = 2 * ring.ntile;
+  int issued = 0;
+  for (; issued < min(nchunk, kAttnNB); ++issued) ring.issue(issued);
   for (int e = tid; e < p.E; e += blockDim.x) dc[e] = p.dctx[(long long)r * p.ld_dctx + e];
+  for (int a = tid; a < p.A; a += blockDim.x) qp[a] = p.qp[(long long)r * p.ld_qp + a];
   __syncthreads();
-  const float* mc = p.mem + (long long)clip * p.Te * p.E;
-  for (int j = wid; j < len; j += nw) {
-    float s = 0.0f;
-    for (int e = lane; e < p.E; e += 32) s = fmaf(dc[e], mc[(long long)j * p.E + e], s);
-    s = warp_sum(s);
-    if (lane == 0) dw[j] = s;
+  for (int c = 0; c < ring.ntile; ++c) {
+    attn_wait_dyn(issued - 1 - c);
+    __syncthreads();
+    const float* tile = ring.tile(c);
+    const int nf = min(kAttnJT, len - c * kAttnJT);
+    for (int jj = wid; jj < nf; jj += nw) {
+      float s = 0.0f;
+      for (int e = lane; e < p.E; e += 32) s = fmaf(dc[e], tile[jj * p.E + e], s);
+      s = warp_sum(s);
+      if (lane == 0) dw[c * kAttnJT + jj] = s;
+    }
+    __syncthreads();
+    if (issued < nchunk) { ring.issue(issued); ++issued; }
   }
-  __syncthreads();
   const float* wr = p.w + (long long)r * p.ld_w;
   float dot = 0.0f;
   for (int j = tid; j < len; j += blockDim.x) dot = fmaf(wr[j], dw[j], dot);
@@ -158,23 +230,46 @@ __global__ void __launch_bounds__(256) attn_bwd_q_kernel(const __grid_constant__
     if (j < len) dw[j] = d;
     p.ds[(long long)r * p.ld_ds + j] = d;
   }
-  __syncthreads();
-  const float* Pc = p.P + (long long)clip * p.Te * p.A;
-  for (int a = tid; a < p.A; a += blockDim.x) {
-    const float q = p.qp[(long long)r * p.ld_qp + a];
-    const float va = __ldg(p.v + a);
-    float acc = 0.0f;
-    for (int j = 0; j < len; ++j) {
-      const float th = tanhf(Pc[(long long)j * p.A + a] + q);
-      acc = fmaf(dw[j] * va, 1.0f - th * th, acc);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = ring.ntile; c < nchunk; ++c) {
+    attn_wait_dyn(issued - 1 - c);
+    __syncthreads();
+    const float* tile = ring.tile(c);
+    const int j0 = (c - ring.ntile) * kAttnJT;
+    const int nf = min(kAttnJT, len - j0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int a = tid + q * blockDim.x;
+      if (a < p.A) {
+        const float qa = qp[a], va = __ldg(p.v + a);
+        float s = 0.0f;
+        for (int jj = 0; jj < nf; ++jj) {
+          const float th = tanhf(tile[jj * p.A + a] + qa);
+          s = fmaf(dw[j0 + jj] * va, 1.0f - th * th, s);
+        }
+        acc[q] += s;
+      }
     }
-    p.dqp[(long long)r * p.ld_dqp + a] = acc;
+    __syncthreads();
+    if (issued < nchunk) { ring.issue(issued); ++issued; }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int a = tid + q * blockDim.x;
+    if (a < p.A) p.dqp[(long long)r * p.ld_dqp + a] = acc[q];
   }
 }
 
 inline int launch_attn_bwd_q(const AttnBwdQParams& p, cudaStream_t st) {
   if (p.rows <= 0) return 0;
-  const size_t smem = (size_t)(p.Te + p.E + 33) * sizeof(float);
+  ACVAE_REQUIRE(p.E <= 1024 && p.A <= 1024 && p.A % 4 == 0 && p.E % 4 == 0, "attention: A, E <= 1024, multiples of 4");
+  const size_t smem = attn_smem_bytes(p.A, p.E, p.Te, p.E);
+  ACVAE_REQUIRE(smem <= 227 * 1024, "attention tile ring exceeds shared memory");
+  static size_t configured = 0;
+  if (smem > configured) {
+    ACVAE_CHECK(cudaFuncSetAttribute(attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
   ACVAE_LAUNCH(attn_bwd_q_kernel, p.rows, 256, smem, st, p);
   return 0;
 }
@@ -193,11 +288,11 @@ struct AttnBwdAccParams {
   float* dv;                               // [A], atomically accumulated (zeroed by the caller)
 };
 
-constexpr int kAttnJT = 4;
+constexpr int kAttnAccJT = 4;
 
 __global__ void __launch_bounds__(256) attn_bwd_acc_kernel(const __grid_constant__ AttnBwdAccParams p) {
   const int clip = blockIdx.y;
-  const int j0 = blockIdx.x * kAttnJT;
+  const int j0 = blockIdx.x * kAttnAccJT;
   const int tid = threadIdx.x;
   const int len = min(p.mem_lens[clip], p.Te);
   const int r0 = clip * p.rows_per_clip;
@@ -205,7 +300,7 @@ __global__ void __launch_bounds__(256) attn_bwd_acc_kernel(const __grid_constant
   for (int a = tid; a < p.A; a += blockDim.x) {
     const float va = __ldg(p.v + a);
     float dvacc = 0.0f;
-    for (int jj = 0; jj < kAttnJT; ++jj) {
+    for (int jj = 0; jj < kAttnAccJT; ++jj) {
       const int j = j0 + jj;
       if (j >= p.Te) break;
       float acc = 0.0f;
@@ -225,7 +320,7 @@ __global__ void __launch_bounds__(256) attn_bwd_acc_kernel(const __grid_constant
   }
   // dmem: threads over e
   for (int e = tid; e < p.E; e += blockDim.x) {
-    for (int jj = 0; jj < kAttnJT; ++jj) {
+    for (int jj = 0; jj < kAttnAccJT; ++jj) {
       const int j = j0 + jj;
       if (j >= p.Te) break;
       float acc = 0.0f;
@@ -243,7 +338,7 @@ __global__ void __launch_bounds__(256) attn_bwd_acc_kernel(const __grid_constant
 
 inline int launch_attn_bwd_acc(const AttnBwdAccParams& p, cudaStream_t st) {
   if (p.clips <= 0) return 0;
-  dim3 grid((p.Te + kAttnJT - 1) / kAttnJT, p.clips);
+  dim3 grid((p.Te + kAttnAccJT - 1) / kAttnAccJT, p.clips);
   ACVAE_LAUNCH(attn_bwd_acc_kernel, grid, 256, 0, st, p);
   return 0;
 }

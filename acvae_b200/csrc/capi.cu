@@ -1,8 +1,10 @@
 // C ABI of libacvae_b200.so (see include/acvae_b200.h).  Thin: argument checks,
 // workspace carve-up and kernel enqueueing; no torch types, no exceptions.
 #include "../../include/acvae_b200.h"
+#include <stdlib.h>
+
 #include "sample.cuh"
-#include "train.cuh"
+#include "train_fast.cuh"
 
 namespace acvae {
 thread_local char g_err[512] = {0};
@@ -25,18 +27,6 @@ static VocabWs carve_vocab_ws(int M, int V, void* base, bool with_dlogits) {
   return w;
 }
 
-__global__ void __launch_bounds__(1024) kl_fwd_kernel(long long n_elem, float inv_rows, const float* __restrict__ mq,
-                                                       const float* __restrict__ lq, const float* __restrict__ mp,
-                                                       const float* __restrict__ lp, float* __restrict__ out) {
-  __shared__ float red[33];
-  float s = 0.0f;
-  for (long long i = threadIdx.x; i < n_elem; i += blockDim.x) {
-    const float d = mq[i] - mp[i];
-    s += 0.5f * lp[i] - 0.5f * lq[i] + (expf(lq[i]) + d * d) / (2.0f * expf(lp[i])) - 0.5f;
-  }
-  s = block_sum(s, red);
-  if (threadIdx.x == 0) out[0] = s * inv_rows;
-}
 }  // namespace acvae
 
 using namespace acvae;
@@ -73,6 +63,7 @@ int acvae_train_fwd(const acvae_dims* d, const acvae_weights* w, const acvae_tra
                     io->seqs && io->sampled_logprobs && io->logit_lse && io->logit_sum,
                 "NULL output");
   ACVAE_REQUIRE(d->variant == 1 || (io->q_means_utt && io->p_means_utt), "hybrid variant needs *_means_utt outputs");
+  if (!getenv("ACVAE_DISABLE_FAST") && fast_path_ok(*d, *io)) return train_fwd_fast(*d, *w, *io, workspace, (cudaStream_t)stream);
   return train_fwd(*d, *w, *io, workspace, (cudaStream_t)stream);
 }
 
@@ -82,6 +73,9 @@ int acvae_train_bwd(const acvae_dims* d, const acvae_weights* w, const acvae_tra
   ACVAE_TRY(check_dims(d));
   ACVAE_REQUIRE(w && io && gin && gw && workspace, "NULL pointer");
   ACVAE_REQUIRE(workspace_bytes >= carve_train_ws(*d, nullptr).bytes, "workspace too small");
+  ACVAE_REQUIRE(io->tf_flags && io->dis_flags, "tf_flags / dis_flags are required");
+  if (!getenv("ACVAE_DISABLE_FAST") && fast_path_ok(*d, *io))
+    return train_bwd_fast(*d, *w, *io, *gin, *gw, d_audio_embeds, workspace, (cudaStream_t)stream);
   return train_bwd(*d, *w, *io, *gin, *gw, d_audio_embeds, workspace, (cudaStream_t)stream);
 }
 
@@ -170,10 +164,16 @@ int acvae_vocab_ce_bwd(int32_t M, int32_t V, int32_t E, const float* hidden, con
 }
 
 int acvae_kl_fwd(int64_t rows, int32_t E, const float* q_mean, const float* q_log, const float* p_mean,
-                 const float* p_log, float* kl_out, void* stream) {
-  ACVAE_REQUIRE(rows > 0 && E > 0 && q_mean && q_log && p_mean && p_log && kl_out, "bad argument");
-  ACVAE_LAUNCH(kl_fwd_kernel, 1, 1024, 0, (cudaStream_t)stream, (long long)rows * E, 1.0f / (float)rows, q_mean, q_log,
-               p_mean, p_log, kl_out);
+                 const float* p_log, float* kl_out, void* workspace, size_t workspace_bytes, void* stream) {
+  ACVAE_REQUIRE(rows > 0 && E > 0 && q_mean && q_log && p_mean && p_log && kl_out && workspace, "bad argument");
+  ACVAE_REQUIRE(workspace_bytes >= 148 * sizeof(float), "workspace too small (need 148 floats)");
+  const long long n = (long long)rows * E;
+  int blocks = (int)((n + 2047) / 2048);
+  blocks = blocks < 1 ? 1 : (blocks > 148 ? 148 : blocks);
+  // deterministic two-stage sum: per-block partials, then one block adds them in a fixed order
+  ACVAE_LAUNCH(kl_partial_kernel, blocks, 256, 0, (cudaStream_t)stream, n, q_mean, q_log, p_mean, p_log, (float*)workspace);
+  ACVAE_LAUNCH(final_sum_kernel, 1, 256, 0, (cudaStream_t)stream, blocks, (const float*)workspace, 1.0f / (float)rows,
+               (const float*)nullptr, kl_out);
   return 0;
 }
 

@@ -28,6 +28,7 @@ struct GemmSeg {
   int a_trans;
   const float* w[kMaxGate];  // B(g,u,k) = w[g][u*ldw + k]   (w_trans: w[g][k*ldw + u]); NULL: no contribution
   long long ldw;
+  long long ldwg[kMaxGate];  // optional per-gate leading dimension (0 => ldw)
   int w_trans;
   int K;
   int a_vec, w_vec;               // set by the launcher: 16-byte vector loads are legal for this operand
@@ -40,7 +41,10 @@ enum EpiKind {
   EPI_GRU = 2,     // G=4 (r,z,n_x,n_h): nn.GRU cell, optional packed-sequence length mask
   EPI_HEAD = 3,    // G=2 (mean,log): Gaussian head + reparameterisation
   EPI_STATS = 4,   // G=1: per-row partial max/argmax/sum-exp/sum over this CTA's columns
-  EPI_DLOGITS = 5  // G=1: label-smoothed softmax-CE gradient wrt logits
+  EPI_DLOGITS = 5, // G=1: label-smoothed softmax-CE gradient wrt logits
+  EPI_GRU_BWD = 6, // G=1: acc = dh_{t-1} partial; fused GRU pointwise backward of step t-1
+  EPI_LSTM_BWD = 7,// G=1: acc = dML_t.W_head; fused LSTM pointwise backward of step t
+  EPI_HEAD_BWD = 8 // G=2: (d last_z, d h_{t-1}); fused Gaussian-head/reparam backward of step t-1
 };
 
 struct EpiParams {
@@ -66,6 +70,10 @@ struct EpiParams {
   // EPI_DLOGITS
   const float* lse; const int* targets; const float* row_w; const float* gscale; // gscale: device [1] = dLoss / count
   float smooth_off, smooth_on;
+  // backward-chain epilogues: generic inputs x0..x5 / outputs y0..y2 (meaning documented per epilogue)
+  const float* x0; long long ld_x0; const float* x1; long long ld_x1; const float* x2; long long ld_x2;
+  const float* x3; long long ld_x3; const float* x4; long long ld_x4; const float* x5; long long ld_x5;
+  float* y0; long long ld_y0; float* y1; long long ld_y1; float* y2; long long ld_y2;
 };
 
 struct GemmParams {
@@ -227,6 +235,76 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const float* 
       const float rw = ep.row_w ? ep.row_w[gm] : 1.0f;
       ep.c[0][(long long)gm * ep.ldc + u] = gs * rw * (pr - td);
     }
+  } else if constexpr (EPI == EPI_GRU_BWD) {
+    // x0: carry_in = dh_t * z_t [M,U] (or NULL); x1: upstream d h_{t-1} (ld_x1) (or NULL);
+    // gates/ld_gates: saved (r,z,n,gh_n) of step t-1; prev/ld_prev: h_{t-2} (or NULL);
+    // lens/t: packed-sequence mask for step t-1.  y0: dGi [.,3U]; y1: dGh [.,3U]; y2: carry_out [M,U].
+    for (int e = tid; e < BM * BN; e += 256) {
+      const int r = e / BN, c = e % BN;
+      const int gm = m0 + r, u = c0 + c;
+      if (gm >= p.M || u >= U) continue;
+      float* gi = ep.y0 + (long long)gm * ep.ld_y0 + u;
+      float* gh = ep.y1 + (long long)gm * ep.ld_y1 + u;
+      if (ep.lens && ep.t >= ep.lens[gm]) {
+        gi[0] = gi[U] = gi[2 * U] = 0.0f; gh[0] = gh[U] = gh[2 * U] = 0.0f;
+        ep.y2[(long long)gm * U + u] = 0.0f;
+        continue;
+      }
+      float dh = Cs[r][c];
+      if (ep.x0) dh += ep.x0[(long long)gm * U + u];
+      if (ep.x1) dh += ep.x1[(long long)gm * ep.ld_x1 + u];
+      const float* g = ep.gates + (long long)gm * ep.ld_gates + u;
+      const float rr = g[0], z = g[U], nn = g[2 * U], ghn = g[3 * U];
+      const float hp = ep.prev ? ep.prev[(long long)gm * ep.ld_prev + u] : 0.0f;
+      const float dn = dh * (1.0f - z), dz = dh * (hp - nn);
+      const float dan = dn * (1.0f - nn * nn);
+      const float dar = dan * ghn * rr * (1.0f - rr), daz = dz * z * (1.0f - z);
+      gi[0] = dar; gi[U] = daz; gi[2 * U] = dan;
+      gh[0] = dar; gh[U] = daz; gh[2 * U] = dan * rr;
+      ep.y2[(long long)gm * U + u] = dh * z;
+    }
+  } else if constexpr (EPI == EPI_LSTM_BWD) {
+    // x0: dh carry [M,U] (or NULL); x1: dc carry in [M,U] (or NULL); gates: saved (i,f,g,o) of step t;
+    // x2/ld_x2: c_t; x3/ld_x3: c_{t-1} (or NULL).  y0: dG [.,4U]; y1: dc carry out [M,U].
+    for (int e = tid; e < BM * BN; e += 256) {
+      const int r = e / BN, c = e % BN;
+      const int gm = m0 + r, u = c0 + c;
+      if (gm >= p.M || u >= U) continue;
+      float dh = Cs[r][c];
+      if (ep.x0) dh += ep.x0[(long long)gm * U + u];
+      const float* g = ep.gates + (long long)gm * ep.ld_gates + u;
+      const float ig = g[0], fg = g[U], gg = g[2 * U], og = g[3 * U];
+      const float tc = tanhf(ep.x2[(long long)gm * ep.ld_x2 + u]);
+      const float cp = ep.x3 ? ep.x3[(long long)gm * ep.ld_x3 + u] : 0.0f;
+      float dc = dh * og * (1.0f - tc * tc);
+      if (ep.x1) dc += ep.x1[(long long)gm * U + u];
+      float* dg = ep.y0 + (long long)gm * ep.ld_y0 + u;
+      dg[0] = dc * gg * ig * (1.0f - ig);
+      dg[U] = dc * cp * fg * (1.0f - fg);
+      dg[2 * U] = dc * ig * (1.0f - gg * gg);
+      dg[3 * U] = dh * tc * og * (1.0f - og);
+      ep.y1[(long long)gm * U + u] = dc * fg;
+    }
+  } else if constexpr (EPI == EPI_HEAD_BWD) {
+    // columns interleave (dz, dh) per unit.  x0/ld_x0: upstream d p_z[t-1] (or NULL); x1: d p_means[t-1] (or NULL);
+    // x2: d p_logs[t-1] (or NULL); x3/ld_x3: eps[t-1]; x4/ld_x4: p_logs[t-1].
+    // y0/ld_y0: dML[t-1] [.,2U]; y1: dh carry out [M,U].
+    const int UT = BN / 2;
+    for (int e = tid; e < BM * UT; e += 256) {
+      const int r = e / UT, ul = e % UT;
+      const int gm = m0 + r, u = c0 / 2 + ul;
+      if (gm >= p.M || u >= U) continue;
+      float dz = Cs[r][ul * 2 + 0];
+      const float dh = Cs[r][ul * 2 + 1];
+      if (ep.x0) dz += ep.x0[(long long)gm * ep.ld_x0 + u];
+      float dm = dz;
+      float dl = dz * ep.x3[(long long)gm * ep.ld_x3 + u] * 0.5f * expf(0.5f * ep.x4[(long long)gm * ep.ld_x4 + u]);
+      if (ep.x1) dm += ep.x1[(long long)gm * ep.ld_x1 + u];
+      if (ep.x2) dl += ep.x2[(long long)gm * ep.ld_x2 + u];
+      float* dml = ep.y0 + (long long)gm * ep.ld_y0 + u;
+      dml[0] = dm; dml[U] = dl;
+      ep.y1[(long long)gm * U + u] = dh;
+    }
   }
 }
 
@@ -250,14 +328,31 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // through shared memory), operands are staged with double-buffered cp.async in KC-wide chunks.  The
 // point is latency: a handful of L2 round trips per launch instead of K/16 synchronous tile loads.
 // =================================================================================================
-constexpr int kSkinnyKC = 64;
+constexpr int kSkinnyKC = 128;
 constexpr int kSkinnyLD = kSkinnyKC + 4;
+constexpr int kSkinnyMaxStages = 8;
 
+__device__ __forceinline__ void cp_async_wait_dyn(int pending) {
+  switch (pending) {
+    case 0: asm volatile("cp.async.wait_group 0;\n" ::); break;
+    case 1: asm volatile("cp.async.wait_group 1;\n" ::); break;
+    case 2: asm volatile("cp.async.wait_group 2;\n" ::); break;
+    case 3: asm volatile("cp.async.wait_group 3;\n" ::); break;
+    case 4: asm volatile("cp.async.wait_group 4;\n" ::); break;
+    case 5: asm volatile("cp.async.wait_group 5;\n" ::); break;
+    case 6: asm volatile("cp.async.wait_group 6;\n" ::); break;
+    default: asm volatile("cp.async.wait_group 7;\n" ::); break;
+  }
+}
+
+// Stage s of the ring: A tile [32][LD] followed by W tile [BN][LD].  Up to 8 stages (K <= 1024) are all
+// issued before the first wait, so the whole operand set of a recurrent-step GEMM is one burst of
+// cp.async traffic and the CTA pays a single L2 round trip.
 template <int BN, int EPI>
-__global__ void __launch_bounds__(256) skinny_gemm_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(256) skinny_gemm_kernel(const __grid_constant__ GemmParams p, int nstages) {
   constexpr int BM = 32, KC = kSkinnyKC, LD = kSkinnyLD, NJ = BN / 4;
-  __shared__ __align__(16) float As[2][BM][LD];
-  __shared__ __align__(16) float Ws[2][BN][LD];
+  constexpr int STAGE = (BM + BN) * LD;
+  extern __shared__ __align__(16) float sk_smem[];
   __shared__ long long rowoff[kMaxSeg][BM];
   if (p.live && *p.live == 0) return;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -274,11 +369,12 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const __grid_constant_
   }
   __syncthreads();
 
-  // chunk schedule: segment s contributes ceil(K_s / KC) chunks
   int nchunk = 0;
   for (int s = 0; s < p.nseg; ++s) nchunk += (p.seg[s].K + KC - 1) / KC;
 
-  auto issue = [&](int chunk, int buf) {
+  auto issue = [&](int chunk) {
+    float* As = sk_smem + (size_t)(chunk % nstages) * STAGE;
+    float* Ws = As + BM * LD;
     int s = 0, k0 = 0, c = chunk;
     for (; s < p.nseg; ++s) {
       const int n = (p.seg[s].K + KC - 1) / KC;
@@ -286,7 +382,6 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const __grid_constant_
       c -= n;
     }
     const GemmSeg& sg = p.seg[s];
-    // A: BM rows x KC/4 float4
 #pragma unroll
     for (int i = 0; i < (BM * KC / 4) / 256; ++i) {
       const int idx = tid + i * 256;
@@ -294,20 +389,18 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const __grid_constant_
       const int gk = k0 + k4;
       const long long off = rowoff[s][r];
       const bool ok = off >= 0 && gk < sg.K;
-      cp_async16(&As[buf][r][k4], ok ? (const void*)(sg.a + off + gk) : (const void*)sg.a, ok);
+      cp_async16(As + r * LD + k4, ok ? (const void*)(sg.a + off + gk) : (const void*)sg.a, ok);
     }
     if (!sg.w_trans) {
 #pragma unroll
-      for (int i = 0; i < (BN * KC / 4 + 255) / 256; ++i) {
+      for (int i = 0; i < (BN * KC / 4) / 256; ++i) {
         const int idx = tid + i * 256;
-        if (idx < BN * KC / 4) {
-          const int c_ = idx / (KC / 4), k4 = (idx % (KC / 4)) * 4;
-          const int gc = c0 + c_, gk = k0 + k4;
-          const int g = gc % G, u = gc / G;
-          const float* wp = gc < NC ? sg.w[g] : nullptr;
-          const bool ok = wp != nullptr && gk < sg.K;
-          cp_async16(&Ws[buf][c_][k4], ok ? (const void*)(wp + (long long)u * sg.ldw + gk) : (const void*)sg.a, ok);
-        }
+        const int c_ = idx / (KC / 4), k4 = (idx % (KC / 4)) * 4;
+        const int gc = c0 + c_, gk = k0 + k4;
+        const int g = gc % G, u = gc / G;
+        const float* wp = gc < NC ? sg.w[g] : nullptr;
+        const bool ok = wp != nullptr && gk < sg.K;
+        cp_async16(Ws + c_ * LD + k4, ok ? (const void*)(wp + (long long)u * (sg.ldwg[g] ? sg.ldwg[g] : sg.ldw) + gk) : (const void*)sg.a, ok);
       }
     } else {
 #pragma unroll
@@ -318,7 +411,7 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const __grid_constant_
         const int g = gc % G, u = gc / G;
         const float* wp = gc < NC ? sg.w[g] : nullptr;
         const bool ok = wp != nullptr && gk < sg.K;
-        cp_async4(&Ws[buf][c_][k], ok ? (const void*)(wp + (long long)gk * sg.ldw + u) : (const void*)sg.a, ok);
+        cp_async4(Ws + c_ * LD + k, ok ? (const void*)(wp + (long long)gk * (sg.ldwg[g] ? sg.ldwg[g] : sg.ldw) + u) : (const void*)sg.a, ok);
       }
     }
     cp_async_commit();
@@ -331,19 +424,21 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const __grid_constant_
     for (int j = 0; j < NJ; ++j) acc[i][j] = 0.0f;
   const int rg = lane >> 2, cg = lane & 3;
 
-  if (nchunk > 0) issue(0, 0);
+  int issued = 0;
+  for (; issued < min(nchunk, nstages); ++issued) issue(issued);
   for (int ch = 0; ch < nchunk; ++ch) {
-    const int buf = ch & 1;
-    if (ch + 1 < nchunk) { issue(ch + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    cp_async_wait_dyn(issued - 1 - ch);
     __syncthreads();
+    const float* As = sk_smem + (size_t)(ch % nstages) * STAGE;
+    const float* Ws = As + BM * LD;
 #pragma unroll
     for (int kk = 0; kk < KC / 32; ++kk) {
       const int k = wid * (KC / 8) + kk * 4;
       float4 a[4], w[NJ];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(&As[buf][rg + 8 * i][k]);
+      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(As + (rg + 8 * i) * LD + k);
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) w[j] = *reinterpret_cast<const float4*>(&Ws[buf][cg + 4 * j][k]);
+      for (int j = 0; j < NJ; ++j) w[j] = *reinterpret_cast<const float4*>(Ws + (cg + 4 * j) * LD + k);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -354,18 +449,22 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const __grid_constant_
           acc[i][j] = fmaf(a[i].w, w[j].w, acc[i][j]);
         }
     }
-    __syncthreads();
+    if (issued < nchunk) {        // ring reuse (K > nstages * KC): refill the slot just consumed
+      __syncthreads();
+      issue(issued);
+      ++issued;
+    }
   }
-  // cross-warp split-K reduction through shared memory (reuses the operand buffers)
-  float* part = &As[0][0][0];                 // [8][BM][BN]  (8*32*16*4 = 16 KB <= sizeof(As))
-  static_assert(8 * BM * BN <= 2 * BM * LD, "partial buffer does not fit");
+  __syncthreads();
+  // cross-warp split-K reduction through shared memory (reuses stage 0 / stage 1)
+  float* part = sk_smem;                       // [8][BM][BN]
+  static_assert(8 * BM * BN <= STAGE, "partial buffer does not fit in one stage");
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < NJ; ++j) part[(wid * BM + rg + 8 * i) * BN + cg + 4 * j] = acc[i][j];
   __syncthreads();
-  float* Cs = &Ws[0][0][0];                    // [BM][BN+1]
-  static_assert(BM * (BN + 1) <= 2 * BN * LD, "C tile does not fit");
+  float* Cs = sk_smem + STAGE;                 // [BM][BN+1]  (the launcher always provides >= 2 stages)
   for (int e = tid; e < BM * BN; e += 256) {
     float s = 0.0f;
 #pragma unroll
@@ -374,6 +473,22 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const __grid_constant_
   }
   __syncthreads();
   gemm_epilogue<EPI, BM, BN>(p, Cs, BN + 1, m0, c0, tid, blockIdx.x, gridDim.x);
+}
+
+template <int BN, int EPI>
+inline int launch_skinny(const GemmParams& p, int NC, cudaStream_t st) {
+  int nchunk = 0;
+  for (int s = 0; s < p.nseg; ++s) nchunk += (p.seg[s].K + kSkinnyKC - 1) / kSkinnyKC;
+  int nstages = nchunk < 2 ? 2 : (nchunk > kSkinnyMaxStages ? kSkinnyMaxStages : nchunk);
+  const size_t smem = (size_t)nstages * (32 + BN) * kSkinnyLD * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    ACVAE_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dim3 grid((NC + BN - 1) / BN, (p.M + 31) / 32);
+  ACVAE_LAUNCH((skinny_gemm_kernel<BN, EPI>), grid, 256, smem, st, p, nstages);
+  return 0;
 }
 
 // =================================================================================================
@@ -415,7 +530,7 @@ __global__ void __launch_bounds__(256) tiled_gemm_kernel(const __grid_constant__
     const float* w_row = nullptr;
     if (!sg.w_trans) {
       const int gc = c0 + nt_r;
-      if (gc < NC) { const float* wp = sg.w[gc % G]; if (wp) w_row = wp + (long long)(gc / G) * sg.ldw; }
+      if (gc < NC) { const int g_ = gc % G; const float* wp = sg.w[g_]; if (wp) w_row = wp + (long long)(gc / G) * (sg.ldwg[g_] ? sg.ldwg[g_] : sg.ldw); }
     }
     const int ntile = (sg.K + BK - 1) / BK;
     float4 ra, rb;
@@ -459,7 +574,7 @@ __global__ void __launch_bounds__(256) tiled_gemm_kernel(const __grid_constant__
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int c_ = gc + q;
-              if (c_ < NC) { const float* wp = sg.w[c_ % G]; if (wp) t4[q] = __ldg(wp + (long long)gk * sg.ldw + c_ / G); }
+              if (c_ < NC) { const int g_ = c_ % G; const float* wp = sg.w[g_]; if (wp) t4[q] = __ldg(wp + (long long)gk * (sg.ldwg[g_] ? sg.ldwg[g_] : sg.ldw) + c_ / G); }
             }
             rb = make_float4(t4[0], t4[1], t4[2], t4[3]);
           }
@@ -507,6 +622,9 @@ inline int launch_gemm(GemmParams p, cudaStream_t st) {
   if (p.M <= 0 || p.U <= 0) return 0;
   const int NC = p.U * p.G;
   bool skinny_ok = EPI != EPI_STATS && EPI != EPI_DLOGITS && p.M <= 64;
+  for (int s = 0; s < p.nseg; ++s)
+    for (int g = 0; g < p.G; ++g)
+      if (p.seg[s].ldwg[g] % 4 != 0) skinny_ok = false;
   for (int s = 0; s < p.nseg; ++s) {
     GemmSeg& sg = p.seg[s];
     bool wal = true;
@@ -518,13 +636,8 @@ inline int launch_gemm(GemmParams p, cudaStream_t st) {
     skinny_ok = skinny_ok && !sg.a_trans && sg.a_vec && (sg.w_trans || sg.w_vec) && sg.k_zero_period == 0;
   }
   if (skinny_ok) {
-    if (NC >= 512) {
-      dim3 grid((NC + 15) / 16, (p.M + 31) / 32);
-      ACVAE_LAUNCH((skinny_gemm_kernel<16, EPI>), grid, 256, 0, st, p);
-    } else {
-      dim3 grid((NC + 7) / 8, (p.M + 31) / 32);
-      ACVAE_LAUNCH((skinny_gemm_kernel<8, EPI>), grid, 256, 0, st, p);
-    }
+    if (NC >= 512) return launch_skinny<16, EPI>(p, NC, st);
+    return launch_skinny<8, EPI>(p, NC, st);
   } else {
     dim3 grid((NC + 63) / 64, (p.M + 63) / 64);
     ACVAE_LAUNCH((tiled_gemm_kernel<EPI>), grid, 256, 0, st, p);

@@ -32,21 +32,35 @@ struct VocabReduceParams {
   const int* live;                                              // optional: skip when *live == 0
 };
 
-__global__ void vocab_reduce_kernel(const __grid_constant__ VocabReduceParams p) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) vocab_reduce_kernel(const __grid_constant__ VocabReduceParams p) {
+  // one warp per row: lanes stride the per-tile partials
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= p.M) return;
   if (p.live && *p.live == 0) return;
   const long long o = (long long)m * p.ntiles;
   float gmax = -INFINITY;
-  for (int i = 0; i < p.ntiles; ++i) gmax = fmaxf(gmax, p.pmax[o + i]);
+  for (int i = lane; i < p.ntiles; i += 32) gmax = fmaxf(gmax, p.pmax[o + i]);
+  gmax = warp_max(gmax);
   float se = 0.0f, ss = 0.0f, best = -INFINITY, bl = 0.0f;
-  int arg = 0;
-  for (int i = 0; i < p.ntiles; ++i) {
+  int arg = 0x7fffffff;
+  for (int i = lane; i < p.ntiles; i += 32) {
     se += p.pexp[o + i] * expf(p.pmax[o + i] - gmax);
     ss += p.psum[o + i];
     const float b = p.pbest[(o + i) * 2];
-    if (b > best) { best = b; bl = p.pbest[(o + i) * 2 + 1]; arg = p.parg[o + i]; }
+    const int a = p.parg[o + i];
+    if (b > best || (b == best && a < arg)) { best = b; bl = p.pbest[(o + i) * 2 + 1]; arg = a; }
   }
+  se = warp_sum(se);
+  ss = warp_sum(ss);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, off);
+    const float ol = __shfl_xor_sync(0xffffffffu, bl, off);
+    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; bl = ol; }
+  }
+  if (lane != 0) return;
   const float lse = gmax + logf(se);
   if (p.lse) p.lse[m * p.ld_row] = lse;
   if (p.lsum) p.lsum[m * p.ld_row] = ss;
@@ -202,21 +216,23 @@ __global__ void __launch_bounds__(256) ce_gscale_kernel(int M, const float* __re
   if (threadIdx.x == 0) gscale[0] = dloss[0] / s;
 }
 
-// out[c] = sum_r x[r*ld + c]   (bias gradients); grid over column chunks of 32, block 256 = 8 row-lanes x 32 cols
-__global__ void __launch_bounds__(256) colsum_kernel(long long rows, int cols, const float* __restrict__ x, long long ld,
-                                                     float* __restrict__ out, int accumulate) {
-  __shared__ float sm[8][33];
+// out[c] = sum_r x[r*ld + c]   (bias gradients); block = 32 columns x 32 row-lanes
+__global__ void __launch_bounds__(1024) colsum_kernel(long long rows, int cols, const float* __restrict__ x, long long ld,
+                                                      float* __restrict__ out, int accumulate) {
+  __shared__ float sm[32][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   float s = 0.0f;
-  if (c < cols)
-    for (long long r = ry; r < rows; r += 8) s += x[r * ld + c];
+  if (c < cols) {
+#pragma unroll 8
+    for (long long r = ry; r < rows; r += 32) s += x[r * ld + c];
+  }
   sm[ry][cx] = s;
   __syncthreads();
   if (ry == 0 && c < cols) {
     float t = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += sm[i][cx];
+    for (int i = 0; i < 32; ++i) t += sm[i][cx];
     out[c] = accumulate ? out[c] + t : t;
   }
 }

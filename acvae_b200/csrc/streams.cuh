@@ -1,0 +1,42 @@
+// Auxiliary streams/events for intra-call concurrency.  The recurrent chains (posterior directions,
+// prior, decoder) are latency-bound and occupy a few dozen SMs each; running them -- and the batched
+// GEMMs that do not depend on them -- on forked streams lets them overlap.  Fork/join is expressed with
+// events, so it is legal under CUDA-graph stream capture (the side streams join the capture).
+// Created once per process on first use (the device current at that time).
+#pragma once
+#include "common.cuh"
+
+namespace acvae {
+
+constexpr int kAuxStreams = 4;
+constexpr int kAuxEvents = 32;
+
+struct Aux {
+  cudaStream_t s[kAuxStreams];
+  cudaEvent_t e[kAuxEvents];
+  int next_event = 0;
+  bool ok = false;
+  cudaEvent_t ev() { cudaEvent_t r = e[next_event]; next_event = (next_event + 1) % kAuxEvents; return r; }
+};
+
+inline Aux* aux() {
+  static Aux a;
+  if (!a.ok) {
+    for (int i = 0; i < kAuxStreams; ++i)
+      if (cudaStreamCreateWithFlags(&a.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (int i = 0; i < kAuxEvents; ++i)
+      if (cudaEventCreateWithFlags(&a.e[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    a.ok = true;
+  }
+  return &a;
+}
+
+// `to` waits for everything enqueued so far on `from`
+inline int stream_dep(cudaStream_t from, cudaStream_t to, Aux* a) {
+  cudaEvent_t e = a->ev();
+  ACVAE_CHECK(cudaEventRecord(e, from));
+  ACVAE_CHECK(cudaStreamWaitEvent(to, e, 0));
+  return 0;
+}
+
+}  // namespace acvae

@@ -121,7 +121,7 @@ inline int linear_bwd_weight(int Nn, int K, int R, const float* dy, long long ld
   return launch_gemm<EPI_PLAIN>(p, st);
 }
 inline int colsum(long long rows, int cols, const float* x, long long ld, float* out, cudaStream_t st, int accumulate = 0) {
-  ACVAE_LAUNCH(colsum_kernel, (cols + 31) / 32, 256, 0, st, rows, cols, x, ld, out, accumulate);
+  ACVAE_LAUNCH(colsum_kernel, (cols + 31) / 32, 1024, 0, st, rows, cols, x, ld, out, accumulate);
   return 0;
 }
 inline int gather_rows(int rows, int E, const float* table, const int* idx, float* out, cudaStream_t st) {
@@ -173,7 +173,7 @@ inline int vocab_stats(VocabStatsArgs a, cudaStream_t st) {
   ACVAE_TRY(launch_gemm<EPI_STATS>(p, st));
   a.red.M = a.M; a.red.ntiles = (a.V + kVocabTile - 1) / kVocabTile;
   a.red.pmax = a.pmax; a.red.pexp = a.pexp; a.red.psum = a.psum; a.red.pbest = a.pbest; a.red.parg = a.parg;
-  ACVAE_LAUNCH(vocab_reduce_kernel, grid1d(a.M, 128), 128, 0, st, a.red);
+  ACVAE_LAUNCH(vocab_reduce_kernel, (a.M + 3) / 4, 128, 0, st, a.red);
   return 0;
 }
 
@@ -195,11 +195,15 @@ inline int prior_step(const StepCtx& c, const StepBufs& b, int slot, int slot_pr
                       const int* words, long long words_stride, const float* eps_t /*[N,E]*/) {
   const int N = c.d.N, E = c.d.E, A = c.d.A, Te = c.d.Te;
   const long long S = b.S;
+  // query projection q.Wq^T with the word embedding as the query (text_encoder.py:249-251)
+  GemmParams qg{};
+  qg.M = N; qg.U = E; qg.G = 1; qg.nseg = 1; qg.live = c.live;
+  qg.seg[0] = seg_gather(c.w.p_emb, E, words, words_stride, c.w.p_attn_w, 2 * E, E);
+  qg.epi.c[0] = b.qp_p + (long long)slot * E; qg.epi.ldc = S * E; qg.epi.scale = 1.0f;
+  ACVAE_TRY(launch_gemm<EPI_PLAIN>(qg, c.st));
   AttnFwdParams a{};
   a.rows = N; a.Te = Te; a.A = E; a.E = E; a.Dq = E; a.rows_per_clip = c.d.mem_rep; a.live = c.live;
-  a.q = c.w.p_emb; a.ld_q = E; a.q_gather = words; a.q_gather_stride = words_stride;
-  a.wq = c.w.p_attn_w; a.ldwq = 2 * E;
-  a.qp_out = b.qp_p + (long long)slot * E; a.ld_qp_out = S * E;
+  a.qp_in = b.qp_p + (long long)slot * E; a.ld_qp_in = S * E;
   a.P = c.Pp; a.mem = c.mem; a.v = c.w.p_attn_v; a.mem_lens = c.mem_lens;
   a.ctx = b.ctx_p + (long long)slot * E; a.ld_ctx = S * E;
   a.w_out = b.w_p + (long long)slot * Te; a.ld_w = S * Te;
@@ -242,11 +246,15 @@ inline int decoder_step(const StepCtx& c, const StepBufs& b, int slot, int slot_
   const int N = c.d.N, E = c.d.E, A = c.d.A, Te = c.d.Te;
   const long long S = b.S;
   const float* hprev = slot_prev >= 0 ? b.hd + (long long)slot_prev * E : nullptr;  // zero at t=0 (decoder.py:94-98)
+  // query projection h_{t-1}.Wq^T (decoder.py:186); zero query at t = 0
+  GemmParams qg{};
+  qg.M = N; qg.U = A; qg.G = 1; qg.nseg = hprev ? 1 : 0; qg.live = c.live;
+  if (hprev) qg.seg[0] = seg_plain(hprev, S * E, c.w.d_attn_w, 2 * E, E);
+  qg.epi.c[0] = b.qp_d + (long long)slot * A; qg.epi.ldc = S * A; qg.epi.scale = 1.0f;
+  ACVAE_TRY(launch_gemm<EPI_PLAIN>(qg, c.st));
   AttnFwdParams a{};
   a.rows = N; a.Te = Te; a.A = A; a.E = E; a.Dq = E; a.rows_per_clip = c.d.mem_rep; a.live = c.live;
-  a.q = hprev; a.ld_q = S * E;
-  a.wq = c.w.d_attn_w; a.ldwq = 2 * E;
-  a.qp_out = b.qp_d + (long long)slot * A; a.ld_qp_out = S * A;
+  a.qp_in = b.qp_d + (long long)slot * A; a.ld_qp_in = S * A;
   a.P = c.Pd; a.mem = c.mem; a.v = c.w.d_attn_v; a.mem_lens = c.mem_lens;
   a.ctx = b.ctx_d + (long long)slot * E; a.ld_ctx = S * E;
   a.w_out = b.w_d + (long long)slot * Te; a.ld_w = S * Te;

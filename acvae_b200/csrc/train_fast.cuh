@@ -1,0 +1,459 @@
+// Fast path of the training step for the default configuration (every step teacher-forced,
+// dis_ratio == 0, Hybrid_VAEModel): same arithmetic and the same saved activations as the general path
+// in train.cuh, re-scheduled for B200:
+//   * everything that does not depend on a recurrent state is hoisted out of the T-step loops and
+//     batched over all N*T rows (prior word attention, all input-side gate pre-activations);
+//   * the four recurrent chains (posterior forward / reverse, prior, decoder) run on forked streams;
+//   * pointwise backward steps are fused into the epilogue of the GEMM that produces their input, so
+//     a reverse step is 3 launches (decoder), 2 (prior) or 1 per direction (posterior).
+#pragma once
+#include "streams.cuh"
+#include "train.cuh"
+
+namespace acvae {
+
+inline bool fast_path_ok(const acvae_dims& d, const acvae_train_io& io) {
+  if (d.variant != 0 || d.mem_rep != 1) return false;
+  for (int t = 0; t < d.T; ++t)
+    if (!io.tf_flags[t] || io.dis_flags[t]) return false;
+  return aux() != nullptr;
+}
+
+inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acvae_train_io& io, void* workspace,
+                          cudaStream_t st) {
+  TrainWs ws = carve_train_ws(d, workspace);
+  Aux* ax = aux();
+  const int N = d.N, T = d.T, E = d.E, A = d.A, Te = d.Te, NT = N * T;
+  const long long s1 = T;
+  cudaStream_t sq0 = ax->s[0], sq1 = ax->s[1], sp = ax->s[2];
+
+  ACVAE_LAUNCH(steplens_kernel, grid1d(N), 256, 0, st, N, io.cap_lens, ws.steplens);
+  ACVAE_LAUNCH(qids_kernel, grid1d(NT), 256, 0, st, N, T, d.L, io.caps_ids, ws.qids);
+  ACVAE_LAUNCH(words_init_kernel, grid1d(NT), 256, 0, st, N, T, d.L, io.caps_ids, flag_mask(io.tf_flags, T), kStartIdx,
+               ws.words);
+  ACVAE_TRY(stream_dep(st, sq0, ax));
+  ACVAE_TRY(stream_dep(st, sq1, ax));
+
+  // ---- posterior (text_encoder.py:182-216): the two directions are independent chains --------------
+  ACVAE_TRY(gather_rows(NT, E, w.q_emb, ws.qids, ws.xq, sq0));
+  ACVAE_TRY(stream_dep(sq0, sq1, ax));
+  cudaStream_t sq[2] = {sq0, sq1};
+  for (int dir = 0; dir < 2; ++dir) {
+    ACVAE_TRY(linear_fwd(NT, 3 * E, E, ws.xq, E, w.q_wih[dir], E, w.q_bih[dir], ws.gxq[dir], 3 * E, sq[dir]));
+    for (int s = 0; s < T; ++s) {
+      const int t = dir == 0 ? s : T - 1 - s;
+      const int tp = dir == 0 ? t - 1 : t + 1;
+      GemmParams g{};
+      g.M = N; g.U = E; g.G = 4; g.nseg = 0;
+      const float* hp = s > 0 ? ws.ho + (long long)tp * 2 * E + dir * E : nullptr;
+      if (hp) {
+        GemmSeg sg = seg_gates(hp, s1 * 2 * E, w.q_whh[dir], E, 0, E, E, 3);
+        sg.w[3] = sg.w[2]; sg.w[2] = nullptr;
+        g.seg[0] = sg; g.nseg = 1;
+      }
+      g.epi.gx = ws.gxq[dir] + (long long)t * 3 * E; g.epi.ld_gx = s1 * 3 * E;
+      g.epi.b_hh = w.q_bhh[dir];
+      g.epi.prev = hp; g.epi.ld_prev = s1 * 2 * E;
+      g.epi.lens = ws.steplens; g.epi.t = t;
+      g.epi.gates = ws.gq[dir] + (long long)t * 4 * E; g.epi.ld_gates = s1 * 4 * E;
+      g.epi.out0 = ws.ho + (long long)t * 2 * E + dir * E; g.epi.ld_out0 = s1 * 2 * E;
+      ACVAE_TRY(launch_gemm<EPI_GRU>(g, sq[dir]));
+    }
+  }
+  ACVAE_TRY(stream_dep(sq1, sq0, ax));
+  {
+    GemmParams h{};
+    h.M = NT; h.U = E; h.G = 2; h.nseg = 1;
+    h.seg[0] = seg_gates(ws.ho, 2 * E, w.q_head_w, 2 * E, 0, 2 * E, E, 2);
+    h.epi.bias[0] = w.q_head_b; h.epi.bias[1] = w.q_head_b + E;
+    h.epi.eps = io.eps_q; h.epi.ld_eps = E;
+    h.epi.out0 = io.q_means; h.epi.out1 = io.q_logs; h.epi.out2 = io.q_z;
+    h.epi.ld_out0 = h.epi.ld_out1 = h.epi.ld_out2 = E;
+    ACVAE_TRY(launch_gemm<EPI_HEAD>(h, sq0));
+    ACVAE_LAUNCH(pool_fwd_kernel, grid1d((long long)N * 2 * E), 256, 0, sq0, N, T, 2 * E, ws.ho, ws.steplens, 0,
+                 io.q_means_utt, ws.amax_q);
+  }
+
+  // ---- memory (vae_model.py:743-744 + factorised attention halves) -------------------------------------
+  ACVAE_TRY(memory_prepare(d, w, io.audio_embeds, ws.mem, ws.Pp, ws.Pd, st));
+  ACVAE_TRY(stream_dep(st, sp, ax));
+
+  // ---- prior (text_encoder.py:247-268): word attention and input-side gates batched over (n,t) ---------
+  ACVAE_TRY(gather_rows(NT, E, w.p_emb, ws.words, ws.xp, sp));
+  ACVAE_TRY(linear_fwd(NT, E, E, ws.xp, E, w.p_attn_w, 2 * E, nullptr, ws.qp_p, E, sp));
+  {
+    AttnFwdParams a{};
+    a.rows = NT; a.Te = Te; a.A = E; a.E = E; a.Dq = E; a.rows_per_clip = T;
+    a.qp_in = ws.qp_p; a.ld_qp_in = E;
+    a.P = ws.Pp; a.mem = ws.mem; a.v = w.p_attn_v; a.mem_lens = io.mem_lens;
+    a.ctx = ws.ctx_p; a.ld_ctx = E; a.w_out = ws.w_p; a.ld_w = Te;
+    ACVAE_TRY(launch_attn_fwd(a, sp));
+    // gx_p = [xe | ctx] . W_ih[:, :2E]^T + b_ih   (4E columns, gate-major), written into the gate buffer
+    GemmParams g{};
+    g.M = NT; g.U = 4 * E; g.G = 1; g.nseg = 2;
+    g.seg[0] = seg_plain(ws.xp, E, w.p_wih, 3 * E, E);
+    g.seg[1] = seg_plain(ws.ctx_p, E, w.p_wih + E, 3 * E, E);
+    g.epi.c[0] = ws.dg_p; g.epi.ldc = 4 * E; g.epi.bias[0] = w.p_bih; g.epi.scale = 1.0f;   // dg_p doubles as gx_p in the forward
+    ACVAE_TRY(launch_gemm<EPI_PLAIN>(g, sp));
+  }
+  for (int t = 0; t < T; ++t) {
+    GemmParams g{};
+    g.M = N; g.U = E; g.G = 4; g.nseg = 0;
+    if (t > 0) {
+      g.seg[0] = seg_gates(io.p_z + (long long)(t - 1) * E, s1 * E, w.p_wih, 3 * E, 2 * E, E, E, 4);   // last_z (vae_model.py:869)
+      g.seg[1] = seg_gates(ws.h_p + (long long)(t - 1) * E, s1 * E, w.p_whh, E, 0, E, E, 4);
+      g.nseg = 2;
+    }
+    g.epi.gx = ws.dg_p + (long long)t * 4 * E; g.epi.ld_gx = s1 * 4 * E;
+    g.epi.b_hh = w.p_bhh;
+    g.epi.prev = t > 0 ? ws.c_p + (long long)(t - 1) * E : nullptr; g.epi.ld_prev = s1 * E;
+    g.epi.gates = ws.gates_p + (long long)t * 4 * E; g.epi.ld_gates = s1 * 4 * E;
+    g.epi.out0 = ws.c_p + (long long)t * E; g.epi.ld_out0 = s1 * E;
+    g.epi.out1 = ws.h_p + (long long)t * E; g.epi.ld_out1 = s1 * E;
+    ACVAE_TRY(launch_gemm<EPI_LSTM>(g, sp));
+    GemmParams h{};
+    h.M = N; h.U = E; h.G = 2; h.nseg = 1;
+    h.seg[0] = seg_gates(ws.h_p + (long long)t * E, s1 * E, w.p_head_w, E, 0, E, E, 2);
+    h.epi.bias[0] = w.p_head_b; h.epi.bias[1] = w.p_head_b + E;
+    h.epi.eps = io.eps_p + (long long)t * N * E; h.epi.ld_eps = E;
+    h.epi.out0 = io.p_means + (long long)t * E; h.epi.ld_out0 = s1 * E;
+    h.epi.out1 = io.p_logs + (long long)t * E; h.epi.ld_out1 = s1 * E;
+    h.epi.out2 = io.p_z + (long long)t * E; h.epi.ld_out2 = s1 * E;
+    ACVAE_TRY(launch_gemm<EPI_HEAD>(h, sp));
+  }
+
+  // ---- decoder (decoder.py:175-203): needs q_z from the posterior -------------------------------------------
+  ACVAE_TRY(gather_rows(NT, E, w.d_emb, ws.words, ws.xd, st));
+  ACVAE_TRY(stream_dep(sq0, st, ax));
+  {
+    // gx_d = [emb | q_z] . W_ih[:, {0:E, 2E:3E}]^T + b_ih  (3E columns), kept in dgi_d until the backward overwrites it
+    GemmParams g{};
+    g.M = NT; g.U = 3 * E; g.G = 1; g.nseg = 2;
+    g.seg[0] = seg_plain(ws.xd, E, w.d_wih, 3 * E, E);
+    g.seg[1] = seg_plain(io.q_z, E, w.d_wih + 2 * E, 3 * E, E);
+    g.epi.c[0] = ws.dgi_d; g.epi.ldc = 3 * E; g.epi.bias[0] = w.d_bih; g.epi.scale = 1.0f;
+    ACVAE_TRY(launch_gemm<EPI_PLAIN>(g, st));
+  }
+  for (int t = 0; t < T; ++t) {
+    const float* hprev = t > 0 ? io.outputs + (long long)(t - 1) * E : nullptr;
+    GemmParams qg{};
+    qg.M = N; qg.U = A; qg.G = 1; qg.nseg = hprev ? 1 : 0;
+    if (hprev) qg.seg[0] = seg_plain(hprev, s1 * E, w.d_attn_w, 2 * E, E);
+    qg.epi.c[0] = ws.qp_d + (long long)t * A; qg.epi.ldc = s1 * A; qg.epi.scale = 1.0f;
+    ACVAE_TRY(launch_gemm<EPI_PLAIN>(qg, st));
+    AttnFwdParams a{};
+    a.rows = N; a.Te = Te; a.A = A; a.E = E; a.Dq = E; a.rows_per_clip = 1;
+    a.qp_in = ws.qp_d + (long long)t * A; a.ld_qp_in = s1 * A;
+    a.P = ws.Pd; a.mem = ws.mem; a.v = w.d_attn_v; a.mem_lens = io.mem_lens;
+    a.ctx = ws.ctx_d + (long long)t * E; a.ld_ctx = s1 * E;
+    a.w_out = ws.w_d + (long long)t * Te; a.ld_w = s1 * Te;
+    if (io.attn_weights) { a.aw_out = io.attn_weights + t; a.aw_ld_r = (long long)Te * T; a.aw_ld_j = T; }
+    ACVAE_TRY(launch_attn_fwd(a, st));
+    GemmParams g{};
+    g.M = N; g.U = E; g.G = 4;
+    int ns = 0;
+    {
+      GemmSeg s = seg_gates(ws.ctx_d + (long long)t * E, s1 * E, w.d_wih, 3 * E, E, E, E, 3);
+      s.w[3] = nullptr;
+      g.seg[ns++] = s;
+    }
+    if (hprev) {
+      GemmSeg s = seg_gates(hprev, s1 * E, w.d_whh, E, 0, E, E, 3);
+      s.w[3] = s.w[2]; s.w[2] = nullptr;
+      g.seg[ns++] = s;
+    }
+    g.nseg = ns;
+    g.epi.gx = ws.dgi_d + (long long)t * 3 * E; g.epi.ld_gx = s1 * 3 * E;
+    g.epi.b_hh = w.d_bhh;
+    g.epi.prev = hprev; g.epi.ld_prev = s1 * E;
+    g.epi.gates = ws.gates_d + (long long)t * 4 * E; g.epi.ld_gates = s1 * 4 * E;
+    g.epi.out0 = io.outputs + (long long)t * E; g.epi.ld_out0 = s1 * E;
+    ACVAE_TRY(launch_gemm<EPI_GRU>(g, st));
+  }
+  // vocabulary statistics over all rows (greedy word, lse, sum; logits never stored)
+  {
+    VocabStatsArgs v{};
+    v.M = NT; v.V = d.V; v.E = E; v.hidden = io.outputs; v.ld_h = E;
+    v.cls_w = w.cls_w; v.cls_b = w.cls_b;
+    v.pmax = ws.pmax; v.pexp = ws.pexp; v.psum = ws.psum; v.pbest = ws.pbest; v.parg = ws.parg;
+    v.red.lse = io.logit_lse; v.red.lsum = io.logit_sum; v.red.logprob = io.sampled_logprobs; v.red.ld_row = 1;
+    v.red.seqs = (long long*)io.seqs; v.red.ld_seqs = 1;
+    ACVAE_TRY(vocab_stats(v, st));
+  }
+  // global-constraint head (vae_model.py:722-729)
+  ACVAE_LAUNCH(pool_fwd_kernel, grid1d((long long)N * E), 256, 0, st, N, T, E, io.outputs, ws.steplens, 0, ws.pool_d,
+               ws.amax_d);
+  ACVAE_TRY(linear_fwd(N, 2 * E, E, ws.pool_d, E, w.g_w, E, w.g_b, io.p_means_utt, 2 * E, st));
+  if (io.logits) ACVAE_TRY(linear_fwd(NT, d.V, E, io.outputs, E, w.cls_w, E, w.cls_b, io.logits, d.V, st));
+  ACVAE_TRY(stream_dep(sp, st, ax));
+  return 0;
+}
+
+// ===================================== backward ===================================================
+inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acvae_train_io& io,
+                          const acvae_train_grads_in& gi, acvae_weight_grads& gw, float* d_audio, void* workspace,
+                          cudaStream_t st) {
+  TrainWs ws = carve_train_ws(d, workspace);
+  Aux* ax = aux();
+  const int N = d.N, T = d.T, E = d.E, A = d.A, Te = d.Te, NT = N * T, V = d.V;
+  const long long s1 = T;
+  cudaStream_t sp = ax->s[2], sx = ax->s[3], sq0 = ax->s[0], sq1 = ax->s[1];
+  auto zero = [&](float* p, size_t n, cudaStream_t s) { return cudaMemsetAsync(p, 0, n * sizeof(float), s); };
+  ACVAE_TRY(stream_dep(st, sp, ax));
+
+  // ================= prior BPTT on its own stream (KL gradients only: dis_ratio == 0) ====================
+  {
+    // step T-1 head backward (standalone), then per step: [dh GEMM + LSTM pointwise] -> [dz|dh GEMM + head pointwise]
+    HeadBwdParams h{};
+    h.rows = N; h.U = E;
+    const int t = T - 1;
+    if (gi.d_p_z) { h.dz0 = gi.d_p_z + (long long)t * E; h.ld_dz0 = s1 * E; }
+    if (gi.d_p_means) { h.dmean = gi.d_p_means + (long long)t * E; h.ld_dmean = s1 * E; }
+    if (gi.d_p_logs) { h.dlog = gi.d_p_logs + (long long)t * E; h.ld_dlog = s1 * E; }
+    h.eps = io.eps_p + (long long)t * N * E; h.ld_eps = E;
+    h.logv = io.p_logs + (long long)t * E; h.ld_logv = s1 * E;
+    h.dml = ws.dml_p + (long long)t * 2 * E; h.ld_dml = s1 * 2 * E;
+    ACVAE_LAUNCH(head_bwd_kernel, grid1d((long long)N * E), 256, 0, sp, h);
+  }
+  for (int t = T - 1; t >= 0; --t) {
+    GemmParams p{};
+    p.M = N; p.U = E; p.G = 1; p.nseg = 1;
+    GemmSeg s{};
+    s.a = ws.dml_p + (long long)t * 2 * E; s.lda = s1 * 2 * E; s.w[0] = w.p_head_w; s.ldw = E; s.w_trans = 1; s.K = 2 * E;
+    p.seg[0] = s;
+    p.epi.x0 = t < T - 1 ? ws.dhp_carry : nullptr;
+    p.epi.x1 = t < T - 1 ? ws.dcp_carry : nullptr;
+    p.epi.gates = ws.gates_p + (long long)t * 4 * E; p.epi.ld_gates = s1 * 4 * E;
+    p.epi.x2 = ws.c_p + (long long)t * E; p.epi.ld_x2 = s1 * E;
+    p.epi.x3 = t > 0 ? ws.c_p + (long long)(t - 1) * E : nullptr; p.epi.ld_x3 = s1 * E;
+    p.epi.y0 = ws.dg_p + (long long)t * 4 * E; p.epi.ld_y0 = s1 * 4 * E;
+    p.epi.y1 = ws.dcp_carry;
+    ACVAE_TRY(launch_gemm<EPI_LSTM_BWD>(p, sp));
+    if (t > 0) {
+      GemmParams q{};
+      q.M = N; q.U = E; q.G = 2; q.nseg = 1;
+      GemmSeg s2{};
+      s2.a = ws.dg_p + (long long)t * 4 * E; s2.lda = s1 * 4 * E; s2.K = 4 * E; s2.w_trans = 1;
+      s2.w[0] = w.p_wih + 2 * E; s2.ldwg[0] = 3 * E;      // d last_z
+      s2.w[1] = w.p_whh; s2.ldwg[1] = E;                  // d h_{t-1}
+      s2.ldw = E;
+      q.seg[0] = s2;
+      const int tm = t - 1;
+      if (gi.d_p_z) { q.epi.x0 = gi.d_p_z + (long long)tm * E; q.epi.ld_x0 = s1 * E; }
+      if (gi.d_p_means) { q.epi.x1 = gi.d_p_means + (long long)tm * E; q.epi.ld_x1 = s1 * E; }
+      if (gi.d_p_logs) { q.epi.x2 = gi.d_p_logs + (long long)tm * E; q.epi.ld_x2 = s1 * E; }
+      q.epi.x3 = io.eps_p + (long long)tm * N * E; q.epi.ld_x3 = E;
+      q.epi.x4 = io.p_logs + (long long)tm * E; q.epi.ld_x4 = s1 * E;
+      q.epi.y0 = ws.dml_p + (long long)tm * 2 * E; q.epi.ld_y0 = s1 * 2 * E;
+      q.epi.y1 = ws.dhp_carry;
+      ACVAE_TRY(launch_gemm<EPI_HEAD_BWD>(q, sp));
+    }
+  }
+  // prior batched remainders
+  ACVAE_TRY(linear_bwd_data(NT, E, 4 * E, ws.dg_p, 4 * E, w.p_wih, 3 * E, ws.dxe_p, E, sp));
+  ACVAE_TRY(linear_bwd_data(NT, E, 4 * E, ws.dg_p, 4 * E, w.p_wih + E, 3 * E, ws.dctx_p, E, sp));
+  {
+    AttnBwdQParams a{};
+    a.rows = NT; a.Te = Te; a.A = E; a.E = E; a.rows_per_clip = T;
+    a.dctx = ws.dctx_p; a.ld_dctx = E; a.w = ws.w_p; a.ld_w = Te; a.qp = ws.qp_p; a.ld_qp = E;
+    a.P = ws.Pp; a.mem = ws.mem; a.v = w.p_attn_v; a.mem_lens = io.mem_lens;
+    a.ds = ws.ds_p; a.ld_ds = Te; a.dqp = ws.dqp_p; a.ld_dqp = E;
+    ACVAE_TRY(launch_attn_bwd_q(a, sp));
+  }
+  ACVAE_TRY(linear_bwd_data(NT, E, E, ws.dqp_p, E, w.p_attn_w, 2 * E, ws.dxe_p, E, sp, 1));
+  ACVAE_CHECK(zero(gw.p_emb, (size_t)V * E, sp));
+  ACVAE_TRY(scatter_rows(NT, E, ws.dxe_p, E, ws.words, gw.p_emb, sp));
+  ACVAE_TRY(linear_bwd_weight(E, E, NT, ws.dqp_p, E, ws.xp, E, gw.p_attn_w, 2 * E, sp));
+  ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.xp, E, gw.p_wih, 3 * E, sp));
+  ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.ctx_p, E, gw.p_wih + E, 3 * E, sp));
+  ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, io.p_z - E, E, gw.p_wih + 2 * E, 3 * E, sp, T, 0));
+  ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.h_p - E, E, gw.p_whh, E, sp, T, 0));
+  ACVAE_TRY(colsum(NT, 4 * E, ws.dg_p, 4 * E, gw.p_bih, sp));
+  ACVAE_CHECK(cudaMemcpyAsync(gw.p_bhh, gw.p_bih, sizeof(float) * 4 * E, cudaMemcpyDeviceToDevice, sp));
+  ACVAE_TRY(linear_bwd_weight(2 * E, E, NT, ws.dml_p, 2 * E, ws.h_p, E, gw.p_head_w, E, sp));
+  ACVAE_TRY(colsum(NT, 2 * E, ws.dml_p, 2 * E, gw.p_head_b, sp));
+  ACVAE_CHECK(zero(gw.p_attn_v, E, sp));
+  {
+    AttnBwdAccParams a{};
+    a.clips = N; a.Te = Te; a.A = E; a.E = E; a.rows_per_clip = T;
+    a.ds = ws.ds_p; a.ld_ds = Te; a.w = ws.w_p; a.ld_w = Te; a.qp = ws.qp_p; a.ld_qp = E;
+    a.dctx = ws.dctx_p; a.ld_dctx = E; a.P = ws.Pp; a.v = w.p_attn_v; a.mem_lens = io.mem_lens;
+    a.dP = ws.dPp; a.dmem = ws.dmem; a.dmem_accumulate = 0; a.dv = gw.p_attn_v;
+    ACVAE_TRY(launch_attn_bwd_acc(a, sp));
+  }
+
+  // ================= decoder BPTT on the main stream ========================================================
+  const float* dpool = nullptr;
+  if (gi.d_p_means_utt) {
+    ACVAE_TRY(linear_bwd_data(N, E, 2 * E, gi.d_p_means_utt, 2 * E, w.g_w, E, ws.dpool, E, st));
+    ACVAE_TRY(linear_bwd_weight(2 * E, E, N, gi.d_p_means_utt, 2 * E, ws.pool_d, E, gw.g_w, E, st));
+    ACVAE_TRY(colsum(N, 2 * E, gi.d_p_means_utt, 2 * E, gw.g_b, st));
+    dpool = ws.dpool;
+  } else {
+    ACVAE_CHECK(zero(gw.g_w, (size_t)2 * E * E, st)); ACVAE_CHECK(zero(gw.g_b, (size_t)2 * E, st));
+  }
+  ACVAE_LAUNCH(pool_bwd_kernel, grid1d((long long)NT * E), 256, 0, st, N, T, E, dpool, ws.steplens, 0, ws.amax_d,
+               gi.d_outputs, ws.dout);
+  {
+    GruBwdParams g{};
+    const int t = T - 1;
+    g.N = N; g.U = E;
+    g.dh_ext = ws.dout + (long long)t * E; g.ld_dh_ext = s1 * E;
+    g.gates = ws.gates_d + (long long)t * 4 * E; g.ld_gates = s1 * 4 * E;
+    g.hprev = t > 0 ? io.outputs + (long long)(t - 1) * E : nullptr; g.ld_hprev = s1 * E;
+    g.dgi = ws.dgi_d + (long long)t * 3 * E; g.ld_dgi = s1 * 3 * E;
+    g.dgh = ws.dgh_d + (long long)t * 3 * E; g.ld_dgh = s1 * 3 * E;
+    g.dh_out = ws.dh_carry;
+    ACVAE_LAUNCH(gru_bwd_kernel, grid1d((long long)N * E), 256, 0, st, g);
+  }
+  for (int t = T - 1; t >= 0; --t) {
+    ACVAE_TRY(linear_bwd_data(N, E, 3 * E, ws.dgi_d + (long long)t * 3 * E, s1 * 3 * E, w.d_wih + E, 3 * E,
+                              ws.dctx_d + (long long)t * E, s1 * E, st));
+    AttnBwdQParams a{};
+    a.rows = N; a.Te = Te; a.A = A; a.E = E; a.rows_per_clip = 1;
+    a.dctx = ws.dctx_d + (long long)t * E; a.ld_dctx = s1 * E;
+    a.w = ws.w_d + (long long)t * Te; a.ld_w = s1 * Te;
+    a.qp = ws.qp_d + (long long)t * A; a.ld_qp = s1 * A;
+    a.P = ws.Pd; a.mem = ws.mem; a.v = w.d_attn_v; a.mem_lens = io.mem_lens;
+    a.ds = ws.ds_d + (long long)t * Te; a.ld_ds = s1 * Te;
+    a.dqp = ws.dqp_d + (long long)t * A; a.ld_dqp = s1 * A;
+    ACVAE_TRY(launch_attn_bwd_q(a, st));
+    if (t > 0) {
+      // dh_{t-1} = dh_t*z_t (carry) + dGh_t.W_hh + dqp_t.Wq + upstream; fused GRU pointwise backward of step t-1
+      GemmParams p{};
+      p.M = N; p.U = E; p.G = 1; p.nseg = 2;
+      GemmSeg s0{}; s0.a = ws.dgh_d + (long long)t * 3 * E; s0.lda = s1 * 3 * E; s0.w[0] = w.d_whh; s0.ldw = E; s0.w_trans = 1; s0.K = 3 * E;
+      GemmSeg s1_{}; s1_.a = ws.dqp_d + (long long)t * A; s1_.lda = s1 * A; s1_.w[0] = w.d_attn_w; s1_.ldw = 2 * E; s1_.w_trans = 1; s1_.K = A;
+      p.seg[0] = s0; p.seg[1] = s1_;
+      const int tm = t - 1;
+      p.epi.x0 = ws.dh_carry;
+      p.epi.x1 = ws.dout + (long long)tm * E; p.epi.ld_x1 = s1 * E;
+      p.epi.gates = ws.gates_d + (long long)tm * 4 * E; p.epi.ld_gates = s1 * 4 * E;
+      p.epi.prev = tm > 0 ? io.outputs + (long long)(tm - 1) * E : nullptr; p.epi.ld_prev = s1 * E;
+      p.epi.y0 = ws.dgi_d + (long long)tm * 3 * E; p.epi.ld_y0 = s1 * 3 * E;
+      p.epi.y1 = ws.dgh_d + (long long)tm * 3 * E; p.epi.ld_y1 = s1 * 3 * E;
+      p.epi.y2 = ws.dh_carry;
+      ACVAE_TRY(launch_gemm<EPI_GRU_BWD>(p, st));
+    }
+  }
+  // d z fed to the decoder -> d q_z (needed by the posterior backward): first thing after the chain
+  ACVAE_TRY(linear_bwd_data(NT, E, 3 * E, ws.dgi_d, 3 * E, w.d_wih + 2 * E, 3 * E, ws.dxz_d, E, st));
+  ACVAE_TRY(stream_dep(st, sx, ax));
+  // decoder batched remainders on a side stream (overlaps the posterior chains)
+  ACVAE_TRY(linear_bwd_data(NT, E, 3 * E, ws.dgi_d, 3 * E, w.d_wih, 3 * E, ws.dxe_d, E, sx));
+  ACVAE_CHECK(zero(gw.d_emb, (size_t)V * E, sx));
+  ACVAE_TRY(scatter_rows(NT, E, ws.dxe_d, E, ws.words, gw.d_emb, sx));
+  ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_d, 3 * E, ws.xd, E, gw.d_wih, 3 * E, sx));
+  ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_d, 3 * E, ws.ctx_d, E, gw.d_wih + E, 3 * E, sx));
+  ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_d, 3 * E, io.q_z, E, gw.d_wih + 2 * E, 3 * E, sx));
+  ACVAE_TRY(colsum(NT, 3 * E, ws.dgi_d, 3 * E, gw.d_bih, sx));
+  ACVAE_TRY(colsum(NT, 3 * E, ws.dgh_d, 3 * E, gw.d_bhh, sx));
+  ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgh_d, 3 * E, io.outputs - E, E, gw.d_whh, E, sx, T, 0));
+  ACVAE_TRY(linear_bwd_weight(A, E, NT, ws.dqp_d, A, io.outputs - E, E, gw.d_attn_w, 2 * E, sx, T, 0));
+  ACVAE_CHECK(zero(gw.d_attn_v, A, sx));
+  // the decoder's attention accumulation adds onto the prior's dmem: order after the prior stream
+  ACVAE_TRY(stream_dep(sp, sx, ax));
+  {
+    AttnBwdAccParams a{};
+    a.clips = N; a.Te = Te; a.A = A; a.E = E; a.rows_per_clip = T;
+    a.ds = ws.ds_d; a.ld_ds = Te; a.w = ws.w_d; a.ld_w = Te; a.qp = ws.qp_d; a.ld_qp = A;
+    a.dctx = ws.dctx_d; a.ld_dctx = E; a.P = ws.Pd; a.v = w.d_attn_v; a.mem_lens = io.mem_lens;
+    a.dP = ws.dPd; a.dmem = ws.dmem; a.dmem_accumulate = 1; a.dv = gw.d_attn_v;
+    ACVAE_TRY(launch_attn_bwd_acc(a, sx));
+  }
+  // memory backward: attention memory halves, ln (vae_model.py:743-744)
+  {
+    const int R = N * Te;
+    ACVAE_TRY(linear_bwd_data(R, E, E, ws.dPp, E, w.p_attn_w + E, 2 * E, ws.dmem, E, sx, 1));
+    ACVAE_TRY(linear_bwd_data(R, E, A, ws.dPd, A, w.d_attn_w + E, 2 * E, ws.dmem, E, sx, 1));
+    ACVAE_TRY(linear_bwd_weight(E, E, R, ws.dPp, E, ws.mem, E, gw.p_attn_w + E, 2 * E, sx));
+    ACVAE_TRY(linear_bwd_weight(A, E, R, ws.dPd, A, ws.mem, E, gw.d_attn_w + E, 2 * E, sx));
+    ACVAE_TRY(colsum(R, E, ws.dPp, E, gw.p_attn_b, sx));
+    ACVAE_TRY(colsum(R, A, ws.dPd, A, gw.d_attn_b, sx));
+    if (w.ln_w) {
+      if (d_audio) ACVAE_TRY(linear_bwd_data(R, d.Eenc, E, ws.dmem, E, w.ln_w, d.Eenc, d_audio, d.Eenc, sx));
+      ACVAE_TRY(linear_bwd_weight(E, d.Eenc, R, ws.dmem, E, io.audio_embeds, d.Eenc, gw.ln_w, d.Eenc, sx));
+      ACVAE_TRY(colsum(R, E, ws.dmem, E, gw.ln_b, sx));
+    } else if (d_audio) {
+      ACVAE_CHECK(cudaMemcpyAsync(d_audio, ws.dmem, sizeof(float) * (size_t)R * E, cudaMemcpyDeviceToDevice, sx));
+    }
+  }
+
+  // ================= posterior backward (main + one side stream per direction) ==============================
+  {
+    HeadBwdParams h{};
+    h.rows = NT; h.U = E;
+    if (gi.d_q_z) { h.dz0 = gi.d_q_z; h.ld_dz0 = E; }
+    h.dz1 = ws.dxz_d; h.ld_dz1 = E;
+    if (gi.d_q_means) { h.dmean = gi.d_q_means; h.ld_dmean = E; }
+    if (gi.d_q_logs) { h.dlog = gi.d_q_logs; h.ld_dlog = E; }
+    h.eps = io.eps_q; h.ld_eps = E; h.logv = io.q_logs; h.ld_logv = E;
+    h.dml = ws.dml_q; h.ld_dml = 2 * E;
+    ACVAE_LAUNCH(head_bwd_kernel, grid1d((long long)NT * E), 256, 0, st, h);
+    ACVAE_LAUNCH(pool_bwd_kernel, grid1d((long long)NT * 2 * E), 256, 0, st, N, T, 2 * E, gi.d_q_means_utt, ws.steplens, 0,
+                 ws.amax_q, (const float*)nullptr, ws.dho);
+    ACVAE_TRY(linear_bwd_data(NT, 2 * E, 2 * E, ws.dml_q, 2 * E, w.q_head_w, 2 * E, ws.dho, 2 * E, st, 1));
+  }
+  ACVAE_TRY(stream_dep(st, sq0, ax));
+  ACVAE_TRY(stream_dep(st, sq1, ax));
+  ACVAE_TRY(linear_bwd_weight(2 * E, 2 * E, NT, ws.dml_q, 2 * E, ws.ho, 2 * E, gw.q_head_w, 2 * E, st));
+  ACVAE_TRY(colsum(NT, 2 * E, ws.dml_q, 2 * E, gw.q_head_b, st));
+  cudaStream_t sq[2] = {sq0, sq1};
+  float* carry[2] = {ws.dhq_carry, ws.dzq_carry};   // one carry buffer per direction
+  for (int dir = 0; dir < 2; ++dir) {
+    cudaStream_t s_ = sq[dir];
+    {
+      const int s = T - 1;
+      const int t = dir == 0 ? s : T - 1 - s;
+      const int tp = dir == 0 ? t - 1 : t + 1;
+      GruBwdParams g{};
+      g.N = N; g.U = E;
+      g.dh_ext = ws.dho + (long long)t * 2 * E + dir * E; g.ld_dh_ext = s1 * 2 * E;
+      g.gates = ws.gq[dir] + (long long)t * 4 * E; g.ld_gates = s1 * 4 * E;
+      g.hprev = s > 0 ? ws.ho + (long long)tp * 2 * E + dir * E : nullptr; g.ld_hprev = s1 * 2 * E;
+      g.lens = ws.steplens; g.len_off = 0; g.t = t;
+      g.dgi = ws.dgi_q[dir] + (long long)t * 3 * E; g.ld_dgi = s1 * 3 * E;
+      g.dgh = ws.dgh_q[dir] + (long long)t * 3 * E; g.ld_dgh = s1 * 3 * E;
+      g.dh_out = carry[dir];
+      ACVAE_LAUNCH(gru_bwd_kernel, grid1d((long long)N * E), 256, 0, s_, g);
+    }
+    for (int s = T - 1; s > 0; --s) {
+      const int t = dir == 0 ? s : T - 1 - s;            // step whose dGh is propagated
+      const int tm = dir == 0 ? t - 1 : t + 1;            // the step before it in this direction's forward order
+      const int sm = s - 1;                               // its position in forward order
+      const int tmp = dir == 0 ? tm - 1 : tm + 1;         // where ITS h_prev lives
+      GemmParams p{};
+      p.M = N; p.U = E; p.G = 1; p.nseg = 1;
+      GemmSeg sg{};
+      sg.a = ws.dgh_q[dir] + (long long)t * 3 * E; sg.lda = s1 * 3 * E; sg.w[0] = w.q_whh[dir]; sg.ldw = E; sg.w_trans = 1; sg.K = 3 * E;
+      p.seg[0] = sg;
+      p.epi.x0 = carry[dir];
+      p.epi.x1 = ws.dho + (long long)tm * 2 * E + dir * E; p.epi.ld_x1 = s1 * 2 * E;
+      p.epi.gates = ws.gq[dir] + (long long)tm * 4 * E; p.epi.ld_gates = s1 * 4 * E;
+      p.epi.prev = sm > 0 ? ws.ho + (long long)tmp * 2 * E + dir * E : nullptr; p.epi.ld_prev = s1 * 2 * E;
+      p.epi.lens = ws.steplens; p.epi.t = tm;
+      p.epi.y0 = ws.dgi_q[dir] + (long long)tm * 3 * E; p.epi.ld_y0 = s1 * 3 * E;
+      p.epi.y1 = ws.dgh_q[dir] + (long long)tm * 3 * E; p.epi.ld_y1 = s1 * 3 * E;
+      p.epi.y2 = carry[dir];
+      ACVAE_TRY(launch_gemm<EPI_GRU_BWD>(p, s_));
+    }
+    ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_q[dir], 3 * E, ws.xq, E, gw.q_wih[dir], E, s_));
+    ACVAE_TRY(colsum(NT, 3 * E, ws.dgi_q[dir], 3 * E, gw.q_bih[dir], s_));
+    ACVAE_TRY(colsum(NT, 3 * E, ws.dgh_q[dir], 3 * E, gw.q_bhh[dir], s_));
+    if (dir == 0)
+      ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgh_q[0], 3 * E, ws.ho - 2 * E, 2 * E, gw.q_whh[0], E, s_, T, 0));
+    else
+      ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgh_q[1], 3 * E, ws.ho + 2 * E + E, 2 * E, gw.q_whh[1], E, s_, T, T - 1));
+  }
+  ACVAE_TRY(stream_dep(sq0, st, ax));
+  ACVAE_TRY(stream_dep(sq1, st, ax));
+  ACVAE_TRY(linear_bwd_data(NT, E, 3 * E, ws.dgi_q[0], 3 * E, w.q_wih[0], E, ws.dxq, E, st, 0));
+  ACVAE_TRY(linear_bwd_data(NT, E, 3 * E, ws.dgi_q[1], 3 * E, w.q_wih[1], E, ws.dxq, E, st, 1));
+  ACVAE_CHECK(zero(gw.q_emb, (size_t)V * E, st));
+  ACVAE_TRY(scatter_rows(NT, E, ws.dxq, E, ws.qids, gw.q_emb, st));
+  ACVAE_TRY(stream_dep(sp, st, ax));
+  ACVAE_TRY(stream_dep(sx, st, ax));
+  return 0;
+}
+
+}  // namespace acvae

@@ -300,7 +300,9 @@ class NormalKLFn(torch.autograd.Function):
         E = ts[0].shape[-1]
         rows = ts[0].numel() // E
         out = torch.empty((), dtype=torch.float32, device=ts[0].device)
-        _lib.check(l.acvae_kl_fwd(rows, E, *[_dev(t) for t in ts], _dev(out), _stream()), "acvae_kl_fwd")
+        ws = _workspace(1024, ts[0].device)
+        _lib.check(l.acvae_kl_fwd(rows, E, *[_dev(t) for t in ts], _dev(out), ws.data_ptr(), ws.numel(), _stream()),
+                   "acvae_kl_fwd")
         ctx.save_for_backward(*ts)
         return out
 

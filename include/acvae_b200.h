@@ -171,7 +171,8 @@ int acvae_vocab_ce_bwd(int32_t M, int32_t V, int32_t E, const float *hidden, con
 /* ---- Gaussian KL (utils/train_util.py:259-266) ---------------------------
  * kl_out[0] = mean over `rows` positions of sum_d KL(q || p).              */
 int acvae_kl_fwd(int64_t rows, int32_t E, const float *q_mean, const float *q_log, const float *p_mean,
-                 const float *p_log, float *kl_out, void *stream);
+                 const float *p_log, float *kl_out, void *workspace /* >= 148 floats */, size_t workspace_bytes,
+                 void *stream);
 int acvae_kl_bwd(int64_t rows, int32_t E, const float *q_mean, const float *q_log, const float *p_mean,
                  const float *p_log, const float *d_kl /* device scalar */, float *d_q_mean, float *d_q_log,
                  float *d_p_mean, float *d_p_log, void *stream);

@@ -55,6 +55,14 @@ def test_train_tiny_golden(name):
     _check_train_golden(name)
 
 
+@pytest.mark.parametrize("name", ["tiny_train", "cfg0_train"])
+def test_train_general_schedule_golden(name, monkeypatch):
+    """The default configuration normally takes the hoisted multi-stream schedule (train_fast.cuh);
+    the general step-by-step schedule (train.cuh) must produce the same numbers."""
+    monkeypatch.setenv("ACVAE_DISABLE_FAST", "1")
+    _check_train_golden(name)
+
+
 def test_train_tiny_vae_golden():
     _check_train_golden("tiny_train_vae", "vae")
 
