@@ -37,6 +37,21 @@ const char* acvae_last_error(void) { return g_err; }
 int acvae_abi_version(void) { return ACVAE_ABI_VERSION; }
 uint64_t acvae_launch_count(void) { return g_launches.load(); }
 
+int acvae_gemm(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, int32_t a_trans, const float* B, int64_t ldb,
+               int32_t b_trans, const float* bias, float* C, int64_t ldc, int32_t accumulate, int32_t* used_tc, void* stream) {
+  ACVAE_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && C, "bad argument");
+  GemmParams p{};
+  p.M = M; p.U = N; p.G = 1; p.nseg = 1;
+  GemmSeg s{};
+  s.a = A; s.lda = lda; s.a_trans = a_trans; s.w[0] = B; s.ldw = ldb; s.w_trans = b_trans; s.K = K;
+  p.seg[0] = s;
+  p.epi.c[0] = C; p.epi.ldc = ldc; p.epi.bias[0] = bias; p.epi.scale = 1.0f; p.epi.accumulate = accumulate;
+  int tc = 0;
+  ACVAE_TRY(launch_gemm<EPI_PLAIN>(p, (cudaStream_t)stream, &tc));
+  if (used_tc) *used_tc = tc;
+  return 0;
+}
+
 size_t acvae_train_workspace_bytes(const acvae_dims* d) {
   if (check_dims(d) != 0) return 0;
   return carve_train_ws(*d, nullptr).bytes;

@@ -33,6 +33,7 @@ struct GemmSeg {
   int K;
   int a_vec, w_vec;               // set by the launcher: 16-byte vector loads are legal for this operand
   int k_zero_period, k_zero_rem;  // if period > 0: k with k % period == rem contribute nothing (shifted operands)
+  int w_row_shift;                // w[0] already points `w_row_shift` K-rows away from the real tensor (TMA path un-shifts)
 };
 
 enum EpiKind {
@@ -618,7 +619,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 // Host-side launch: annotates vector-load legality, then picks the kernel by shape.
 template <int EPI>
-inline int launch_gemm(GemmParams p, cudaStream_t st) {
+inline int launch_gemm_simt(GemmParams p, cudaStream_t st) {
   if (p.M <= 0 || p.U <= 0) return 0;
   const int NC = p.U * p.G;
   bool skinny_ok = EPI != EPI_STATS && EPI != EPI_DLOGITS && p.M <= 64;

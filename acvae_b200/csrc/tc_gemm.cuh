@@ -1,0 +1,380 @@
+// tcgen05 / TMEM / TMA GEMM for the batched (non-recurrent) contractions of the step, fp32-accurate.
+//
+//   C[M, NC] = sum_seg  A_s[M, K_s] . B_s[NC, K_s]^T        (same GemmParams / epilogues as gemm.cuh)
+//
+// Tensor cores have no fp32 input format; kind::tf32 keeps 10 mantissa bits, which would break the
+// 1e-4 parity bar.  Every operand word x is therefore split in shared memory into
+//     hi = x rounded to tf32 (10 explicit mantissa bits)
+//     lo = (x - hi) rounded to tf32                   (x - hi is exact in fp32, |lo| <= 2^-11 |x|)
+// and each 128x128x8 step issues three MMAs  hi*hi + lo*hi + hi*lo  (error ~2^-21 relative, i.e. fp32
+// grade; the dropped lo*lo term is ~2^-20 smaller than hi*hi).  The split is position-wise, so it is
+// oblivious to the 128-byte swizzle TMA wrote the tile with.
+//
+// Pipeline (one 128x128 output tile per CTA, 256 threads):
+//   warp 0      : TMA producer  -- cp.async.bulk.tensor.2d into a 3-stage ring, mbarrier complete_tx
+//   warps 4..7  : split workers -- hi/lo split of the landed stage, then TMEM -> smem in the epilogue
+//   warp 1      : MMA issuer    -- one elected lane, tcgen05.mma.cta_group::1.kind::tf32, accumulator
+//                                  in TMEM (128 lanes x 128 fp32 columns), tcgen05.commit frees the stage
+//   all warps   : fused epilogue of gemm.cuh on the staged tile (bias / accumulate / vocab statistics /
+//                 label-smoothed CE gradient), so logits are still never written to HBM.
+// Operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]); both are loaded with
+// 128B-swizzled TMA boxes and described to the MMA with the matching canonical layouts, so forward
+// (x.W^T), backward-data (dY.W) and backward-weight (dY^T.X) GEMMs need no transposed copies.
+#pragma once
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "gemm.cuh"
+
+namespace acvae {
+
+constexpr int kTcBM = 128, kTcBN = 128, kTcBK = 32, kTcStages = 3;
+constexpr int kTcTileBytes = kTcBM * kTcBK * 4;                 // 16 KB (A or B, hi or lo)
+constexpr int kTcStageBytes = 4 * kTcTileBytes;                 // A_hi, A_lo, B_hi, B_lo
+constexpr int kTcSmemBytes = kTcStages * kTcStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TcSeg {
+  int a_mn_major, b_mn_major;      // 0: K-major (row-major [rows,K]); 1: MN-major (row-major [K,rows])
+  int K;
+  int a_row_shift, b_row_shift;    // added to the K-row coordinate of an MN-major operand (shifted recurrent inputs)
+  int k_zero_period, k_zero_rem;   // K rows with (k % period == rem) contribute nothing
+};
+struct TcParams {
+  int nseg;
+  int lolo;     // also issue the lo*lo MMA (4 MMAs per step): operands are then exact to ~2^-23
+  TcSeg seg[2];
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0;
+  for (long long spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (spin > (1ll << 24)) __trap();   // a protocol bug must abort, never hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// x = hi + lo with hi, lo representable in tf32 (10 explicit mantissa bits): round-to-nearest on the bit
+// pattern (add half an ulp of the kept field, clear the 13 dropped bits), so |lo| <= 2^-11 |x| and the
+// rounding of lo itself costs 2^-22 |x|.
+__device__ __forceinline__ void tc_split(uint32_t x, uint32_t& hi, uint32_t& lo) {
+  hi = (x + 0x1000u) & 0xffffe000u;
+  const float r = __uint_as_float(x) - __uint_as_float(hi);
+  lo = (__float_as_uint(r) + 0x1000u) & 0xffffe000u;
+}
+
+// UMMA shared-memory descriptor, SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp SmemDescriptor)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;     // descriptor version (Blackwell)
+  d |= (uint64_t)layout << 61;  // 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms)
+  return d;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(256, 1)
+tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcParams tp,
+               const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
+               const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcStages * kTcStageBytes);
+  uint64_t* full = bars;                       // TMA bytes landed           (count 1 + tx)
+  uint64_t* ready = bars + kTcStages;          // hi/lo split done           (count 4: one per worker warp)
+  uint64_t* empty = bars + 2 * kTcStages;      // MMAs reading the stage retired (tcgen05.commit)
+  uint64_t* accum = bars + 3 * kTcStages;      // accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kTcStages + 1);
+
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * kTcBM, c0 = blockIdx.x * kTcBN;
+
+  if (tid == 0) {
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 4); mbar_init(&empty[s], 1); }
+    mbar_init(accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (wid == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  int nblk[2] = {0, 0};
+  for (int s = 0; s < tp.nseg; ++s) nblk[s] = (tp.seg[s].K + kTcBK - 1) / kTcBK;
+  const int total = nblk[0] + nblk[1];
+
+  if (wid == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int i = 0; i < total; ++i) {
+        const int st = i % kTcStages, it = i / kTcStages;
+        if (it > 0) mbar_wait(&empty[st], (it - 1) & 1);
+        const int sgi = i < nblk[0] ? 0 : 1;
+        const int kb = (sgi == 0 ? i : i - nblk[0]) * kTcBK;
+        const TcSeg& sg = tp.seg[sgi];
+        const CUtensorMap* ma = sgi == 0 ? &mapA0 : &mapA1;
+        const CUtensorMap* mb = sgi == 0 ? &mapB0 : &mapB1;
+        uint8_t* sa = smem + st * kTcStageBytes;
+        uint8_t* sb = sa + 2 * kTcTileBytes;
+        mbar_expect_tx(&full[st], 2 * kTcTileBytes);
+        if (!sg.a_mn_major) tma_load_2d(sa, ma, &full[st], kb, m0);                      // box {32 k, 128 rows}
+        else
+          for (int q = 0; q < 4; ++q) tma_load_2d(sa + q * 4096, ma, &full[st], m0 + q * 32, kb + sg.a_row_shift);  // box {32 m, 32 k}
+        if (!sg.b_mn_major) tma_load_2d(sb, mb, &full[st], kb, c0);
+        else
+          for (int q = 0; q < 4; ++q) tma_load_2d(sb + q * 4096, mb, &full[st], c0 + q * 32, kb + sg.b_row_shift);
+      }
+    }
+  } else if (wid == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      for (int i = 0; i < total; ++i) {
+        const int st = i % kTcStages, it = i / kTcStages;
+        mbar_wait(&ready[st], it & 1);
+        tc_fence_after();
+        const int sgi = i < nblk[0] ? 0 : 1;
+        const TcSeg& sg = tp.seg[sgi];
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)sg.a_mn_major << 15) |
+                               ((uint32_t)sg.b_mn_major << 16) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+        const uint32_t a_hi = smem_u32(smem + st * kTcStageBytes), a_lo = a_hi + kTcTileBytes;
+        const uint32_t b_hi = a_hi + 2 * kTcTileBytes, b_lo = b_hi + kTcTileBytes;
+        const uint32_t a_step = sg.a_mn_major ? 1024u : 32u, b_step = sg.b_mn_major ? 1024u : 32u;
+        // K-major: 8-row groups 1024 B apart (SBO), LBO unused.  MN-major tf32 must use the 32-byte-atom swizzle
+        // (cutlass sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the only available smem layout"):
+        // 32-element MN chunks 4096 B apart (LBO), 4-row K groups 512 B apart (SBO).
+        const uint32_t a_lbo = sg.a_mn_major ? 4096u : 16u, b_lbo = sg.b_mn_major ? 4096u : 16u;
+        const uint32_t a_sbo = sg.a_mn_major ? 512u : 1024u, b_sbo = sg.b_mn_major ? 512u : 1024u;
+        const uint32_t a_lay = sg.a_mn_major ? 1u : 2u, b_lay = sg.b_mn_major ? 1u : 2u;
+#pragma unroll
+        for (int j = 0; j < kTcBK / 8; ++j) {
+          const uint64_t dah = tc_smem_desc(a_hi + j * a_step, a_lbo, a_sbo, a_lay), dal = tc_smem_desc(a_lo + j * a_step, a_lbo, a_sbo, a_lay);
+          const uint64_t dbh = tc_smem_desc(b_hi + j * b_step, b_lbo, b_sbo, b_lay), dbl = tc_smem_desc(b_lo + j * b_step, b_lbo, b_sbo, b_lay);
+          // small terms first, the dominant hi*hi product last
+          if (tp.lolo) tc_mma_tf32(tmem_d, dal, dbl, idesc, (i | j) != 0);
+          tc_mma_tf32(tmem_d, dal, dbh, idesc, tp.lolo ? 1u : (uint32_t)((i | j) != 0));
+          tc_mma_tf32(tmem_d, dah, dbl, idesc, 1);
+          tc_mma_tf32(tmem_d, dah, dbh, idesc, 1);
+        }
+        tc_commit(&empty[st]);
+      }
+      tc_commit(accum);
+    }
+  } else if (wid >= 4) {
+    // ===== split workers: x -> (hi, lo), 128 threads over 2 x 4096 words =====
+    const int wt = tid - 128;
+    for (int i = 0; i < total; ++i) {
+      const int st = i % kTcStages, it = i / kTcStages;
+      mbar_wait(&full[st], it & 1);
+      const int sgi = i < nblk[0] ? 0 : 1;
+      const TcSeg& sg = tp.seg[sgi];
+      const int kb = (sgi == 0 ? i : i - nblk[0]) * kTcBK;
+      uint4* hiA = reinterpret_cast<uint4*>(smem + st * kTcStageBytes);
+      uint4* loA = hiA + kTcTileBytes / 16;
+      uint4* hiB = loA + kTcTileBytes / 16;
+      uint4* loB = hiB + kTcTileBytes / 16;
+#pragma unroll 4
+      for (int q = wt; q < kTcTileBytes / 16; q += 128) {
+        uint4 x = hiA[q], h, l;
+        tc_split(x.x, h.x, l.x); tc_split(x.y, h.y, l.y); tc_split(x.z, h.z, l.z); tc_split(x.w, h.w, l.w);
+        hiA[q] = h; loA[q] = l;
+      }
+      const bool kmask = sg.k_zero_period > 0 && sg.b_mn_major;
+#pragma unroll 4
+      for (int q = wt; q < kTcTileBytes / 16; q += 128) {
+        uint4 x = hiB[q], h, l;
+        if (kmask) {
+          const int krow = kb + ((q >> 3) & 31);            // MN-major tile: 128-byte row r of each 4 KB slab is K row r
+          if (krow % sg.k_zero_period == sg.k_zero_rem) x = make_uint4(0u, 0u, 0u, 0u);
+        }
+        tc_split(x.x, h.x, l.x); tc_split(x.y, h.y, l.y); tc_split(x.z, h.z, l.z); tc_split(x.w, h.w, l.w);
+        hiB[q] = h; loB[q] = l;
+      }
+      fence_async_smem();          // generic-proxy writes -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ready[st]);
+    }
+    // ===== accumulator: TMEM -> registers -> shared staging tile =====
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    float* Cs = reinterpret_cast<float*>(smem);               // [128][129], operand stages are free now
+    const int row = (wid - 4) * 32 + lane;                     // warp (wid % 4) owns TMEM lanes 32*(wid%4)..+31
+#pragma unroll 1
+    for (int cc = 0; cc < kTcBN; cc += 32) {
+      uint32_t v[32];
+      tc_ld32(tmem_d + ((uint32_t)((wid - 4) * 32) << 16) + (uint32_t)cc, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) Cs[row * (kTcBN + 1) + cc + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  gemm_epilogue<EPI, kTcBM, kTcBN>(p, reinterpret_cast<const float*>(smem), kTcBN + 1, m0, c0, tid, blockIdx.x, gridDim.x);
+  __syncthreads();
+  if (wid == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(128));
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled tc_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(f);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] (cols contiguous, leading dimension ld elements), box {32 cols, box_rows}, 128B swizzle
+inline bool tc_make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows,
+                        bool atom32 = false) {
+  PFN_encodeTiled fn = tc_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline bool tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ACVAE_DISABLE_TC");
+    v = (e && e[0] == '1') ? 0 : (tc_encode_fn() ? 1 : 0);
+  }
+  return v == 1;
+}
+
+// Extra description of shifted operands: the tensor map is built on `base` (the real allocation) and the
+// K-row coordinate is shifted, so rows outside [0, R) are zero-filled by TMA instead of being read.
+struct TcShift { int a_shift = 0, b_shift = 0; };
+
+// Returns 1 if the GEMM was issued on the tensor cores, 0 if the caller must use the SIMT kernels, <0 on error.
+template <int EPI>
+inline int try_launch_tc(const GemmParams& p, cudaStream_t st) {
+  if (!tc_enabled()) return 0;
+  if (p.G != 1 || p.nseg < 1 || p.nseg > 2 || p.M < 96 || p.live) return 0;
+  const int NC = p.U;
+  TcParams tp{};
+  tp.nseg = p.nseg;
+  {
+    static int lolo = -1;
+    if (lolo < 0) { const char* e = getenv("ACVAE_TC_MMAS"); lolo = (e && e[0] == '3') ? 0 : 1; }
+    tp.lolo = lolo;
+  }
+  CUtensorMap maps[4];
+  memset(maps, 0, sizeof(maps));
+  for (int s = 0; s < p.nseg; ++s) {
+    const GemmSeg& sg = p.seg[s];
+    if (sg.gather || sg.K < 8) return 0;
+    if (sg.lda % 4 || sg.ldw % 4 || !aligned16(sg.a) || !aligned16(sg.w[0])) return 0;
+    if (sg.k_zero_period && !(sg.a_trans && sg.w_trans)) return 0;
+    TcSeg& t = tp.seg[s];
+    t.K = sg.K; t.a_mn_major = sg.a_trans; t.b_mn_major = sg.w_trans;
+    t.k_zero_period = sg.k_zero_period; t.k_zero_rem = sg.k_zero_rem;
+    t.a_row_shift = 0; t.b_row_shift = sg.w_row_shift;
+    const float* wbase = sg.w[0] - (long long)sg.w_row_shift * sg.ldw;   // undo the pointer shift: map the real tensor
+    bool ok = true;
+    if (!sg.a_trans) ok = ok && tc_make_map(&maps[2 * s], sg.a, p.M, sg.K, sg.lda, kTcBM);
+    else ok = ok && tc_make_map(&maps[2 * s], sg.a, sg.K, p.M, sg.lda, kTcBK, true);
+    if (!sg.w_trans) ok = ok && tc_make_map(&maps[2 * s + 1], sg.w[0], NC, sg.K, sg.ldw, kTcBN);
+    else ok = ok && tc_make_map(&maps[2 * s + 1], wbase, sg.K, NC, sg.ldw, kTcBK, true);
+    if (!ok) return 0;
+  }
+  if (p.nseg == 1) { maps[2] = maps[0]; maps[3] = maps[1]; }
+  static bool configured = false;
+  if (!configured) {
+    ACVAE_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+    configured = true;
+  }
+  dim3 grid((NC + kTcBN - 1) / kTcBN, (p.M + kTcBM - 1) / kTcBM);
+  ACVAE_LAUNCH((tc_gemm_kernel<EPI>), grid, 256, kTcSmemBytes, st, p, tp, maps[0], maps[1], maps[2], maps[3]);
+  return 1;
+}
+
+// Dispatcher used by the whole library: tensor cores for the batched G == 1 contractions, SIMT kernels for
+// the skinny recurrent-step GEMMs and everything the TMA path cannot describe (gathers, gate interleave).
+template <int EPI>
+inline int launch_gemm(const GemmParams& p, cudaStream_t st, int* used_tc = nullptr) {
+  if (used_tc) *used_tc = 0;
+  if (p.M <= 0 || p.U <= 0) return 0;
+  if constexpr (EPI == EPI_PLAIN || EPI == EPI_STATS || EPI == EPI_DLOGITS) {
+    const int r = try_launch_tc<EPI>(p, st);
+    if (r < 0) return r;
+    if (r == 1) { if (used_tc) *used_tc = 1; return 0; }
+  }
+  return launch_gemm_simt<EPI>(p, st);
+}
+
+}  // namespace acvae

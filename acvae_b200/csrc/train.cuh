@@ -5,7 +5,7 @@
 #pragma once
 #include "../../include/acvae_b200.h"
 #include "attention.cuh"
-#include "gemm.cuh"
+#include "tc_gemm.cuh"
 #include "pointwise.cuh"
 
 namespace acvae {
@@ -110,12 +110,13 @@ inline int linear_bwd_data(int M, int K, int Nn, const float* dy, long long lddy
 // dW[Nn,K] (lddw) = dY[R,Nn](lddy)^T . X[R,K](ldx)             (nn.Linear backward-weight)
 // k_zero_period/rem: rows r with r % period == rem are skipped (shifted recurrent operands).
 inline int linear_bwd_weight(int Nn, int K, int R, const float* dy, long long lddy, const float* x, long long ldx,
-                             float* dw, long long lddw, cudaStream_t st, int k_zero_period = 0, int k_zero_rem = 0) {
+                             float* dw, long long lddw, cudaStream_t st, int k_zero_period = 0, int k_zero_rem = 0,
+                             int x_row_shift = 0) {
   GemmParams p{};
   p.M = Nn; p.U = K; p.G = 1; p.nseg = 1;
   GemmSeg s{};
   s.a = dy; s.lda = lddy; s.a_trans = 1; s.w[0] = x; s.ldw = ldx; s.w_trans = 1; s.K = R;
-  s.k_zero_period = k_zero_period; s.k_zero_rem = k_zero_rem;
+  s.k_zero_period = k_zero_period; s.k_zero_rem = k_zero_rem; s.w_row_shift = x_row_shift;
   p.seg[0] = s;
   p.epi.c[0] = dw; p.epi.ldc = lddw; p.epi.scale = 1.0f;
   return launch_gemm<EPI_PLAIN>(p, st);
@@ -170,8 +171,10 @@ inline int vocab_stats(VocabStatsArgs a, cudaStream_t st) {
   p.epi.pmax = a.pmax; p.epi.pexp = a.pexp; p.epi.psum = a.psum; p.epi.pbest = a.pbest; p.epi.parg = a.parg;
   p.epi.noise = a.noise; p.epi.ld_noise = a.ld_noise; p.epi.inv_temp = a.inv_temp;
   p.live = a.live; a.red.live = a.live;
-  ACVAE_TRY(launch_gemm<EPI_STATS>(p, st));
-  a.red.M = a.M; a.red.ntiles = (a.V + kVocabTile - 1) / kVocabTile;
+  int used_tc = 0;
+  ACVAE_TRY(launch_gemm<EPI_STATS>(p, st, &used_tc));
+  const int tile = used_tc ? kTcBN : kVocabTile;      // column-tile width of the kernel that ran
+  a.red.M = a.M; a.red.ntiles = (a.V + tile - 1) / tile;
   a.red.pmax = a.pmax; a.red.pexp = a.pexp; a.red.psum = a.psum; a.red.pbest = a.pbest; a.red.parg = a.parg;
   ACVAE_LAUNCH(vocab_reduce_kernel, (a.M + 3) / 4, 128, 0, st, a.red);
   return 0;
@@ -513,8 +516,8 @@ inline int train_bwd(const acvae_dims& d, const acvae_weights& w, const acvae_tr
   ACVAE_TRY(colsum(NT, 3 * E, ws.dgi_d, 3 * E, gw.d_bih, st));
   ACVAE_TRY(colsum(NT, 3 * E, ws.dgh_d, 3 * E, gw.d_bhh, st));
   // W_hh and the attention query half see h_{t-1}: shifted rows, t == 0 rows skipped
-  ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgh_d, 3 * E, io.outputs - E, E, gw.d_whh, E, st, T, 0));
-  ACVAE_TRY(linear_bwd_weight(A, E, NT, ws.dqp_d, A, io.outputs - E, E, gw.d_attn_w, 2 * E, st, T, 0));
+  ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgh_d, 3 * E, io.outputs - E, E, gw.d_whh, E, st, T, 0, -1));
+  ACVAE_TRY(linear_bwd_weight(A, E, NT, ws.dqp_d, A, io.outputs - E, E, gw.d_attn_w, 2 * E, st, T, 0, -1));
 
   // ---- prior BPTT (text_encoder.py:247-268 reversed; chain through last_z, vae_model.py:869) ----
   for (int t = T - 1; t >= 0; --t) {
@@ -563,8 +566,8 @@ inline int train_bwd(const acvae_dims& d, const acvae_weights& w, const acvae_tr
   ACVAE_TRY(linear_bwd_weight(E, E, NT, ws.dqp_p, E, ws.xp, E, gw.p_attn_w, 2 * E, st));
   ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.xp, E, gw.p_wih, 3 * E, st));
   ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.ctx_p, E, gw.p_wih + E, 3 * E, st));
-  ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, io.p_z - E, E, gw.p_wih + 2 * E, 3 * E, st, T, 0));
-  ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.h_p - E, E, gw.p_whh, E, st, T, 0));
+  ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, io.p_z - E, E, gw.p_wih + 2 * E, 3 * E, st, T, 0, -1));
+  ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.h_p - E, E, gw.p_whh, E, st, T, 0, -1));
   ACVAE_TRY(colsum(NT, 4 * E, ws.dg_p, 4 * E, gw.p_bih, st));
   ACVAE_TRY(colsum(NT, 4 * E, ws.dg_p, 4 * E, gw.p_bhh, st));
   ACVAE_TRY(linear_bwd_weight(2 * E, E, NT, ws.dml_p, 2 * E, ws.h_p, E, gw.p_head_w, E, st));
@@ -625,7 +628,7 @@ inline int train_bwd(const acvae_dims& d, const acvae_weights& w, const acvae_tr
     }
     ACVAE_TRY(linear_bwd_data(NT, 2 * E, 2 * E, ws.dml_q, 2 * E, w.q_head_w, 3 * E, ws.dho, 2 * E, st));
     ACVAE_TRY(linear_bwd_weight(2 * E, 2 * E, NT, ws.dml_q, 2 * E, ws.ho, 2 * E, gw.q_head_w, 3 * E, st));
-    ACVAE_TRY(linear_bwd_weight(2 * E, E, NT, ws.dml_q, 2 * E, io.q_z - E, E, gw.q_head_w + 2 * E, 3 * E, st, T, 0));
+    ACVAE_TRY(linear_bwd_weight(2 * E, E, NT, ws.dml_q, 2 * E, io.q_z - E, E, gw.q_head_w + 2 * E, 3 * E, st, T, 0, -1));
     ACVAE_TRY(colsum(NT, 2 * E, ws.dml_q, 2 * E, gw.q_head_b, st));
   }
   // biGRU BPTT with the packed-sequence mask
@@ -653,9 +656,9 @@ inline int train_bwd(const acvae_dims& d, const acvae_weights& w, const acvae_tr
     ACVAE_TRY(colsum(NT, 3 * E, ws.dgi_q[dir], 3 * E, gw.q_bih[dir], st));
     ACVAE_TRY(colsum(NT, 3 * E, ws.dgh_q[dir], 3 * E, gw.q_bhh[dir], st));
     if (dir == 0)
-      ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgh_q[0], 3 * E, ws.ho - 2 * E, 2 * E, gw.q_whh[0], E, st, T, 0));
+      ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgh_q[0], 3 * E, ws.ho - 2 * E, 2 * E, gw.q_whh[0], E, st, T, 0, -1));
     else
-      ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgh_q[1], 3 * E, ws.ho + 2 * E + E, 2 * E, gw.q_whh[1], E, st, T, T - 1));
+      ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgh_q[1], 3 * E, ws.ho + 2 * E + E, 2 * E, gw.q_whh[1], E, st, T, T - 1, 1));
   }
   ACVAE_CHECK(zero(gw.q_emb, (size_t)V * E));
   ACVAE_TRY(scatter_rows(NT, E, ws.dxq, E, ws.qids, gw.q_emb, st));

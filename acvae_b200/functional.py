@@ -102,6 +102,20 @@ def launch_count() -> int:
     return int(_lib.lib().acvae_launch_count())
 
 
+def gemm(a, b, a_trans=False, b_trans=False, bias=None, out=None, accumulate=False):
+    """C = op(A) . op(B)^T (+bias) through `acvae_gemm`; returns (C, used_tensor_cores)."""
+    l = _lib.lib()
+    M = a.shape[1] if a_trans else a.shape[0]
+    K = a.shape[0] if a_trans else a.shape[1]
+    N = b.shape[1] if b_trans else b.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    used = C.c_int32(0)
+    _lib.check(l.acvae_gemm(M, N, K, _dev(a), a.stride(0), int(a_trans), _dev(b), b.stride(0), int(b_trans),
+                            _opt(bias), _dev(out), out.stride(0), int(accumulate), C.byref(used), _stream()), "acvae_gemm")
+    return out, bool(used.value)
+
+
 # --------------------------------------------------------------------------------
 class TrainMeta:
     """Non-tensor inputs of one training forward (ids, lengths, noise, decisions)."""

@@ -113,6 +113,16 @@ int acvae_abi_version(void);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 uint64_t acvae_launch_count(void);
 
+/* ---- dense contraction (the building block of every batched GEMM of the step) ----------------
+ * C[M,N] (ldc) = op(A) . op(B)^T [+ bias[N]] [+ C]   in fp32-grade accuracy.
+ *   a_trans = 0: A is row-major [M,K] (lda);   1: A is row-major [K,M] (lda)
+ *   b_trans = 0: B is row-major [N,K] (ldb) -- nn.Linear weight layout;  1: B is row-major [K,N] (ldb)
+ * Large shapes run on the tcgen05 tensor cores with a 3xTF32 hi/lo split (tc_gemm.cuh); small or
+ * unaligned shapes on the CUDA-core kernels.  *used_tc (host int, may be NULL) reports which. */
+int acvae_gemm(int32_t M, int32_t N, int32_t K, const float *A, int64_t lda, int32_t a_trans, const float *B,
+               int64_t ldb, int32_t b_trans, const float *bias, float *C, int64_t ldc, int32_t accumulate,
+               int32_t *used_tc, void *stream);
+
 /* ---- training ---------------------------------------------------------- */
 size_t acvae_train_workspace_bytes(const acvae_dims *d);
 

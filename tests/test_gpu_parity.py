@@ -246,3 +246,23 @@ def test_kl_vs_oracle():
     assert abs(float(kl) - float(ref)) < 1e-5 * abs(float(ref))
     for a, b in zip(ts, ts2):
         assert harness.rel_err(a.grad, b.grad) < 1e-5
+
+
+@pytest.mark.parametrize("a_trans,b_trans", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(608, 768, 256), (128, 128, 32), (1984, 256, 512), (300, 200, 100), (608, 4400, 256)])
+def test_gemm_tensor_core_vs_fp64(M, N, K, a_trans, b_trans):
+    """tcgen05 3xTF32 GEMM (all four operand-major combinations, ragged tails) is fp32-grade accurate."""
+    _require_cuda()
+    from acvae_b200 import functional as F
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn((K, M) if a_trans else (M, K), generator=g).cuda()
+    B = torch.randn((K, N) if b_trans else (N, K), generator=g).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    C, used = F.gemm(A, B, a_trans, b_trans, bias)
+    ref = (A.double().t() if a_trans else A.double()) @ (B.double() if b_trans else B.double().t()) + bias.double()
+    err = harness.rel_err(C, ref)
+    assert err < 5e-6, (err, used)
+    assert used, "expected the tensor-core path for this shape"
+    # accumulate epilogue
+    C2, _ = F.gemm(A, B, a_trans, b_trans, None, out=C.clone(), accumulate=True)
+    assert harness.rel_err(C2, ref + ref - bias.double()) < 5e-6
