@@ -10,9 +10,17 @@
 // grade; the dropped lo*lo term is ~2^-20 smaller than hi*hi).  The split is position-wise, so it is
 // oblivious to the 128-byte swizzle TMA wrote the tile with.
 //
-// Pipeline (one 128x128 output tile per CTA, 256 threads):
+// The tensor core's fp32 accumulation truncates, and the bias grows linearly with the number of chained
+// MMAs (measured 7e-9 * K relative on B200, profiles/prec_probe.py).  The accumulator therefore lives in
+// TMEM only for kTcChunk k-blocks (64 values of k); two TMEM buffers alternate, and four accumulator
+// warps drain each finished chunk with tcgen05.ld and add it to fp32 registers with round-to-nearest
+// while the next chunk is being multiplied.
+//
+// Pipeline (one 128x128 output tile per CTA, 512 threads):
 //   warp 0      : TMA producer  -- cp.async.bulk.tensor.2d into a 3-stage ring, mbarrier complete_tx
-//   warps 4..7  : split workers -- hi/lo split of the landed stage, then TMEM -> smem in the epilogue
+//   warps 4..7  : split workers -- hi/lo split of the landed stage
+//   warps 8..15 : accumulators  -- drain TMEM chunk by chunk into registers (warp w: lane quadrant w%4,
+//                                  column half (w-8)/4), stage the tile for the epilogue
 //   warp 1      : MMA issuer    -- one elected lane, tcgen05.mma.cta_group::1.kind::tf32, accumulator
 //                                  in TMEM (128 lanes x 128 fp32 columns), tcgen05.commit frees the stage
 //   all warps   : fused epilogue of gemm.cuh on the staged tile (bias / accumulate / vocab statistics /
@@ -30,9 +38,12 @@
 namespace acvae {
 
 constexpr int kTcBM = 128, kTcBN = 128, kTcBK = 32, kTcStages = 3;
+constexpr int kTcChunk = 2;      // k-blocks accumulated inside TMEM before the partial sum is drained to fp32 registers
+constexpr int kTcThreads = 512;  // warps 0-3: TMA / MMA / idle, 4-7: hi-lo split workers, 8-15: accumulator warps
 constexpr int kTcTileBytes = kTcBM * kTcBK * 4;                 // 16 KB (A or B, hi or lo)
 constexpr int kTcStageBytes = 4 * kTcTileBytes;                 // A_hi, A_lo, B_hi, B_lo
 constexpr int kTcSmemBytes = kTcStages * kTcStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+static_assert(kTcBM * (kTcBN + 1) * 4 <= kTcStages * kTcStageBytes, "staging tile must fit in the operand ring");
 
 struct TcSeg {
   int a_mn_major, b_mn_major;      // 0: K-major (row-major [rows,K]); 1: MN-major (row-major [K,rows])
@@ -127,7 +138,7 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_by
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcParams tp,
                const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
                const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1) {
@@ -137,19 +148,20 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
   uint64_t* full = bars;                       // TMA bytes landed           (count 1 + tx)
   uint64_t* ready = bars + kTcStages;          // hi/lo split done           (count 4: one per worker warp)
   uint64_t* empty = bars + 2 * kTcStages;      // MMAs reading the stage retired (tcgen05.commit)
-  uint64_t* accum = bars + 3 * kTcStages;      // accumulator complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kTcStages + 1);
+  uint64_t* cfull = bars + 3 * kTcStages;      // [2] TMEM chunk buffer complete (tcgen05.commit)
+  uint64_t* cempty = cfull + 2;                // [2] TMEM chunk buffer drained  (count 8: one per accumulator warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cempty + 2);
 
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * kTcBM, c0 = blockIdx.x * kTcBN;
 
   if (tid == 0) {
     for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 4); mbar_init(&empty[s], 1); }
-    mbar_init(accum, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&cfull[b], 1); mbar_init(&cempty[b], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (wid == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(128));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
   }
   tc_fence_before();
@@ -161,6 +173,7 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
   for (int s = 0; s < tp.nseg; ++s) nblk[s] = (tp.seg[s].K + kTcBK - 1) / kTcBK;
   const int total = nblk[0] + nblk[1];
 
+  float acc_reg[kTcBN / 2];   // only the accumulator warps (8..15) touch it
   if (wid == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
@@ -188,6 +201,8 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
     if (lane == 0) {
       for (int i = 0; i < total; ++i) {
         const int st = i % kTcStages, it = i / kTcStages;
+        const int chunk = i / kTcChunk, cb = chunk & 1, first_in_chunk = (i % kTcChunk) == 0;
+        if (first_in_chunk && chunk >= 2) { mbar_wait(&cempty[cb], ((chunk >> 1) - 1) & 1); tc_fence_after(); }
         mbar_wait(&ready[st], it & 1);
         tc_fence_after();
         const int sgi = i < nblk[0] ? 0 : 1;
@@ -203,19 +218,43 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
         const uint32_t a_lbo = sg.a_mn_major ? 4096u : 16u, b_lbo = sg.b_mn_major ? 4096u : 16u;
         const uint32_t a_sbo = sg.a_mn_major ? 512u : 1024u, b_sbo = sg.b_mn_major ? 512u : 1024u;
         const uint32_t a_lay = sg.a_mn_major ? 1u : 2u, b_lay = sg.b_mn_major ? 1u : 2u;
+        const uint32_t tmem_c = tmem_d + (uint32_t)cb * kTcBN;
 #pragma unroll
         for (int j = 0; j < kTcBK / 8; ++j) {
           const uint64_t dah = tc_smem_desc(a_hi + j * a_step, a_lbo, a_sbo, a_lay), dal = tc_smem_desc(a_lo + j * a_step, a_lbo, a_sbo, a_lay);
           const uint64_t dbh = tc_smem_desc(b_hi + j * b_step, b_lbo, b_sbo, b_lay), dbl = tc_smem_desc(b_lo + j * b_step, b_lbo, b_sbo, b_lay);
+          const uint32_t fresh = (first_in_chunk && j == 0) ? 0u : 1u;
           // small terms first, the dominant hi*hi product last
-          if (tp.lolo) tc_mma_tf32(tmem_d, dal, dbl, idesc, (i | j) != 0);
-          tc_mma_tf32(tmem_d, dal, dbh, idesc, tp.lolo ? 1u : (uint32_t)((i | j) != 0));
-          tc_mma_tf32(tmem_d, dah, dbl, idesc, 1);
-          tc_mma_tf32(tmem_d, dah, dbh, idesc, 1);
+          if (tp.lolo) tc_mma_tf32(tmem_c, dal, dbl, idesc, fresh);
+          tc_mma_tf32(tmem_c, dal, dbh, idesc, tp.lolo ? 1u : fresh);
+          tc_mma_tf32(tmem_c, dah, dbl, idesc, 1);
+          tc_mma_tf32(tmem_c, dah, dbh, idesc, 1);
         }
         tc_commit(&empty[st]);
+        if ((i % kTcChunk) == kTcChunk - 1 || i == total - 1) tc_commit(&cfull[cb]);
       }
-      tc_commit(accum);
+    }
+  } else if (wid >= 8) {
+// ===== accumulator warps: drain finished TMEM chunks into fp32 registers (round-to-nearest adds) =====
+    const int q = wid & 3;                                     // TMEM lane quadrant this warp may access
+    const int ch = (wid - 8) >> 2;                             // which 64-column half it owns
+    const int nchunks = (total + kTcChunk - 1) / kTcChunk;
+#pragma unroll
+    for (int j = 0; j < kTcBN / 2; ++j) acc_reg[j] = 0.0f;
+    for (int c = 0; c < nchunks; ++c) {
+      const int cb = c & 1;
+      mbar_wait(&cfull[cb], (c >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < kTcBN / 2; cc += 32) {
+        uint32_t v[32];
+        tc_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * kTcBN + ch * (kTcBN / 2) + cc), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc_reg[cc + j] += __uint_as_float(v[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&cempty[cb]);
     }
   } else if (wid >= 4) {
     // ===== split workers: x -> (hi, lo), 128 threads over 2 x 4096 words =====
@@ -251,26 +290,22 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
       __syncwarp();
       if (lane == 0) mbar_arrive(&ready[st]);
     }
-    // ===== accumulator: TMEM -> registers -> shared staging tile =====
-    mbar_wait(accum, 0);
-    tc_fence_after();
-    float* Cs = reinterpret_cast<float*>(smem);               // [128][129], operand stages are free now
-    const int row = (wid - 4) * 32 + lane;                     // warp (wid % 4) owns TMEM lanes 32*(wid%4)..+31
-#pragma unroll 1
-    for (int cc = 0; cc < kTcBN; cc += 32) {
-      uint32_t v[32];
-      tc_ld32(tmem_d + ((uint32_t)((wid - 4) * 32) << 16) + (uint32_t)cc, v);
+  }
+  // every role has passed its last use of the operand ring before the staging tile overwrites it
+  __syncthreads();
+  if (wid >= 8) {
+    float* Cs = reinterpret_cast<float*>(smem);               // [128][129] staging tile over the (now idle) operand ring
+    const int row = (wid & 3) * 32 + lane, col0 = ((wid - 8) >> 2) * (kTcBN / 2);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) Cs[row * (kTcBN + 1) + cc + j] = __uint_as_float(v[j]);
-    }
-    tc_fence_before();
+    for (int j = 0; j < kTcBN / 2; ++j) Cs[row * (kTcBN + 1) + col0 + j] = acc_reg[j];
   }
   __syncthreads();
-  gemm_epilogue<EPI, kTcBM, kTcBN>(p, reinterpret_cast<const float*>(smem), kTcBN + 1, m0, c0, tid, blockIdx.x, gridDim.x);
+  if (tid < 256)   // the shared epilogue strides by 256 threads
+    gemm_epilogue<EPI, kTcBM, kTcBN>(p, reinterpret_cast<const float*>(smem), kTcBN + 1, m0, c0, tid, blockIdx.x, gridDim.x);
   __syncthreads();
   if (wid == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(128));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(256));
   }
 }
 
@@ -330,7 +365,7 @@ inline int try_launch_tc(const GemmParams& p, cudaStream_t st) {
   tp.nseg = p.nseg;
   {
     static int lolo = -1;
-    if (lolo < 0) { const char* e = getenv("ACVAE_TC_MMAS"); lolo = (e && e[0] == '3') ? 0 : 1; }
+    if (lolo < 0) { const char* e = getenv("ACVAE_TC_MMAS"); lolo = (e && e[0] == '4') ? 1 : 0; }
     tp.lolo = lolo;
   }
   CUtensorMap maps[4];
@@ -359,7 +394,7 @@ inline int try_launch_tc(const GemmParams& p, cudaStream_t st) {
     configured = true;
   }
   dim3 grid((NC + kTcBN - 1) / kTcBN, (p.M + kTcBM - 1) / kTcBM);
-  ACVAE_LAUNCH((tc_gemm_kernel<EPI>), grid, 256, kTcSmemBytes, st, p, tp, maps[0], maps[1], maps[2], maps[3]);
+  ACVAE_LAUNCH((tc_gemm_kernel<EPI>), grid, kTcThreads, kTcSmemBytes, st, p, tp, maps[0], maps[1], maps[2], maps[3]);
   return 1;
 }
 
