@@ -104,20 +104,37 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const float* 
   const int U = p.U;
 
   if constexpr (EPI == EPI_PLAIN) {
-    // iterate gate-major so that stores of one gate are coalesced along u
-    const int UT = BN / G;  // units per tile (BN is a multiple of G for all supported G)
-    for (int e = tid; e < G * BM * UT; e += 256) {
-      const int gg = e / (BM * UT);
-      const int r = (e / UT) % BM;
-      const int ul = e % UT;
-      const int gm = m0 + r;
-      const int u = c0 / G + ul;
-      if (gm < p.M && u < U && ep.c[gg]) {
-        float v = ep.scale * Cs[r][ul * G + gg];
-        if (ep.bias[gg]) v += __ldg(ep.bias[gg] + u);
-        float* dst = ep.c[gg] + (long long)gm * ep.ldc + u;
-        if (ep.accumulate) v += *dst;
-        *dst = v;
+    if (G == 1) {
+      // common case: compile-time index arithmetic, coalesced 128-byte row segments
+      float* __restrict__ cbase = ep.c[0];
+      const float* __restrict__ bias = ep.bias[0];
+      for (int e = tid; e < BM * BN; e += 256) {
+        const int r = e / BN, c = e % BN;
+        const int gm = m0 + r, u = c0 + c;
+        if (gm < p.M && u < U) {
+          float v = ep.scale * Cs[r][c];
+          if (bias) v += __ldg(bias + u);
+          float* dst = cbase + (long long)gm * ep.ldc + u;
+          if (ep.accumulate) v += *dst;
+          *dst = v;
+        }
+      }
+    } else {
+      // iterate gate-major so that stores of one gate are coalesced along u
+      const int UT = BN / G;  // units per tile (BN is a multiple of G for all supported G)
+      for (int e = tid; e < G * BM * UT; e += 256) {
+        const int gg = e / (BM * UT);
+        const int r = (e / UT) % BM;
+        const int ul = e % UT;
+        const int gm = m0 + r;
+        const int u = c0 / G + ul;
+        if (gm < p.M && u < U && ep.c[gg]) {
+          float v = ep.scale * Cs[r][ul * G + gg];
+          if (ep.bias[gg]) v += __ldg(ep.bias[gg] + u);
+          float* dst = ep.c[gg] + (long long)gm * ep.ldc + u;
+          if (ep.accumulate) v += *dst;
+          *dst = v;
+        }
       }
     }
   } else if constexpr (EPI == EPI_LSTM) {

@@ -53,6 +53,7 @@ struct TcSeg {
 };
 struct TcParams {
   int nseg;
+  int debug;    // timing experiments only (ACVAE_TC_DEBUG): bit0 skip the hi/lo split, bit1 issue 1 MMA instead of 3
   int lolo;     // also issue the lo*lo MMA (4 MMAs per step): operands are then exact to ~2^-23
   TcSeg seg[2];
 };
@@ -201,7 +202,8 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
     if (lane == 0) {
       for (int i = 0; i < total; ++i) {
         const int st = i % kTcStages, it = i / kTcStages;
-        const int chunk = i / kTcChunk, cb = chunk & 1, first_in_chunk = (i % kTcChunk) == 0;
+        const int kch = (tp.debug & 4) ? (1 << 20) : kTcChunk;
+        const int chunk = i / kch, cb = chunk & 1, first_in_chunk = (i % kch) == 0;
         if (first_in_chunk && chunk >= 2) { mbar_wait(&cempty[cb], ((chunk >> 1) - 1) & 1); tc_fence_after(); }
         mbar_wait(&ready[st], it & 1);
         tc_fence_after();
@@ -226,19 +228,21 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
           const uint32_t fresh = (first_in_chunk && j == 0) ? 0u : 1u;
           // small terms first, the dominant hi*hi product last
           if (tp.lolo) tc_mma_tf32(tmem_c, dal, dbl, idesc, fresh);
+          if (tp.debug & 2) { tc_mma_tf32(tmem_c, dah, dbh, idesc, fresh); continue; }
           tc_mma_tf32(tmem_c, dal, dbh, idesc, tp.lolo ? 1u : fresh);
           tc_mma_tf32(tmem_c, dah, dbl, idesc, 1);
           tc_mma_tf32(tmem_c, dah, dbh, idesc, 1);
         }
         tc_commit(&empty[st]);
-        if ((i % kTcChunk) == kTcChunk - 1 || i == total - 1) tc_commit(&cfull[cb]);
+        if ((i % kch) == kch - 1 || i == total - 1) tc_commit(&cfull[cb]);
       }
     }
   } else if (wid >= 8) {
 // ===== accumulator warps: drain finished TMEM chunks into fp32 registers (round-to-nearest adds) =====
     const int q = wid & 3;                                     // TMEM lane quadrant this warp may access
     const int ch = (wid - 8) >> 2;                             // which 64-column half it owns
-    const int nchunks = (total + kTcChunk - 1) / kTcChunk;
+    const int kch = (tp.debug & 4) ? (1 << 20) : kTcChunk;
+    const int nchunks = (total + kch - 1) / kch;
 #pragma unroll
     for (int j = 0; j < kTcBN / 2; ++j) acc_reg[j] = 0.0f;
     for (int c = 0; c < nchunks; ++c) {
@@ -269,6 +273,7 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
       uint4* loA = hiA + kTcTileBytes / 16;
       uint4* hiB = loA + kTcTileBytes / 16;
       uint4* loB = hiB + kTcTileBytes / 16;
+      if (!(tp.debug & 1)) {
 #pragma unroll 4
       for (int q = wt; q < kTcTileBytes / 16; q += 128) {
         uint4 x = hiA[q], h, l;
@@ -285,6 +290,7 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
         }
         tc_split(x.x, h.x, l.x); tc_split(x.y, h.y, l.y); tc_split(x.z, h.z, l.z); tc_split(x.w, h.w, l.w);
         hiB[q] = h; loB[q] = l;
+      }
       }
       fence_async_smem();          // generic-proxy writes -> visible to the tensor core's async proxy
       __syncwarp();
@@ -367,6 +373,9 @@ inline int try_launch_tc(const GemmParams& p, cudaStream_t st) {
     static int lolo = -1;
     if (lolo < 0) { const char* e = getenv("ACVAE_TC_MMAS"); lolo = (e && e[0] == '4') ? 1 : 0; }
     tp.lolo = lolo;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("ACVAE_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    tp.debug = dbg;
   }
   CUtensorMap maps[4];
   memset(maps, 0, sizeof(maps));

@@ -90,20 +90,17 @@ def make_host_batches(d, n, seed0):
 
 
 # ----------------------------------------------------------------------------------------- ours
-def run_ours(args):
+class TrainStep:
+    """The benchmarked step: model + optimiser + static device buffers (+ optional whole-step CUDA graph)."""
+
+
+def make_train_step(dev, world, rank, use_graph=True):
     import torch.distributed as dist
     import acvae_b200 as models
     from acvae_b200 import functional as F, parallel, synthetic
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import harness
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    ts = TrainStep()
     d = synthetic.CFG1
     model = harness.build_model(d, seed=1, device=dev).train()
     n_params = sum(p.numel() for p in model.parameters())
@@ -155,7 +152,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches_per_step = F.launch_count() - l0
     graph = None
-    if not args.no_graph:
+    if use_graph:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -179,6 +176,28 @@ def run_ours(args):
             graph.replay()
         else:
             step_body()
+
+    ts.__dict__.update(dict(model=model, d=d, n_params=n_params, run_step=run_step, load_resident=load_resident,
+                            pinned=pinned, resident=resident, st_audio=st_audio, st_mem_lens=st_mem_lens, st_prep=st_prep,
+                            st_targets=st_targets, loss_buf=loss_buf, M=M, graph=graph, launches_per_step=launches_per_step,
+                            step_body=step_body))
+    return ts
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from acvae_b200 import functional as F, parallel, synthetic
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ts = make_train_step(dev, world, rank, use_graph=not args.no_graph)
+    model, d, n_params, run_step, load_resident = ts.model, ts.d, ts.n_params, ts.run_step, ts.load_resident
+    pinned, resident, st_audio, st_mem_lens, st_prep, st_targets = ts.pinned, ts.resident, ts.st_audio, ts.st_mem_lens, ts.st_prep, ts.st_targets
+    loss_buf, M, graph, launches_per_step = ts.loss_buf, ts.M, ts.graph, ts.launches_per_step
 
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
