@@ -199,6 +199,18 @@ def run_ours(args):
     pinned, resident, st_audio, st_mem_lens, st_prep, st_targets = ts.pinned, ts.resident, ts.st_audio, ts.st_mem_lens, ts.st_prep, ts.st_targets
     loss_buf, M, graph, launches_per_step = ts.loss_buf, ts.M, ts.graph, ts.launches_per_step
 
+    if args.profile == "train":
+        # one eager step between cudaProfilerStart/Stop for `ncu --profile-from-start off` (never a bench value)
+        for i in range(3):
+            load_resident(i); ts.step_body()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        load_resident(3); ts.step_body()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profile": "train", "launches": int(launches_per_step)}), flush=True)
+        return
+
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -277,6 +289,12 @@ def run_ours(args):
             return model.inference_forward({"audio_embeds": s_audio, "audio_embeds_lens": s_lens}, method="sample",
                                            max_length=SAMPLE_LEN, n_captions=SAMPLE_K)
     sample_once(); torch.cuda.synchronize()
+    if args.profile == "sample":
+        torch.cuda.profiler.start()
+        sample_once(); torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profile": "sample"}), flush=True)
+        return
     l1 = F.launch_count()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(); a.record()
@@ -408,7 +426,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", default="", choices=["", "train", "sample"],
+                    help="run ONE eager train step / sampling pass between cudaProfilerStart/Stop (for ncu) and exit")
     args = ap.parse_args()
+    if args.profile:
+        args.steps, args.no_graph, args.no_cpu_baseline = 1, True, True
     if args.impl == "reference":
         if args.steps > 40:
             args.steps = 40      # bounded: ~0.5-1 s per CPU step
