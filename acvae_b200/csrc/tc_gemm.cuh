@@ -4,8 +4,8 @@
 //
 // Tensor cores have no fp32 input format; kind::tf32 keeps 10 mantissa bits, which would break the
 // 1e-4 parity bar.  Every operand word x is therefore split in shared memory into
-//     hi = x rounded to tf32 (10 explicit mantissa bits)
-//     lo = (x - hi) rounded to tf32                   (x - hi is exact in fp32, |lo| <= 2^-11 |x|)
+//     hi = x truncated to tf32 (10 explicit mantissa bits) = what the tensor core reads from the raw fp32 word
+//     lo = (x - hi) rounded to tf32                   (x - hi is exact in fp32, |lo| < 2^-10 |x|)
 // and each 128x128x8 step issues three MMAs  hi*hi + lo*hi + hi*lo  (error ~2^-21 relative, i.e. fp32
 // grade; the dropped lo*lo term is ~2^-20 smaller than hi*hi).  The split is position-wise, so it is
 // oblivious to the 128-byte swizzle TMA wrote the tile with.
@@ -53,8 +53,6 @@ struct TcSeg {
 };
 struct TcParams {
   int nseg;
-  int debug;    // timing experiments only (ACVAE_TC_DEBUG): bit0 skip the hi/lo split, bit1 issue 1 MMA instead of 3
-  int lolo;     // also issue the lo*lo MMA (4 MMAs per step): operands are then exact to ~2^-23
   TcSeg seg[2];
 };
 
@@ -83,6 +81,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (spin > (1ll << 24)) __trap();   // a protocol bug must abort, never hang the GPU
   }
 }
+// Same wait for the roles that are off the critical path (accumulator warps): sleep between polls so the spin
+// does not compete for issue slots with the MMA / TMA issuing warps on the same scheduler.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0;
+  for (long long spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (!done) __nanosleep(64);
+    if (spin > (1ll << 22)) __trap();
+  }
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
@@ -95,6 +110,30 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// One lane of a converged warp (elect.sync).  The issuing loops below are executed by ALL lanes of their warp and
+// only the tcgen05 / TMA instruction itself is predicated on the elected lane: operands are then provably
+// warp-uniform and live in uniform registers.  Issuing from inside `if (lane == 0)` makes ptxas wrap every
+// UTCHMMA / UTMALDG in an R2UR + BRA.U.ANY waterfall loop, and the single issuing thread becomes the bottleneck of
+// the whole pipeline (measured: 1.3 us per k-block, independent of the number of MMAs; profiles/ubench_tc.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// accumulate = compile-time constant (no predicate register traffic in the issue loop)
+template <int ACC>
+__device__ __forceinline__ void tc_mma_tf32_c(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACC)
+      : "memory");
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -118,13 +157,13 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
-// x = hi + lo with hi, lo representable in tf32 (10 explicit mantissa bits): round-to-nearest on the bit
-// pattern (add half an ulp of the kept field, clear the 13 dropped bits), so |lo| <= 2^-11 |x| and the
-// rounding of lo itself costs 2^-22 |x|.
-__device__ __forceinline__ void tc_split(uint32_t x, uint32_t& hi, uint32_t& lo) {
-  hi = (x + 0x1000u) & 0xffffe000u;
-  const float r = __uint_as_float(x) - __uint_as_float(hi);
-  lo = (__float_as_uint(r) + 0x1000u) & 0xffffe000u;
+// x = hi + lo.  kind::tf32 reads 32-bit words and ignores the 13 low mantissa bits, so the RAW fp32 word already
+// acts as hi = trunc_tf32(x) and needs no rewrite; only lo = x - trunc_tf32(x) (exact in fp32, same sign,
+// |lo| < 2^-10 |x|) is written, rounded to nearest tf32 so that its own representation error (2^-21 |x|) is
+// unbiased.  Halves the shared-memory store traffic of the split pass (the pipeline is shared-memory bound).
+__device__ __forceinline__ uint32_t tc_lo(uint32_t x) {
+  const float r = __uint_as_float(x) - __uint_as_float(x & 0xffffe000u);
+  return (__float_as_uint(r) + 0x1000u) & 0xffffe000u;
 }
 
 // UMMA shared-memory descriptor, SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp SmemDescriptor)
@@ -144,7 +183,9 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
                const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
                const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1) {
   extern __shared__ uint8_t tc_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by pointer arithmetic on the __shared__ array (keeps the shared address space visible to the
+  // compiler: the split workers' accesses become LDS/STS instead of generic LD/ST)
+  uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcStages * kTcStageBytes);
   uint64_t* full = bars;                       // TMA bytes landed           (count 1 + tx)
   uint64_t* ready = bars + kTcStages;          // hi/lo split done           (count 4: one per worker warp)
@@ -170,84 +211,100 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
-  int nblk[2] = {0, 0};
-  for (int s = 0; s < tp.nseg; ++s) nblk[s] = (tp.seg[s].K + kTcBK - 1) / kTcBK;
-  const int total = nblk[0] + nblk[1];
+  const int nblk0 = (tp.seg[0].K + kTcBK - 1) / kTcBK;
+  const int nblk1 = tp.nseg > 1 ? (tp.seg[1].K + kTcBK - 1) / kTcBK : 0;
+  const int total = nblk0 + nblk1;
 
   float acc_reg[kTcBN / 2];   // only the accumulator warps (8..15) touch it
   if (wid == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      for (int i = 0; i < total; ++i) {
-        const int st = i % kTcStages, it = i / kTcStages;
-        if (it > 0) mbar_wait(&empty[st], (it - 1) & 1);
-        const int sgi = i < nblk[0] ? 0 : 1;
-        const int kb = (sgi == 0 ? i : i - nblk[0]) * kTcBK;
-        const TcSeg& sg = tp.seg[sgi];
-        const CUtensorMap* ma = sgi == 0 ? &mapA0 : &mapA1;
-        const CUtensorMap* mb = sgi == 0 ? &mapB0 : &mapB1;
-        uint8_t* sa = smem + st * kTcStageBytes;
-        uint8_t* sb = sa + 2 * kTcTileBytes;
+    // ===== TMA producer: the whole warp runs the loop, one elected lane issues =====
+    int st = 0, par = 0;                        // parity of the `empty` phase to wait for (first pass: no wait)
+    for (int i = 0; i < total; ++i) {
+      if (i >= kTcStages) mbar_wait(&empty[st], par);
+      const bool s1 = i >= nblk0;
+      const TcSeg& sg = tp.seg[s1 ? 1 : 0];
+      const int kb = (s1 ? i - nblk0 : i) * kTcBK;
+      const CUtensorMap* ma = s1 ? &mapA1 : &mapA0;
+      const CUtensorMap* mb = s1 ? &mapB1 : &mapB0;
+      uint8_t* sa = smem + st * kTcStageBytes;
+      uint8_t* sb = sa + 2 * kTcTileBytes;
+      if (elect_one()) {
         mbar_expect_tx(&full[st], 2 * kTcTileBytes);
         if (!sg.a_mn_major) tma_load_2d(sa, ma, &full[st], kb, m0);                      // box {32 k, 128 rows}
-        else
+        else {
+#pragma unroll
           for (int q = 0; q < 4; ++q) tma_load_2d(sa + q * 4096, ma, &full[st], m0 + q * 32, kb + sg.a_row_shift);  // box {32 m, 32 k}
+        }
         if (!sg.b_mn_major) tma_load_2d(sb, mb, &full[st], kb, c0);
-        else
+        else {
+#pragma unroll
           for (int q = 0; q < 4; ++q) tma_load_2d(sb + q * 4096, mb, &full[st], c0 + q * 32, kb + sg.b_row_shift);
+        }
       }
+      __syncwarp();
+      if (++st == kTcStages) { st = 0; if (i >= kTcStages) par ^= 1; }
     }
   } else if (wid == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      for (int i = 0; i < total; ++i) {
-        const int st = i % kTcStages, it = i / kTcStages;
-        const int kch = (tp.debug & 4) ? (1 << 20) : kTcChunk;
-        const int chunk = i / kch, cb = chunk & 1, first_in_chunk = (i % kch) == 0;
-        if (first_in_chunk && chunk >= 2) { mbar_wait(&cempty[cb], ((chunk >> 1) - 1) & 1); tc_fence_after(); }
-        mbar_wait(&ready[st], it & 1);
-        tc_fence_after();
-        const int sgi = i < nblk[0] ? 0 : 1;
-        const TcSeg& sg = tp.seg[sgi];
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)sg.a_mn_major << 15) |
-                               ((uint32_t)sg.b_mn_major << 16) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
-        const uint32_t a_hi = smem_u32(smem + st * kTcStageBytes), a_lo = a_hi + kTcTileBytes;
-        const uint32_t b_hi = a_hi + 2 * kTcTileBytes, b_lo = b_hi + kTcTileBytes;
-        const uint32_t a_step = sg.a_mn_major ? 1024u : 32u, b_step = sg.b_mn_major ? 1024u : 32u;
-        // K-major: 8-row groups 1024 B apart (SBO), LBO unused.  MN-major tf32 must use the 32-byte-atom swizzle
-        // (cutlass sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the only available smem layout"):
-        // 32-element MN chunks 4096 B apart (LBO), 4-row K groups 512 B apart (SBO).
-        const uint32_t a_lbo = sg.a_mn_major ? 4096u : 16u, b_lbo = sg.b_mn_major ? 4096u : 16u;
-        const uint32_t a_sbo = sg.a_mn_major ? 512u : 1024u, b_sbo = sg.b_mn_major ? 512u : 1024u;
-        const uint32_t a_lay = sg.a_mn_major ? 1u : 2u, b_lay = sg.b_mn_major ? 1u : 2u;
-        const uint32_t tmem_c = tmem_d + (uint32_t)cb * kTcBN;
+    // ===== MMA issuer: the whole warp runs the loop, one elected lane issues =====
+    // Per-segment descriptor templates (everything but the 14-bit start-address field) and k-step strides.
+    // K-major: 8-row groups 1024 B apart (SBO), LBO unused.  MN-major tf32 must use the 32-byte-atom swizzle
+    // (cutlass sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the only available smem layout"):
+    // 32-element MN chunks 4096 B apart (LBO), 4-row K groups 512 B apart (SBO).
+    uint64_t a_tmpl[2], b_tmpl[2];
+    uint32_t a_step[2], b_step[2], idesc[2];
 #pragma unroll
-        for (int j = 0; j < kTcBK / 8; ++j) {
-          const uint64_t dah = tc_smem_desc(a_hi + j * a_step, a_lbo, a_sbo, a_lay), dal = tc_smem_desc(a_lo + j * a_step, a_lbo, a_sbo, a_lay);
-          const uint64_t dbh = tc_smem_desc(b_hi + j * b_step, b_lbo, b_sbo, b_lay), dbl = tc_smem_desc(b_lo + j * b_step, b_lbo, b_sbo, b_lay);
-          const uint32_t fresh = (first_in_chunk && j == 0) ? 0u : 1u;
-          // small terms first, the dominant hi*hi product last
-          if (tp.lolo) tc_mma_tf32(tmem_c, dal, dbl, idesc, fresh);
-          if (tp.debug & 2) { tc_mma_tf32(tmem_c, dah, dbh, idesc, fresh); continue; }
-          tc_mma_tf32(tmem_c, dal, dbh, idesc, tp.lolo ? 1u : fresh);
-          tc_mma_tf32(tmem_c, dah, dbl, idesc, 1);
-          tc_mma_tf32(tmem_c, dah, dbh, idesc, 1);
+    for (int s = 0; s < 2; ++s) {
+      const TcSeg& sg = tp.seg[s];
+      a_tmpl[s] = tc_smem_desc(0, sg.a_mn_major ? 4096u : 16u, sg.a_mn_major ? 512u : 1024u, sg.a_mn_major ? 1u : 2u);
+      b_tmpl[s] = tc_smem_desc(0, sg.b_mn_major ? 4096u : 16u, sg.b_mn_major ? 512u : 1024u, sg.b_mn_major ? 1u : 2u);
+      a_step[s] = (sg.a_mn_major ? 1024u : 32u) >> 4;
+      b_step[s] = (sg.b_mn_major ? 1024u : 32u) >> 4;
+      idesc[s] = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)sg.a_mn_major << 15) | ((uint32_t)sg.b_mn_major << 16) |
+                 ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+    }
+    const uint32_t ring = smem_u32(smem) >> 4;
+    int st = 0, par = 0, in_chunk = 0, chunk = 0;
+    for (int i = 0; i < total; ++i) {
+      const int cb = chunk & 1;
+      if (in_chunk == 0 && chunk >= 2) mbar_wait(&cempty[cb], ((chunk >> 1) - 1) & 1);
+      mbar_wait(&ready[st], par);
+      tc_fence_after();
+      if (elect_one()) {
+        const int s = i >= nblk0 ? 1 : 0;
+        const uint64_t dah = a_tmpl[s] + (uint64_t)(ring + (uint32_t)(st * (kTcStageBytes >> 4)));
+        const uint64_t dal = dah + (kTcTileBytes >> 4);
+        const uint64_t dbh = b_tmpl[s] + (uint64_t)(ring + (uint32_t)(st * (kTcStageBytes >> 4)) + 2 * (kTcTileBytes >> 4));
+        const uint64_t dbl = dbh + (kTcTileBytes >> 4);
+        const uint32_t tmem_c = tmem_d + (uint32_t)cb * kTcBN;
+        const uint32_t as = a_step[s], bs = b_step[s], id = idesc[s];
+        // small terms first, the dominant hi*hi product last
+        if (in_chunk == 0) tc_mma_tf32_c<0>(tmem_c, dal, dbh, id);
+        else tc_mma_tf32_c<1>(tmem_c, dal, dbh, id);
+        tc_mma_tf32_c<1>(tmem_c, dah, dbl, id);
+        tc_mma_tf32_c<1>(tmem_c, dah, dbh, id);
+#pragma unroll
+        for (int j = 1; j < kTcBK / 8; ++j) {
+          tc_mma_tf32_c<1>(tmem_c, dal + j * as, dbh + j * bs, id);
+          tc_mma_tf32_c<1>(tmem_c, dah + j * as, dbl + j * bs, id);
+          tc_mma_tf32_c<1>(tmem_c, dah + j * as, dbh + j * bs, id);
         }
         tc_commit(&empty[st]);
-        if ((i % kch) == kch - 1 || i == total - 1) tc_commit(&cfull[cb]);
+        if (in_chunk == kTcChunk - 1 || i == total - 1) tc_commit(&cfull[cb]);
       }
+      __syncwarp();
+      if (++st == kTcStages) { st = 0; par ^= 1; }
+      if (++in_chunk == kTcChunk) { in_chunk = 0; ++chunk; }
     }
   } else if (wid >= 8) {
 // ===== accumulator warps: drain finished TMEM chunks into fp32 registers (round-to-nearest adds) =====
     const int q = wid & 3;                                     // TMEM lane quadrant this warp may access
     const int ch = (wid - 8) >> 2;                             // which 64-column half it owns
-    const int kch = (tp.debug & 4) ? (1 << 20) : kTcChunk;
-    const int nchunks = (total + kch - 1) / kch;
+    const int nchunks = (total + kTcChunk - 1) / kTcChunk;
 #pragma unroll
     for (int j = 0; j < kTcBN / 2; ++j) acc_reg[j] = 0.0f;
     for (int c = 0; c < nchunks; ++c) {
       const int cb = c & 1;
-      mbar_wait(&cfull[cb], (c >> 1) & 1);
+      mbar_wait_backoff(&cfull[cb], (c >> 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < kTcBN / 2; cc += 32) {
@@ -263,38 +320,45 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
   } else if (wid >= 4) {
     // ===== split workers: x -> (hi, lo), 128 threads over 2 x 4096 words =====
     const int wt = tid - 128;
+    int st = 0, par = 0;
     for (int i = 0; i < total; ++i) {
-      const int st = i % kTcStages, it = i / kTcStages;
-      mbar_wait(&full[st], it & 1);
-      const int sgi = i < nblk[0] ? 0 : 1;
-      const TcSeg& sg = tp.seg[sgi];
-      const int kb = (sgi == 0 ? i : i - nblk[0]) * kTcBK;
+      mbar_wait(&full[st], par);
+      const bool s1 = i >= nblk0;
+      const TcSeg& sg = tp.seg[s1 ? 1 : 0];
+      const int kb = (s1 ? i - nblk0 : i) * kTcBK;
       uint4* hiA = reinterpret_cast<uint4*>(smem + st * kTcStageBytes);
       uint4* loA = hiA + kTcTileBytes / 16;
       uint4* hiB = loA + kTcTileBytes / 16;
       uint4* loB = hiB + kTcTileBytes / 16;
-      if (!(tp.debug & 1)) {
-#pragma unroll 4
-      for (int q = wt; q < kTcTileBytes / 16; q += 128) {
-        uint4 x = hiA[q], h, l;
-        tc_split(x.x, h.x, l.x); tc_split(x.y, h.y, l.y); tc_split(x.z, h.z, l.z); tc_split(x.w, h.w, l.w);
-        hiA[q] = h; loA[q] = l;
+#pragma unroll
+      for (int q0 = 0; q0 < kTcTileBytes / 16; q0 += 128 * 4) {
+        uint4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = hiA[q0 + u * 128 + wt];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          loA[q0 + u * 128 + wt] = make_uint4(tc_lo(x[u].x), tc_lo(x[u].y), tc_lo(x[u].z), tc_lo(x[u].w));
       }
       const bool kmask = sg.k_zero_period > 0 && sg.b_mn_major;
-#pragma unroll 4
-      for (int q = wt; q < kTcTileBytes / 16; q += 128) {
-        uint4 x = hiB[q], h, l;
-        if (kmask) {
-          const int krow = kb + ((q >> 3) & 31);            // MN-major tile: 128-byte row r of each 4 KB slab is K row r
-          if (krow % sg.k_zero_period == sg.k_zero_rem) x = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int q0 = 0; q0 < kTcTileBytes / 16; q0 += 128 * 4) {
+        uint4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = hiB[q0 + u * 128 + wt];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int q = q0 + u * 128 + wt;
+          if (kmask) {
+            const int krow = kb + ((q >> 3) & 31);            // MN-major tile: 128-byte row r of each 4 KB slab is K row r
+            if (krow % sg.k_zero_period == sg.k_zero_rem) { x[u] = make_uint4(0u, 0u, 0u, 0u); hiB[q] = x[u]; }
+          }
+          loB[q] = make_uint4(tc_lo(x[u].x), tc_lo(x[u].y), tc_lo(x[u].z), tc_lo(x[u].w));
         }
-        tc_split(x.x, h.x, l.x); tc_split(x.y, h.y, l.y); tc_split(x.z, h.z, l.z); tc_split(x.w, h.w, l.w);
-        hiB[q] = h; loB[q] = l;
-      }
       }
       fence_async_smem();          // generic-proxy writes -> visible to the tensor core's async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(&ready[st]);
+      if (++st == kTcStages) { st = 0; par ^= 1; }
     }
   }
   // every role has passed its last use of the operand ring before the staging tile overwrites it
@@ -369,14 +433,6 @@ inline int try_launch_tc(const GemmParams& p, cudaStream_t st) {
   const int NC = p.U;
   TcParams tp{};
   tp.nseg = p.nseg;
-  {
-    static int lolo = -1;
-    if (lolo < 0) { const char* e = getenv("ACVAE_TC_MMAS"); lolo = (e && e[0] == '4') ? 1 : 0; }
-    tp.lolo = lolo;
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("ACVAE_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
-    tp.debug = dbg;
-  }
   CUtensorMap maps[4];
   memset(maps, 0, sizeof(maps));
   for (int s = 0; s < p.nseg; ++s) {

@@ -17,6 +17,10 @@ shapes = [  # (M, N, K, a_trans, b_trans, what)
     (10450, 1024, 1024, 0, 0, "sampling LSTM gates (M=10450)"),
     (10450, 4400, 256, 0, 0, "sampling vocab (M=10450)"),
 ]
+sel = os.environ.get('GEMM_SHAPES')
+if sel:
+    shapes = [shapes[int(i)] for i in sel.split(',')]
+reps = int(os.environ.get('GEMM_REPS', '20'))
 for (M, N, K, at, bt, what) in shapes:
     A = torch.randn((K, M) if at else (M, K), device="cuda")
     B = torch.randn((K, N) if bt else (N, K), device="cuda")
@@ -25,7 +29,7 @@ for (M, N, K, at, bt, what) in shapes:
         _, used = F.gemm(A, B, bool(at), bool(bt), out=C)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 20
+    n = reps
     e0.record()
     for _ in range(n):
         F.gemm(A, B, bool(at), bool(bt), out=C)
