@@ -54,6 +54,7 @@ struct EpiParams {
   long long ldc;
   const float* bias[kMaxGate];
   int accumulate;
+  int atomic;       // split-K (tc_gemm.cuh): several CTAs add partial tiles into a pre-zeroed / accumulated C
   float scale;
   // cells: precomputed input-side pre-activations (x-part incl. b_ih) or NULL
   const float* gx; long long ld_gx;
@@ -113,10 +114,15 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const float* 
         const int gm = m0 + r, u = c0 + c;
         if (gm < p.M && u < U) {
           float v = ep.scale * Cs[r][c];
-          if (bias) v += __ldg(bias + u);
           float* dst = cbase + (long long)gm * ep.ldc + u;
-          if (ep.accumulate) v += *dst;
-          *dst = v;
+          if (ep.atomic) {
+            if (bias && blockIdx.z == 0) v += __ldg(bias + u);
+            atomicAdd(dst, v);
+          } else {
+            if (bias) v += __ldg(bias + u);
+            if (ep.accumulate) v += *dst;
+            *dst = v;
+          }
         }
       }
     } else {

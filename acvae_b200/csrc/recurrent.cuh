@@ -1,0 +1,774 @@
+// Persistent recurrent-chain kernels: a whole T-step chain of the training step in ONE cooperative launch.
+//
+// At batch 32 every recurrent step is a [32 x K] . [K x cols] product followed by a pointwise cell -- a few
+// MFLOP that a launch-per-step schedule spends 9-22 us on (launch, weight fetch from L2, drain).  Here the
+// chain runs inside one kernel of kChainCtas CTAs:
+//   * the weight matrix is COLUMN-partitioned: CTA b owns hidden units {2b, 2b+1} (all their gates) and keeps
+//     that weight slice resident in shared memory for all T steps -- weights are read from L2 exactly once;
+//   * per step a CTA reads the [N, K] state rows written by all CTAs in the previous phase (L2, ld.cg),
+//     computes its columns for all N rows (8-way K split inside a row group, shuffle-reduced), applies the
+//     cell arithmetic in registers and writes its units;
+//   * phases are separated by a grid barrier (one global atomic counter, release/acquire);
+//   * per-unit carries (dh*z, dc*f, ...) never leave registers: the unit partition is the same in every phase.
+// The decoder chains add a per-clip phase: CTA c keeps clip c's projected memory P_d[c] and memory mem[c]
+// resident in shared memory (Te*(A+E)*4 bytes) and runs the additive attention / its backward for that clip.
+//
+// Reference arithmetic: models/text_encoder.py:182-216 (posterior biGRU), :247-268 (prior LSTM + head),
+// models/decoder.py:175-203 + models/attn_model.py:20-46 (decoder step); same saved activations and the same
+// formulas as the launch-per-step schedule in train.cuh / train_fast.cuh (which remains the general path).
+#pragma once
+#include "common.cuh"
+
+namespace acvae {
+
+constexpr int kChainE = 256;                 // E == H == Hq == A handled by the persistent kernels
+constexpr int kChainCtas = kChainE / 2;      // 2 hidden units per CTA
+constexpr int kChainThreads = 256;           // thread = (row n = tid / 8, K-slice kp = tid % 8)
+constexpr int kChainMaxN = kChainThreads / 8;
+
+struct GridBar {
+  unsigned* flags;    // [nctas] one arrival flag per CTA (zeroed before the launch)
+  unsigned epoch;
+  unsigned nctas;     // <= 128
+};
+// Barrier over all CTAs of the (cooperatively launched, hence co-resident) grid, without atomics: CTA b
+// publishes the epoch it has reached in flags[b] (fence + volatile store), warp 0 of every CTA polls all flags
+// (volatile loads, 4 per lane, one fence after the last poll).  Same-address L2 atomics serialise at ~27 cycles each, which made a 128-CTA
+// counter barrier cost ~2 us; distinct flags cost one L2 write + one L2 read round trip.
+// Writes made by any thread of a CTA before the barrier are visible to every thread of every CTA after it
+// (bar.sync -> release store; acquire loads -> bar.sync).  Cross-CTA data is read with ld.global.cg (L1 is not
+// coherent).  A protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void grid_sync(GridBar& gb) {
+  __syncthreads();
+  gb.epoch += 1;
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) {
+      __threadfence();                                                  // release: the CTA's writes before the flag
+      *reinterpret_cast<volatile unsigned*>(gb.flags + blockIdx.x) = gb.epoch;
+    }
+    long long spin = 0;
+    bool done;
+    do {                                                                // plain volatile polls: no fence per iteration
+      done = true;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const unsigned idx = threadIdx.x + 32u * i;
+        if (idx < gb.nctas) done = done && (*reinterpret_cast<volatile unsigned*>(gb.flags + idx) >= gb.epoch);
+      }
+      done = __all_sync(0xffffffffu, done);
+      if (++spin > (1ll << 26)) __trap();
+    } while (!done);
+    __threadfence();                                                    // acquire
+  }
+  __syncthreads();
+}
+
+// A step's phase is latency-bound: ONE L2 round trip for all of its operands, not one per load.  The row loads
+// are therefore issued as a block of `asm volatile` ld.global.cg (program order is kept, so nothing is sunk
+// next to its use) into registers, and consumed afterwards.
+__device__ __forceinline__ float4 ldcg4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldcg1(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];\n" : "=f"(v) : "l"(p));
+  return v;
+}
+// src: one global row (K floats, 16-byte aligned).  Lane kp of the 8-lane row group takes the float4s
+// {kp, kp+8, ...}: a row group reads 128 contiguous bytes per iteration.
+template <int K>
+__device__ __forceinline__ void rowload(const float* __restrict__ src, int kp, float4 (&a)[K / 32]) {
+#pragma unroll
+  for (int i = 0; i < K / 32; ++i) a[i] = ldcg4(src + (i * 8 + kp) * 4);
+}
+// acc[c] += sum over this lane's K slice of a[k] * W[c][k];  W: shared [COLS][ldw] (conflict-free: 8 lanes read
+// 128 contiguous bytes, the 4 row groups of a warp read the same addresses).
+template <int COLS, int K>
+__device__ __forceinline__ void rowfma(const float4 (&a)[K / 32], const float* W, int ldw, int kp, float (&acc)[COLS]) {
+#pragma unroll
+  for (int i = 0; i < K / 32; ++i) {
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      const float4 w = *(reinterpret_cast<const float4*>(W + c * ldw) + i * 8 + kp);
+      acc[c] = fmaf(a[i].x, w.x, acc[c]);
+      acc[c] = fmaf(a[i].y, w.y, acc[c]);
+      acc[c] = fmaf(a[i].z, w.z, acc[c]);
+      acc[c] = fmaf(a[i].w, w.w, acc[c]);
+    }
+  }
+}
+// load block | __syncwarp (a scheduling fence for ptxas: every load is issued before the first FMA) | FMA block
+template <int COLS, int K>
+__device__ __forceinline__ void rowdot(bool row, const float* __restrict__ src, const float* W, int ldw, int kp, float (&acc)[COLS]) {
+  float4 a[K / 32];
+  if (row) rowload<K>(src, kp, a);
+  __syncwarp();
+  if (row) rowfma<COLS, K>(a, W, ldw, kp, acc);
+}
+// butterfly over the 8 lanes of a row group: every lane ends with the full sum
+template <int COLS>
+__device__ __forceinline__ void reduce8(float (&acc)[COLS]) {
+#pragma unroll
+  for (int c = 0; c < COLS; ++c) {
+    acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 4);
+    acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
+    acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+  }
+}
+
+// =====================================================================================================
+// posterior biGRU forward, both directions in one kernel (text_encoder.py:188-191)
+// =====================================================================================================
+struct PostChainFwd {
+  int N, T;
+  const float* gx[2];    // [N,T,3E] input-side pre-activations incl. b_ih
+  const float* whh[2];   // [3E,E]
+  const float* bhh[2];   // [3E]
+  const int* lens;       // [N] valid steps
+  float* ho;             // [N,T,2E]
+  float* gq[2];          // [N,T,4E] saved (r,z,n,gh_n)
+  unsigned* bar;
+};
+__global__ void __launch_bounds__(kChainThreads) post_chain_fwd_kernel(const __grid_constant__ PostChainFwd p) {
+  constexpr int E = kChainE;
+  __shared__ __align__(16) float W[2][6][E];
+  const int tid = threadIdx.x, n = tid >> 3, kp = tid & 7;
+  const int u0 = blockIdx.x * 2;
+  for (int i = tid; i < 2 * 6 * E; i += kChainThreads) {
+    const int dir = i / (6 * E), r = (i / E) % 6, k = i % E;
+    W[dir][r][k] = p.whh[dir][(long long)((r >> 1) * E + u0 + (r & 1)) * E + k];
+  }
+  __syncthreads();
+  GridBar gb{p.bar, 0u, gridDim.x};
+  const int T = p.T;
+  const bool row = n < p.N;
+  const int len = row ? p.lens[n] : 0;
+  const int dir = (kp >> 1) & 1, j = kp & 1, u = u0 + j;      // epilogue role of lanes kp < 4
+  const float bh_r = p.bhh[dir][u], bh_z = p.bhh[dir][E + u], bh_n = p.bhh[dir][2 * E + u];
+  for (int s = 0; s < T; ++s) {
+    float acc[2][6];
+#pragma unroll
+    for (int d = 0; d < 2; ++d)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) acc[d][c] = 0.0f;
+    const int t = dir ? T - 1 - s : s;
+    const int tp = dir ? t + 1 : t - 1;
+    float gxr = 0.f, gxz = 0.f, gxn = 0.f, hp = 0.f;
+    if (row && kp < 4) {                               // pointwise operands: issued with the row loads
+      const float* gx = p.gx[dir] + ((long long)n * T + t) * 3 * E + u;
+      gxr = ldcg1(gx); gxz = ldcg1(gx + E); gxn = ldcg1(gx + 2 * E);
+      if (s > 0) hp = ldcg1(p.ho + ((long long)n * T + tp) * 2 * E + dir * E + u);
+    }
+    if (s > 0) {
+      float4 a0[E / 32], a1[E / 32];
+      if (row) {
+        rowload<E>(p.ho + ((long long)n * T + (s - 1)) * 2 * E, kp, a0);
+        rowload<E>(p.ho + ((long long)n * T + (T - s)) * 2 * E + E, kp, a1);
+      }
+      __syncwarp();
+      if (row) {
+        rowfma<6, E>(a0, &W[0][0][0], E, kp, acc[0]);
+        rowfma<6, E>(a1, &W[1][0][0], E, kp, acc[1]);
+      }
+      reduce8(acc[0]);
+      reduce8(acc[1]);
+    }
+    if (row && kp < 4) {
+      // static register indices only (a runtime index would spill the accumulators to local memory)
+      const float hr = (dir ? (j ? acc[1][1] : acc[1][0]) : (j ? acc[0][1] : acc[0][0])) + bh_r;
+      const float hz = (dir ? (j ? acc[1][3] : acc[1][2]) : (j ? acc[0][3] : acc[0][2])) + bh_z;
+      const float hn = (dir ? (j ? acc[1][5] : acc[1][4]) : (j ? acc[0][5] : acc[0][4])) + bh_n;
+      const float rg = sigmoidf_(gxr + hr), zg = sigmoidf_(gxz + hz);
+      const float ng = tanhf(gxn + rg * hn);
+      float hnew = (1.0f - zg) * ng + zg * hp;
+      if (t >= len) hnew = 0.0f;                       // packed sequence: padded outputs are zero
+      float* gs = p.gq[dir] + ((long long)n * T + t) * 4 * E + u;
+      gs[0] = rg; gs[E] = zg; gs[2 * E] = ng; gs[3 * E] = hn;
+      p.ho[((long long)n * T + t) * 2 * E + dir * E + u] = hnew;
+    }
+    if (s + 1 < T) grid_sync(gb);
+  }
+}
+
+// =====================================================================================================
+// prior LSTM + Gaussian head forward (text_encoder.py:253-262); word attention and the input-side gate
+// pre-activations are hoisted (train_fast.cuh)
+// =====================================================================================================
+struct PriorChainFwd {
+  int N, T;
+  const float* gx;       // [N,T,4E] = [xe | ctx] . W_ih[:, :2E]^T + b_ih
+  const float* wih;      // [4E,3E] (columns 2E..3E act on last_z)
+  const float* whh;      // [4E,E]
+  const float* bhh;      // [4E]
+  const float* head_w;   // [2E,E]
+  const float* head_b;   // [2E]
+  const float* eps;      // [T,N,E]
+  float *gates, *c, *h;  // [N,T,4E], [N,T,E], [N,T,E]
+  float *pm, *pl, *pz;   // [N,T,E]
+  unsigned* bar;
+};
+__global__ void __launch_bounds__(kChainThreads) prior_chain_fwd_kernel(const __grid_constant__ PriorChainFwd p) {
+  constexpr int E = kChainE;
+  __shared__ __align__(16) float Wl[8][2 * E];   // rows g*2+j over K = [last_z | h]
+  __shared__ __align__(16) float Wh[4][E];       // rows (mean j0, mean j1, log j0, log j1)
+  const int tid = threadIdx.x, n = tid >> 3, kp = tid & 7;
+  const int u0 = blockIdx.x * 2;
+  for (int i = tid; i < 8 * 2 * E; i += kChainThreads) {
+    const int r = i / (2 * E), k = i % (2 * E);
+    const long long wr = (long long)((r >> 1) * E + u0 + (r & 1));
+    Wl[r][k] = k < E ? p.wih[wr * 3 * E + 2 * E + k] : p.whh[wr * E + (k - E)];
+  }
+  for (int i = tid; i < 4 * E; i += kChainThreads) {
+    const int r = i / E, k = i % E;
+    Wh[r][k] = p.head_w[(long long)((r >> 1) * E + u0 + (r & 1)) * E + k];
+  }
+  __syncthreads();
+  GridBar gb{p.bar, 0u, gridDim.x};
+  const int T = p.T, N = p.N;
+  const bool row = n < N;
+  const int j = kp & 1, u = u0 + j;
+  float bh[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) bh[g] = p.bhh[g * E + u];
+  const float hb_m = p.head_b[u], hb_l = p.head_b[E + u];
+  float c_prev = 0.0f;                                  // lanes kp < 2: cell state of unit u, row n
+  for (int t = 0; t < T; ++t) {
+    // ---- LSTM cell ----
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.0f;
+    float gxv[4] = {0.f, 0.f, 0.f, 0.f}, eps_t = 0.f;
+    if (row && kp < 2) {
+      const float* gx = p.gx + ((long long)n * T + t) * 4 * E + u;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) gxv[g] = ldcg1(gx + g * E);
+      eps_t = ldcg1(p.eps + ((long long)t * N + n) * E + u);
+    }
+    if (t > 0) {
+      float4 a0[E / 32], a1[E / 32];
+      if (row) {
+        rowload<E>(p.pz + ((long long)n * T + t - 1) * E, kp, a0);
+        rowload<E>(p.h + ((long long)n * T + t - 1) * E, kp, a1);
+      }
+      __syncwarp();
+      if (row) {
+        rowfma<8, E>(a0, &Wl[0][0], 2 * E, kp, acc);
+        rowfma<8, E>(a1, &Wl[0][E], 2 * E, kp, acc);
+      }
+      reduce8(acc);
+    }
+    if (row && kp < 2) {
+      const float ig = sigmoidf_((j ? acc[1] : acc[0]) + gxv[0] + bh[0]);
+      const float fg = sigmoidf_((j ? acc[3] : acc[2]) + gxv[1] + bh[1]);
+      const float gg = tanhf((j ? acc[5] : acc[4]) + gxv[2] + bh[2]);
+      const float og = sigmoidf_((j ? acc[7] : acc[6]) + gxv[3] + bh[3]);
+      const float cn = fg * c_prev + ig * gg;
+      const float hn = og * tanhf(cn);
+      c_prev = cn;
+      float* gs = p.gates + ((long long)n * T + t) * 4 * E + u;
+      gs[0] = ig; gs[E] = fg; gs[2 * E] = gg; gs[3 * E] = og;
+      p.c[((long long)n * T + t) * E + u] = cn;
+      p.h[((long long)n * T + t) * E + u] = hn;
+    }
+    grid_sync(gb);
+    // ---- Gaussian head + reparameterisation ----
+    float hc[4] = {0.f, 0.f, 0.f, 0.f};
+    rowdot<4, E>(row, p.h + ((long long)n * T + t) * E, &Wh[0][0], E, kp, hc);
+    reduce8(hc);
+    if (row && kp < 2) {
+      const float mean = (j ? hc[1] : hc[0]) + hb_m;
+      const float lg = (j ? hc[3] : hc[2]) + hb_l;
+      const long long o = ((long long)n * T + t) * E + u;
+      p.pm[o] = mean; p.pl[o] = lg; p.pz[o] = eps_t * expf(0.5f * lg) + mean;
+    }
+    if (t + 1 < T) grid_sync(gb);
+  }
+}
+
+// =====================================================================================================
+// posterior biGRU backward (BPTT with the packed-sequence mask), both directions in one kernel
+// =====================================================================================================
+struct PostChainBwd {
+  int N, T;
+  const float* dho;      // [N,T,2E] upstream gradient of the GRU outputs
+  const float* whh[2];   // [3E,E]
+  const float* gq[2];    // [N,T,4E]
+  const float* ho;       // [N,T,2E]
+  const int* lens;
+  float* dgi[2];         // [N,T,3E]
+  float* dgh[2];         // [N,T,3E]
+  unsigned* bar;
+};
+__global__ void __launch_bounds__(kChainThreads) post_chain_bwd_kernel(const __grid_constant__ PostChainBwd p) {
+  constexpr int E = kChainE;
+  __shared__ __align__(16) float Wt[2][2][3 * E];   // Wt[dir][j][c] = W_hh[c][u0+j]
+  const int tid = threadIdx.x, n = tid >> 3, kp = tid & 7;
+  const int u0 = blockIdx.x * 2;
+  for (int i = tid; i < 2 * 2 * 3 * E; i += kChainThreads) {
+    const int dir = i / (2 * 3 * E), jj = (i / (3 * E)) & 1, c = i % (3 * E);
+    Wt[dir][jj][c] = p.whh[dir][(long long)c * E + u0 + jj];
+  }
+  __syncthreads();
+  GridBar gb{p.bar, 0u, gridDim.x};
+  const int T = p.T;
+  const bool row = n < p.N;
+  const int len = row ? p.lens[n] : 0;
+  const int dir = (kp >> 1) & 1, j = kp & 1, u = u0 + j;
+  float carry = 0.0f;
+  for (int s = T - 1; s >= 0; --s) {
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    const int t = dir ? T - 1 - s : s;
+    const int tp = dir ? t + 1 : t - 1;
+    float dho = 0.f, rr = 0.f, z = 0.f, nn = 0.f, ghn = 0.f, hp = 0.f;
+    if (row && kp < 4) {                               // pointwise operands: issued with the row loads
+      dho = ldcg1(p.dho + ((long long)n * T + t) * 2 * E + dir * E + u);
+      const float* g = p.gq[dir] + ((long long)n * T + t) * 4 * E + u;
+      rr = ldcg1(g); z = ldcg1(g + E); nn = ldcg1(g + 2 * E); ghn = ldcg1(g + 3 * E);
+      if (s > 0) hp = ldcg1(p.ho + ((long long)n * T + tp) * 2 * E + dir * E + u);
+    }
+    if (s < T - 1) {
+      rowdot<2, 3 * E>(row, p.dgh[0] + ((long long)n * T + (s + 1)) * 3 * E, &Wt[0][0][0], 3 * E, kp, acc[0]);
+      rowdot<2, 3 * E>(row, p.dgh[1] + ((long long)n * T + (T - 2 - s)) * 3 * E, &Wt[1][0][0], 3 * E, kp, acc[1]);
+      reduce8(acc[0]);
+      reduce8(acc[1]);
+    }
+    if (row && kp < 4) {
+      float* gi = p.dgi[dir] + ((long long)n * T + t) * 3 * E + u;
+      float* gh = p.dgh[dir] + ((long long)n * T + t) * 3 * E + u;
+      if (t >= len) {
+        gi[0] = gi[E] = gi[2 * E] = 0.0f;
+        gh[0] = gh[E] = gh[2 * E] = 0.0f;
+        carry = 0.0f;
+      } else {
+        float dh = dho;
+        if (s < T - 1) dh += carry + (dir ? (j ? acc[1][1] : acc[1][0]) : (j ? acc[0][1] : acc[0][0]));
+        const float dn = dh * (1.0f - z), dz = dh * (hp - nn);
+        const float dan = dn * (1.0f - nn * nn);
+        const float dar = dan * ghn * rr * (1.0f - rr), daz = dz * z * (1.0f - z);
+        gi[0] = dar; gi[E] = daz; gi[2 * E] = dan;
+        gh[0] = dar; gh[E] = daz; gh[2 * E] = dan * rr;
+        carry = dh * z;
+      }
+    }
+    if (s > 0) grid_sync(gb);
+  }
+}
+
+// =====================================================================================================
+// prior backward: BPTT through the LSTM, the Gaussian head and the last_z chain (vae_model.py:869)
+// =====================================================================================================
+struct PriorChainBwd {
+  int N, T;
+  const float *d_pz, *d_pm, *d_pl;   // [N,T,E] upstream gradients or NULL
+  const float* eps;                  // [T,N,E]
+  const float* p_logs;               // [N,T,E]
+  const float* head_w;               // [2E,E]
+  const float* wih;                  // [4E,3E]
+  const float* whh;                  // [4E,E]
+  const float* gates;                // [N,T,4E]
+  const float* c;                    // [N,T,E]
+  float* dml;                        // [N,T,2E]
+  float* dg;                         // [N,T,4E]
+  unsigned* bar;
+};
+__global__ void __launch_bounds__(kChainThreads) prior_chain_bwd_kernel(const __grid_constant__ PriorChainBwd p) {
+  constexpr int E = kChainE;
+  __shared__ __align__(16) float WA[2][2 * E];   // WA[j][c] = W_head[c][u0+j]
+  __shared__ __align__(16) float WB[4][4 * E];   // (d last_z j0, j1, d h j0, j1): W_ih[c][2E+u], W_hh[c][u]
+  const int tid = threadIdx.x, n = tid >> 3, kp = tid & 7;
+  const int u0 = blockIdx.x * 2;
+  for (int i = tid; i < 2 * 2 * E; i += kChainThreads) {
+    const int jj = i / (2 * E), c = i % (2 * E);
+    WA[jj][c] = p.head_w[(long long)c * E + u0 + jj];
+  }
+  for (int i = tid; i < 4 * 4 * E; i += kChainThreads) {
+    const int r = i / (4 * E), c = i % (4 * E);
+    WB[r][c] = r < 2 ? p.wih[(long long)c * 3 * E + 2 * E + u0 + r] : p.whh[(long long)c * E + u0 + (r - 2)];
+  }
+  __syncthreads();
+  GridBar gb{p.bar, 0u, gridDim.x};
+  const int T = p.T, N = p.N;
+  const bool row = n < N;
+  const int j = kp & 1, u = u0 + j;
+  auto head_bwd = [&](int t, float dz) {
+    const long long o = ((long long)n * T + t) * E + u;
+    if (p.d_pz) dz += p.d_pz[o];
+    float dm = dz;
+    float dl = dz * p.eps[((long long)t * N + n) * E + u] * 0.5f * expf(0.5f * p.p_logs[o]);
+    if (p.d_pm) dm += p.d_pm[o];
+    if (p.d_pl) dl += p.d_pl[o];
+    float* d = p.dml + ((long long)n * T + t) * 2 * E + u;
+    d[0] = dm; d[E] = dl;
+  };
+  if (row && kp < 2) head_bwd(T - 1, 0.0f);
+  grid_sync(gb);
+  float dh_carry = 0.0f, dc_carry = 0.0f;
+  for (int t = T - 1; t >= 0; --t) {
+    // ---- dh_t = dML_t . W_head (+ carry); LSTM pointwise backward ----
+    float a2[2] = {0.f, 0.f};
+    float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, cc = 0.f, cp = 0.f;
+    if (row && kp < 2) {
+      const float* g = p.gates + ((long long)n * T + t) * 4 * E + u;
+      ig = ldcg1(g); fg = ldcg1(g + E); gg = ldcg1(g + 2 * E); og = ldcg1(g + 3 * E);
+      cc = ldcg1(p.c + ((long long)n * T + t) * E + u);
+      if (t > 0) cp = ldcg1(p.c + ((long long)n * T + t - 1) * E + u);
+    }
+    rowdot<2, 2 * E>(row, p.dml + ((long long)n * T + t) * 2 * E, &WA[0][0], 2 * E, kp, a2);
+    reduce8(a2);
+    if (row && kp < 2) {
+      const float dh = (j ? a2[1] : a2[0]) + dh_carry;
+      const float tc = tanhf(cc);
+      const float dc = dh * og * (1.0f - tc * tc) + dc_carry;
+      float* dg = p.dg + ((long long)n * T + t) * 4 * E + u;
+      dg[0] = dc * gg * ig * (1.0f - ig);
+      dg[E] = dc * cp * fg * (1.0f - fg);
+      dg[2 * E] = dc * ig * (1.0f - gg * gg);
+      dg[3 * E] = dh * tc * og * (1.0f - og);
+      dc_carry = dc * fg;
+    }
+    if (t == 0) break;
+    grid_sync(gb);
+    // ---- [d last_z | d h_{t-1}] = dG_t . [W_ih[:, 2E:3E] | W_hh]; head backward of step t-1 ----
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+    float u_pz = 0.f, u_pm = 0.f, u_pl = 0.f, e_ = 0.f, lv = 0.f;
+    if (row && kp < 2) {
+      const long long o = ((long long)n * T + t - 1) * E + u;
+      if (p.d_pz) u_pz = ldcg1(p.d_pz + o);
+      if (p.d_pm) u_pm = ldcg1(p.d_pm + o);
+      if (p.d_pl) u_pl = ldcg1(p.d_pl + o);
+      e_ = ldcg1(p.eps + ((long long)(t - 1) * N + n) * E + u);
+      lv = ldcg1(p.p_logs + o);
+    }
+    rowdot<4, 4 * E>(row, p.dg + ((long long)n * T + t) * 4 * E, &WB[0][0], 4 * E, kp, a4);
+    reduce8(a4);
+    if (row && kp < 2) {
+      dh_carry = j ? a4[3] : a4[2];
+      const float dz = (j ? a4[1] : a4[0]) + u_pz;
+      float* d = p.dml + ((long long)n * T + t - 1) * 2 * E + u;
+      d[0] = dz + u_pm;
+      d[E] = dz * e_ * 0.5f * expf(0.5f * lv) + u_pl;
+    }
+    grid_sync(gb);
+  }
+}
+
+// =====================================================================================================
+// decoder forward chain: query projection -> additive attention over the clip's frames -> GRU
+// (decoder.py:183-199, attn_model.py:20-46); the [emb | z] half of the gate pre-activations is hoisted
+// =====================================================================================================
+struct DecChainFwd {
+  int N, T, Te;
+  const float* gx;        // [N,T,3E] = [emb | z] . W_ih[:, {0:E, 2E:3E}]^T + b_ih
+  const float* attn_w;    // [A,2E] (query columns first)
+  const float* attn_v;    // [A]
+  const float* wih;       // [3E,3E]
+  const float* whh;       // [3E,E]
+  const float* bhh;       // [3E]
+  const float *Pd, *mem;  // [N,Te,A], [N,Te,E]
+  const int* mem_lens;
+  float *qp, *w, *ctx, *gates, *out;   // [N,T,A], [N,T,Te], [N,T,E], [N,T,4E], [N,T,E]
+  float* aw;              // [N,Te,T] user-visible attention weights or NULL
+  unsigned* bar;
+};
+inline size_t dec_chain_fwd_smem(int Te) { return ((size_t)Te * 2 * kChainE + 2 * kChainE + 12 * kChainE + 2 * kChainE + Te + 64) * sizeof(float); }
+
+__global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __grid_constant__ DecChainFwd p) {
+  constexpr int E = kChainE, A = kChainE;
+  extern __shared__ __align__(16) float dsm[];
+  const int Te = p.Te, T = p.T, N = p.N;
+  float* Ps = dsm;                        // [Te][A]   clip blockIdx.x
+  float* Ms = Ps + (size_t)Te * A;        // [Te][E]
+  float* Wq = Ms + (size_t)Te * E;        // [2][E]
+  float* Wg = Wq + 2 * E;                 // [12][E]: rows 0..5 (r,z,n)x2 on ctx, rows 6..11 on h
+  float* qps = Wg + 12 * E;               // [A]
+  float* vs = qps + A;                    // [A]
+  float* sc = vs + A;                     // [Te]
+  float* red = sc + Te;                   // [64]
+  const int tid = threadIdx.x, n = tid >> 3, kp = tid & 7, lane = tid & 31, wid = tid >> 5;
+  const int u0 = blockIdx.x * 2;
+  const int clip = blockIdx.x;
+  const bool own_clip = clip < N;
+  const int len = own_clip ? max(1, min(p.mem_lens[clip], Te)) : 0;
+  if (own_clip) {
+    const float4* sp = reinterpret_cast<const float4*>(p.Pd + (long long)clip * Te * A);
+    const float4* sm_ = reinterpret_cast<const float4*>(p.mem + (long long)clip * Te * E);
+    for (int i = tid; i < len * A / 4; i += kChainThreads) reinterpret_cast<float4*>(Ps)[i] = sp[i];
+    for (int i = tid; i < len * E / 4; i += kChainThreads) reinterpret_cast<float4*>(Ms)[i] = sm_[i];
+  }
+  vs[tid] = p.attn_v[tid];                 // blockDim == A
+  for (int i = tid; i < 2 * E; i += kChainThreads) Wq[i] = p.attn_w[(long long)(u0 + i / E) * 2 * E + (i % E)];
+  for (int i = tid; i < 12 * E; i += kChainThreads) {
+    const int r = i / E, k = i % E, rr = r % 6;
+    const long long wr = (long long)((rr >> 1) * E + u0 + (rr & 1));
+    Wg[i] = r < 6 ? p.wih[wr * 3 * E + E + k] : p.whh[wr * E + k];
+  }
+  __syncthreads();
+  GridBar gb{p.bar, 0u, gridDim.x};
+  const bool row = n < N;
+  const int j = kp & 1, u = u0 + j;
+  const float bh_r = p.bhh[u], bh_z = p.bhh[E + u], bh_n = p.bhh[2 * E + u];
+  for (int t = 0; t < T; ++t) {
+    // ---- P1: query projection q.Wq^T, columns {u0, u0+1} of A ----
+    if (t > 0) {
+      float a2[2] = {0.f, 0.f};
+      rowdot<2, E>(row, p.out + ((long long)n * T + t - 1) * E, Wq, E, kp, a2);
+      reduce8(a2);
+      if (row && kp < 2) p.qp[((long long)n * T + t) * A + u] = j ? a2[1] : a2[0];
+      grid_sync(gb);
+    } else if (row && kp < 2) {
+      p.qp[((long long)n * T) * A + u] = 0.0f;     // zero query at t = 0 (decoder.py:94-98)
+    }
+    // ---- P2: attention of clip `clip` ----
+    if (own_clip) {
+      qps[tid] = t > 0 ? ldcg1(p.qp + ((long long)clip * T + t) * A + tid) : 0.0f;
+      __syncthreads();
+      for (int jj = wid; jj < len; jj += kChainThreads / 32) {
+        const float* pr = Ps + (size_t)jj * A;
+        float s = 0.0f;
+#pragma unroll
+        for (int a = lane; a < A; a += 32) s = fmaf(vs[a], tanhf(pr[a] + qps[a]), s);
+        s = warp_sum(s);
+        if (lane == 0) sc[jj] = s;
+      }
+      __syncthreads();
+      float mx = -INFINITY;
+      for (int jj = tid; jj < len; jj += kChainThreads) mx = fmaxf(mx, sc[jj]);
+      mx = block_max(mx, red);
+      float sum = 0.0f;
+      for (int jj = tid; jj < len; jj += kChainThreads) {
+        const float e = expf(sc[jj] - mx);
+        sc[jj] = e;
+        sum += e;
+      }
+      sum = block_sum(sum, red);
+      const float inv = 1.0f / sum;
+      for (int jj = tid; jj < Te; jj += kChainThreads) {
+        const float wv = jj < len ? sc[jj] * inv : 0.0f;
+        if (jj < len) sc[jj] = wv;
+        p.w[((long long)clip * T + t) * Te + jj] = wv;
+        if (p.aw) p.aw[((long long)clip * Te + jj) * T + t] = wv;
+      }
+      __syncthreads();
+      float c0 = 0.f, c1 = 0.f;
+      int jj = 0;
+      for (; jj + 2 <= len; jj += 2) {
+        c0 = fmaf(sc[jj], Ms[(size_t)jj * E + tid], c0);
+        c1 = fmaf(sc[jj + 1], Ms[(size_t)(jj + 1) * E + tid], c1);
+      }
+      if (jj < len) c0 = fmaf(sc[jj], Ms[(size_t)jj * E + tid], c0);
+      p.ctx[((long long)clip * T + t) * E + tid] = c0 + c1;
+    }
+    grid_sync(gb);
+    // ---- P3: GRU cell, units {u0, u0+1} ----
+    float ax[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ah[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float gxr = 0.f, gxz = 0.f, gxn = 0.f, hp = 0.f;
+    if (row && kp < 2) {
+      const float* gx = p.gx + ((long long)n * T + t) * 3 * E + u;
+      gxr = ldcg1(gx); gxz = ldcg1(gx + E); gxn = ldcg1(gx + 2 * E);
+      if (t > 0) hp = ldcg1(p.out + ((long long)n * T + t - 1) * E + u);
+    }
+    {
+      float4 a0[E / 32], a1[E / 32];
+      if (row) {
+        rowload<E>(p.ctx + ((long long)n * T + t) * E, kp, a0);
+        if (t > 0) rowload<E>(p.out + ((long long)n * T + t - 1) * E, kp, a1);
+      }
+      __syncwarp();
+      if (row) {
+        rowfma<6, E>(a0, Wg, E, kp, ax);
+        if (t > 0) rowfma<6, E>(a1, Wg + 6 * E, E, kp, ah);
+      }
+    }
+    reduce8(ax);
+    reduce8(ah);
+    if (row && kp < 2) {
+      const float hn = (j ? ah[5] : ah[4]) + bh_n;
+      const float rg = sigmoidf_((j ? ax[1] : ax[0]) + gxr + (j ? ah[1] : ah[0]) + bh_r);
+      const float zg = sigmoidf_((j ? ax[3] : ax[2]) + gxz + (j ? ah[3] : ah[2]) + bh_z);
+      const float ng = tanhf((j ? ax[5] : ax[4]) + gxn + rg * hn);
+      float* gs = p.gates + ((long long)n * T + t) * 4 * E + u;
+      gs[0] = rg; gs[E] = zg; gs[2 * E] = ng; gs[3 * E] = hn;
+      p.out[((long long)n * T + t) * E + u] = (1.0f - zg) * ng + zg * hp;
+    }
+    if (t + 1 < T) grid_sync(gb);
+  }
+}
+
+// =====================================================================================================
+// decoder backward chain: GRU pointwise backward -> d ctx -> attention backward (d score, d query proj)
+// =====================================================================================================
+struct DecChainBwd {
+  int N, T, Te;
+  const float* dout;      // [N,T,E] upstream gradient of the GRU outputs (incl. the pooled global head)
+  const float* attn_w;    // [A,2E]
+  const float* attn_v;    // [A]
+  const float* wih;       // [3E,3E]
+  const float* whh;       // [3E,E]
+  const float *Pd, *mem;
+  const int* mem_lens;
+  const float *qp, *w, *gates, *out;   // saved by the forward
+  float *dgi, *dgh;       // [N,T,3E]
+  float *dctx, *ds, *dqp; // [N,T,E], [N,T,Te], [N,T,A]
+  unsigned* bar;
+};
+inline size_t dec_chain_bwd_smem(int Te) { return ((size_t)Te * 2 * kChainE + 2 * 4 * kChainE + 2 * 3 * kChainE + 2 * kChainE + Te + 64) * sizeof(float); }
+
+__global__ void __launch_bounds__(kChainThreads) dec_chain_bwd_kernel(const __grid_constant__ DecChainBwd p) {
+  constexpr int E = kChainE, A = kChainE;
+  extern __shared__ __align__(16) float dsm[];
+  const int Te = p.Te, T = p.T, N = p.N;
+  float* Ps = dsm;                        // [Te][A]
+  float* Ms = Ps + (size_t)Te * A;        // [Te][E]
+  float* W1 = Ms + (size_t)Te * E;        // [2][4E]: W1[j][c] = c < 3E ? W_hh[c][u0+j] : Wq[c-3E][u0+j]
+  float* W2 = W1 + 2 * 4 * E;             // [2][3E]: W2[j][c] = W_ih[c][E + u0+j]
+  float* qps = W2 + 2 * 3 * E;            // [A]
+  float* dcs = qps + A;                   // [E]
+  float* dw = dcs + E;                    // [Te]
+  float* red = dw + Te;                   // [64]
+  const int tid = threadIdx.x, n = tid >> 3, kp = tid & 7, lane = tid & 31, wid = tid >> 5;
+  const int u0 = blockIdx.x * 2;
+  const int clip = blockIdx.x;
+  const bool own_clip = clip < N;
+  const int len = own_clip ? max(1, min(p.mem_lens[clip], Te)) : 0;
+  if (own_clip) {
+    const float4* sp = reinterpret_cast<const float4*>(p.Pd + (long long)clip * Te * A);
+    const float4* sm_ = reinterpret_cast<const float4*>(p.mem + (long long)clip * Te * E);
+    for (int i = tid; i < len * A / 4; i += kChainThreads) reinterpret_cast<float4*>(Ps)[i] = sp[i];
+    for (int i = tid; i < len * E / 4; i += kChainThreads) reinterpret_cast<float4*>(Ms)[i] = sm_[i];
+  }
+  for (int i = tid; i < 2 * 4 * E; i += kChainThreads) {
+    const int jj = i / (4 * E), c = i % (4 * E);
+    W1[i] = c < 3 * E ? p.whh[(long long)c * E + u0 + jj] : p.attn_w[(long long)(c - 3 * E) * 2 * E + u0 + jj];
+  }
+  for (int i = tid; i < 2 * 3 * E; i += kChainThreads) {
+    const int jj = i / (3 * E), c = i % (3 * E);
+    W2[i] = p.wih[(long long)c * 3 * E + E + u0 + jj];
+  }
+  __syncthreads();
+  GridBar gb{p.bar, 0u, gridDim.x};
+  const bool row = n < N;
+  const int j = kp & 1, u = u0 + j;
+  const float va = p.attn_v[tid];
+  float carry = 0.0f;
+  for (int t = T - 1; t >= 0; --t) {
+    // ---- B1: dh_t (units u0, u0+1) and the GRU pointwise backward of step t ----
+    float a2[2] = {0.f, 0.f};
+    float dh = 0.f, rr = 0.f, z = 0.f, nn = 0.f, ghn = 0.f, hp = 0.f;
+    if (row && kp < 2) {
+      dh = ldcg1(p.dout + ((long long)n * T + t) * E + u);
+      const float* g = p.gates + ((long long)n * T + t) * 4 * E + u;
+      rr = ldcg1(g); z = ldcg1(g + E); nn = ldcg1(g + 2 * E); ghn = ldcg1(g + 3 * E);
+      if (t > 0) hp = ldcg1(p.out + ((long long)n * T + t - 1) * E + u);
+    }
+    if (t < T - 1) {
+      float4 a0[3 * E / 32], a1[A / 32];
+      if (row) {
+        rowload<3 * E>(p.dgh + ((long long)n * T + t + 1) * 3 * E, kp, a0);
+        rowload<A>(p.dqp + ((long long)n * T + t + 1) * A, kp, a1);
+      }
+      __syncwarp();
+      if (row) {
+        rowfma<2, 3 * E>(a0, W1, 4 * E, kp, a2);
+        rowfma<2, A>(a1, W1 + 3 * E, 4 * E, kp, a2);
+      }
+      reduce8(a2);
+    }
+    if (row && kp < 2) {
+      if (t < T - 1) dh += carry + (j ? a2[1] : a2[0]);
+      const float dn = dh * (1.0f - z), dz = dh * (hp - nn);
+      const float dan = dn * (1.0f - nn * nn);
+      const float dar = dan * ghn * rr * (1.0f - rr), daz = dz * z * (1.0f - z);
+      float* gi = p.dgi + ((long long)n * T + t) * 3 * E + u;
+      float* gh = p.dgh + ((long long)n * T + t) * 3 * E + u;
+      gi[0] = dar; gi[E] = daz; gi[2 * E] = dan;
+      gh[0] = dar; gh[E] = daz; gh[2 * E] = dan * rr;
+      carry = dh * z;
+    }
+    grid_sync(gb);
+    // ---- B1.5: d ctx_t = dGi_t . W_ih[:, E:2E], columns {u0, u0+1} ----
+    float b2[2] = {0.f, 0.f};
+    rowdot<2, 3 * E>(row, p.dgi + ((long long)n * T + t) * 3 * E, W2, 3 * E, kp, b2);
+    reduce8(b2);
+    if (row && kp < 2) p.dctx[((long long)n * T + t) * E + u] = j ? b2[1] : b2[0];
+    grid_sync(gb);
+    // ---- B2: attention backward of clip `clip` ----
+    if (own_clip) {
+      dcs[tid] = ldcg1(p.dctx + ((long long)clip * T + t) * E + tid);
+      qps[tid] = p.qp[((long long)clip * T + t) * A + tid];
+      __syncthreads();
+      for (int jj = wid; jj < len; jj += kChainThreads / 32) {
+        float s = 0.0f;
+#pragma unroll
+        for (int e = lane; e < E; e += 32) s = fmaf(dcs[e], Ms[(size_t)jj * E + e], s);
+        s = warp_sum(s);
+        if (lane == 0) dw[jj] = s;
+      }
+      __syncthreads();
+      const float* wr = p.w + ((long long)clip * T + t) * Te;
+      float dot = 0.0f;
+      for (int jj = tid; jj < len; jj += kChainThreads) dot = fmaf(wr[jj], dw[jj], dot);
+      dot = block_sum(dot, red);
+      for (int jj = tid; jj < Te; jj += kChainThreads) {
+        const float d = jj < len ? wr[jj] * (dw[jj] - dot) : 0.0f;
+        if (jj < len) dw[jj] = d;
+        p.ds[((long long)clip * T + t) * Te + jj] = d;
+      }
+      __syncthreads();
+      const float qa = qps[tid];
+      float s = 0.0f;
+      for (int jj = 0; jj < len; ++jj) {
+        const float th = tanhf(Ps[(size_t)jj * A + tid] + qa);
+        s = fmaf(dw[jj] * va, 1.0f - th * th, s);
+      }
+      p.dqp[((long long)clip * T + t) * A + tid] = s;
+    }
+    if (t > 0) grid_sync(gb);
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+template <typename Kern, typename P>
+inline int launch_chain(Kern kern, size_t smem, cudaStream_t st, const P& p, const char* name) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(kChainCtas);
+  cfg.blockDim = dim3(kChainThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) return set_error(name, cudaGetErrorString(e));
+  return 0;
+}
+
+// Can the persistent chains run this problem?  (E == A == 256, batch <= 32 rows, the clip's projected memory
+// and memory fit in shared memory, and all kChainCtas CTAs are co-resident.)
+inline bool chain_supported(int N, int T, int Te, int E, int A) {
+  if (E != kChainE || A != kChainE || N > kChainMaxN || N > kChainCtas || T < 1) return false;
+  static int ok = -1;
+  static int max_te = 0;
+  if (ok < 0) {
+    ok = 0;
+    const char* env = getenv("ACVAE_DISABLE_CHAIN");
+    int dev = 0, sms = 0, coop = 0, optin = 0;
+    if (!(env && env[0] == '1') && cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess && coop && sms >= kChainCtas) {
+      // largest Te whose resident clip fits next to the weight slices
+      max_te = (int)(((size_t)optin / sizeof(float) - (2 * 4 + 2 * 3 + 2 + 12 + 2) * kChainE - 256) / (2 * kChainE + 1));   // ~97 on B200
+      if (cudaFuncSetAttribute(dec_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) == cudaSuccess &&
+          cudaFuncSetAttribute(dec_chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) == cudaSuccess)
+        ok = 1;
+    }
+  }
+  return ok == 1 && Te <= max_te;
+}
+
+}  // namespace acvae

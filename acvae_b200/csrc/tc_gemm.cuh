@@ -213,7 +213,11 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
 
   const int nblk0 = (tp.seg[0].K + kTcBK - 1) / kTcBK;
   const int nblk1 = tp.nseg > 1 ? (tp.seg[1].K + kTcBK - 1) / kTcBK : 0;
-  const int total = nblk0 + nblk1;
+  // split-K: grid.z CTAs share one output tile, each owns a contiguous range of k-blocks and adds its partial
+  // tile with atomics (few-tile, long-K shapes such as dH = dlogits.W would otherwise use 10 of 148 SMs)
+  const int per_split = (nblk0 + nblk1 + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int i0 = (int)blockIdx.z * per_split;
+  const int total = min(nblk0 + nblk1, i0 + per_split) - i0;      // k-blocks of this CTA (>= 1 by construction)
 
   float acc_reg[kTcBN / 2];   // only the accumulator warps (8..15) touch it
   if (wid == 0) {
@@ -221,9 +225,9 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
     int st = 0, par = 0;                        // parity of the `empty` phase to wait for (first pass: no wait)
     for (int i = 0; i < total; ++i) {
       if (i >= kTcStages) mbar_wait(&empty[st], par);
-      const bool s1 = i >= nblk0;
+      const bool s1 = i0 + i >= nblk0;
       const TcSeg& sg = tp.seg[s1 ? 1 : 0];
-      const int kb = (s1 ? i - nblk0 : i) * kTcBK;
+      const int kb = (s1 ? i0 + i - nblk0 : i0 + i) * kTcBK;
       const CUtensorMap* ma = s1 ? &mapA1 : &mapA0;
       const CUtensorMap* mb = s1 ? &mapB1 : &mapB0;
       uint8_t* sa = smem + st * kTcStageBytes;
@@ -270,7 +274,7 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
       mbar_wait(&ready[st], par);
       tc_fence_after();
       if (elect_one()) {
-        const int s = i >= nblk0 ? 1 : 0;
+        const int s = i0 + i >= nblk0 ? 1 : 0;
         const uint64_t dah = a_tmpl[s] + (uint64_t)(ring + (uint32_t)(st * (kTcStageBytes >> 4)));
         const uint64_t dal = dah + (kTcTileBytes >> 4);
         const uint64_t dbh = b_tmpl[s] + (uint64_t)(ring + (uint32_t)(st * (kTcStageBytes >> 4)) + 2 * (kTcTileBytes >> 4));
@@ -323,9 +327,9 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
     int st = 0, par = 0;
     for (int i = 0; i < total; ++i) {
       mbar_wait(&full[st], par);
-      const bool s1 = i >= nblk0;
+      const bool s1 = i0 + i >= nblk0;
       const TcSeg& sg = tp.seg[s1 ? 1 : 0];
-      const int kb = (s1 ? i - nblk0 : i) * kTcBK;
+      const int kb = (s1 ? i0 + i - nblk0 : i0 + i) * kTcBK;
       uint4* hiA = reinterpret_cast<uint4*>(smem + st * kTcStageBytes);
       uint4* loA = hiA + kTcTileBytes / 16;
       uint4* hiB = loA + kTcTileBytes / 16;
@@ -459,7 +463,23 @@ inline int try_launch_tc(const GemmParams& p, cudaStream_t st) {
     configured = true;
   }
   dim3 grid((NC + kTcBN - 1) / kTcBN, (p.M + kTcBM - 1) / kTcBM);
-  ACVAE_LAUNCH((tc_gemm_kernel<EPI>), grid, kTcThreads, kTcSmemBytes, st, p, tp, maps[0], maps[1], maps[2], maps[3]);
+  GemmParams pl = p;
+  if constexpr (EPI == EPI_PLAIN) {
+    int nblk = 0;
+    for (int s = 0; s < p.nseg; ++s) nblk += (p.seg[s].K + kTcBK - 1) / kTcBK;
+    const int tiles = (int)(grid.x * grid.y);
+    int splits = 148 / tiles;                       // fill the machine once
+    if (splits > nblk / 8) splits = nblk / 8;       // at least 8 k-blocks per CTA
+    if (splits >= 2) {
+      const int per = (nblk + splits - 1) / splits;
+      splits = (nblk + per - 1) / per;              // no empty CTA
+      grid.z = splits;
+      pl.epi.atomic = 1;
+      if (!p.epi.accumulate)
+        ACVAE_CHECK(cudaMemset2DAsync(p.epi.c[0], (size_t)p.epi.ldc * sizeof(float), 0, (size_t)NC * sizeof(float), (size_t)p.M, st));
+    }
+  }
+  ACVAE_LAUNCH((tc_gemm_kernel<EPI>), grid, kTcThreads, kTcSmemBytes, st, pl, tp, maps[0], maps[1], maps[2], maps[3]);
   return 1;
 }
 

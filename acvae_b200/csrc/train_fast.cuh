@@ -7,6 +7,7 @@
 //   * pointwise backward steps are fused into the epilogue of the GEMM that produces their input, so
 //     a reverse step is 3 launches (decoder), 2 (prior) or 1 per direction (posterior).
 #pragma once
+#include "recurrent.cuh"
 #include "streams.cuh"
 #include "train.cuh"
 
@@ -27,6 +28,8 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   const long long s1 = T;
   cudaStream_t sq0 = ax->s[0], sq1 = ax->s[1], sp = ax->s[2];
 
+  const bool chain = chain_supported(N, T, Te, E, A);   // persistent recurrent-chain kernels (recurrent.cuh)
+  if (chain) ACVAE_CHECK(cudaMemsetAsync(ws.bars, 0, 8 * 128 * sizeof(unsigned), st));
   ACVAE_LAUNCH(steplens_kernel, grid1d(N), 256, 0, st, N, io.cap_lens, ws.steplens);
   ACVAE_LAUNCH(qids_kernel, grid1d(NT), 256, 0, st, N, T, d.L, io.caps_ids, ws.qids);
   ACVAE_LAUNCH(words_init_kernel, grid1d(NT), 256, 0, st, N, T, d.L, io.caps_ids, flag_mask(io.tf_flags, T), kStartIdx,
@@ -40,6 +43,7 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   cudaStream_t sq[2] = {sq0, sq1};
   for (int dir = 0; dir < 2; ++dir) {
     ACVAE_TRY(linear_fwd(NT, 3 * E, E, ws.xq, E, w.q_wih[dir], E, w.q_bih[dir], ws.gxq[dir], 3 * E, sq[dir]));
+    if (chain) continue;
     for (int s = 0; s < T; ++s) {
       const int t = dir == 0 ? s : T - 1 - s;
       const int tp = dir == 0 ? t - 1 : t + 1;
@@ -61,6 +65,12 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     }
   }
   ACVAE_TRY(stream_dep(sq1, sq0, ax));
+  if (chain) {
+    PostChainFwd pc{};
+    pc.N = N; pc.T = T; pc.lens = ws.steplens; pc.ho = ws.ho; pc.bar = ws.bars + 0 * 128;
+    for (int dir = 0; dir < 2; ++dir) { pc.gx[dir] = ws.gxq[dir]; pc.whh[dir] = w.q_whh[dir]; pc.bhh[dir] = w.q_bhh[dir]; pc.gq[dir] = ws.gq[dir]; }
+    ACVAE_TRY(launch_chain(post_chain_fwd_kernel, 0, sq0, pc, "post_chain_fwd_kernel"));
+  }
   {
     GemmParams h{};
     h.M = NT; h.U = E; h.G = 2; h.nseg = 1;
@@ -96,7 +106,15 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     g.epi.c[0] = ws.dg_p; g.epi.ldc = 4 * E; g.epi.bias[0] = w.p_bih; g.epi.scale = 1.0f;   // dg_p doubles as gx_p in the forward
     ACVAE_TRY(launch_gemm<EPI_PLAIN>(g, sp));
   }
-  for (int t = 0; t < T; ++t) {
+  if (chain) {
+    PriorChainFwd pc{};
+    pc.N = N; pc.T = T; pc.gx = ws.dg_p; pc.wih = w.p_wih; pc.whh = w.p_whh; pc.bhh = w.p_bhh;
+    pc.head_w = w.p_head_w; pc.head_b = w.p_head_b; pc.eps = io.eps_p;
+    pc.gates = ws.gates_p; pc.c = ws.c_p; pc.h = ws.h_p; pc.pm = io.p_means; pc.pl = io.p_logs; pc.pz = io.p_z;
+    pc.bar = ws.bars + 1 * 128;
+    ACVAE_TRY(launch_chain(prior_chain_fwd_kernel, 0, sp, pc, "prior_chain_fwd_kernel"));
+  }
+  for (int t = 0; t < T && !chain; ++t) {
     GemmParams g{};
     g.M = N; g.U = E; g.G = 4; g.nseg = 0;
     if (t > 0) {
@@ -134,7 +152,15 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     g.epi.c[0] = ws.dgi_d; g.epi.ldc = 3 * E; g.epi.bias[0] = w.d_bih; g.epi.scale = 1.0f;
     ACVAE_TRY(launch_gemm<EPI_PLAIN>(g, st));
   }
-  for (int t = 0; t < T; ++t) {
+  if (chain) {
+    DecChainFwd dc{};
+    dc.N = N; dc.T = T; dc.Te = Te; dc.gx = ws.dgi_d; dc.attn_w = w.d_attn_w; dc.attn_v = w.d_attn_v;
+    dc.wih = w.d_wih; dc.whh = w.d_whh; dc.bhh = w.d_bhh; dc.Pd = ws.Pd; dc.mem = ws.mem; dc.mem_lens = io.mem_lens;
+    dc.qp = ws.qp_d; dc.w = ws.w_d; dc.ctx = ws.ctx_d; dc.gates = ws.gates_d; dc.out = io.outputs; dc.aw = io.attn_weights;
+    dc.bar = ws.bars + 2 * 128;
+    ACVAE_TRY(launch_chain(dec_chain_fwd_kernel, dec_chain_fwd_smem(Te), st, dc, "dec_chain_fwd_kernel"));
+  }
+  for (int t = 0; t < T && !chain; ++t) {
     const float* hprev = t > 0 ? io.outputs + (long long)(t - 1) * E : nullptr;
     GemmParams qg{};
     qg.M = N; qg.U = A; qg.G = 1; qg.nseg = hprev ? 1 : 0;
@@ -199,9 +225,18 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   const long long s1 = T;
   cudaStream_t sp = ax->s[2], sx = ax->s[3], sq0 = ax->s[0], sq1 = ax->s[1];
   auto zero = [&](float* p, size_t n, cudaStream_t s) { return cudaMemsetAsync(p, 0, n * sizeof(float), s); };
+  const bool chain = chain_supported(N, T, Te, E, A);   // persistent recurrent-chain kernels (recurrent.cuh)
+  if (chain) ACVAE_CHECK(cudaMemsetAsync(ws.bars + 4 * 128, 0, 4 * 128 * sizeof(unsigned), st));
   ACVAE_TRY(stream_dep(st, sp, ax));
 
   // ================= prior BPTT on its own stream (KL gradients only: dis_ratio == 0) ====================
+  if (chain) {
+    PriorChainBwd pc{};
+    pc.N = N; pc.T = T; pc.d_pz = gi.d_p_z; pc.d_pm = gi.d_p_means; pc.d_pl = gi.d_p_logs; pc.eps = io.eps_p;
+    pc.p_logs = io.p_logs; pc.head_w = w.p_head_w; pc.wih = w.p_wih; pc.whh = w.p_whh; pc.gates = ws.gates_p; pc.c = ws.c_p;
+    pc.dml = ws.dml_p; pc.dg = ws.dg_p; pc.bar = ws.bars + 4 * 128;
+    ACVAE_TRY(launch_chain(prior_chain_bwd_kernel, 0, sp, pc, "prior_chain_bwd_kernel"));
+  } else
   {
     // step T-1 head backward (standalone), then per step: [dh GEMM + LSTM pointwise] -> [dz|dh GEMM + head pointwise]
     HeadBwdParams h{};
@@ -215,7 +250,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     h.dml = ws.dml_p + (long long)t * 2 * E; h.ld_dml = s1 * 2 * E;
     ACVAE_LAUNCH(head_bwd_kernel, grid1d((long long)N * E), 256, 0, sp, h);
   }
-  for (int t = T - 1; t >= 0; --t) {
+  for (int t = T - 1; t >= 0 && !chain; --t) {
     GemmParams p{};
     p.M = N; p.U = E; p.G = 1; p.nseg = 1;
     GemmSeg s{};
@@ -294,6 +329,14 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   }
   ACVAE_LAUNCH(pool_bwd_kernel, grid1d((long long)NT * E), 256, 0, st, N, T, E, dpool, ws.steplens, 0, ws.amax_d,
                gi.d_outputs, ws.dout);
+  if (chain) {
+    DecChainBwd dc{};
+    dc.N = N; dc.T = T; dc.Te = Te; dc.dout = ws.dout; dc.attn_w = w.d_attn_w; dc.attn_v = w.d_attn_v; dc.wih = w.d_wih;
+    dc.whh = w.d_whh; dc.Pd = ws.Pd; dc.mem = ws.mem; dc.mem_lens = io.mem_lens; dc.qp = ws.qp_d; dc.w = ws.w_d;
+    dc.gates = ws.gates_d; dc.out = io.outputs; dc.dgi = ws.dgi_d; dc.dgh = ws.dgh_d; dc.dctx = ws.dctx_d; dc.ds = ws.ds_d;
+    dc.dqp = ws.dqp_d; dc.bar = ws.bars + 5 * 128;
+    ACVAE_TRY(launch_chain(dec_chain_bwd_kernel, dec_chain_bwd_smem(Te), st, dc, "dec_chain_bwd_kernel"));
+  } else
   {
     GruBwdParams g{};
     const int t = T - 1;
@@ -306,7 +349,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     g.dh_out = ws.dh_carry;
     ACVAE_LAUNCH(gru_bwd_kernel, grid1d((long long)N * E), 256, 0, st, g);
   }
-  for (int t = T - 1; t >= 0; --t) {
+  for (int t = T - 1; t >= 0 && !chain; --t) {
     ACVAE_TRY(linear_bwd_data(N, E, 3 * E, ws.dgi_d + (long long)t * 3 * E, s1 * 3 * E, w.d_wih + E, 3 * E,
                               ws.dctx_d + (long long)t * E, s1 * E, st));
     AttnBwdQParams a{};
@@ -400,9 +443,16 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   ACVAE_TRY(colsum(NT, 2 * E, ws.dml_q, 2 * E, gw.q_head_b, st));
   cudaStream_t sq[2] = {sq0, sq1};
   float* carry[2] = {ws.dhq_carry, ws.dzq_carry};   // one carry buffer per direction
+  if (chain) {
+    PostChainBwd pc{};
+    pc.N = N; pc.T = T; pc.dho = ws.dho; pc.ho = ws.ho; pc.lens = ws.steplens; pc.bar = ws.bars + 6 * 128;
+    for (int dir = 0; dir < 2; ++dir) { pc.whh[dir] = w.q_whh[dir]; pc.gq[dir] = ws.gq[dir]; pc.dgi[dir] = ws.dgi_q[dir]; pc.dgh[dir] = ws.dgh_q[dir]; }
+    ACVAE_TRY(launch_chain(post_chain_bwd_kernel, 0, sq0, pc, "post_chain_bwd_kernel"));
+    ACVAE_TRY(stream_dep(sq0, sq1, ax));
+  }
   for (int dir = 0; dir < 2; ++dir) {
     cudaStream_t s_ = sq[dir];
-    {
+    if (!chain) {
       const int s = T - 1;
       const int t = dir == 0 ? s : T - 1 - s;
       const int tp = dir == 0 ? t - 1 : t + 1;
@@ -417,7 +467,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
       g.dh_out = carry[dir];
       ACVAE_LAUNCH(gru_bwd_kernel, grid1d((long long)N * E), 256, 0, s_, g);
     }
-    for (int s = T - 1; s > 0; --s) {
+    for (int s = T - 1; s > 0 && !chain; --s) {
       const int t = dir == 0 ? s : T - 1 - s;            // step whose dGh is propagated
       const int tm = dir == 0 ? t - 1 : t + 1;            // the step before it in this direction's forward order
       const int sm = s - 1;                               // its position in forward order

@@ -121,8 +121,11 @@ class TrainMeta:
     """Non-tensor inputs of one training forward (ids, lengths, noise, decisions)."""
 
     def __init__(self, dims, keys, caps_ids, cap_lens, mem_lens, eps_q, eps_p, tf_flags, dis_flags,
-                 want_logits=False):
+                 want_logits=False, grad_sink=None):
         self.dims, self.keys = dims, list(keys)
+        #: optional {state_dict key: tensor}: the backward WRITES (overwrites) that weight's gradient straight
+        #: into the given tensor (a view of a flat all-reduce buffer) and returns None for it to autograd
+        self.grad_sink = grad_sink
         self.caps_ids, self.cap_lens, self.mem_lens = caps_ids, cap_lens, mem_lens
         self.eps_q, self.eps_p = eps_q, eps_p
         self.tf_flags = np.ascontiguousarray(np.asarray(tf_flags, dtype=np.uint8))
@@ -210,19 +213,30 @@ class LatentDecodeTrainFn(torch.autograd.Function):
             gt = gt.contiguous()
             keep.append(gt)
             setattr(gin, name, _dev(gt))
-        # one flat gradient buffer, carved per weight (a single NCCL all-reduce can cover it)
-        sizes = [ctx.wmap[k].numel() for k in meta.keys]
-        offs = np.concatenate([[0], np.cumsum([(s + 63) // 64 * 64 for s in sizes])])
-        flat = torch.zeros(int(offs[-1]), dtype=torch.float32, device=dev)
-        gmap = {k: flat[int(offs[i]):int(offs[i]) + sizes[i]].view_as(ctx.wmap[k]) for i, k in enumerate(meta.keys)}
-        gstruct = pack_weights(gmap, _lib.WeightGrads)
+        # one flat gradient buffer, carved per weight (a single NCCL all-reduce can cover it); weights with a
+        # caller-provided sink are written in place there instead
+        sink = meta.grad_sink or {}
+        own = [k for k in meta.keys if k not in sink and not k.startswith("decoder.classifier")]
+        sizes = [ctx.wmap[k].numel() for k in own]
+        offs = np.concatenate([[0], np.cumsum([(s + 63) // 64 * 64 for s in sizes])]) if own else np.zeros(1)
+        gmap = {}
+        if own:
+            flat = torch.zeros(int(offs[-1]), dtype=torch.float32, device=dev)
+            gmap = {k: flat[int(offs[i]):int(offs[i]) + sizes[i]].view_as(ctx.wmap[k]) for i, k in enumerate(own)}
+        for k, t in sink.items():
+            if k in ctx.wmap:
+                if t.shape != ctx.wmap[k].shape or not t.is_contiguous():
+                    raise RuntimeError(f"grad sink for {k} must be a contiguous tensor of the weight's shape")
+                gmap[k] = t
+        # cls_w / cls_b are produced by VocabCEFn (acvae_vocab_ce_bwd), never here
+        gstruct = pack_weights({k: v for k, v in gmap.items() if not k.startswith("decoder.classifier")}, _lib.WeightGrads)
         d_audio = torch.empty_like(ctx.audio) if ctx.need_audio_grad else None
         wstruct = pack_weights(ctx.wmap)
         _lib.check(l.acvae_train_bwd(C.byref(d), C.byref(wstruct), C.byref(ctx.io), C.byref(gin), C.byref(gstruct),
                                      _opt(d_audio), ctx.ws.data_ptr(), ctx.ws.numel(), _stream()), "acvae_train_bwd")
         grads = []
         for k in meta.keys:
-            grads.append(None if k.startswith("decoder.classifier") else gmap[k])
+            grads.append(None if (k.startswith("decoder.classifier") or k in sink) else gmap[k])
         return (None, d_audio, *grads)
 
 
@@ -266,8 +280,9 @@ class VocabCEFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, hidden, cls_w, cls_b, targets, smoothing, row_lse, row_sum):
+    def forward(ctx, hidden, cls_w, cls_b, targets, smoothing, row_lse, row_sum, grad_sink=None):
         l = _lib.lib()
+        ctx.grad_sink = grad_sink     # optional (dW, db) tensors written in place (see TrainMeta.grad_sink)
         h2 = hidden.contiguous()
         M, E = h2.shape
         V = cls_w.shape[0]
@@ -296,12 +311,18 @@ class VocabCEFn(torch.autograd.Function):
         M, E = h2.shape
         V = w.shape[0]
         g = g.contiguous().to(torch.float32)
-        dh = torch.empty_like(h2); dw = torch.empty_like(w)
-        db = torch.empty(V, dtype=torch.float32, device=h2.device)
+        dh = torch.empty_like(h2)
+        if ctx.grad_sink is not None:
+            dw, db = ctx.grad_sink
+        else:
+            dw = torch.empty_like(w)
+            db = torch.empty(V, dtype=torch.float32, device=h2.device)
         _lib.check(l.acvae_vocab_ce_bwd(M, V, E, _dev(h2), _dev(w), _dev(b), _dev(tg, torch.int32), None, ctx.smoothing,
                                         _dev(row_lse), _dev(g), _dev(dh), _dev(dw), _dev(db),
                                         ctx.ws.data_ptr(), ctx.ws.numel(), _stream()), "acvae_vocab_ce_bwd")
-        return dh, dw, db, None, None, None, None
+        if ctx.grad_sink is not None:
+            return dh, None, None, None, None, None, None, None
+        return dh, dw, db, None, None, None, None, None
 
 
 class NormalKLFn(torch.autograd.Function):

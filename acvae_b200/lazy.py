@@ -21,11 +21,41 @@ import torch
 from . import functional as F
 
 
+_PACK_CACHE = {}
+
+
+def _pack_index(lengths, d0, d1, batch_first, device):
+    """Flat row indices of `pack_padded_sequence(x, lengths, batch_first)` into x.reshape(d0*d1, ...) and the
+    PackedSequence batch_sizes (CPU int64).  lengths: CPU int64, sorted descending (enforce_sorted=True)."""
+    lens = [int(v) for v in torch.as_tensor(lengths).tolist()]
+    key = (tuple(lens), d0, d1, batch_first, str(device))
+    hit = _PACK_CACHE.get(key)
+    if hit is not None:
+        return hit
+    if any(lens[i] < lens[i + 1] for i in range(len(lens) - 1)) or (lens and lens[-1] <= 0):
+        raise RuntimeError("`lengths` array must be sorted in decreasing order and positive (enforce_sorted=True)")
+    T = lens[0] if lens else 0
+    idx, bs = [], []
+    for t in range(T):
+        n_t = sum(1 for v in lens if v > t)
+        bs.append(n_t)
+        if batch_first:
+            idx.extend(n * d1 + t for n in range(n_t))
+        else:
+            idx.extend(t * d1 + n for n in range(n_t))
+    out = (torch.tensor(idx, dtype=torch.int64).to(device), torch.tensor(bs, dtype=torch.int64))
+    if len(_PACK_CACHE) > 256:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = out
+    return out
+
+
 class LazyLogits:
     def __init__(self, hidden, cls_w, cls_b, row_lse=None, row_sum=None):
         self.hidden, self.cls_w, self.cls_b = hidden, cls_w, cls_b
         self.row_lse, self.row_sum = row_lse, row_sum
         self._dense = None
+        self.grad_sink = None       # optional (dW, db) destination of the fused CE backward
 
     # ---- tensor-like surface -----------------------------------------------------
     @property
@@ -81,13 +111,17 @@ class LazyLogits:
         name = getattr(func, "__name__", "")
         if name == "_pack_padded_sequence":
             lazy, lengths, batch_first = args[0], args[1], (args[2] if len(args) > 2 else kwargs.get("batch_first", False))
-            hid, bs = func(lazy.hidden, lengths, batch_first)
+            # row-wise Linear commutes with packing: gather the hidden rows (and their statistics) in packed
+            # order with ONE index_select each instead of the per-time-step copies of the stock pack kernel
+            idx, bs = _pack_index(lengths, lazy.hidden.shape[0], lazy.hidden.shape[1], bool(batch_first), lazy.hidden.device)
+            hid = lazy.hidden.reshape(-1, lazy.hidden.shape[-1]).index_select(0, idx)
             lse = ssum = None
             if lazy.row_lse is not None:
-                lse, _ = func(lazy.row_lse.unsqueeze(-1), lengths, batch_first)
-                ssum, _ = func(lazy.row_sum.unsqueeze(-1), lengths, batch_first)
-                lse, ssum = lse.squeeze(-1), ssum.squeeze(-1)
-            return LazyLogits(hid, lazy.cls_w, lazy.cls_b, lse, ssum), bs
+                lse = lazy.row_lse.reshape(-1).index_select(0, idx)
+                ssum = lazy.row_sum.reshape(-1).index_select(0, idx)
+            packed = LazyLogits(hid, lazy.cls_w, lazy.cls_b, lse, ssum)
+            packed.grad_sink = lazy.grad_sink
+            return packed, bs
 
         def dense(x):
             return x.materialize() if isinstance(x, LazyLogits) else x

@@ -189,6 +189,10 @@ class _FusedVAEBase(CaptionModel):
     noise_source = "device"
     #: False: output["logits"] is a LazyLogits handle; True: a dense [N,T,V] tensor
     materialize_logits = False
+    #: optional `parallel.FlatGradBuffer`: the fused backward then writes every hot-path weight gradient straight
+    #: into the flat all-reduce buffer (OVERWRITE semantics: one backward per optimiser step) instead of handing
+    #: ~35 tensors to autograd for accumulation
+    grad_sink = None
 
     def __init__(self, Audioencoder, Textdecoder, **kwargs):
         super().__init__(Audioencoder, Textdecoder, **kwargs)
@@ -296,11 +300,16 @@ class _FusedVAEBase(CaptionModel):
         weights = self._hot_weights()
         keys = list(weights.keys())
         dims = self._dims(N, Te, T, L)
+        sink = None
+        if self.grad_sink is not None and torch.is_grad_enabled():
+            sink = self.grad_sink.views_for(self, prefix_skip="encoder.")
         meta = F.TrainMeta(dims, keys, caps_ids, cap_lens_dev, mem_lens, eps_q, eps_p, tf_flags, dis_flags,
-                           want_logits=False)
+                           want_logits=False, grad_sink=sink)
         (q_means, q_logs, q_z, p_means, p_logs, p_z, outputs, q_utt, p_utt, attn_w, seqs, slp, lse, lsum, rnn_input,
          _logits) = F.LatentDecodeTrainFn.apply(meta, audio, *[weights[k] for k in keys])
         lazy = LazyLogits(outputs, self.decoder.classifier.weight, self.decoder.classifier.bias, lse, lsum)
+        if sink is not None and "decoder.classifier.weight" in sink:
+            lazy.grad_sink = (sink["decoder.classifier.weight"], sink["decoder.classifier.bias"])
         out = {
             "seqs": seqs, "logits": lazy.materialize() if self.materialize_logits else lazy,
             "outputs": outputs, "sampled_logprobs": slp, "attn_weights": attn_w,

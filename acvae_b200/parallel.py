@@ -35,6 +35,15 @@ class FlatGradBuffer:
         for p, o in zip(self.params, self.offsets):
             p.grad = self.flat[o:o + p.numel()].view_as(p)
 
+    def views_for(self, module: torch.nn.Module, prefix_skip: str = ""):
+        """{state_dict key: grad view} for `module`'s parameters held by this buffer (the gradient sink the fused
+        backward writes into, `Hybrid_VAEModel.grad_sink`)."""
+        if getattr(self, "_views_cache", None) is None:
+            by_id = {id(p): self.flat[o:o + p.numel()].view_as(p) for p, o in zip(self.params, self.offsets)}
+            self._views_cache = {k: by_id[id(p)] for k, p in module.named_parameters()
+                                 if id(p) in by_id and not (prefix_skip and k.startswith(prefix_skip))}
+        return self._views_cache
+
     def zero(self) -> None:
         self.flat.zero_()
 

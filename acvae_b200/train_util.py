@@ -28,7 +28,7 @@ class LabelSmoothingLoss(torch.nn.Module):
             if logit.dim() != 2:
                 raise ValueError("fused CE expects packed rows [M,V] (pack_padded_sequence(...).data)")
             return F.VocabCEFn.apply(logit.hidden, logit.cls_w, logit.cls_b, target, self.smoothing,
-                                     logit.row_lse, logit.row_sum)
+                                     logit.row_lse, logit.row_sum, logit.grad_sink)
         pred = logit.log_softmax(dim=self.dim)
         with torch.no_grad():
             true_dist = torch.zeros_like(pred)
@@ -43,7 +43,8 @@ class CrossEntropyLoss(torch.nn.Module):
 
     def forward(self, logit, target):
         if isinstance(logit, LazyLogits):
-            return F.VocabCEFn.apply(logit.hidden, logit.cls_w, logit.cls_b, target, 0.0, logit.row_lse, logit.row_sum)
+            return F.VocabCEFn.apply(logit.hidden, logit.cls_w, logit.cls_b, target, 0.0, logit.row_lse, logit.row_sum,
+                                     logit.grad_sink)
         return torch.nn.functional.cross_entropy(logit, target.long().to(logit.device))
 
 

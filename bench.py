@@ -105,6 +105,7 @@ def make_train_step(dev, world, rank, use_graph=True):
     model = harness.build_model(d, seed=1, device=dev).train()
     n_params = sum(p.numel() for p in model.parameters())
     flat = parallel.FlatGradBuffer(model.parameters())
+    model.grad_sink = flat          # fused backward writes weight gradients straight into the all-reduce buffer
     opt = torch.optim.Adam(model.parameters(), lr=LR, fused=True, capturable=True)
     crit = models.LabelSmoothingLoss(d.V, smoothing=SMOOTHING, device=dev)
     klf = models.Normal_kl_loss(device=dev)

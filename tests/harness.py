@@ -83,7 +83,7 @@ def build_model(d, seed, variant="hybrid", device="cuda"):
 
 
 def run_cuda_train(d, seed, ss_ratio=1.0, dis_ratio=0.0, variant="hybrid", smoothing=0.1, kl_weight=0.5, alpha=1.0,
-                   dense_logits=False, backward=True, model=None):
+                   dense_logits=False, backward=True, model=None, keep_grads=False):
     """Runner._forward(mode="train") + loss composition + backward on the product."""
     import acvae_b200 as models
     dev = "cuda"
@@ -92,7 +92,8 @@ def run_cuda_train(d, seed, ss_ratio=1.0, dis_ratio=0.0, variant="hybrid", smoot
     tf, dis = flags_for(b, T, ss_ratio, dis_ratio)
     m = model if model is not None else build_model(d, seed, variant, dev)
     m.train()
-    m.zero_grad(set_to_none=True)
+    if not keep_grads:
+        m.zero_grad(set_to_none=True)
     m.materialize_logits = dense_logits
     feats = torch.from_numpy(b["audio_embeds"]).to(dev).requires_grad_(backward)
     caps = torch.from_numpy(b["caps"])                     # float32 on the CPU, as the collate_fn leaves it

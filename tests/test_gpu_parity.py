@@ -97,6 +97,26 @@ def test_train_dense_logits_path_matches_fused():
         assert harness.rel_err(a["grads"][k], b["grads"][k]) < 1e-4, k
 
 
+def test_train_grad_sink_matches_autograd():
+    """DP fast path: gradients written straight into the flat all-reduce buffer == autograd-accumulated ones."""
+    _require_cuda()
+    from acvae_b200 import parallel
+    d = synthetic.CFG0
+    a = harness.run_cuda_train(d, 5)
+    m = harness.build_model(d, 5)
+    flat = parallel.FlatGradBuffer(m.parameters())
+    m.grad_sink = flat
+    b = harness.run_cuda_train(d, 5, model=m, keep_grads=True)
+    assert abs(float(a["terms"]["loss"]) - float(b["terms"]["loss"])) < 1e-6
+    for k, p in m.named_parameters():
+        assert p.grad.data_ptr() == flat.views_for(m)[k].data_ptr(), k        # still the flat views
+        assert harness.rel_err(p.grad, a["grads"][k]) < 1e-5, k
+    # nothing may land in the padding between the views: the flat 2-norm is the global gradient norm (clip)
+    total = float(flat.flat.double().pow(2).sum())
+    parts = sum(float(v.double().pow(2).sum()) for v in flat.views_for(m).values())
+    assert abs(total - parts) <= 1e-9 * total, (total, parts)
+
+
 def test_train_ragged_edges_vs_oracle():
     """min-length caption (<start>,<end>), a one-frame clip, odd sizes (N=5, Te=7, V=37)."""
     _require_cuda()
