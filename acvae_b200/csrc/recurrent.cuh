@@ -8,7 +8,7 @@
 //   * per step a CTA reads the [N, K] state rows written by all CTAs in the previous phase (L2, ld.cg),
 //     computes its columns for all N rows (8-way K split inside a row group, shuffle-reduced), applies the
 //     cell arithmetic in registers and writes its units;
-//   * phases are separated by a grid barrier (one global atomic counter, release/acquire);
+//   * phases are separated by a grid barrier (one global atomic counter);
 //   * per-unit carries (dh*z, dc*f, ...) never leave registers: the unit partition is the same in every phase.
 // The decoder chains add a per-clip phase: CTA c keeps clip c's projected memory P_d[c] and memory mem[c]
 // resident in shared memory (Te*(A+E)*4 bytes) and runs the additive attention / its backward for that clip.
@@ -27,38 +27,26 @@ constexpr int kChainThreads = 256;           // thread = (row n = tid / 8, K-sli
 constexpr int kChainMaxN = kChainThreads / 8;
 
 struct GridBar {
-  unsigned* flags;    // [nctas] one arrival flag per CTA (zeroed before the launch)
-  unsigned epoch;
-  unsigned nctas;     // <= 128
+  unsigned* counter;  // one arrival counter (zeroed before the launch); the target grows by nctas per barrier
+  unsigned target;
+  unsigned nctas;
 };
-// Barrier over all CTAs of the (cooperatively launched, hence co-resident) grid, without atomics: CTA b
-// publishes the epoch it has reached in flags[b] (fence + volatile store), warp 0 of every CTA polls all flags
-// (volatile loads, 4 per lane, one fence after the last poll).  Same-address L2 atomics serialise at ~27 cycles each, which made a 128-CTA
-// counter barrier cost ~2 us; distinct flags cost one L2 write + one L2 read round trip.
-// Writes made by any thread of a CTA before the barrier are visible to every thread of every CTA after it
-// (bar.sync -> release store; acquire loads -> bar.sync).  Cross-CTA data is read with ld.global.cg (L1 is not
-// coherent).  A protocol bug traps instead of hanging the GPU.
+// Barrier over all CTAs of the (cooperatively launched, hence co-resident) grid: bar.sync; thread 0: gpu-scope
+// fence, atomic increment, volatile polling of the counter, fence; bar.sync.  Measured on B200 with 128 CTAs
+// (profiles/ubench_gridbar.cu): 2500 cycles for this form, 5200 for per-CTA flags polled by every CTA (hot L2
+// lines), 8800 with a store before / loads after it.  Writes made by any thread of a CTA before the barrier are
+// visible to every thread of every CTA after it; cross-CTA data is read with ld.global.cg (L1 is not coherent).
+// A protocol bug traps instead of hanging the GPU.
 __device__ __forceinline__ void grid_sync(GridBar& gb) {
   __syncthreads();
-  gb.epoch += 1;
-  if (threadIdx.x < 32) {
-    if (threadIdx.x == 0) {
-      __threadfence();                                                  // release: the CTA's writes before the flag
-      *reinterpret_cast<volatile unsigned*>(gb.flags + blockIdx.x) = gb.epoch;
-    }
+  if (threadIdx.x == 0) {
+    gb.target += gb.nctas;
+    __threadfence();
+    atomicAdd(gb.counter, 1u);
     long long spin = 0;
-    bool done;
-    do {                                                                // plain volatile polls: no fence per iteration
-      done = true;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const unsigned idx = threadIdx.x + 32u * i;
-        if (idx < gb.nctas) done = done && (*reinterpret_cast<volatile unsigned*>(gb.flags + idx) >= gb.epoch);
-      }
-      done = __all_sync(0xffffffffu, done);
+    while (*reinterpret_cast<volatile unsigned*>(gb.counter) < gb.target)
       if (++spin > (1ll << 26)) __trap();
-    } while (!done);
-    __threadfence();                                                    // acquire
+    __threadfence();
   }
   __syncthreads();
 }
@@ -209,81 +197,101 @@ struct PriorChainFwd {
   float *pm, *pl, *pz;   // [N,T,E]
   unsigned* bar;
 };
-__global__ void __launch_bounds__(kChainThreads) prior_chain_fwd_kernel(const __grid_constant__ PriorChainFwd p) {
+// The prior chain as phase functions: used by the stand-alone kernel below and, merged phase by phase, by the
+// decoder kernel (the two chains are independent and have the same barrier structure, and two cooperative
+// kernels never overlap on the device, so sharing the barriers hides the prior chain completely).
+struct PriorFwdRegs { float bh[4]; float hb_m, hb_l, c_prev, eps_t; };
+constexpr int kPriorFwdSmemFloats = 8 * 2 * kChainE + 4 * kChainE;   // Wl[8][2E] | Wh[4][E]
+
+__device__ __forceinline__ void prior_fwd_setup(const PriorChainFwd& p, float* Wl, float* Wh, PriorFwdRegs& r, int u0, int u) {
   constexpr int E = kChainE;
-  __shared__ __align__(16) float Wl[8][2 * E];   // rows g*2+j over K = [last_z | h]
-  __shared__ __align__(16) float Wh[4][E];       // rows (mean j0, mean j1, log j0, log j1)
+  for (int i = threadIdx.x; i < 8 * 2 * E; i += kChainThreads) {        // rows g*2+j over K = [last_z | h]
+    const int rr = i / (2 * E), k = i % (2 * E);
+    const long long wr = (long long)((rr >> 1) * E + u0 + (rr & 1));
+    Wl[i] = k < E ? p.wih[wr * 3 * E + 2 * E + k] : p.whh[wr * E + (k - E)];
+  }
+  for (int i = threadIdx.x; i < 4 * E; i += kChainThreads) {            // rows (mean j0, mean j1, log j0, log j1)
+    const int rr = i / E, k = i % E;
+    Wh[i] = p.head_w[(long long)((rr >> 1) * E + u0 + (rr & 1)) * E + k];
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) r.bh[g] = p.bhh[g * E + u];
+  r.hb_m = p.head_b[u]; r.hb_l = p.head_b[E + u];
+  r.c_prev = 0.0f; r.eps_t = 0.0f;
+}
+// LSTM cell of step t (needs z_{t-1}, h_{t-1} of all units: one barrier after the previous head phase)
+__device__ __forceinline__ void prior_fwd_lstm(const PriorChainFwd& p, const float* Wl, PriorFwdRegs& r, int t, int n, int kp,
+                                               bool row, int j, int u) {
+  constexpr int E = kChainE;
+  const int T = p.T, N = p.N;
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = 0.0f;
+  float gxv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (row && kp < 2) {
+    const float* gx = p.gx + ((long long)n * T + t) * 4 * E + u;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) gxv[g] = ldcg1(gx + g * E);
+    r.eps_t = ldcg1(p.eps + ((long long)t * N + n) * E + u);
+  }
+  if (t > 0) {
+    float4 a0[E / 32], a1[E / 32];
+    if (row) {
+      rowload<E>(p.pz + ((long long)n * T + t - 1) * E, kp, a0);
+      rowload<E>(p.h + ((long long)n * T + t - 1) * E, kp, a1);
+    }
+    __syncwarp();
+    if (row) {
+      rowfma<8, E>(a0, Wl, 2 * E, kp, acc);
+      rowfma<8, E>(a1, Wl + E, 2 * E, kp, acc);
+    }
+    reduce8(acc);
+  }
+  if (row && kp < 2) {
+    const float ig = sigmoidf_((j ? acc[1] : acc[0]) + gxv[0] + r.bh[0]);
+    const float fg = sigmoidf_((j ? acc[3] : acc[2]) + gxv[1] + r.bh[1]);
+    const float gg = tanhf((j ? acc[5] : acc[4]) + gxv[2] + r.bh[2]);
+    const float og = sigmoidf_((j ? acc[7] : acc[6]) + gxv[3] + r.bh[3]);
+    const float cn = fg * r.c_prev + ig * gg;
+    const float hn = og * tanhf(cn);
+    r.c_prev = cn;
+    float* gs = p.gates + ((long long)n * T + t) * 4 * E + u;
+    gs[0] = ig; gs[E] = fg; gs[2 * E] = gg; gs[3 * E] = og;
+    p.c[((long long)n * T + t) * E + u] = cn;
+    p.h[((long long)n * T + t) * E + u] = hn;
+  }
+}
+// Gaussian head + reparameterisation of step t (needs h_t of all units: one barrier after the LSTM phase)
+__device__ __forceinline__ void prior_fwd_head(const PriorChainFwd& p, const float* Wh, PriorFwdRegs& r, int t, int n, int kp,
+                                               bool row, int j, int u) {
+  constexpr int E = kChainE;
+  const int T = p.T;
+  float hc[4] = {0.f, 0.f, 0.f, 0.f};
+  rowdot<4, E>(row, p.h + ((long long)n * T + t) * E, Wh, E, kp, hc);
+  reduce8(hc);
+  if (row && kp < 2) {
+    const float mean = (j ? hc[1] : hc[0]) + r.hb_m;
+    const float lg = (j ? hc[3] : hc[2]) + r.hb_l;
+    const long long o = ((long long)n * T + t) * E + u;
+    p.pm[o] = mean; p.pl[o] = lg; p.pz[o] = r.eps_t * expf(0.5f * lg) + mean;
+  }
+}
+
+__global__ void __launch_bounds__(kChainThreads) prior_chain_fwd_kernel(const __grid_constant__ PriorChainFwd p) {
+  __shared__ __align__(16) float Wsm[kPriorFwdSmemFloats];
+  float* Wl = Wsm; float* Wh = Wsm + 8 * 2 * kChainE;
   const int tid = threadIdx.x, n = tid >> 3, kp = tid & 7;
-  const int u0 = blockIdx.x * 2;
-  for (int i = tid; i < 8 * 2 * E; i += kChainThreads) {
-    const int r = i / (2 * E), k = i % (2 * E);
-    const long long wr = (long long)((r >> 1) * E + u0 + (r & 1));
-    Wl[r][k] = k < E ? p.wih[wr * 3 * E + 2 * E + k] : p.whh[wr * E + (k - E)];
-  }
-  for (int i = tid; i < 4 * E; i += kChainThreads) {
-    const int r = i / E, k = i % E;
-    Wh[r][k] = p.head_w[(long long)((r >> 1) * E + u0 + (r & 1)) * E + k];
-  }
+  const int u0 = blockIdx.x * 2, j = kp & 1, u = u0 + j;
+  PriorFwdRegs r;
+  prior_fwd_setup(p, Wl, Wh, r, u0, u);
   __syncthreads();
   GridBar gb{p.bar, 0u, gridDim.x};
-  const int T = p.T, N = p.N;
-  const bool row = n < N;
-  const int j = kp & 1, u = u0 + j;
-  float bh[4];
-#pragma unroll
-  for (int g = 0; g < 4; ++g) bh[g] = p.bhh[g * E + u];
-  const float hb_m = p.head_b[u], hb_l = p.head_b[E + u];
-  float c_prev = 0.0f;                                  // lanes kp < 2: cell state of unit u, row n
-  for (int t = 0; t < T; ++t) {
-    // ---- LSTM cell ----
-    float acc[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = 0.0f;
-    float gxv[4] = {0.f, 0.f, 0.f, 0.f}, eps_t = 0.f;
-    if (row && kp < 2) {
-      const float* gx = p.gx + ((long long)n * T + t) * 4 * E + u;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) gxv[g] = ldcg1(gx + g * E);
-      eps_t = ldcg1(p.eps + ((long long)t * N + n) * E + u);
-    }
-    if (t > 0) {
-      float4 a0[E / 32], a1[E / 32];
-      if (row) {
-        rowload<E>(p.pz + ((long long)n * T + t - 1) * E, kp, a0);
-        rowload<E>(p.h + ((long long)n * T + t - 1) * E, kp, a1);
-      }
-      __syncwarp();
-      if (row) {
-        rowfma<8, E>(a0, &Wl[0][0], 2 * E, kp, acc);
-        rowfma<8, E>(a1, &Wl[0][E], 2 * E, kp, acc);
-      }
-      reduce8(acc);
-    }
-    if (row && kp < 2) {
-      const float ig = sigmoidf_((j ? acc[1] : acc[0]) + gxv[0] + bh[0]);
-      const float fg = sigmoidf_((j ? acc[3] : acc[2]) + gxv[1] + bh[1]);
-      const float gg = tanhf((j ? acc[5] : acc[4]) + gxv[2] + bh[2]);
-      const float og = sigmoidf_((j ? acc[7] : acc[6]) + gxv[3] + bh[3]);
-      const float cn = fg * c_prev + ig * gg;
-      const float hn = og * tanhf(cn);
-      c_prev = cn;
-      float* gs = p.gates + ((long long)n * T + t) * 4 * E + u;
-      gs[0] = ig; gs[E] = fg; gs[2 * E] = gg; gs[3 * E] = og;
-      p.c[((long long)n * T + t) * E + u] = cn;
-      p.h[((long long)n * T + t) * E + u] = hn;
-    }
+  const bool row = n < p.N;
+  for (int t = 0; t < p.T; ++t) {
+    prior_fwd_lstm(p, Wl, r, t, n, kp, row, j, u);
     grid_sync(gb);
-    // ---- Gaussian head + reparameterisation ----
-    float hc[4] = {0.f, 0.f, 0.f, 0.f};
-    rowdot<4, E>(row, p.h + ((long long)n * T + t) * E, &Wh[0][0], E, kp, hc);
-    reduce8(hc);
-    if (row && kp < 2) {
-      const float mean = (j ? hc[1] : hc[0]) + hb_m;
-      const float lg = (j ? hc[3] : hc[2]) + hb_l;
-      const long long o = ((long long)n * T + t) * E + u;
-      p.pm[o] = mean; p.pl[o] = lg; p.pz[o] = eps_t * expf(0.5f * lg) + mean;
-    }
-    if (t + 1 < T) grid_sync(gb);
+    prior_fwd_head(p, Wh, r, t, n, kp, row, j, u);
+    if (t + 1 < p.T) grid_sync(gb);
   }
 }
 
@@ -373,83 +381,108 @@ struct PriorChainBwd {
   float* dg;                         // [N,T,4E]
   unsigned* bar;
 };
-__global__ void __launch_bounds__(kChainThreads) prior_chain_bwd_kernel(const __grid_constant__ PriorChainBwd p) {
+struct PriorBwdRegs { float dh_carry, dc_carry; };
+constexpr int kPriorBwdSmemFloats = 2 * 2 * kChainE + 4 * 4 * kChainE;   // WA[2][2E] | WB[4][4E]
+
+__device__ __forceinline__ void prior_bwd_setup(const PriorChainBwd& p, float* WA, float* WB, PriorBwdRegs& r, int u0) {
   constexpr int E = kChainE;
-  __shared__ __align__(16) float WA[2][2 * E];   // WA[j][c] = W_head[c][u0+j]
-  __shared__ __align__(16) float WB[4][4 * E];   // (d last_z j0, j1, d h j0, j1): W_ih[c][2E+u], W_hh[c][u]
-  const int tid = threadIdx.x, n = tid >> 3, kp = tid & 7;
-  const int u0 = blockIdx.x * 2;
-  for (int i = tid; i < 2 * 2 * E; i += kChainThreads) {
+  for (int i = threadIdx.x; i < 2 * 2 * E; i += kChainThreads) {        // WA[j][c] = W_head[c][u0+j]
     const int jj = i / (2 * E), c = i % (2 * E);
-    WA[jj][c] = p.head_w[(long long)c * E + u0 + jj];
+    WA[i] = p.head_w[(long long)c * E + u0 + jj];
   }
-  for (int i = tid; i < 4 * 4 * E; i += kChainThreads) {
-    const int r = i / (4 * E), c = i % (4 * E);
-    WB[r][c] = r < 2 ? p.wih[(long long)c * 3 * E + 2 * E + u0 + r] : p.whh[(long long)c * E + u0 + (r - 2)];
+  for (int i = threadIdx.x; i < 4 * 4 * E; i += kChainThreads) {        // (d last_z j0, j1, d h j0, j1)
+    const int rr = i / (4 * E), c = i % (4 * E);
+    WB[i] = rr < 2 ? p.wih[(long long)c * 3 * E + 2 * E + u0 + rr] : p.whh[(long long)c * E + u0 + (rr - 2)];
   }
-  __syncthreads();
-  GridBar gb{p.bar, 0u, gridDim.x};
-  const int T = p.T, N = p.N;
-  const bool row = n < N;
-  const int j = kp & 1, u = u0 + j;
-  auto head_bwd = [&](int t, float dz) {
+  r.dh_carry = 0.0f; r.dc_carry = 0.0f;
+}
+// head backward of the LAST step (no chain input): must be followed by a barrier before prior_bwd_lstm(T-1)
+__device__ __forceinline__ void prior_bwd_first(const PriorChainBwd& p, int n, int kp, bool row, int u) {
+  constexpr int E = kChainE;
+  const int T = p.T, N = p.N, t = T - 1;
+  if (row && kp < 2) {
     const long long o = ((long long)n * T + t) * E + u;
-    if (p.d_pz) dz += p.d_pz[o];
+    float dz = p.d_pz ? p.d_pz[o] : 0.0f;
     float dm = dz;
     float dl = dz * p.eps[((long long)t * N + n) * E + u] * 0.5f * expf(0.5f * p.p_logs[o]);
     if (p.d_pm) dm += p.d_pm[o];
     if (p.d_pl) dl += p.d_pl[o];
     float* d = p.dml + ((long long)n * T + t) * 2 * E + u;
     d[0] = dm; d[E] = dl;
-  };
-  if (row && kp < 2) head_bwd(T - 1, 0.0f);
+  }
+}
+// dh_t = dML_t . W_head (+ carry); LSTM pointwise backward of step t
+__device__ __forceinline__ void prior_bwd_lstm(const PriorChainBwd& p, const float* WA, PriorBwdRegs& r, int t, int n, int kp,
+                                               bool row, int j, int u) {
+  constexpr int E = kChainE;
+  const int T = p.T;
+  float a2[2] = {0.f, 0.f};
+  float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, cc = 0.f, cp = 0.f;
+  if (row && kp < 2) {
+    const float* g = p.gates + ((long long)n * T + t) * 4 * E + u;
+    ig = ldcg1(g); fg = ldcg1(g + E); gg = ldcg1(g + 2 * E); og = ldcg1(g + 3 * E);
+    cc = ldcg1(p.c + ((long long)n * T + t) * E + u);
+    if (t > 0) cp = ldcg1(p.c + ((long long)n * T + t - 1) * E + u);
+  }
+  rowdot<2, 2 * E>(row, p.dml + ((long long)n * T + t) * 2 * E, WA, 2 * E, kp, a2);
+  reduce8(a2);
+  if (row && kp < 2) {
+    const float dh = (j ? a2[1] : a2[0]) + r.dh_carry;
+    const float tc = tanhf(cc);
+    const float dc = dh * og * (1.0f - tc * tc) + r.dc_carry;
+    float* dg = p.dg + ((long long)n * T + t) * 4 * E + u;
+    dg[0] = dc * gg * ig * (1.0f - ig);
+    dg[E] = dc * cp * fg * (1.0f - fg);
+    dg[2 * E] = dc * ig * (1.0f - gg * gg);
+    dg[3 * E] = dh * tc * og * (1.0f - og);
+    r.dc_carry = dc * fg;
+  }
+}
+// [d last_z | d h_{t-1}] = dG_t . [W_ih[:, 2E:3E] | W_hh]; head backward of step t-1   (t > 0)
+__device__ __forceinline__ void prior_bwd_head(const PriorChainBwd& p, const float* WB, PriorBwdRegs& r, int t, int n, int kp,
+                                               bool row, int j, int u) {
+  constexpr int E = kChainE;
+  const int T = p.T, N = p.N;
+  float a4[4] = {0.f, 0.f, 0.f, 0.f};
+  float u_pz = 0.f, u_pm = 0.f, u_pl = 0.f, e_ = 0.f, lv = 0.f;
+  if (row && kp < 2) {
+    const long long o = ((long long)n * T + t - 1) * E + u;
+    if (p.d_pz) u_pz = ldcg1(p.d_pz + o);
+    if (p.d_pm) u_pm = ldcg1(p.d_pm + o);
+    if (p.d_pl) u_pl = ldcg1(p.d_pl + o);
+    e_ = ldcg1(p.eps + ((long long)(t - 1) * N + n) * E + u);
+    lv = ldcg1(p.p_logs + o);
+  }
+  // two halves of K = 4E: 16 instead of 32 float4 of operands in flight (register pressure of the merged kernel)
+  rowdot<4, 2 * E>(row, p.dg + ((long long)n * T + t) * 4 * E, WB, 4 * E, kp, a4);
+  rowdot<4, 2 * E>(row, p.dg + ((long long)n * T + t) * 4 * E + 2 * E, WB + 2 * E, 4 * E, kp, a4);
+  reduce8(a4);
+  if (row && kp < 2) {
+    r.dh_carry = j ? a4[3] : a4[2];
+    const float dz = (j ? a4[1] : a4[0]) + u_pz;
+    float* d = p.dml + ((long long)n * T + t - 1) * 2 * E + u;
+    d[0] = dz + u_pm;
+    d[E] = dz * e_ * 0.5f * expf(0.5f * lv) + u_pl;
+  }
+}
+
+__global__ void __launch_bounds__(kChainThreads) prior_chain_bwd_kernel(const __grid_constant__ PriorChainBwd p) {
+  __shared__ __align__(16) float Wsm[kPriorBwdSmemFloats];
+  float* WA = Wsm; float* WB = Wsm + 2 * 2 * kChainE;
+  const int tid = threadIdx.x, n = tid >> 3, kp = tid & 7;
+  const int u0 = blockIdx.x * 2, j = kp & 1, u = u0 + j;
+  PriorBwdRegs r;
+  prior_bwd_setup(p, WA, WB, r, u0);
+  __syncthreads();
+  GridBar gb{p.bar, 0u, gridDim.x};
+  const bool row = n < p.N;
+  prior_bwd_first(p, n, kp, row, u);
   grid_sync(gb);
-  float dh_carry = 0.0f, dc_carry = 0.0f;
-  for (int t = T - 1; t >= 0; --t) {
-    // ---- dh_t = dML_t . W_head (+ carry); LSTM pointwise backward ----
-    float a2[2] = {0.f, 0.f};
-    float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, cc = 0.f, cp = 0.f;
-    if (row && kp < 2) {
-      const float* g = p.gates + ((long long)n * T + t) * 4 * E + u;
-      ig = ldcg1(g); fg = ldcg1(g + E); gg = ldcg1(g + 2 * E); og = ldcg1(g + 3 * E);
-      cc = ldcg1(p.c + ((long long)n * T + t) * E + u);
-      if (t > 0) cp = ldcg1(p.c + ((long long)n * T + t - 1) * E + u);
-    }
-    rowdot<2, 2 * E>(row, p.dml + ((long long)n * T + t) * 2 * E, &WA[0][0], 2 * E, kp, a2);
-    reduce8(a2);
-    if (row && kp < 2) {
-      const float dh = (j ? a2[1] : a2[0]) + dh_carry;
-      const float tc = tanhf(cc);
-      const float dc = dh * og * (1.0f - tc * tc) + dc_carry;
-      float* dg = p.dg + ((long long)n * T + t) * 4 * E + u;
-      dg[0] = dc * gg * ig * (1.0f - ig);
-      dg[E] = dc * cp * fg * (1.0f - fg);
-      dg[2 * E] = dc * ig * (1.0f - gg * gg);
-      dg[3 * E] = dh * tc * og * (1.0f - og);
-      dc_carry = dc * fg;
-    }
+  for (int t = p.T - 1; t >= 0; --t) {
+    prior_bwd_lstm(p, WA, r, t, n, kp, row, j, u);
     if (t == 0) break;
     grid_sync(gb);
-    // ---- [d last_z | d h_{t-1}] = dG_t . [W_ih[:, 2E:3E] | W_hh]; head backward of step t-1 ----
-    float a4[4] = {0.f, 0.f, 0.f, 0.f};
-    float u_pz = 0.f, u_pm = 0.f, u_pl = 0.f, e_ = 0.f, lv = 0.f;
-    if (row && kp < 2) {
-      const long long o = ((long long)n * T + t - 1) * E + u;
-      if (p.d_pz) u_pz = ldcg1(p.d_pz + o);
-      if (p.d_pm) u_pm = ldcg1(p.d_pm + o);
-      if (p.d_pl) u_pl = ldcg1(p.d_pl + o);
-      e_ = ldcg1(p.eps + ((long long)(t - 1) * N + n) * E + u);
-      lv = ldcg1(p.p_logs + o);
-    }
-    rowdot<4, 4 * E>(row, p.dg + ((long long)n * T + t) * 4 * E, &WB[0][0], 4 * E, kp, a4);
-    reduce8(a4);
-    if (row && kp < 2) {
-      dh_carry = j ? a4[3] : a4[2];
-      const float dz = (j ? a4[1] : a4[0]) + u_pz;
-      float* d = p.dml + ((long long)n * T + t - 1) * 2 * E + u;
-      d[0] = dz + u_pm;
-      d[E] = dz * e_ * 0.5f * expf(0.5f * lv) + u_pl;
-    }
+    prior_bwd_head(p, WB, r, t, n, kp, row, j, u);
     grid_sync(gb);
   }
 }
@@ -474,9 +507,14 @@ struct DecChainFwd {
 };
 inline size_t dec_chain_fwd_smem(int Te) { return ((size_t)Te * 2 * kChainE + 2 * kChainE + 12 * kChainE + 2 * kChainE + Te + 64) * sizeof(float); }
 
-__global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __grid_constant__ DecChainFwd p) {
+// `pp.N > 0`: the (independent) prior chain of the same step count is run inside the same phases: LSTM next to the
+// query projection, Gaussian head next to the attention; its barriers are the decoder's.
+__global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __grid_constant__ DecChainFwd p,
+                                                                      const __grid_constant__ PriorChainFwd pp) {
   constexpr int E = kChainE, A = kChainE;
   extern __shared__ __align__(16) float dsm[];
+  __shared__ __align__(16) float Wprior[kPriorFwdSmemFloats];
+  const bool prior = pp.N > 0;
   const int Te = p.Te, T = p.T, N = p.N;
   float* Ps = dsm;                        // [Te][A]   clip blockIdx.x
   float* Ms = Ps + (size_t)Te * A;        // [Te][E]
@@ -504,22 +542,25 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __gr
     const long long wr = (long long)((rr >> 1) * E + u0 + (rr & 1));
     Wg[i] = r < 6 ? p.wih[wr * 3 * E + E + k] : p.whh[wr * E + k];
   }
-  __syncthreads();
-  GridBar gb{p.bar, 0u, gridDim.x};
   const bool row = n < N;
   const int j = kp & 1, u = u0 + j;
+  PriorFwdRegs pr;
+  if (prior) prior_fwd_setup(pp, Wprior, Wprior + 8 * 2 * E, pr, u0, u);
+  __syncthreads();
+  GridBar gb{p.bar, 0u, gridDim.x};
   const float bh_r = p.bhh[u], bh_z = p.bhh[E + u], bh_n = p.bhh[2 * E + u];
   for (int t = 0; t < T; ++t) {
-    // ---- P1: query projection q.Wq^T, columns {u0, u0+1} of A ----
+    // ---- P1: query projection q.Wq^T, columns {u0, u0+1} of A  [+ prior LSTM cell] ----
     if (t > 0) {
       float a2[2] = {0.f, 0.f};
       rowdot<2, E>(row, p.out + ((long long)n * T + t - 1) * E, Wq, E, kp, a2);
       reduce8(a2);
       if (row && kp < 2) p.qp[((long long)n * T + t) * A + u] = j ? a2[1] : a2[0];
-      grid_sync(gb);
     } else if (row && kp < 2) {
       p.qp[((long long)n * T) * A + u] = 0.0f;     // zero query at t = 0 (decoder.py:94-98)
     }
+    if (prior) prior_fwd_lstm(pp, Wprior, pr, t, n, kp, row, j, u);
+    if (t > 0 || prior) grid_sync(gb);
     // ---- P2: attention of clip `clip` ----
     if (own_clip) {
       qps[tid] = t > 0 ? ldcg1(p.qp + ((long long)clip * T + t) * A + tid) : 0.0f;
@@ -560,6 +601,7 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __gr
       if (jj < len) c0 = fmaf(sc[jj], Ms[(size_t)jj * E + tid], c0);
       p.ctx[((long long)clip * T + t) * E + tid] = c0 + c1;
     }
+    if (prior) prior_fwd_head(pp, Wprior + 8 * 2 * E, pr, t, n, kp, row, j, u);
     grid_sync(gb);
     // ---- P3: GRU cell, units {u0, u0+1} ----
     float ax[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ah[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -615,9 +657,17 @@ struct DecChainBwd {
 };
 inline size_t dec_chain_bwd_smem(int Te) { return ((size_t)Te * 2 * kChainE + 2 * 4 * kChainE + 2 * 3 * kChainE + 2 * kChainE + Te + 64) * sizeof(float); }
 
-__global__ void __launch_bounds__(kChainThreads) dec_chain_bwd_kernel(const __grid_constant__ DecChainBwd p) {
+// `pp.N > 0`: the prior backward chain runs inside the same phases (LSTM backward next to the GRU backward, head
+// backward next to the d ctx projection).
+// (MERGE = true currently spills ~800 bytes per thread on sm_100a and is slower than the two kernels back to back;
+// train_fast.cuh launches MERGE = false plus prior_chain_bwd_kernel.)
+template <bool MERGE>
+__global__ void __launch_bounds__(kChainThreads) dec_chain_bwd_kernel(const __grid_constant__ DecChainBwd p,
+                                                                      const __grid_constant__ PriorChainBwd pp) {
   constexpr int E = kChainE, A = kChainE;
   extern __shared__ __align__(16) float dsm[];
+  __shared__ __align__(16) float Wprior[MERGE ? kPriorBwdSmemFloats : 4];
+  const bool prior = MERGE && pp.N > 0;
   const int Te = p.Te, T = p.T, N = p.N;
   float* Ps = dsm;                        // [Te][A]
   float* Ms = Ps + (size_t)Te * A;        // [Te][E]
@@ -646,10 +696,16 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_bwd_kernel(const __gr
     const int jj = i / (3 * E), c = i % (3 * E);
     W2[i] = p.wih[(long long)c * 3 * E + E + u0 + jj];
   }
-  __syncthreads();
-  GridBar gb{p.bar, 0u, gridDim.x};
   const bool row = n < N;
   const int j = kp & 1, u = u0 + j;
+  PriorBwdRegs pr;
+  if (prior) prior_bwd_setup(pp, Wprior, Wprior + 2 * 2 * E, pr, u0);
+  __syncthreads();
+  GridBar gb{p.bar, 0u, gridDim.x};
+  if (prior) {
+    prior_bwd_first(pp, n, kp, row, u);
+    grid_sync(gb);
+  }
   const float va = p.attn_v[tid];
   float carry = 0.0f;
   for (int t = T - 1; t >= 0; --t) {
@@ -663,15 +719,18 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_bwd_kernel(const __gr
       if (t > 0) hp = ldcg1(p.out + ((long long)n * T + t - 1) * E + u);
     }
     if (t < T - 1) {
-      float4 a0[3 * E / 32], a1[A / 32];
-      if (row) {
-        rowload<3 * E>(p.dgh + ((long long)n * T + t + 1) * 3 * E, kp, a0);
-        rowload<A>(p.dqp + ((long long)n * T + t + 1) * A, kp, a1);
-      }
-      __syncwarp();
-      if (row) {
-        rowfma<2, 3 * E>(a0, W1, 4 * E, kp, a2);
-        rowfma<2, A>(a1, W1 + 3 * E, 4 * E, kp, a2);
+      rowdot<2, 2 * E>(row, p.dgh + ((long long)n * T + t + 1) * 3 * E, W1, 4 * E, kp, a2);
+      {
+        float4 a0[E / 32], a1[A / 32];
+        if (row) {
+          rowload<E>(p.dgh + ((long long)n * T + t + 1) * 3 * E + 2 * E, kp, a0);
+          rowload<A>(p.dqp + ((long long)n * T + t + 1) * A, kp, a1);
+        }
+        __syncwarp();
+        if (row) {
+          rowfma<2, E>(a0, W1 + 2 * E, 4 * E, kp, a2);
+          rowfma<2, A>(a1, W1 + 3 * E, 4 * E, kp, a2);
+        }
       }
       reduce8(a2);
     }
@@ -686,12 +745,15 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_bwd_kernel(const __gr
       gh[0] = dar; gh[E] = daz; gh[2 * E] = dan * rr;
       carry = dh * z;
     }
+    if (prior) prior_bwd_lstm(pp, Wprior, pr, t, n, kp, row, j, u);
     grid_sync(gb);
     // ---- B1.5: d ctx_t = dGi_t . W_ih[:, E:2E], columns {u0, u0+1} ----
     float b2[2] = {0.f, 0.f};
-    rowdot<2, 3 * E>(row, p.dgi + ((long long)n * T + t) * 3 * E, W2, 3 * E, kp, b2);
+    rowdot<2, 2 * E>(row, p.dgi + ((long long)n * T + t) * 3 * E, W2, 3 * E, kp, b2);
+    rowdot<2, E>(row, p.dgi + ((long long)n * T + t) * 3 * E + 2 * E, W2 + 2 * E, 3 * E, kp, b2);
     reduce8(b2);
     if (row && kp < 2) p.dctx[((long long)n * T + t) * E + u] = j ? b2[1] : b2[0];
+    if (prior && t > 0) prior_bwd_head(pp, Wprior + 2 * 2 * E, pr, t, n, kp, row, j, u);
     grid_sync(gb);
     // ---- B2: attention backward of clip `clip` ----
     if (own_clip) {
@@ -729,8 +791,8 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_bwd_kernel(const __gr
 }
 
 // ---- host side -------------------------------------------------------------------------------------
-template <typename Kern, typename P>
-inline int launch_chain(Kern kern, size_t smem, cudaStream_t st, const P& p, const char* name) {
+template <typename Kern, typename... P>
+inline int launch_chain(Kern kern, size_t smem, cudaStream_t st, const char* name, const P&... p) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(kChainCtas);
   cfg.blockDim = dim3(kChainThreads);
@@ -741,7 +803,7 @@ inline int launch_chain(Kern kern, size_t smem, cudaStream_t st, const P& p, con
   at[0].val.cooperative = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p...);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return set_error(name, cudaGetErrorString(e));
   return 0;
@@ -761,10 +823,12 @@ inline bool chain_supported(int N, int T, int Te, int E, int A) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess &&
         cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess && coop && sms >= kChainCtas) {
-      // largest Te whose resident clip fits next to the weight slices
-      max_te = (int)(((size_t)optin / sizeof(float) - (2 * 4 + 2 * 3 + 2 + 12 + 2) * kChainE - 256) / (2 * kChainE + 1));   // ~97 on B200
-      if (cudaFuncSetAttribute(dec_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) == cudaSuccess &&
-          cudaFuncSetAttribute(dec_chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) == cudaSuccess)
+      // largest Te whose resident clip fits next to the weight slices (the merged prior phases keep 20 KB of
+      // weights in static shared memory)
+      const int dyn_max = optin - 24 * 1024;
+      max_te = (int)(((size_t)dyn_max / sizeof(float) - (2 * 4 + 2 * 3 + 2 + 12 + 2) * kChainE - 256) / (2 * kChainE + 1));   // ~85 on B200
+      if (cudaFuncSetAttribute(dec_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max) == cudaSuccess &&
+          cudaFuncSetAttribute(dec_chain_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max) == cudaSuccess)
         ok = 1;
     }
   }

@@ -69,7 +69,7 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     PostChainFwd pc{};
     pc.N = N; pc.T = T; pc.lens = ws.steplens; pc.ho = ws.ho; pc.bar = ws.bars + 0 * 128;
     for (int dir = 0; dir < 2; ++dir) { pc.gx[dir] = ws.gxq[dir]; pc.whh[dir] = w.q_whh[dir]; pc.bhh[dir] = w.q_bhh[dir]; pc.gq[dir] = ws.gq[dir]; }
-    ACVAE_TRY(launch_chain(post_chain_fwd_kernel, 0, sq0, pc, "post_chain_fwd_kernel"));
+    ACVAE_TRY(launch_chain(post_chain_fwd_kernel, 0, sq0, "post_chain_fwd_kernel", pc));
   }
   {
     GemmParams h{};
@@ -106,13 +106,11 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     g.epi.c[0] = ws.dg_p; g.epi.ldc = 4 * E; g.epi.bias[0] = w.p_bih; g.epi.scale = 1.0f;   // dg_p doubles as gx_p in the forward
     ACVAE_TRY(launch_gemm<EPI_PLAIN>(g, sp));
   }
+  PriorChainFwd ppc{};      // chain mode: the prior chain runs inside the decoder's persistent kernel (same barriers)
   if (chain) {
-    PriorChainFwd pc{};
-    pc.N = N; pc.T = T; pc.gx = ws.dg_p; pc.wih = w.p_wih; pc.whh = w.p_whh; pc.bhh = w.p_bhh;
-    pc.head_w = w.p_head_w; pc.head_b = w.p_head_b; pc.eps = io.eps_p;
-    pc.gates = ws.gates_p; pc.c = ws.c_p; pc.h = ws.h_p; pc.pm = io.p_means; pc.pl = io.p_logs; pc.pz = io.p_z;
-    pc.bar = ws.bars + 1 * 128;
-    ACVAE_TRY(launch_chain(prior_chain_fwd_kernel, 0, sp, pc, "prior_chain_fwd_kernel"));
+    ppc.N = N; ppc.T = T; ppc.gx = ws.dg_p; ppc.wih = w.p_wih; ppc.whh = w.p_whh; ppc.bhh = w.p_bhh;
+    ppc.head_w = w.p_head_w; ppc.head_b = w.p_head_b; ppc.eps = io.eps_p;
+    ppc.gates = ws.gates_p; ppc.c = ws.c_p; ppc.h = ws.h_p; ppc.pm = io.p_means; ppc.pl = io.p_logs; ppc.pz = io.p_z;
   }
   for (int t = 0; t < T && !chain; ++t) {
     GemmParams g{};
@@ -158,7 +156,8 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     dc.wih = w.d_wih; dc.whh = w.d_whh; dc.bhh = w.d_bhh; dc.Pd = ws.Pd; dc.mem = ws.mem; dc.mem_lens = io.mem_lens;
     dc.qp = ws.qp_d; dc.w = ws.w_d; dc.ctx = ws.ctx_d; dc.gates = ws.gates_d; dc.out = io.outputs; dc.aw = io.attn_weights;
     dc.bar = ws.bars + 2 * 128;
-    ACVAE_TRY(launch_chain(dec_chain_fwd_kernel, dec_chain_fwd_smem(Te), st, dc, "dec_chain_fwd_kernel"));
+    ACVAE_TRY(stream_dep(sp, st, ax));      // the prior's hoisted inputs (gx_p) are produced on sp
+    ACVAE_TRY(launch_chain(dec_chain_fwd_kernel, dec_chain_fwd_smem(Te), st, "dec_chain_fwd_kernel", dc, ppc));
   }
   for (int t = 0; t < T && !chain; ++t) {
     const float* hprev = t > 0 ? io.outputs + (long long)(t - 1) * E : nullptr;
@@ -230,12 +229,12 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   ACVAE_TRY(stream_dep(st, sp, ax));
 
   // ================= prior BPTT on its own stream (KL gradients only: dis_ratio == 0) ====================
+  PriorChainBwd ppc{};      // chain mode: the prior chain runs inside the decoder's persistent kernel (same barriers)
   if (chain) {
-    PriorChainBwd pc{};
-    pc.N = N; pc.T = T; pc.d_pz = gi.d_p_z; pc.d_pm = gi.d_p_means; pc.d_pl = gi.d_p_logs; pc.eps = io.eps_p;
-    pc.p_logs = io.p_logs; pc.head_w = w.p_head_w; pc.wih = w.p_wih; pc.whh = w.p_whh; pc.gates = ws.gates_p; pc.c = ws.c_p;
-    pc.dml = ws.dml_p; pc.dg = ws.dg_p; pc.bar = ws.bars + 4 * 128;
-    ACVAE_TRY(launch_chain(prior_chain_bwd_kernel, 0, sp, pc, "prior_chain_bwd_kernel"));
+    ppc.N = N; ppc.T = T; ppc.d_pz = gi.d_p_z; ppc.d_pm = gi.d_p_means; ppc.d_pl = gi.d_p_logs; ppc.eps = io.eps_p;
+    ppc.p_logs = io.p_logs; ppc.head_w = w.p_head_w; ppc.wih = w.p_wih; ppc.whh = w.p_whh; ppc.gates = ws.gates_p; ppc.c = ws.c_p;
+    ppc.dml = ws.dml_p; ppc.dg = ws.dg_p; ppc.bar = ws.bars + 4 * 128;
+    ACVAE_TRY(launch_chain(prior_chain_bwd_kernel, 0, sp, "prior_chain_bwd_kernel", ppc));
   } else
   {
     // step T-1 head backward (standalone), then per step: [dh GEMM + LSTM pointwise] -> [dz|dh GEMM + head pointwise]
@@ -284,38 +283,44 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
       ACVAE_TRY(launch_gemm<EPI_HEAD_BWD>(q, sp));
     }
   }
-  // prior batched remainders
+  // prior batched remainders (after the prior chain: at once in the launch-per-step schedule, after the merged
+  // decoder+prior kernel in chain mode)
+  auto prior_remainders = [&]() -> int {
   ACVAE_TRY(linear_bwd_data(NT, E, 4 * E, ws.dg_p, 4 * E, w.p_wih, 3 * E, ws.dxe_p, E, sp));
-  ACVAE_TRY(linear_bwd_data(NT, E, 4 * E, ws.dg_p, 4 * E, w.p_wih + E, 3 * E, ws.dctx_p, E, sp));
-  {
-    AttnBwdQParams a{};
-    a.rows = NT; a.Te = Te; a.A = E; a.E = E; a.rows_per_clip = T;
-    a.dctx = ws.dctx_p; a.ld_dctx = E; a.w = ws.w_p; a.ld_w = Te; a.qp = ws.qp_p; a.ld_qp = E;
-    a.P = ws.Pp; a.mem = ws.mem; a.v = w.p_attn_v; a.mem_lens = io.mem_lens;
-    a.ds = ws.ds_p; a.ld_ds = Te; a.dqp = ws.dqp_p; a.ld_dqp = E;
-    ACVAE_TRY(launch_attn_bwd_q(a, sp));
-  }
-  ACVAE_TRY(linear_bwd_data(NT, E, E, ws.dqp_p, E, w.p_attn_w, 2 * E, ws.dxe_p, E, sp, 1));
-  ACVAE_CHECK(zero(gw.p_emb, (size_t)V * E, sp));
-  ACVAE_TRY(scatter_rows(NT, E, ws.dxe_p, E, ws.words, gw.p_emb, sp));
-  ACVAE_TRY(linear_bwd_weight(E, E, NT, ws.dqp_p, E, ws.xp, E, gw.p_attn_w, 2 * E, sp));
-  ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.xp, E, gw.p_wih, 3 * E, sp));
-  ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.ctx_p, E, gw.p_wih + E, 3 * E, sp));
-  ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, io.p_z - E, E, gw.p_wih + 2 * E, 3 * E, sp, T, 0, -1));
-  ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.h_p - E, E, gw.p_whh, E, sp, T, 0, -1));
-  ACVAE_TRY(colsum(NT, 4 * E, ws.dg_p, 4 * E, gw.p_bih, sp));
-  ACVAE_CHECK(cudaMemcpyAsync(gw.p_bhh, gw.p_bih, sizeof(float) * 4 * E, cudaMemcpyDeviceToDevice, sp));
-  ACVAE_TRY(linear_bwd_weight(2 * E, E, NT, ws.dml_p, 2 * E, ws.h_p, E, gw.p_head_w, E, sp));
-  ACVAE_TRY(colsum(NT, 2 * E, ws.dml_p, 2 * E, gw.p_head_b, sp));
-  ACVAE_CHECK(zero(gw.p_attn_v, E, sp));
-  {
-    AttnBwdAccParams a{};
-    a.clips = N; a.Te = Te; a.A = E; a.E = E; a.rows_per_clip = T;
-    a.ds = ws.ds_p; a.ld_ds = Te; a.w = ws.w_p; a.ld_w = Te; a.qp = ws.qp_p; a.ld_qp = E;
-    a.dctx = ws.dctx_p; a.ld_dctx = E; a.P = ws.Pp; a.v = w.p_attn_v; a.mem_lens = io.mem_lens;
-    a.dP = ws.dPp; a.dmem = ws.dmem; a.dmem_accumulate = 0; a.dv = gw.p_attn_v;
-    ACVAE_TRY(launch_attn_bwd_acc(a, sp));
-  }
+    ACVAE_TRY(linear_bwd_data(NT, E, 4 * E, ws.dg_p, 4 * E, w.p_wih + E, 3 * E, ws.dctx_p, E, sp));
+    {
+      AttnBwdQParams a{};
+      a.rows = NT; a.Te = Te; a.A = E; a.E = E; a.rows_per_clip = T;
+      a.dctx = ws.dctx_p; a.ld_dctx = E; a.w = ws.w_p; a.ld_w = Te; a.qp = ws.qp_p; a.ld_qp = E;
+      a.P = ws.Pp; a.mem = ws.mem; a.v = w.p_attn_v; a.mem_lens = io.mem_lens;
+      a.ds = ws.ds_p; a.ld_ds = Te; a.dqp = ws.dqp_p; a.ld_dqp = E;
+      ACVAE_TRY(launch_attn_bwd_q(a, sp));
+    }
+    ACVAE_TRY(linear_bwd_data(NT, E, E, ws.dqp_p, E, w.p_attn_w, 2 * E, ws.dxe_p, E, sp, 1));
+    ACVAE_CHECK(zero(gw.p_emb, (size_t)V * E, sp));
+    ACVAE_TRY(scatter_rows(NT, E, ws.dxe_p, E, ws.words, gw.p_emb, sp));
+    ACVAE_TRY(linear_bwd_weight(E, E, NT, ws.dqp_p, E, ws.xp, E, gw.p_attn_w, 2 * E, sp));
+    ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.xp, E, gw.p_wih, 3 * E, sp));
+    ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.ctx_p, E, gw.p_wih + E, 3 * E, sp));
+    ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, io.p_z - E, E, gw.p_wih + 2 * E, 3 * E, sp, T, 0, -1));
+    ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.h_p - E, E, gw.p_whh, E, sp, T, 0, -1));
+    ACVAE_TRY(colsum(NT, 4 * E, ws.dg_p, 4 * E, gw.p_bih, sp));
+    ACVAE_CHECK(cudaMemcpyAsync(gw.p_bhh, gw.p_bih, sizeof(float) * 4 * E, cudaMemcpyDeviceToDevice, sp));
+    ACVAE_TRY(linear_bwd_weight(2 * E, E, NT, ws.dml_p, 2 * E, ws.h_p, E, gw.p_head_w, E, sp));
+    ACVAE_TRY(colsum(NT, 2 * E, ws.dml_p, 2 * E, gw.p_head_b, sp));
+    ACVAE_CHECK(zero(gw.p_attn_v, E, sp));
+    {
+      AttnBwdAccParams a{};
+      a.clips = N; a.Te = Te; a.A = E; a.E = E; a.rows_per_clip = T;
+      a.ds = ws.ds_p; a.ld_ds = Te; a.w = ws.w_p; a.ld_w = Te; a.qp = ws.qp_p; a.ld_qp = E;
+      a.dctx = ws.dctx_p; a.ld_dctx = E; a.P = ws.Pp; a.v = w.p_attn_v; a.mem_lens = io.mem_lens;
+      a.dP = ws.dPp; a.dmem = ws.dmem; a.dmem_accumulate = 0; a.dv = gw.p_attn_v;
+      ACVAE_TRY(launch_attn_bwd_acc(a, sp));
+    }
+
+    return 0;
+  };
+  ACVAE_TRY(prior_remainders());
 
   // ================= decoder BPTT on the main stream ========================================================
   const float* dpool = nullptr;
@@ -335,7 +340,8 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     dc.whh = w.d_whh; dc.Pd = ws.Pd; dc.mem = ws.mem; dc.mem_lens = io.mem_lens; dc.qp = ws.qp_d; dc.w = ws.w_d;
     dc.gates = ws.gates_d; dc.out = io.outputs; dc.dgi = ws.dgi_d; dc.dgh = ws.dgh_d; dc.dctx = ws.dctx_d; dc.ds = ws.ds_d;
     dc.dqp = ws.dqp_d; dc.bar = ws.bars + 5 * 128;
-    ACVAE_TRY(launch_chain(dec_chain_bwd_kernel, dec_chain_bwd_smem(Te), st, dc, "dec_chain_bwd_kernel"));
+    PriorChainBwd none{};
+    ACVAE_TRY(launch_chain(dec_chain_bwd_kernel<false>, dec_chain_bwd_smem(Te), st, "dec_chain_bwd_kernel", dc, none));
   } else
   {
     GruBwdParams g{};
@@ -447,7 +453,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     PostChainBwd pc{};
     pc.N = N; pc.T = T; pc.dho = ws.dho; pc.ho = ws.ho; pc.lens = ws.steplens; pc.bar = ws.bars + 6 * 128;
     for (int dir = 0; dir < 2; ++dir) { pc.whh[dir] = w.q_whh[dir]; pc.gq[dir] = ws.gq[dir]; pc.dgi[dir] = ws.dgi_q[dir]; pc.dgh[dir] = ws.dgh_q[dir]; }
-    ACVAE_TRY(launch_chain(post_chain_bwd_kernel, 0, sq0, pc, "post_chain_bwd_kernel"));
+    ACVAE_TRY(launch_chain(post_chain_bwd_kernel, 0, sq0, "post_chain_bwd_kernel", pc));
     ACVAE_TRY(stream_dep(sq0, sq1, ax));
   }
   for (int dir = 0; dir < 2; ++dir) {
