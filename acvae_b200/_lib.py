@@ -66,6 +66,8 @@ SYMBOLS = {
     "acvae_last_error": (C.c_char_p, []),
     "acvae_abi_version": (C.c_int, []),
     "acvae_launch_count": (C.c_uint64, []),
+    "acvae_set_kernel_probe": (C.c_int, [C.c_char_p, _vp, _vp]),
+    "acvae_kernel_probe_hits": (C.c_int, []),
     "acvae_gemm": (C.c_int, [_i32, _i32, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _i64, _i32,
                              C.POINTER(C.c_int32), _vp]),
     "acvae_train_workspace_bytes": (_sz, [_DP]),

@@ -9,6 +9,7 @@
 namespace acvae {
 thread_local char g_err[512] = {0};
 std::atomic<unsigned long long> g_launches{0};
+KernelProbe g_probe{};
 
 struct VocabWs {
   float *pmax, *pexp, *psum, *pbest; int* parg;
@@ -36,6 +37,18 @@ extern "C" {
 const char* acvae_last_error(void) { return g_err; }
 int acvae_abi_version(void) { return ACVAE_ABI_VERSION; }
 uint64_t acvae_launch_count(void) { return g_launches.load(); }
+
+int acvae_set_kernel_probe(const char* kernel_name, void* ev_start, void* ev_stop) {
+  if (!kernel_name || !kernel_name[0]) { g_probe.active = 0; return 0; }
+  ACVAE_REQUIRE(ev_start && ev_stop, "kernel probe needs two CUDA events");
+  ACVAE_REQUIRE(strlen(kernel_name) < sizeof(g_probe.name), "kernel name too long");
+  strcpy(g_probe.name, kernel_name);
+  g_probe.e0 = (cudaEvent_t)ev_start; g_probe.e1 = (cudaEvent_t)ev_stop;
+  g_probe.hits = 0;
+  g_probe.active = 1;
+  return 0;
+}
+int acvae_kernel_probe_hits(void) { return g_probe.hits; }
 
 int acvae_gemm(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, int32_t a_trans, const float* B, int64_t ldb,
                int32_t b_trans, const float* bias, float* C, int64_t ldc, int32_t accumulate, int32_t* used_tc, void* stream) {

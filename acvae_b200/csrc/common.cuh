@@ -3,12 +3,24 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <atomic>
 
 namespace acvae {
 
 extern thread_local char g_err[512];
 extern std::atomic<unsigned long long> g_launches;
+
+// Kernel probe (acvae_set_kernel_probe): CUDA events recorded on the launching stream right before / after every
+// launch whose kernel name contains `name`.  bench.py uses it to time ONE kernel live inside a step.
+struct KernelProbe {
+  char name[96];
+  cudaEvent_t e0, e1;
+  int active;
+  int hits;
+};
+extern KernelProbe g_probe;
+inline bool probe_match(const char* kernel) { return g_probe.active && strstr(kernel, g_probe.name) != nullptr; }
 
 inline int set_error(const char* what, const char* detail = "") {
   snprintf(g_err, sizeof(g_err), "%s%s%s", what, detail[0] ? ": " : "", detail);
@@ -20,7 +32,10 @@ inline int set_error(const char* what, const char* detail = "") {
 // error code instead of an exception.
 #define ACVAE_LAUNCH(kernel, grid, block, smem, stream, ...)                       \
   do {                                                                              \
+    const bool probe__ = acvae::probe_match(#kernel);                               \
+    if (probe__) cudaEventRecord(acvae::g_probe.e0, (stream));                      \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                     \
+    if (probe__) { cudaEventRecord(acvae::g_probe.e1, (stream)); ++acvae::g_probe.hits; } \
     acvae::g_launches.fetch_add(1, std::memory_order_relaxed);                      \
     cudaError_t e__ = cudaPeekAtLastError();                                        \
     if (e__ != cudaSuccess) return acvae::set_error(#kernel, cudaGetErrorString(e__)); \

@@ -357,6 +357,56 @@ __global__ void copy2d_kernel(long long rows, int cols, const float* __restrict_
   dst[r * ldd + c] = src[r * lds + c];
 }
 
+// ---- recurrent cells on precomputed pre-activations (large-batch sampling: the GEMMs run on the tensor cores) ----
+// LSTM (text_encoder.py:253): pre [N,4E] gate-major (i,f,g,o) incl. b_ih; rows strided by ld_*.
+__global__ void lstm_cell_kernel(int N, int E, const float* __restrict__ pre, const float* __restrict__ b_hh,
+                                 const float* __restrict__ c_prev, long long ld_cprev, float* __restrict__ c_out,
+                                 float* __restrict__ h_out, long long ld_out, const int* __restrict__ live) {
+  if (live && *live == 0) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * E) return;
+  const long long n = i / E;
+  const int u = (int)(i % E);
+  const float* pr = pre + n * 4 * E + u;
+  const float ig = sigmoidf_(pr[0] + b_hh[u]), fg = sigmoidf_(pr[E] + b_hh[E + u]);
+  const float gg = tanhf(pr[2 * E] + b_hh[2 * E + u]), og = sigmoidf_(pr[3 * E] + b_hh[3 * E + u]);
+  const float cp = c_prev ? c_prev[n * ld_cprev + u] : 0.0f;
+  const float cn = fg * cp + ig * gg;
+  c_out[n * ld_out + u] = cn;
+  h_out[n * ld_out + u] = og * tanhf(cn);
+}
+// GRU (decoder.py:194): pre_x [N,3E] (r,z,n) incl. b_ih; pre_h [N,3E] without bias (NULL = zero state).
+__global__ void gru_cell_kernel(int N, int E, const float* __restrict__ pre_x, const float* __restrict__ pre_h,
+                                const float* __restrict__ b_hh, const float* __restrict__ h_prev, long long ld_hprev,
+                                float* __restrict__ h_out, long long ld_out, const int* __restrict__ live) {
+  if (live && *live == 0) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * E) return;
+  const long long n = i / E;
+  const int u = (int)(i % E);
+  const float* px = pre_x + n * 3 * E + u;
+  float hr = b_hh[u], hz = b_hh[E + u], hn = b_hh[2 * E + u];
+  if (pre_h) { const float* ph = pre_h + n * 3 * E + u; hr += ph[0]; hz += ph[E]; hn += ph[2 * E]; }
+  const float rg = sigmoidf_(px[0] + hr), zg = sigmoidf_(px[E] + hz);
+  const float ng = tanhf(px[2 * E] + rg * hn);
+  const float hp = h_prev ? h_prev[n * ld_hprev + u] : 0.0f;
+  h_out[n * ld_out + u] = (1.0f - zg) * ng + zg * hp;
+}
+// Gaussian head + reparameterisation (text_encoder.py:255-262): ml [N,2E] = (mean | log) incl. bias.
+__global__ void head_cell_kernel(int N, int E, const float* __restrict__ ml, const float* __restrict__ eps,
+                                 float* __restrict__ pm, float* __restrict__ pl, float* __restrict__ pz, long long ld_out,
+                                 const int* __restrict__ live) {
+  if (live && *live == 0) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * E) return;
+  const long long n = i / E;
+  const int u = (int)(i % E);
+  const float mean = ml[n * 2 * E + u], lg = ml[n * 2 * E + E + u];
+  pm[n * ld_out + u] = mean;
+  pl[n * ld_out + u] = lg;
+  pz[n * ld_out + u] = eps[n * E + u] * expf(0.5f * lg) + mean;
+}
+
 inline int grid1d(long long n, int block = 256) { return (int)((n + block - 1) / block); }
 
 }  // namespace acvae

@@ -803,7 +803,10 @@ inline int launch_chain(Kern kern, size_t smem, cudaStream_t st, const char* nam
   at[0].val.cooperative = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
+  const bool probe = probe_match(name);
+  if (probe) cudaEventRecord(g_probe.e0, st);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p...);
+  if (probe) { cudaEventRecord(g_probe.e1, st); ++g_probe.hits; }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return set_error(name, cudaGetErrorString(e));
   return 0;

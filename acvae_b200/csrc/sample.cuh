@@ -18,6 +18,7 @@ struct SampleWs {
   int *words, *unfinished, *active;
   float *qp_p, *w_p, *ctx_p, *gates_p, *c_p, *h_p, *pm, *pl, *pz, *qp_d, *w_d, *ctx_d, *gates_d, *hd;
   float *pmax, *pexp, *psum, *pbest; int* parg;
+  float *xe_p, *xe_d, *pre, *pre_h;   // tensor-core step: gathered embeddings, gate pre-activations
   size_t bytes;
 };
 
@@ -35,6 +36,7 @@ inline SampleWs carve_sample_ws(const acvae_dims& d, void* base) {
   w.gates_d = ar.take<float>(N * 2 * 4 * E); w.hd = ar.take<float>(N * 2 * E);
   w.pmax = ar.take<float>(N * nt); w.pexp = ar.take<float>(N * nt); w.psum = ar.take<float>(N * nt);
   w.pbest = ar.take<float>(N * nt * 2); w.parg = ar.take<int>(N * nt);
+  w.xe_p = ar.take<float>(N * E); w.xe_d = ar.take<float>(N * E); w.pre = ar.take<float>(N * 4 * E); w.pre_h = ar.take<float>(N * 3 * E);
   w.bytes = ar.off;
   return w;
 }
@@ -57,6 +59,95 @@ __global__ void sample_nsteps_kernel(int T, const int* __restrict__ active, int*
   }
 }
 
+// ---- one decode step with every contraction on the tensor cores (large sequence counts) ----------------------
+// Same arithmetic as prior_step / decoder_step; the gate GEMMs write pre-activations ([N,4E] / [N,3E], L2-resident)
+// and small pointwise kernels apply the cells.  C = sum of up to two (A_s, W_s) segments, optionally accumulated.
+inline int tc_linear2(int M, int Nn, const float* a0, long long lda0, const float* w0, long long ldw0, int K0,
+                      const float* a1, long long lda1, const float* w1, long long ldw1, int K1, const float* bias,
+                      float* c, long long ldc, int accumulate, const int* live, cudaStream_t st) {
+  GemmParams p{};
+  p.M = M; p.U = Nn; p.G = 1; p.nseg = a1 ? 2 : 1; p.live = live;
+  p.seg[0] = seg_plain(a0, lda0, w0, ldw0, K0);
+  if (a1) p.seg[1] = seg_plain(a1, lda1, w1, ldw1, K1);
+  p.epi.c[0] = c; p.epi.ldc = ldc; p.epi.bias[0] = bias; p.epi.scale = 1.0f; p.epi.accumulate = accumulate;
+  return launch_gemm<EPI_PLAIN>(p, st);
+}
+__global__ void gather2_kernel(int rows, int E, const float* __restrict__ t0, const float* __restrict__ t1,
+                               const int* __restrict__ idx, long long idx_stride, float* __restrict__ o0,
+                               float* __restrict__ o1, const int* __restrict__ live) {
+  if (live && *live == 0) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * E) return;
+  const int r = (int)(i / E), e = (int)(i % E);
+  const long long src = (long long)idx[r * idx_stride] * E + e;
+  o0[i] = t0[src]; o1[i] = t1[src];
+}
+
+inline int sample_step_tc(const StepCtx& c, const StepBufs& b, SampleWs& ws, int slot, int prev, const int* words,
+                          long long words_stride, const float* eps_t) {
+  const int N = c.d.N, E = c.d.E, A = c.d.A, Te = c.d.Te;
+  const long long S = b.S;
+  const acvae_weights& w = c.w;
+  cudaStream_t st = c.st;
+  const int* live = c.live;
+  ACVAE_LAUNCH(gather2_kernel, grid1d((long long)N * E), 256, 0, st, N, E, w.p_emb, w.d_emb, words, words_stride, ws.xe_p,
+               ws.xe_d, live);
+  // ---- prior (text_encoder.py:247-268) ----
+  ACVAE_TRY(tc_linear2(N, E, ws.xe_p, E, w.p_attn_w, 2 * E, E, nullptr, 0, nullptr, 0, 0, nullptr,
+                       b.qp_p + (long long)slot * E, S * E, 0, live, st));
+  {
+    AttnFwdParams a{};
+    a.rows = N; a.Te = Te; a.A = E; a.E = E; a.Dq = E; a.rows_per_clip = c.d.mem_rep; a.live = live;
+    a.qp_in = b.qp_p + (long long)slot * E; a.ld_qp_in = S * E;
+    a.P = c.Pp; a.mem = c.mem; a.v = w.p_attn_v; a.mem_lens = c.mem_lens;
+    a.ctx = b.ctx_p + (long long)slot * E; a.ld_ctx = S * E;
+    a.w_out = nullptr;
+    ACVAE_TRY(launch_attn_fwd(a, st));
+  }
+  ACVAE_TRY(tc_linear2(N, 4 * E, ws.xe_p, E, w.p_wih, 3 * E, E, b.ctx_p + (long long)slot * E, S * E, w.p_wih + E, 3 * E, E,
+                       w.p_bih, ws.pre, 4 * E, 0, live, st));
+  if (prev >= 0)
+    ACVAE_TRY(tc_linear2(N, 4 * E, b.pz + (long long)prev * E, S * E, w.p_wih + 2 * E, 3 * E, E, b.h_p + (long long)prev * E,
+                         S * E, w.p_whh, E, E, nullptr, ws.pre, 4 * E, 1, live, st));
+  ACVAE_LAUNCH(lstm_cell_kernel, grid1d((long long)N * E), 256, 0, st, N, E, (const float*)ws.pre, w.p_bhh,
+               prev >= 0 ? (const float*)(b.c_p + (long long)prev * E) : (const float*)nullptr, S * E,
+               b.c_p + (long long)slot * E, b.h_p + (long long)slot * E, S * E, live);
+  ACVAE_TRY(tc_linear2(N, 2 * E, b.h_p + (long long)slot * E, S * E, w.p_head_w, E, E, nullptr, 0, nullptr, 0, 0, w.p_head_b,
+                       ws.pre, 2 * E, 0, live, st));
+  ACVAE_LAUNCH(head_cell_kernel, grid1d((long long)N * E), 256, 0, st, N, E, (const float*)ws.pre, eps_t,
+               b.pm + (long long)slot * E, b.pl + (long long)slot * E, b.pz + (long long)slot * E, S * E, live);
+  // ---- decoder (decoder.py:175-203), fed the prior's sample (vae_model.py:808) ----
+  const float* hprev = prev >= 0 ? b.hd + (long long)prev * E : nullptr;
+  if (hprev)
+    ACVAE_TRY(tc_linear2(N, A, hprev, S * E, w.d_attn_w, 2 * E, E, nullptr, 0, nullptr, 0, 0, nullptr,
+                         b.qp_d + (long long)slot * A, S * A, 0, live, st));
+  {
+    AttnFwdParams a{};
+    a.rows = N; a.Te = Te; a.A = A; a.E = E; a.Dq = E; a.rows_per_clip = c.d.mem_rep; a.live = live;
+    a.qp_in = hprev ? b.qp_d + (long long)slot * A : nullptr; a.ld_qp_in = S * A;
+    a.P = c.Pd; a.mem = c.mem; a.v = w.d_attn_v; a.mem_lens = c.mem_lens;
+    a.ctx = b.ctx_d + (long long)slot * E; a.ld_ctx = S * E;
+    a.w_out = nullptr;
+    ACVAE_TRY(launch_attn_fwd(a, st));
+  }
+  ACVAE_TRY(tc_linear2(N, 3 * E, ws.xe_d, E, w.d_wih, 3 * E, E, b.ctx_d + (long long)slot * E, S * E, w.d_wih + E, 3 * E, E,
+                       w.d_bih, ws.pre, 3 * E, 0, live, st));
+  ACVAE_TRY(tc_linear2(N, 3 * E, b.pz + (long long)slot * E, S * E, w.d_wih + 2 * E, 3 * E, E, nullptr, 0, nullptr, 0, 0,
+                       nullptr, ws.pre, 3 * E, 1, live, st));
+  if (hprev)
+    ACVAE_TRY(tc_linear2(N, 3 * E, hprev, S * E, w.d_whh, E, E, nullptr, 0, nullptr, 0, 0, nullptr, ws.pre_h, 3 * E, 0, live, st));
+  ACVAE_LAUNCH(gru_cell_kernel, grid1d((long long)N * E), 256, 0, st, N, E, (const float*)ws.pre,
+               hprev ? (const float*)ws.pre_h : (const float*)nullptr, w.d_bhh, hprev, S * E, b.hd + (long long)slot * E, S * E,
+               live);
+  return 0;
+}
+
+inline bool sample_tc_ok(const acvae_dims& d) {
+  static int dis = -1;
+  if (dis < 0) { const char* e = getenv("ACVAE_DISABLE_SAMPLE_TC"); dis = (e && e[0] == '1') ? 1 : 0; }
+  return !dis && tc_enabled() && d.N >= 256 && d.E % 32 == 0 && d.A % 32 == 0;
+}
+
 inline int decode_sample(const acvae_dims& d, const acvae_weights& w, const acvae_sample_io& io, void* workspace,
                          cudaStream_t st) {
   SampleWs ws = carve_sample_ws(d, workspace);
@@ -66,13 +157,18 @@ inline int decode_sample(const acvae_dims& d, const acvae_weights& w, const acva
                ws.unfinished, ws.active, (long long*)io.seqs, io.sampled_logprobs);
   StepBufs b{2, ws.qp_p, ws.w_p, ws.ctx_p, ws.gates_p, ws.c_p, ws.h_p, ws.pm, ws.pl, ws.pz,
              ws.qp_d, ws.w_d, ws.ctx_d, ws.gates_d, ws.hd};
+  const bool use_tc = sample_tc_ok(d);
   for (int t = 0; t < T; ++t) {
     const int slot = t & 1, prev = t > 0 ? (t - 1) & 1 : -1;
     const int* live = t > 0 ? ws.active + (t - 1) : nullptr;
     StepCtx c{d, w, st, io.mem_lens, ws.mem, ws.Pp, ws.Pd, live};
-    ACVAE_TRY(prior_step(c, b, slot, prev, ws.words + slot, 2, io.eps_p + (long long)t * N * E));
-    // inference: the decoder consumes the prior's sample (vae_model.py:808)
-    ACVAE_TRY(decoder_step(c, b, slot, prev, ws.words + slot, 2, ws.pz + (long long)slot * E, 2LL * E, nullptr, 0, 0));
+    if (use_tc) {
+      ACVAE_TRY(sample_step_tc(c, b, ws, slot, prev, ws.words + slot, 2, io.eps_p + (long long)t * N * E));
+    } else {
+      ACVAE_TRY(prior_step(c, b, slot, prev, ws.words + slot, 2, io.eps_p + (long long)t * N * E));
+      // inference: the decoder consumes the prior's sample (vae_model.py:808)
+      ACVAE_TRY(decoder_step(c, b, slot, prev, ws.words + slot, 2, ws.pz + (long long)slot * E, 2LL * E, nullptr, 0, 0));
+    }
     VocabStatsArgs v{};
     v.M = N; v.V = d.V; v.E = E; v.hidden = ws.hd + (long long)slot * E; v.ld_h = 2LL * E;
     v.cls_w = w.cls_w; v.cls_b = w.cls_b; v.live = live;

@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcParams tp,
                const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
                const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1) {
+  if (p.live && *p.live == 0) return;   // sampling early stop: uniform over the grid, before any barrier / TMEM allocation
   extern __shared__ uint8_t tc_smem_raw[];
   // 1 KB alignment by pointer arithmetic on the __shared__ array (keeps the shared address space visible to the
   // compiler: the split workers' accesses become LDS/STS instead of generic LD/ST)
@@ -433,7 +434,7 @@ struct TcShift { int a_shift = 0, b_shift = 0; };
 template <int EPI>
 inline int try_launch_tc(const GemmParams& p, cudaStream_t st) {
   if (!tc_enabled()) return 0;
-  if (p.G != 1 || p.nseg < 1 || p.nseg > 2 || p.M < 96 || p.live) return 0;
+  if (p.G != 1 || p.nseg < 1 || p.nseg > 2 || p.M < 96) return 0;
   const int NC = p.U;
   TcParams tp{};
   tp.nseg = p.nseg;

@@ -44,6 +44,36 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback (B200_PROFILING.md)"}
 
 
+def chain_kernel_bytes(d):
+    """Algorithmic bytes of ONE launch of dec_chain_fwd_kernel (decoder + prior forward chains, all T steps;
+    DESIGN.md section 4.3): the weight slices and the clips' memory read once, the per-step inputs read once and
+    every saved activation / output written once.  fp32."""
+    N, Te, T, E = d.N, d.Te, d.T, d.E
+    weights = 17 * E * E            # Wq, W_ih[:,E:2E], W_hh (decoder); W_ih[:,2E:3E], W_hh, head (prior)
+    memory = 2 * N * Te * E         # P_d, mem
+    per_nt = 24 * E + Te            # gx_d 3E, gx_p 4E, eps E | qp, ctx, out E each, gates_d 4E, w Te | gates_p 4E, c, h, pm, pl, pz
+    return 4 * (weights + memory + N * T * per_nt)
+
+
+def probe_kernel(lib, name, run, n, flush):
+    """Average duration (us) of the kernel whose name contains `name`, timed with CUDA events recorded on ITS
+    launching stream inside the library (acvae_set_kernel_probe), over `n` eager runs of `run`."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+    us = []
+    for a, b in ev:
+        flush()
+        a.record(); b.record()                    # materialise the underlying cudaEvent_t handles
+        torch.cuda.synchronize()
+        lib.acvae_set_kernel_probe(name.encode(), a.cuda_event, b.cuda_event)
+        run()
+        torch.cuda.synchronize()
+        hits = lib.acvae_kernel_probe_hits()
+        lib.acvae_set_kernel_probe(None, None, None)
+        if hits > 0:
+            us.append(a.elapsed_time(b) * 1e3)
+    return (sum(us) / len(us), len(us)) if us else (None, 0)
+
+
 def algorithmic_bytes_train(d, n_params):
     """fp32 algorithmic bytes of one fused train step (logits not materialised)."""
     N, Te, T, E = d.N, d.Te, d.T, d.E
@@ -277,6 +307,27 @@ def run_ours(args):
     ms_e2e = timed_e2e(args.steps)
     clk = clocks.stop()
 
+    # ---- dominant kernel, timed live with CUDA events on its own launching stream (eager steps, L2 flushed) ----
+    from acvae_b200 import _lib
+    lib = _lib.lib()
+    n_probe = min(10, max(3, args.steps))
+
+    def eager_step():
+        load_resident(0); ts.step_body()
+    chain_us, chain_n = probe_kernel(lib, "dec_chain_fwd_kernel", eager_step, n_probe, lambda: flush.fill_(1.0))
+    attn_us, _ = probe_kernel(lib, "attn_fwd_kernel", eager_step, n_probe, lambda: flush.fill_(1.0))
+    # the largest tcgen05 GEMM of the step (vocabulary statistics, [N*T, E] x [E, V]) on its own
+    hid = torch.randn(d.N * st_prep.T, d.E, device=dev)
+    cw, cb = model.decoder.classifier.weight.detach(), model.decoder.classifier.bias.detach()
+    F.vocab_stats(hid, cw, cb); torch.cuda.synchronize()
+    gemm_us = []
+    for _ in range(n_probe):
+        flush.fill_(2.0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); F.vocab_stats(hid, cw, cb); b.record(); torch.cuda.synchronize()
+        gemm_us.append(a.elapsed_time(b) * 1e3)
+    gemm_us = sum(gemm_us) / len(gemm_us)
+
     # ---- diverse sampling: clips partitioned across ranks, K captions share a clip's memory --------
     lo, hi = parallel.shard_range(SAMPLE_CLIPS, rank, world)
     ds = synthetic.Dims(N=hi - lo, Te=d.Te, L=SAMPLE_LEN + 1)
@@ -316,6 +367,49 @@ def run_ours(args):
         e2e = clips / (ms_e2e * 1e-3)
         bytes_step = algorithmic_bytes_train(d, n_params)
         ach = bytes_step / (ms_resident * 1e-3) / 1e9
+        ncu = {}
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
+        except Exception:
+            pass
+        if chain_us:
+            kb = chain_kernel_bytes(d)
+            k_ach = kb / (chain_us * 1e-6) / 1e9
+            roofline = {"bound": "hbm", "achieved": round(k_ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": round(k_ach / peaks["hbm_gbs"], 4),
+                        "traffic": ncu.get("dec_chain_fwd_kernel", {}).get("dram_bytes_per_launch"),
+                        "kernel": "dec_chain_fwd_kernel: decoder + prior forward chains, all T steps in ONE persistent "
+                                  "cooperative launch (largest single kernel of the step); bound by its serial chain of "
+                                  "3 grid barriers per step, not by bandwidth (DESIGN.md 4.3)",
+                        "us_per_launch": round(chain_us, 1), "launches_timed": chain_n,
+                        "share_of_step": round(chain_us * 1e-3 / ms_resident, 3),
+                        "algorithmic_bytes_per_launch": int(kb), "peak_source": peaks["src"],
+                        "timing": "CUDA events recorded on the kernel's launching stream (acvae_set_kernel_probe), eager steps, L2 flushed"}
+        else:   # launch-per-step schedule (chain kernels unavailable for this shape): whole-step figure
+            roofline = {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None,
+                        "kernel": "whole step (launch sequence)", "algorithmic_bytes_per_launch": int(bytes_step),
+                        "peak_source": peaks["src"]}
+        M_, V_, E_ = d.N * st_prep.T, d.V, d.E
+        gflop = 2.0 * M_ * V_ * E_
+        roofline_other = [
+            {"kernel": "tc_gemm_kernel<EPI_STATS> + vocab_reduce_kernel: vocabulary projection with fused "
+                       "lse / sum / argmax epilogue, [N*T,E]x[E,V], 3xTF32 on tcgen05 (logits never stored)",
+             "bound": "tensor", "achieved": round(gflop / (gemm_us * 1e-6) / 1e12, 2), "peak": peaks["bf16_tflops"],
+             "unit": "TFLOP/s", "frac": round(gflop / (gemm_us * 1e-6) / 1e12 / peaks["bf16_tflops"], 4),
+             "us_per_launch": round(gemm_us, 1), "flops_per_launch": int(gflop),
+             "note": "peak is the measured bf16 figure; 3 tf32 MMAs per product cap this kernel at 1/6 of it"},
+            {"kernel": "whole train step (all kernels; algorithmic bytes of SURVEY.md 8d)", "bound": "hbm",
+             "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4),
+             "algorithmic_bytes_per_step": int(bytes_step)},
+        ]
+        if attn_us:
+            ab = 4.0 * d.N * st_prep.T * d.Te * 2 * d.E          # every query row streams its clip's P and mem
+            roofline_other.append(
+                {"kernel": "attn_fwd_kernel: prior word attention, all (n,t) rows batched", "bound": "hbm",
+                 "achieved": round(ab / (attn_us * 1e-6) / 1e9, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                 "frac": round(ab / (attn_us * 1e-6) / 1e9 / peaks["hbm_gbs"], 4), "us_per_launch": round(attn_us, 1),
+                 "algorithmic_bytes_per_launch": int(ab), "note": "P and mem of a clip are L2-resident across its T rows"})
         line = {
             "metric": "train_clips_per_s", "value": round(value, 1), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_resident, 4), "higher_is_better": True, "scaling": "weak",
@@ -330,11 +424,8 @@ def run_ours(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "clocks": clk,
-            "roofline": {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None,
-                         "kernel": "whole fused step (launch sequence of acvae_train_fwd/bwd + vocab CE); "
-                                   "algorithmic bytes per step from SURVEY.md 8d",
-                         "algorithmic_bytes_per_step": int(bytes_step), "peak_source": peaks["src"]},
+            "roofline": roofline,
+            "roofline_other": roofline_other,
             "sampling": {"metric": "sampled_captions_per_s", "value": round(SAMPLE_CLIPS * SAMPLE_K / (ms_sample * 1e-3), 1),
                          "unit": "captions/s", "ms": round(ms_sample, 3), "clips": SAMPLE_CLIPS, "captions_per_clip": SAMPLE_K,
                          "max_length": SAMPLE_LEN, "method": "sample", "launches": int(sample_launches),

@@ -112,6 +112,12 @@ const char *acvae_last_error(void);
 int acvae_abi_version(void);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 uint64_t acvae_launch_count(void);
+/* Measurement hook (bench.py): record `ev_start` / `ev_stop` (cudaEvent_t, created WITH timing) on the launching
+ * stream right before / after every launch of a kernel whose name contains `kernel_name` (e.g.
+ * "dec_chain_fwd_kernel"); the last matching launch wins.  NULL or "" disables the probe.  Not for use under
+ * CUDA-graph capture.  acvae_kernel_probe_hits() = matching launches since the probe was set. */
+int acvae_set_kernel_probe(const char *kernel_name, void *ev_start, void *ev_stop);
+int acvae_kernel_probe_hits(void);
 
 /* ---- dense contraction (the building block of every batched GEMM of the step) ----------------
  * C[M,N] (ldc) = op(A) . op(B)^T [+ bias[N]] [+ C]   in fp32-grade accuracy.

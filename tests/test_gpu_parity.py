@@ -210,6 +210,26 @@ def test_sampling_k_captions_share_clip_memory():
     assert np.array_equal(out["seqs"].cpu().numpy().reshape(d.N * K, ml), o["seqs"].numpy())
 
 
+def test_sampling_large_batch_tensor_core_step_vs_oracle():
+    """>= 256 sequences take the tensor-core decode step (sample.cuh:sample_step_tc): token ids identical to the
+    oracle under the same injected noise (26 clips x 10 captions, E=256, V=4400)."""
+    _require_cuda()
+    import acvae_oracle as oracle
+    d, seed, ml, K = synthetic.Dims(N=26, Te=62, L=20), 8, 6, 10
+    m = harness.build_model(d, seed).eval()
+    b = synthetic.make_batch(d, seed)
+    rs = np.random.RandomState(1)
+    eps = torch.from_numpy(rs.standard_normal((ml, d.N * K, d.E)).astype(np.float32))
+    u = torch.from_numpy(rs.uniform(size=(ml, d.N * K, d.V)).astype(np.float32))
+    with torch.no_grad():
+        out = m(torch.from_numpy(b["audio_embeds"]).cuda(), torch.from_numpy(b["mem_lens"].copy()), method="sample",
+                max_length=ml, n_captions=K, eps_p=eps, u=u)
+        p = harness.oracle_params(d, seed)
+        o = oracle.inference_forward(p, torch.from_numpy(b["audio_embeds"]).repeat_interleave(K, 0),
+                                     np.repeat(b["mem_lens"], K), eps, "sample", ml, 1.0, u)
+    assert np.array_equal(out["seqs"].cpu().numpy().reshape(d.N * K, ml), o["seqs"].numpy())
+
+
 @pytest.mark.parametrize("name", ["tiny_beam", "cfg0_beam"])
 def test_beam_golden(name):
     _require_cuda()
