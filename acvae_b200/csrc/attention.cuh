@@ -53,18 +53,19 @@ struct AttnRing {
   const float *src0, *src1;
   int W0, W1, len, ntile, WMAX;
   float* bufs;
+  int nb = kAttnNB;   // ring depth actually used (<= kAttnNB)
   __device__ __forceinline__ void issue(int c) const {
     const bool second = c >= ntile;
     const int t = second ? c - ntile : c;
     const float* src = (second ? src1 : src0) + (long long)t * kAttnJT * (second ? W1 : W0);
     const int W = second ? W1 : W0;
     const int nf = min(kAttnJT, len - t * kAttnJT);
-    float* dst = bufs + (size_t)(c % kAttnNB) * kAttnJT * WMAX;
+    float* dst = bufs + (size_t)(c % nb) * kAttnJT * WMAX;
     const int n4 = nf * W / 4;
     for (int i = threadIdx.x; i < n4; i += blockDim.x) attn_cp16(dst + i * 4, src + i * 4);   // tile stored densely [nf][W]
     attn_commit();
   }
-  __device__ __forceinline__ const float* tile(int c) const { return bufs + (size_t)(c % kAttnNB) * kAttnJT * WMAX; }
+  __device__ __forceinline__ const float* tile(int c) const { return bufs + (size_t)(c % nb) * kAttnJT * WMAX; }
 };
 
 // dynamic smem: A (qp) + Te (scores) + 64 (reduction scratch) + ring
@@ -155,6 +156,107 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const __grid_constant__ A
   }
 }
 
+// ---- forward for K query rows that share one clip (diverse sampling: K captions per clip) ------------------------
+// One CTA per clip: the clip's P and mem tiles are streamed ONCE through the cp.async ring and reused by all
+// R = rows_per_clip queries (the one-CTA-per-row kernel above re-reads them R times from L2: 1.3 GB per call at
+// 10 450 rows).  tanh-bound: R * Te * A evaluations per clip.
+constexpr int kAttnMaxR = 16;
+// dynamic smem: ring + R*A (qp) + R*Te (scores) + 64
+__global__ void __launch_bounds__(256) attn_fwd_multi_kernel(const __grid_constant__ AttnFwdParams p) {
+  extern __shared__ __align__(16) float sm[];
+  if (p.live && *p.live == 0) return;
+  const int WMAX = max(p.A, p.E), R = p.rows_per_clip, A = p.A, E = p.E, Te = p.Te;
+  constexpr int NB = 2;                                  // shallow ring: 3 CTAs per SM hide the tanh latency
+  float* bufs = sm;
+  float* qp = bufs + (size_t)NB * kAttnJT * WMAX;        // [R][A]
+  float* sc = qp + R * A;                                // [R][Te]
+  const int clip = blockIdx.x;
+  const int r0 = clip * R;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const int len = max(1, min(p.mem_lens[clip], Te));
+  AttnRing ring{p.P + (long long)clip * Te * A, p.mem + (long long)clip * Te * E, A, E, len, (len + kAttnJT - 1) / kAttnJT, WMAX, bufs, NB};
+  const int nchunk = 2 * ring.ntile;
+  int issued = 0;
+  for (; issued < min(nchunk, NB); ++issued) ring.issue(issued);
+  for (int i = tid; i < R * A; i += blockDim.x) {
+    const int r = i / A, a = i % A;
+    qp[i] = p.qp_in ? p.qp_in[(long long)(r0 + r) * p.ld_qp_in + a] : 0.0f;
+  }
+  __syncthreads();
+  // pass 1: scores; a warp owns a frame, lanes stride A, all R queries per loaded P value
+  for (int c = 0; c < ring.ntile; ++c) {
+    attn_wait_dyn(issued - 1 - c);
+    __syncthreads();
+    const float* tile = ring.tile(c);
+    const int nf = min(kAttnJT, len - c * kAttnJT);
+    for (int jj = wid; jj < nf; jj += nw) {
+      const float* pr = tile + jj * A;
+      float s[kAttnMaxR];
+#pragma unroll
+      for (int r = 0; r < kAttnMaxR; ++r) s[r] = 0.0f;
+      for (int a = lane; a < A; a += 32) {
+        const float pv = pr[a], vv = __ldg(p.v + a);
+#pragma unroll
+        for (int r = 0; r < kAttnMaxR; ++r)
+          if (r < R) s[r] = fmaf(vv, tanhf(pv + qp[r * A + a]), s[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < kAttnMaxR; ++r)
+        if (r < R) {
+          const float t = warp_sum(s[r]);
+          if (lane == 0) sc[r * Te + c * kAttnJT + jj] = t;
+        }
+    }
+    __syncthreads();
+    if (issued < nchunk) { ring.issue(issued); ++issued; }
+  }
+  // masked softmax, one warp per query row
+  for (int r = wid; r < R; r += nw) {
+    float* sr = sc + r * Te;
+    float mx = -INFINITY;
+    for (int j = lane; j < len; j += 32) mx = fmaxf(mx, sr[j]);
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int j = lane; j < len; j += 32) { const float e = expf(sr[j] - mx); sr[j] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int j = lane; j < Te; j += 32) {
+      const float w = j < len ? sr[j] * inv : 0.0f;
+      if (j < len) sr[j] = w;
+      if (p.w_out) p.w_out[(long long)(r0 + r) * p.ld_w + j] = w;
+    }
+  }
+  // pass 2: context; a thread owns features e, e + 256, ... for all R queries
+  for (int e0 = 0; e0 < E; e0 += blockDim.x) {   // E <= 256 in practice: one sweep of the ring
+    float acc[kAttnMaxR];
+#pragma unroll
+    for (int r = 0; r < kAttnMaxR; ++r) acc[r] = 0.0f;
+    const int e = e0 + tid;
+    for (int c = ring.ntile; c < nchunk; ++c) {
+      attn_wait_dyn(issued - 1 - c);
+      __syncthreads();
+      const float* tile = ring.tile(c);
+      const int j0 = (c - ring.ntile) * kAttnJT;
+      const int nf = min(kAttnJT, len - j0);
+      if (e < E) {
+        for (int jj = 0; jj < nf; ++jj) {
+          const float mv = tile[jj * E + e];
+#pragma unroll
+          for (int r = 0; r < kAttnMaxR; ++r)
+            if (r < R) acc[r] = fmaf(sc[r * Te + j0 + jj], mv, acc[r]);
+        }
+      }
+      __syncthreads();
+      if (issued < nchunk) { ring.issue(issued); ++issued; }
+    }
+    if (e < E) {
+#pragma unroll
+      for (int r = 0; r < kAttnMaxR; ++r)
+        if (r < R) p.ctx[(long long)(r0 + r) * p.ld_ctx + e] = acc[r];
+    }
+  }
+}
+
 inline size_t attn_smem_bytes(int A, int E, int Te, int extra) {
   const int WMAX = A > E ? A : E;
   return ((size_t)kAttnNB * kAttnJT * WMAX + A + Te + 64 + extra) * sizeof(float);
@@ -163,6 +265,19 @@ inline size_t attn_smem_bytes(int A, int E, int Te, int extra) {
 inline int launch_attn_fwd(const AttnFwdParams& p, cudaStream_t st) {
   if (p.rows <= 0) return 0;
   ACVAE_REQUIRE(p.E <= 1024 && p.A % 4 == 0 && p.E % 4 == 0, "attention: E <= 1024 and A, E multiples of 4");
+  if (p.rows_per_clip > 1 && p.rows_per_clip <= kAttnMaxR && p.rows % p.rows_per_clip == 0 && p.E <= 256 && !p.aw_out) {
+    const int WMAX = p.A > p.E ? p.A : p.E;
+    const size_t smem_m = ((size_t)2 * kAttnJT * WMAX + (size_t)p.rows_per_clip * (p.A + p.Te) + 64) * sizeof(float);
+    if (smem_m <= 227 * 1024) {
+      static size_t configured_m = 0;
+      if (smem_m > configured_m) {
+        ACVAE_CHECK(cudaFuncSetAttribute(attn_fwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
+        configured_m = smem_m;
+      }
+      ACVAE_LAUNCH(attn_fwd_multi_kernel, p.rows / p.rows_per_clip, 256, smem_m, st, p);
+      return 0;
+    }
+  }
   const size_t smem = attn_smem_bytes(p.A, p.E, p.Te, 0);
   ACVAE_REQUIRE(smem <= 227 * 1024, "attention tile ring exceeds shared memory");
   static size_t configured = 0;

@@ -9,6 +9,7 @@
 // K tiled copies (the reference tiles the clip K times through the encoder,
 // runners/pytorch_runner_vae.py:101-104).
 #pragma once
+#include "streams.cuh"
 #include "train.cuh"
 
 namespace acvae {
@@ -19,6 +20,7 @@ struct SampleWs {
   float *qp_p, *w_p, *ctx_p, *gates_p, *c_p, *h_p, *pm, *pl, *pz, *qp_d, *w_d, *ctx_d, *gates_d, *hd;
   float *pmax, *pexp, *psum, *pbest; int* parg;
   float *xe_p, *xe_d, *pre, *pre_h;   // tensor-core step: gathered embeddings, gate pre-activations
+  float* gum[2];                      // tensor-core step: Gumbel variates of the current / next step [N,V]
   size_t bytes;
 };
 
@@ -37,6 +39,8 @@ inline SampleWs carve_sample_ws(const acvae_dims& d, void* base) {
   w.pmax = ar.take<float>(N * nt); w.pexp = ar.take<float>(N * nt); w.psum = ar.take<float>(N * nt);
   w.pbest = ar.take<float>(N * nt * 2); w.parg = ar.take<int>(N * nt);
   w.xe_p = ar.take<float>(N * E); w.xe_d = ar.take<float>(N * E); w.pre = ar.take<float>(N * 4 * E); w.pre_h = ar.take<float>(N * 3 * E);
+  const size_t gum = N >= 256 ? N * (size_t)d.V : 0;   // only the large-batch tensor-core step uses it
+  w.gum[0] = ar.take<float>(gum); w.gum[1] = ar.take<float>(gum);
   w.bytes = ar.off;
   return w;
 }
@@ -142,6 +146,19 @@ inline int sample_step_tc(const StepCtx& c, const StepBufs& b, SampleWs& ws, int
   return 0;
 }
 
+// g = -log(-log(u + 1e-20) + 1e-20) (word_model.py:188-190), elementwise at full occupancy on a side stream:
+// inside the vocabulary GEMM's epilogue the two logs per logit cost more than the GEMM itself.
+__global__ void gumbel_kernel(long long n, const float* __restrict__ u, float* __restrict__ g) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const bool vec = ((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(g)) & 15) == 0;
+  if (vec && i + 3 < n) {
+    const float4 x = *reinterpret_cast<const float4*>(u + i);
+    *reinterpret_cast<float4*>(g + i) = make_float4(gumbel_from_u(x.x), gumbel_from_u(x.y), gumbel_from_u(x.z), gumbel_from_u(x.w));
+  } else {
+    for (long long k = i; k < n && k < i + 4; ++k) g[k] = gumbel_from_u(u[k]);
+  }
+}
+
 inline bool sample_tc_ok(const acvae_dims& d) {
   static int dis = -1;
   if (dis < 0) { const char* e = getenv("ACVAE_DISABLE_SAMPLE_TC"); dis = (e && e[0] == '1') ? 1 : 0; }
@@ -158,6 +175,15 @@ inline int decode_sample(const acvae_dims& d, const acvae_weights& w, const acva
   StepBufs b{2, ws.qp_p, ws.w_p, ws.ctx_p, ws.gates_p, ws.c_p, ws.h_p, ws.pm, ws.pl, ws.pz,
              ws.qp_d, ws.w_d, ws.ctx_d, ws.gates_d, ws.hd};
   const bool use_tc = sample_tc_ok(d);
+  Aux* ax = (use_tc && io.method != 0) ? aux() : nullptr;    // side stream: Gumbel variates one step ahead
+  const long long nv = (long long)N * d.V;
+  auto gumbel_ahead = [&](int t) -> int {
+    cudaStream_t sg = ax->s[0];
+    ACVAE_TRY(stream_dep(st, sg, ax));     // gum[t & 1] was last read by step t-2 (already enqueued on st)
+    ACVAE_LAUNCH(gumbel_kernel, grid1d((nv + 3) / 4), 256, 0, sg, nv, io.u + (long long)t * nv, ws.gum[t & 1]);
+    return 0;
+  };
+  if (ax) ACVAE_TRY(gumbel_ahead(0));
   for (int t = 0; t < T; ++t) {
     const int slot = t & 1, prev = t > 0 ? (t - 1) & 1 : -1;
     const int* live = t > 0 ? ws.active + (t - 1) : nullptr;
@@ -173,7 +199,12 @@ inline int decode_sample(const acvae_dims& d, const acvae_weights& w, const acva
     v.M = N; v.V = d.V; v.E = E; v.hidden = ws.hd + (long long)slot * E; v.ld_h = 2LL * E;
     v.cls_w = w.cls_w; v.cls_b = w.cls_b; v.live = live;
     v.pmax = ws.pmax; v.pexp = ws.pexp; v.psum = ws.psum; v.pbest = ws.pbest; v.parg = ws.parg;
-    if (io.method != 0) {
+    if (io.method != 0 && ax) {
+      ACVAE_TRY(stream_dep(ax->s[0], st, ax));             // this step's variates are ready
+      if (t + 1 < T) ACVAE_TRY(gumbel_ahead(t + 1));
+      v.noise = ws.gum[t & 1]; v.ld_noise = d.V; v.noise_is_gumbel = 1;
+      v.inv_temp = io.method == 1 ? 1.0f / io.temp : 1.0f;
+    } else if (io.method != 0) {
       v.noise = io.u + (long long)t * N * d.V; v.ld_noise = d.V;
       v.inv_temp = io.method == 1 ? 1.0f / io.temp : 1.0f;   // word_model.py:187-198
     }

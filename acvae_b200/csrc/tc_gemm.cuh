@@ -375,8 +375,11 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
     for (int j = 0; j < kTcBN / 2; ++j) Cs[row * (kTcBN + 1) + col0 + j] = acc_reg[j];
   }
   __syncthreads();
-  if (tid < 256)   // the shared epilogue strides by 256 threads
+  if constexpr (EPI == EPI_STATS) {   // row-per-warp epilogue: all 16 warps
+    gemm_epilogue<EPI, kTcBM, kTcBN, kTcThreads>(p, reinterpret_cast<const float*>(smem), kTcBN + 1, m0, c0, tid, blockIdx.x, gridDim.x);
+  } else if (tid < 256) {             // the element-wise epilogues stride by 256 threads
     gemm_epilogue<EPI, kTcBM, kTcBN>(p, reinterpret_cast<const float*>(smem), kTcBN + 1, m0, c0, tid, blockIdx.x, gridDim.x);
+  }
   __syncthreads();
   if (wid == 1) {
     tc_fence_after();

@@ -161,7 +161,7 @@ struct VocabStatsArgs {
   const float* hidden; long long ld_h;
   const float* cls_w; const float* cls_b;
   float *pmax, *pexp, *psum, *pbest; int* parg;       // partial buffers [M, ntiles]
-  const float* noise; long long ld_noise; float inv_temp;
+  const float* noise; long long ld_noise; float inv_temp; int noise_is_gumbel;
   const int* live;
   VocabReduceParams red;                                // outputs (M/ntiles/partials filled in here)
 };
@@ -171,7 +171,7 @@ inline int vocab_stats(VocabStatsArgs a, cudaStream_t st) {
   p.seg[0] = seg_plain(a.hidden, a.ld_h, a.cls_w, a.E, a.E);
   p.epi.bias[0] = a.cls_b;
   p.epi.pmax = a.pmax; p.epi.pexp = a.pexp; p.epi.psum = a.psum; p.epi.pbest = a.pbest; p.epi.parg = a.parg;
-  p.epi.noise = a.noise; p.epi.ld_noise = a.ld_noise; p.epi.inv_temp = a.inv_temp;
+  p.epi.noise = a.noise; p.epi.ld_noise = a.ld_noise; p.epi.inv_temp = a.inv_temp; p.epi.noise_is_gumbel = a.noise_is_gumbel;
   p.live = a.live; a.red.live = a.live;
   int used_tc = 0;
   ACVAE_TRY(launch_gemm<EPI_STATS>(p, st, &used_tc));
