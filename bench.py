@@ -224,6 +224,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the ONE JSON line: NCCL prints its version banner / debug log there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     ts = make_train_step(dev, world, rank, use_graph=not args.no_graph)
     model, d, n_params, run_step, load_resident = ts.model, ts.d, ts.n_params, ts.run_step, ts.load_resident
@@ -436,7 +440,11 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(d, budget_s=20.0)
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # graphs that captured NCCL work can stall the process-group teardown: settle, then leave without it
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 # ------------------------------------------------------------------------------ CPU reference arm
