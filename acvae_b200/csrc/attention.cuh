@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const __grid_constant__ A
     for (int jj = wid; jj < nf; jj += nw) {
       const float* pr = tile + jj * p.A;
       float s = 0.0f;
-      for (int a = lane; a < p.A; a += 32) s = fmaf(__ldg(p.v + a), tanhf(pr[a] + qp[a]), s);
+      for (int a = lane; a < p.A; a += 32) s = fmaf(__ldg(p.v + a), attn_tanh(pr[a] + qp[a]), s);
       s = warp_sum(s);
       if (lane == 0) sc[c * kAttnJT + jj] = s;
     }
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) attn_fwd_multi_kernel(const __grid_consta
         const float pv = pr[a], vv = __ldg(p.v + a);
 #pragma unroll
         for (int r = 0; r < kAttnMaxR; ++r)
-          if (r < R) s[r] = fmaf(vv, tanhf(pv + qp[r * A + a]), s[r]);
+          if (r < R) s[r] = fmaf(vv, attn_tanh(pv + qp[r * A + a]), s[r]);
       }
 #pragma unroll
       for (int r = 0; r < kAttnMaxR; ++r)
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(256) attn_bwd_q_kernel(const __grid_constant__
         const float qa = qp[a], va = __ldg(p.v + a);
         float s = 0.0f;
         for (int jj = 0; jj < nf; ++jj) {
-          const float th = tanhf(tile[jj * p.A + a] + qa);
+          const float th = attn_tanh(tile[jj * p.A + a] + qa);
           s = fmaf(dw[j0 + jj] * va, 1.0f - th * th, s);
         }
         acc[q] += s;
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(256) attn_bwd_acc_kernel(const __grid_constant
         for (int i = 0; i < p.rows_per_clip; ++i) {
           const long long r = r0 + i;
           const float d = p.ds[r * p.ld_ds + j];
-          const float th = tanhf(pj + p.qp[r * p.ld_qp + a]);
+          const float th = attn_tanh(pj + p.qp[r * p.ld_qp + a]);
           acc = fmaf(d * va, 1.0f - th * th, acc);
           dvacc = fmaf(d, th, dvacc);
         }

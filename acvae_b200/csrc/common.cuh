@@ -60,6 +60,17 @@ inline int set_error(const char* what, const char* detail = "") {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// tanh for the additive-attention scores (attn_model.py:32): T = Te*A evaluations per query row make the
+// attention kernels MUFU/issue bound, and libdevice tanhf costs ~100 issue slots per warp there (branchy, two
+// paths).  (e^{2x} - 1) / (e^{2x} + 1) with one ex2.approx and one rcp.approx: absolute error < 2e-7 over the
+// whole range (the subtraction only loses RELATIVE accuracy near 0, where tanh itself is ~x), clamped where
+// fp32 tanh is 1.  Used consistently by the forward, its backward and the sampling kernels.
+__device__ __forceinline__ float attn_tanh(float x) {
+  const float xc = fminf(fmaxf(x, -9.0f), 9.0f);
+  const float t = __expf(2.0f * xc);
+  return __fdividef(t - 1.0f, t + 1.0f);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

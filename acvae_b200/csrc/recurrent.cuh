@@ -31,8 +31,8 @@ struct GridBar {
   unsigned target;
   unsigned nctas;
 };
-// Barrier over all CTAs of the (cooperatively launched, hence co-resident) grid: bar.sync; thread 0: gpu-scope
-// fence, atomic increment, volatile polling of the counter, fence; bar.sync.  Measured on B200 with 128 CTAs
+// Barrier over all CTAs of the (cooperatively launched, hence co-resident) grid: bar.sync; thread 0: release
+// increment of one counter, volatile polling of the counter; bar.sync.  Measured on B200 with 128 CTAs
 // (profiles/ubench_gridbar.cu): 2500 cycles for this form, 5200 for per-CTA flags polled by every CTA (hot L2
 // lines), 8800 with a store before / loads after it.  Writes made by any thread of a CTA before the barrier are
 // visible to every thread of every CTA after it; cross-CTA data is read with ld.global.cg (L1 is not coherent).
@@ -41,12 +41,14 @@ __device__ __forceinline__ void grid_sync(GridBar& gb) {
   __syncthreads();
   if (threadIdx.x == 0) {
     gb.target += gb.nctas;
-    __threadfence();
-    atomicAdd(gb.counter, 1u);
+    // release-increment without a return value: orders the CTA's earlier writes (bar.sync makes them
+    // happen-before this thread) and does not wait for the atomic's round trip
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(gb.counter) : "memory");
     long long spin = 0;
     while (*reinterpret_cast<volatile unsigned*>(gb.counter) < gb.target)
       if (++spin > (1ll << 26)) __trap();
-    __threadfence();
+    // no trailing fence: every cross-CTA read after the barrier is an ld.global.cg (served by L2, where the
+    // producers' writes were performed before their release-increment), so there is no stale L1 line to invalidate
   }
   __syncthreads();
 }
@@ -118,6 +120,7 @@ struct PostChainFwd {
   float* ho;             // [N,T,2E]
   float* gq[2];          // [N,T,4E] saved (r,z,n,gh_n)
   unsigned* bar;
+  long long* trace;      // optional [T][8] clock64 stamps of thread 0 of CTA 0 (profiles/ubench_chain.cu) or NULL
 };
 __global__ void __launch_bounds__(kChainThreads) post_chain_fwd_kernel(const __grid_constant__ PostChainFwd p) {
   constexpr int E = kChainE;
@@ -143,6 +146,8 @@ __global__ void __launch_bounds__(kChainThreads) post_chain_fwd_kernel(const __g
       for (int c = 0; c < 6; ++c) acc[d][c] = 0.0f;
     const int t = dir ? T - 1 - s : s;
     const int tp = dir ? t + 1 : t - 1;
+    const bool tr = p.trace && blockIdx.x == 0 && tid == 0;
+    if (tr) p.trace[s * 8 + 0] = clock64();
     float gxr = 0.f, gxz = 0.f, gxn = 0.f, hp = 0.f;
     if (row && kp < 4) {                               // pointwise operands: issued with the row loads
       const float* gx = p.gx[dir] + ((long long)n * T + t) * 3 * E + u;
@@ -160,9 +165,11 @@ __global__ void __launch_bounds__(kChainThreads) post_chain_fwd_kernel(const __g
         rowfma<6, E>(a0, &W[0][0][0], E, kp, acc[0]);
         rowfma<6, E>(a1, &W[1][0][0], E, kp, acc[1]);
       }
+      if (tr) p.trace[s * 8 + 1] = clock64();
       reduce8(acc[0]);
       reduce8(acc[1]);
     }
+    if (tr) p.trace[s * 8 + 2] = clock64();
     if (row && kp < 4) {
       // static register indices only (a runtime index would spill the accumulators to local memory)
       const float hr = (dir ? (j ? acc[1][1] : acc[1][0]) : (j ? acc[0][1] : acc[0][0])) + bh_r;
@@ -176,7 +183,9 @@ __global__ void __launch_bounds__(kChainThreads) post_chain_fwd_kernel(const __g
       gs[0] = rg; gs[E] = zg; gs[2 * E] = ng; gs[3 * E] = hn;
       p.ho[((long long)n * T + t) * 2 * E + dir * E + u] = hnew;
     }
+    if (tr) p.trace[s * 8 + 3] = clock64();
     if (s + 1 < T) grid_sync(gb);
+    if (tr) p.trace[s * 8 + 4] = clock64();
   }
 }
 
@@ -569,7 +578,7 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __gr
         const float* pr = Ps + (size_t)jj * A;
         float s = 0.0f;
 #pragma unroll
-        for (int a = lane; a < A; a += 32) s = fmaf(vs[a], tanhf(pr[a] + qps[a]), s);
+        for (int a = lane; a < A; a += 32) s = fmaf(vs[a], attn_tanh(pr[a] + qps[a]), s);
         s = warp_sum(s);
         if (lane == 0) sc[jj] = s;
       }
@@ -781,7 +790,7 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_bwd_kernel(const __gr
       const float qa = qps[tid];
       float s = 0.0f;
       for (int jj = 0; jj < len; ++jj) {
-        const float th = tanhf(Ps[(size_t)jj * A + tid] + qa);
+        const float th = attn_tanh(Ps[(size_t)jj * A + tid] + qa);
         s = fmaf(dw[jj] * va, 1.0f - th * th, s);
       }
       p.dqp[((long long)clip * T + t) * A + tid] = s;

@@ -33,7 +33,7 @@ struct TrainWs {
   float *dout, *dgi_d, *dgh_d, *dh_carry, *dctx_d, *ds_d, *dqp_d, *dxz_d, *dxe_d;
   float *dml_p, *dg_p, *dhp_carry, *dcp_carry, *dzp_carry, *dxe_p, *dctx_p, *ds_p, *dqp_p;
   float *dml_q, *dho, *dgi_q[2], *dgh_q[2], *dhq_carry, *dxq, *dzq_carry;
-  float *dPp, *dPd, *dmem, *dpool;
+  float *dPp, *dPd, *dmem, *dmem2, *dpool;
   unsigned* bars;   // grid-barrier counters of the persistent chain kernels (recurrent.cuh)
   size_t bytes;
 };
@@ -66,6 +66,7 @@ inline TrainWs carve_train_ws(const acvae_dims& d, void* base) {
   for (int k = 0; k < 2; ++k) { w.dgi_q[k] = ar.take<float>(NT * 3 * E); w.dgh_q[k] = ar.take<float>(NT * 3 * E); }
   w.dhq_carry = ar.take<float>(N * E); w.dxq = ar.take<float>(NT * E); w.dzq_carry = ar.take<float>(N * E);
   w.dPp = ar.take<float>(N * Te * E); w.dPd = ar.take<float>(N * Te * A); w.dmem = ar.take<float>(N * Te * E);
+  w.dmem2 = ar.take<float>(N * Te * E);
   w.dpool = ar.take<float>(N * 2 * E);
   w.bars = ar.take<unsigned>(8 * 128);
   w.bytes = ar.off;

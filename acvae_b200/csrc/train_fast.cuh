@@ -79,7 +79,15 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     h.epi.eps = io.eps_q; h.epi.ld_eps = E;
     h.epi.out0 = io.q_means; h.epi.out1 = io.q_logs; h.epi.out2 = io.q_z;
     h.epi.ld_out0 = h.epi.ld_out1 = h.epi.ld_out2 = E;
-    ACVAE_TRY(launch_gemm<EPI_HEAD>(h, sq0));
+    if (NT >= 96 && tc_enabled()) {
+      // tensor cores: [mean | log] = ho . W^T + b into a scratch (dml_q is free during the forward), then the
+      // reparameterisation as a small pointwise kernel
+      ACVAE_TRY(linear_fwd(NT, 2 * E, 2 * E, ws.ho, 2 * E, w.q_head_w, 2 * E, w.q_head_b, ws.dml_q, 2 * E, sq0));
+      ACVAE_LAUNCH(head_cell_kernel, grid1d((long long)NT * E), 256, 0, sq0, NT, E, (const float*)ws.dml_q, io.eps_q,
+                   io.q_means, io.q_logs, io.q_z, (long long)E, (const int*)nullptr);
+    } else {
+      ACVAE_TRY(launch_gemm<EPI_HEAD>(h, sq0));
+    }
     ACVAE_LAUNCH(pool_fwd_kernel, grid1d((long long)N * 2 * E), 256, 0, sq0, N, T, 2 * E, ws.ho, ws.steplens, 0,
                  io.q_means_utt, ws.amax_q);
   }
@@ -285,8 +293,9 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   }
   // prior batched remainders (after the prior chain: at once in the launch-per-step schedule, after the merged
   // decoder+prior kernel in chain mode)
+  cudaEvent_t ev_prior_acc = ax->ev();      // recorded on sp once the prior's dPp / dmem are complete
   auto prior_remainders = [&]() -> int {
-  ACVAE_TRY(linear_bwd_data(NT, E, 4 * E, ws.dg_p, 4 * E, w.p_wih, 3 * E, ws.dxe_p, E, sp));
+    // critical first: d ctx -> attention backward -> per-clip accumulation (the memory backward waits for it)
     ACVAE_TRY(linear_bwd_data(NT, E, 4 * E, ws.dg_p, 4 * E, w.p_wih + E, 3 * E, ws.dctx_p, E, sp));
     {
       AttnBwdQParams a{};
@@ -296,6 +305,18 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
       a.ds = ws.ds_p; a.ld_ds = Te; a.dqp = ws.dqp_p; a.ld_dqp = E;
       ACVAE_TRY(launch_attn_bwd_q(a, sp));
     }
+    ACVAE_CHECK(zero(gw.p_attn_v, E, sp));
+    {
+      AttnBwdAccParams a{};
+      a.clips = N; a.Te = Te; a.A = E; a.E = E; a.rows_per_clip = T;
+      a.ds = ws.ds_p; a.ld_ds = Te; a.w = ws.w_p; a.ld_w = Te; a.qp = ws.qp_p; a.ld_qp = E;
+      a.dctx = ws.dctx_p; a.ld_dctx = E; a.P = ws.Pp; a.v = w.p_attn_v; a.mem_lens = io.mem_lens;
+      a.dP = ws.dPp; a.dmem = ws.dmem; a.dmem_accumulate = 0; a.dv = gw.p_attn_v;
+      ACVAE_TRY(launch_attn_bwd_acc(a, sp));
+    }
+    ACVAE_CHECK(cudaEventRecord(ev_prior_acc, sp));
+    // the rest: embedding / weight / bias gradients
+    ACVAE_TRY(linear_bwd_data(NT, E, 4 * E, ws.dg_p, 4 * E, w.p_wih, 3 * E, ws.dxe_p, E, sp));
     ACVAE_TRY(linear_bwd_data(NT, E, E, ws.dqp_p, E, w.p_attn_w, 2 * E, ws.dxe_p, E, sp, 1));
     ACVAE_CHECK(zero(gw.p_emb, (size_t)V * E, sp));
     ACVAE_TRY(scatter_rows(NT, E, ws.dxe_p, E, ws.words, gw.p_emb, sp));
@@ -308,16 +329,6 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     ACVAE_CHECK(cudaMemcpyAsync(gw.p_bhh, gw.p_bih, sizeof(float) * 4 * E, cudaMemcpyDeviceToDevice, sp));
     ACVAE_TRY(linear_bwd_weight(2 * E, E, NT, ws.dml_p, 2 * E, ws.h_p, E, gw.p_head_w, E, sp));
     ACVAE_TRY(colsum(NT, 2 * E, ws.dml_p, 2 * E, gw.p_head_b, sp));
-    ACVAE_CHECK(zero(gw.p_attn_v, E, sp));
-    {
-      AttnBwdAccParams a{};
-      a.clips = N; a.Te = Te; a.A = E; a.E = E; a.rows_per_clip = T;
-      a.ds = ws.ds_p; a.ld_ds = Te; a.w = ws.w_p; a.ld_w = Te; a.qp = ws.qp_p; a.ld_qp = E;
-      a.dctx = ws.dctx_p; a.ld_dctx = E; a.P = ws.Pp; a.v = w.p_attn_v; a.mem_lens = io.mem_lens;
-      a.dP = ws.dPp; a.dmem = ws.dmem; a.dmem_accumulate = 0; a.dv = gw.p_attn_v;
-      ACVAE_TRY(launch_attn_bwd_acc(a, sp));
-    }
-
     return 0;
   };
   ACVAE_TRY(prior_remainders());
@@ -388,7 +399,38 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   // d z fed to the decoder -> d q_z (needed by the posterior backward): first thing after the chain
   ACVAE_TRY(linear_bwd_data(NT, E, 3 * E, ws.dgi_d, 3 * E, w.d_wih + 2 * E, 3 * E, ws.dxz_d, E, st));
   ACVAE_TRY(stream_dep(st, sx, ax));
-  // decoder batched remainders on a side stream (overlaps the posterior chains)
+  // ---- side stream sx (overlaps the posterior chains) ----
+  // critical first: the decoder's per-clip attention accumulation (into its own buffer: no ordering against the
+  // prior's), then the memory backward as soon as the prior's accumulation is done too
+  ACVAE_CHECK(zero(gw.d_attn_v, A, sx));
+  {
+    AttnBwdAccParams a{};
+    a.clips = N; a.Te = Te; a.A = A; a.E = E; a.rows_per_clip = T;
+    a.ds = ws.ds_d; a.ld_ds = Te; a.w = ws.w_d; a.ld_w = Te; a.qp = ws.qp_d; a.ld_qp = A;
+    a.dctx = ws.dctx_d; a.ld_dctx = E; a.P = ws.Pd; a.v = w.d_attn_v; a.mem_lens = io.mem_lens;
+    a.dP = ws.dPd; a.dmem = ws.dmem2; a.dmem_accumulate = 0; a.dv = gw.d_attn_v;
+    ACVAE_TRY(launch_attn_bwd_acc(a, sx));
+  }
+  ACVAE_CHECK(cudaStreamWaitEvent(sx, ev_prior_acc, 0));
+  // memory backward: attention memory halves, ln (vae_model.py:743-744)
+  {
+    const int R = N * Te;
+    ACVAE_LAUNCH(add_inplace_kernel, grid1d((long long)R * E), 256, 0, sx, (long long)R * E, ws.dmem, (const float*)ws.dmem2);
+    ACVAE_TRY(linear_bwd_data(R, E, E, ws.dPp, E, w.p_attn_w + E, 2 * E, ws.dmem, E, sx, 1));
+    ACVAE_TRY(linear_bwd_data(R, E, A, ws.dPd, A, w.d_attn_w + E, 2 * E, ws.dmem, E, sx, 1));
+    if (w.ln_w) {
+      if (d_audio) ACVAE_TRY(linear_bwd_data(R, d.Eenc, E, ws.dmem, E, w.ln_w, d.Eenc, d_audio, d.Eenc, sx));
+      ACVAE_TRY(linear_bwd_weight(E, d.Eenc, R, ws.dmem, E, io.audio_embeds, d.Eenc, gw.ln_w, d.Eenc, sx));
+      ACVAE_TRY(colsum(R, E, ws.dmem, E, gw.ln_b, sx));
+    } else if (d_audio) {
+      ACVAE_CHECK(cudaMemcpyAsync(d_audio, ws.dmem, sizeof(float) * (size_t)R * E, cudaMemcpyDeviceToDevice, sx));
+    }
+    ACVAE_TRY(linear_bwd_weight(E, E, R, ws.dPp, E, ws.mem, E, gw.p_attn_w + E, 2 * E, sx));
+    ACVAE_TRY(linear_bwd_weight(A, E, R, ws.dPd, A, ws.mem, E, gw.d_attn_w + E, 2 * E, sx));
+    ACVAE_TRY(colsum(R, E, ws.dPp, E, gw.p_attn_b, sx));
+    ACVAE_TRY(colsum(R, A, ws.dPd, A, gw.d_attn_b, sx));
+  }
+  // decoder embedding / weight / bias gradients
   ACVAE_TRY(linear_bwd_data(NT, E, 3 * E, ws.dgi_d, 3 * E, w.d_wih, 3 * E, ws.dxe_d, E, sx));
   ACVAE_CHECK(zero(gw.d_emb, (size_t)V * E, sx));
   ACVAE_TRY(scatter_rows(NT, E, ws.dxe_d, E, ws.words, gw.d_emb, sx));
@@ -399,34 +441,6 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   ACVAE_TRY(colsum(NT, 3 * E, ws.dgh_d, 3 * E, gw.d_bhh, sx));
   ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgh_d, 3 * E, io.outputs - E, E, gw.d_whh, E, sx, T, 0, -1));
   ACVAE_TRY(linear_bwd_weight(A, E, NT, ws.dqp_d, A, io.outputs - E, E, gw.d_attn_w, 2 * E, sx, T, 0, -1));
-  ACVAE_CHECK(zero(gw.d_attn_v, A, sx));
-  // the decoder's attention accumulation adds onto the prior's dmem: order after the prior stream
-  ACVAE_TRY(stream_dep(sp, sx, ax));
-  {
-    AttnBwdAccParams a{};
-    a.clips = N; a.Te = Te; a.A = A; a.E = E; a.rows_per_clip = T;
-    a.ds = ws.ds_d; a.ld_ds = Te; a.w = ws.w_d; a.ld_w = Te; a.qp = ws.qp_d; a.ld_qp = A;
-    a.dctx = ws.dctx_d; a.ld_dctx = E; a.P = ws.Pd; a.v = w.d_attn_v; a.mem_lens = io.mem_lens;
-    a.dP = ws.dPd; a.dmem = ws.dmem; a.dmem_accumulate = 1; a.dv = gw.d_attn_v;
-    ACVAE_TRY(launch_attn_bwd_acc(a, sx));
-  }
-  // memory backward: attention memory halves, ln (vae_model.py:743-744)
-  {
-    const int R = N * Te;
-    ACVAE_TRY(linear_bwd_data(R, E, E, ws.dPp, E, w.p_attn_w + E, 2 * E, ws.dmem, E, sx, 1));
-    ACVAE_TRY(linear_bwd_data(R, E, A, ws.dPd, A, w.d_attn_w + E, 2 * E, ws.dmem, E, sx, 1));
-    ACVAE_TRY(linear_bwd_weight(E, E, R, ws.dPp, E, ws.mem, E, gw.p_attn_w + E, 2 * E, sx));
-    ACVAE_TRY(linear_bwd_weight(A, E, R, ws.dPd, A, ws.mem, E, gw.d_attn_w + E, 2 * E, sx));
-    ACVAE_TRY(colsum(R, E, ws.dPp, E, gw.p_attn_b, sx));
-    ACVAE_TRY(colsum(R, A, ws.dPd, A, gw.d_attn_b, sx));
-    if (w.ln_w) {
-      if (d_audio) ACVAE_TRY(linear_bwd_data(R, d.Eenc, E, ws.dmem, E, w.ln_w, d.Eenc, d_audio, d.Eenc, sx));
-      ACVAE_TRY(linear_bwd_weight(E, d.Eenc, R, ws.dmem, E, io.audio_embeds, d.Eenc, gw.ln_w, d.Eenc, sx));
-      ACVAE_TRY(colsum(R, E, ws.dmem, E, gw.ln_b, sx));
-    } else if (d_audio) {
-      ACVAE_CHECK(cudaMemcpyAsync(d_audio, ws.dmem, sizeof(float) * (size_t)R * E, cudaMemcpyDeviceToDevice, sx));
-    }
-  }
 
   // ================= posterior backward (main + one side stream per direction) ==============================
   {
