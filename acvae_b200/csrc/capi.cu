@@ -3,6 +3,7 @@
 #include "../../include/acvae_b200.h"
 #include <stdlib.h>
 
+#include "optim.cuh"
 #include "sample.cuh"
 #include "train_fast.cuh"
 
@@ -247,6 +248,30 @@ int acvae_beam_search(const acvae_dims* d, const acvae_weights* w, const float* 
   ACVAE_REQUIRE(d->mem_rep == 1, "beam search takes one row per clip (mem_rep == 1)");
   ACVAE_REQUIRE(workspace_bytes >= carve_beam_ws(*d, beam, nullptr).bytes, "workspace too small");
   return beam_search(*d, *w, audio_embeds, mem_lens, eps_b, beam, start_idx, seqs, workspace, (cudaStream_t)stream);
+}
+
+size_t acvae_clip_adam_workspace_bytes(void) { return sizeof(float) * kOptBlocks; }
+
+int acvae_clip_adam(int64_t n, float* params, float* grads, float* exp_avg, float* exp_avg_sq, float max_norm, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int32_t* step, float* total_norm,
+                    int32_t write_clipped_grads, void* workspace, size_t workspace_bytes, void* stream) {
+  ACVAE_REQUIRE(n > 0 && n % 4 == 0, "n must be a positive multiple of 4 (pad the flat buffers)");
+  ACVAE_REQUIRE(params && grads && exp_avg && exp_avg_sq && step && workspace, "NULL pointer");
+  ACVAE_REQUIRE(aligned16(params) && aligned16(grads) && aligned16(exp_avg) && aligned16(exp_avg_sq), "flat buffers must be 16-byte aligned");
+  ACVAE_REQUIRE(workspace_bytes >= sizeof(float) * kOptBlocks, "workspace too small");
+  ACVAE_REQUIRE(lr >= 0.0f && beta1 >= 0.0f && beta1 < 1.0f && beta2 >= 0.0f && beta2 < 1.0f && eps >= 0.0f, "bad hyper-parameter");
+  const long long n4 = n / 4;
+  int blocks = (int)((n4 + kOptThreads - 1) / kOptThreads);
+  blocks = blocks < 1 ? 1 : (blocks > kOptBlocks ? kOptBlocks : blocks);
+  cudaStream_t st = (cudaStream_t)stream;
+  ACVAE_LAUNCH(sumsq_partial_kernel, blocks, kOptThreads, 0, st, n4, (const float4*)grads, (float*)workspace);
+  ClipAdamParams a{};
+  a.n4 = n4; a.p = (float4*)params; a.g = (float4*)grads; a.m = (float4*)exp_avg; a.v = (float4*)exp_avg_sq;
+  a.partial = (const float*)workspace; a.npartial = blocks; a.max_norm = max_norm; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2;
+  a.eps = eps; a.weight_decay = weight_decay; a.step = step; a.total_norm = total_norm; a.write_grad = write_clipped_grads;
+  ACVAE_LAUNCH(clip_adam_kernel, blocks, kOptThreads, 0, st, a);
+  ACVAE_LAUNCH(step_advance_kernel, 1, 1, 0, st, step);
+  return 0;
 }
 
 }  // extern "C"

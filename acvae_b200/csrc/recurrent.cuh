@@ -161,6 +161,13 @@ __global__ void __launch_bounds__(kChainThreads) post_chain_fwd_kernel(const __g
         rowload<E>(p.ho + ((long long)n * T + (T - s)) * 2 * E + E, kp, a1);
       }
       __syncwarp();
+      if (tr) {                                        // stamp 5: this thread's row loads have landed
+        float chk = 0.0f;
+#pragma unroll
+        for (int i = 0; i < E / 32; ++i) chk += a0[i].x + a1[i].x;
+        if (chk == 1234.5f) p.trace[s * 8 + 6] = 0;
+        p.trace[s * 8 + 5] = clock64();
+      }
       if (row) {
         rowfma<6, E>(a0, &W[0][0][0], E, kp, acc[0]);
         rowfma<6, E>(a1, &W[1][0][0], E, kp, acc[1]);
@@ -807,11 +814,17 @@ inline int launch_chain(Kern kern, size_t smem, cudaStream_t st, const char* nam
   cfg.blockDim = dim3(kChainThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeCooperative;
   at[0].val.cooperative = 1;
+  // the chains are the critical path of the step: their CTAs are placed before those of the batched GEMMs that
+  // are queued on the side streams at the same time (a cooperative grid needs all its SMs at once)
+  static int prio = 1;
+  if (prio > 0) { int lo = 0, hi = 0; prio = (cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess) ? hi : 0; }
+  at[1].id = cudaLaunchAttributePriority;
+  at[1].val.priority = prio;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   const bool probe = probe_match(name);
   if (probe) cudaEventRecord(g_probe.e0, st);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p...);

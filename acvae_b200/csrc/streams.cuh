@@ -8,8 +8,8 @@
 
 namespace acvae {
 
-constexpr int kAuxStreams = 4;
-constexpr int kAuxEvents = 32;
+constexpr int kAuxStreams = 8;      // 0,1: posterior directions; 2: prior; 3: memory backward; 4..7: weight-gradient fan
+constexpr int kAuxEvents = 64;
 
 struct Aux {
   cudaStream_t s[kAuxStreams];

@@ -473,7 +473,9 @@ inline int try_launch_tc(const GemmParams& p, cudaStream_t st) {
     for (int s = 0; s < p.nseg; ++s) nblk += (p.seg[s].K + kTcBK - 1) / kTcBK;
     const int tiles = (int)(grid.x * grid.y);
     int splits = 148 / tiles;                       // fill the machine once
-    if (splits > nblk / 8) splits = nblk / 8;       // at least 8 k-blocks per CTA
+    static int min_blk = 0;                         // k-blocks per CTA below which splitting stops paying (profiles/r1/gemm_split.log: 16 -> 11 us at 2)
+    if (!min_blk) { const char* e = getenv("ACVAE_TC_MIN_KBLK"); min_blk = e ? atoi(e) : 2; if (min_blk < 1) min_blk = 1; }
+    if (splits > nblk / min_blk) splits = nblk / min_blk;
     if (splits >= 2) {
       const int per = (nblk + splits - 1) / splits;
       splits = (nblk + per - 1) / per;              // no empty CTA

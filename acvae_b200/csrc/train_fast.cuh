@@ -412,6 +412,17 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     ACVAE_TRY(launch_attn_bwd_acc(a, sx));
   }
   ACVAE_CHECK(cudaStreamWaitEvent(sx, ev_prior_acc, 0));
+  {
+    // weight / bias gradients of the two memory projections need only dPp / dPd: off the memory-backward chain
+    const int R = N * Te;
+    cudaStream_t f0 = ax->s[4], f1 = ax->s[5];
+    ACVAE_TRY(stream_dep(sx, f0, ax));
+    ACVAE_TRY(stream_dep(sx, f1, ax));
+    ACVAE_TRY(linear_bwd_weight(E, E, R, ws.dPp, E, ws.mem, E, gw.p_attn_w + E, 2 * E, f0));
+    ACVAE_TRY(colsum(R, E, ws.dPp, E, gw.p_attn_b, f0));
+    ACVAE_TRY(linear_bwd_weight(A, E, R, ws.dPd, A, ws.mem, E, gw.d_attn_w + E, 2 * E, f1));
+    ACVAE_TRY(colsum(R, A, ws.dPd, A, gw.d_attn_b, f1));
+  }
   // memory backward: attention memory halves, ln (vae_model.py:743-744)
   {
     const int R = N * Te;
@@ -425,22 +436,24 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     } else if (d_audio) {
       ACVAE_CHECK(cudaMemcpyAsync(d_audio, ws.dmem, sizeof(float) * (size_t)R * E, cudaMemcpyDeviceToDevice, sx));
     }
-    ACVAE_TRY(linear_bwd_weight(E, E, R, ws.dPp, E, ws.mem, E, gw.p_attn_w + E, 2 * E, sx));
-    ACVAE_TRY(linear_bwd_weight(A, E, R, ws.dPd, A, ws.mem, E, gw.d_attn_w + E, 2 * E, sx));
-    ACVAE_TRY(colsum(R, E, ws.dPp, E, gw.p_attn_b, sx));
-    ACVAE_TRY(colsum(R, A, ws.dPd, A, gw.d_attn_b, sx));
   }
-  // decoder embedding / weight / bias gradients
-  ACVAE_TRY(linear_bwd_data(NT, E, 3 * E, ws.dgi_d, 3 * E, w.d_wih, 3 * E, ws.dxe_d, E, sx));
-  ACVAE_CHECK(zero(gw.d_emb, (size_t)V * E, sx));
-  ACVAE_TRY(scatter_rows(NT, E, ws.dxe_d, E, ws.words, gw.d_emb, sx));
-  ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_d, 3 * E, ws.xd, E, gw.d_wih, 3 * E, sx));
-  ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_d, 3 * E, ws.ctx_d, E, gw.d_wih + E, 3 * E, sx));
-  ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_d, 3 * E, io.q_z, E, gw.d_wih + 2 * E, 3 * E, sx));
-  ACVAE_TRY(colsum(NT, 3 * E, ws.dgi_d, 3 * E, gw.d_bih, sx));
-  ACVAE_TRY(colsum(NT, 3 * E, ws.dgh_d, 3 * E, gw.d_bhh, sx));
-  ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgh_d, 3 * E, io.outputs - E, E, gw.d_whh, E, sx, T, 0, -1));
-  ACVAE_TRY(linear_bwd_weight(A, E, NT, ws.dqp_d, A, io.outputs - E, E, gw.d_attn_w, 2 * E, sx, T, 0, -1));
+  // decoder embedding / weight / bias gradients: independent of each other and of the memory backward, so they fan
+  // out over four more streams (each GEMM is a ~10 us launch of a few dozen CTAs; in one stream they serialise)
+  {
+    cudaStream_t f[4] = {ax->s[4], ax->s[5], ax->s[6], ax->s[7]};
+    for (int i = 0; i < 4; ++i) ACVAE_TRY(stream_dep(st, f[i], ax));
+    ACVAE_TRY(linear_bwd_data(NT, E, 3 * E, ws.dgi_d, 3 * E, w.d_wih, 3 * E, ws.dxe_d, E, f[0]));
+    ACVAE_CHECK(zero(gw.d_emb, (size_t)V * E, f[0]));
+    ACVAE_TRY(scatter_rows(NT, E, ws.dxe_d, E, ws.words, gw.d_emb, f[0]));
+    ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_d, 3 * E, ws.xd, E, gw.d_wih, 3 * E, f[1]));
+    ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_d, 3 * E, ws.ctx_d, E, gw.d_wih + E, 3 * E, f[2]));
+    ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_d, 3 * E, io.q_z, E, gw.d_wih + 2 * E, 3 * E, f[3]));
+    ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgh_d, 3 * E, io.outputs - E, E, gw.d_whh, E, f[1], T, 0, -1));
+    ACVAE_TRY(linear_bwd_weight(A, E, NT, ws.dqp_d, A, io.outputs - E, E, gw.d_attn_w, 2 * E, f[2], T, 0, -1));
+    ACVAE_TRY(colsum(NT, 3 * E, ws.dgi_d, 3 * E, gw.d_bih, f[3]));
+    ACVAE_TRY(colsum(NT, 3 * E, ws.dgh_d, 3 * E, gw.d_bhh, f[3]));
+    for (int i = 0; i < 4; ++i) ACVAE_TRY(stream_dep(f[i], sx, ax));
+  }
 
   // ================= posterior backward (main + one side stream per direction) ==============================
   {

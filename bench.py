@@ -136,7 +136,8 @@ def make_train_step(dev, world, rank, use_graph=True):
     n_params = sum(p.numel() for p in model.parameters())
     flat = parallel.FlatGradBuffer(model.parameters())
     model.grad_sink = flat          # fused backward writes weight gradients straight into the all-reduce buffer
-    opt = torch.optim.Adam(model.parameters(), lr=LR, fused=True, capturable=True)
+    # clip_grad_norm_ + Adam (pytorch_runner_vae.py:322-324) as two launches over the flat buffers
+    opt = models.FusedClipAdam(flat, lr=LR, max_grad_norm=MAX_GRAD_NORM)
     crit = models.LabelSmoothingLoss(d.V, smoothing=SMOOTHING, device=dev)
     klf = models.Normal_kl_loss(device=dev)
     mse = torch.nn.MSELoss()
@@ -172,7 +173,6 @@ def make_train_step(dev, world, rank, use_graph=True):
             + ALPHA * mse(out["q_means_utt"], out["p_means_utt"])
         loss.backward()
         flat.all_reduce()
-        flat.clip_grad_norm_(MAX_GRAD_NORM)
         opt.step()
         loss_buf.copy_(loss.detach())
 

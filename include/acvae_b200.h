@@ -224,6 +224,19 @@ int acvae_beam_search(const acvae_dims *d, const acvae_weights *w, const float *
                       const int32_t *mem_lens, const float *eps_b, int32_t beam, int32_t start_idx,
                       int64_t *seqs, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- fused optimizer tail --------------------------------
+ * Global-norm gradient clipping (runners/pytorch_runner_vae.py:322, clip_grad_norm_ semantics:
+ * coef = min(1, max_norm / (||g||_2 + 1e-6)); max_norm <= 0 disables it) chained with the Adam
+ * update (:324; torch.optim.Adam, no amsgrad) over FLAT fp32 buffers of n elements (n % 4 == 0,
+ * 16-byte aligned; padding elements must be zero in `grads`).  `step` is a device counter of
+ * completed steps (read, then incremented), so the call is CUDA-graph capturable.
+ * total_norm (device scalar, may be NULL) receives the pre-clip norm.                          */
+size_t acvae_clip_adam_workspace_bytes(void);
+int acvae_clip_adam(int64_t n, float *params, float *grads, float *exp_avg, float *exp_avg_sq,
+                    float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
+                    int32_t *step, float *total_norm, int32_t write_clipped_grads,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

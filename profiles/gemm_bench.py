@@ -30,9 +30,15 @@ for (M, N, K, at, bt, what) in shapes:
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n = reps
+    # back-to-back launches replayed from a CUDA graph: the ctypes call (~20 us of CPU) must not be what is timed
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.graph(g, stream=side):
+        for _ in range(n):
+            F.gemm(A, B, bool(at), bool(bt), out=C)
+    g.replay(); torch.cuda.synchronize()
     e0.record()
-    for _ in range(n):
-        F.gemm(A, B, bool(at), bool(bt), out=C)
+    g.replay()
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / n * 1e3
     print(f"{what:34s} M={M:5d} N={N:5d} K={K:5d} tc={int(used)} {us:8.1f} us  {2*M*N*K/us/1e6:8.2f} TFLOP/s")

@@ -25,8 +25,8 @@ int main() {
     float ms; cudaEventElapsedTime(&ms, a, b);
     printf("rep %d rc=%d %s: %.1f us total, %.2f us/step\n", rep, rc, cudaGetErrorString(e), ms * 1e3, ms * 1e3 / T);
   }
-  printf("step: loads+fma  reduce  pointwise+store  grid_sync  (cycles, thread 0 of CTA 0)\n");
+  printf("step: loads  fma  reduce  pointwise+store  grid_sync  (cycles, thread 0 of CTA 0)\n");
   for (int s = 1; s < T - 1; ++s)
-    printf("%2d: %6lld %6lld %6lld %6lld   step total %6lld\n", s, tr[s*8+1]-tr[s*8+0], tr[s*8+2]-tr[s*8+1], tr[s*8+3]-tr[s*8+2], tr[s*8+4]-tr[s*8+3], tr[s*8+4]-tr[s*8+0]);
+    printf("%2d: %6lld %6lld %6lld %6lld %6lld   step total %6lld\n", s, tr[s*8+5]-tr[s*8+0], tr[s*8+1]-tr[s*8+5], tr[s*8+2]-tr[s*8+1], tr[s*8+3]-tr[s*8+2], tr[s*8+4]-tr[s*8+3], tr[s*8+4]-tr[s*8+0]);
   return 0;
 }

@@ -306,3 +306,31 @@ def test_gemm_tensor_core_vs_fp64(M, N, K, a_trans, b_trans):
     # accumulate epilogue
     C2, _ = F.gemm(A, B, a_trans, b_trans, None, out=C.clone(), accumulate=True)
     assert harness.rel_err(C2, ref + ref - bias.double()) < 5e-6
+
+
+def test_fused_clip_adam_vs_torch():
+    """acvae_clip_adam == clip_grad_norm_ (pytorch_runner_vae.py:322) + torch.optim.Adam.step() (:324) over 3 steps,
+    ragged tensor sizes, one step that clips and steps that do not."""
+    from acvae_b200 import FusedClipAdam
+    from acvae_b200.parallel import FlatGradBuffer
+    torch.manual_seed(3)
+    shapes = [(4400, 256), (768, 768), (256,), (1, 7), (513, 3)]
+    ours = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    flat = FlatGradBuffer(ours)
+    opt = FusedClipAdam(flat, lr=5e-4, max_grad_norm=1.0)
+    ropt = torch.optim.Adam(ref, lr=5e-4)
+    for it, scale in enumerate((1.0, 1e-4, 3.0)):          # clipped, not clipped, clipped
+        grads = [torch.randn(s, device="cuda") * scale for s in shapes]
+        flat.zero()
+        for p, r, g in zip(ours, ref, grads):
+            p.grad.copy_(g)
+            r.grad = g.clone()
+        want_norm = torch.nn.utils.clip_grad_norm_(ref, 1.0)
+        ropt.step()
+        got_norm = opt.step()
+        assert abs(float(got_norm) - float(want_norm)) <= 1e-5 * float(want_norm)
+        for p, r in zip(ours, ref):
+            torch.testing.assert_close(p.grad, r.grad, rtol=1e-5, atol=1e-9)          # clipped gradient written back
+            torch.testing.assert_close(p.data, r.data, rtol=1e-6, atol=1e-7)
+    assert int(opt.step_count) == 3
