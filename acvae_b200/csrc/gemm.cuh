@@ -106,11 +106,40 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const float* 
   const int U = p.U;
 
   if constexpr (EPI == EPI_PLAIN) {
-    if (G == 1) {
+    if (G == 1 && (ldcs & 3) == 0 && (ep.ldc & 3) == 0 && (c0 & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.c[0]) & 15) == 0 &&
+        c0 + BN <= U) {
+      // vector path (16-byte aligned staging rows and output rows): one 16-byte store / read-modify-write /
+      // red.global.add.v4.f32 per 4 columns.  The scalar split-K epilogue was RED-issue bound: 64 RED.32 per
+      // thread took 8300 cycles of a 13 000-cycle launch (profiles/r1/gemm_trace.log).
+      float* __restrict__ cbase = ep.c[0];
+      const float* __restrict__ bias = ep.bias[0];
+      const bool add_bias = bias && (!ep.atomic || blockIdx.z == 0);
+      for (int e = tid; e < BM * (BN / 4); e += NT) {
+        const int r = e / (BN / 4), c = (e % (BN / 4)) * 4;
+        const int gm = m0 + r, u = c0 + c;
+        if (gm >= p.M) continue;
+        float4 v = *reinterpret_cast<const float4*>(Cs[r] + c);
+        v.x *= ep.scale; v.y *= ep.scale; v.z *= ep.scale; v.w *= ep.scale;
+        if (add_bias) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(bias + u));
+          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        float* dst = cbase + (long long)gm * ep.ldc + u;
+        if (ep.atomic) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        } else {
+          if (ep.accumulate) {
+            const float4 o = *reinterpret_cast<const float4*>(dst);
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+          }
+          *reinterpret_cast<float4*>(dst) = v;
+        }
+      }
+    } else if (G == 1) {
       // common case: compile-time index arithmetic, coalesced 128-byte row segments
       float* __restrict__ cbase = ep.c[0];
       const float* __restrict__ bias = ep.bias[0];
-      for (int e = tid; e < BM * BN; e += 256) {
+      for (int e = tid; e < BM * BN; e += NT) {
         const int r = e / BN, c = e % BN;
         const int gm = m0 + r, u = c0 + c;
         if (gm < p.M && u < U) {
@@ -129,7 +158,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const float* 
     } else {
       // iterate gate-major so that stores of one gate are coalesced along u
       const int UT = BN / G;  // units per tile (BN is a multiple of G for all supported G)
-      for (int e = tid; e < G * BM * UT; e += 256) {
+      for (int e = tid; e < G * BM * UT; e += NT) {
         const int gg = e / (BM * UT);
         const int r = (e / UT) % BM;
         const int ul = e % UT;

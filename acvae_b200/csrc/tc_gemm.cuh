@@ -43,7 +43,8 @@ constexpr int kTcThreads = 512;  // warps 0-3: TMA / MMA / idle, 4-7: hi-lo spli
 constexpr int kTcTileBytes = kTcBM * kTcBK * 4;                 // 16 KB (A or B, hi or lo)
 constexpr int kTcStageBytes = 4 * kTcTileBytes;                 // A_hi, A_lo, B_hi, B_lo
 constexpr int kTcSmemBytes = kTcStages * kTcStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-static_assert(kTcBM * (kTcBN + 1) * 4 <= kTcStages * kTcStageBytes, "staging tile must fit in the operand ring");
+constexpr int kTcLdCs = kTcBN + 4;   // staging row stride: 16-byte aligned rows, conflict-free 128-bit stores by row-per-lane warps
+static_assert(kTcBM * kTcLdCs * 4 <= kTcStages * kTcStageBytes, "staging tile must fit in the operand ring");
 
 struct TcSeg {
   int a_mn_major, b_mn_major;      // 0: K-major (row-major [rows,K]); 1: MN-major (row-major [K,rows])
@@ -54,7 +55,11 @@ struct TcSeg {
 struct TcParams {
   int nseg;
   TcSeg seg[2];
+  long long* trace;    // optional clock64 stamps of CTA (0,0,0) (profiles/ubench_gemm_trace.cu) or NULL
 };
+// process-wide trace destination picked up by try_launch_tc (micro-benchmark only)
+inline long long*& tc_trace_ptr() { static long long* p = nullptr; return p; }
+#define TC_STAMP(slot) do { if (tr) tp.trace[slot] = clock64(); } while (0)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -197,6 +202,8 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
 
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * kTcBM, c0 = blockIdx.x * kTcBN;
+  const bool tr = tp.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+  if (tid == 0) TC_STAMP(0);
 
   if (tid == 0) {
     for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 4); mbar_init(&empty[s], 1); }
@@ -211,6 +218,7 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  if (tid == 0) TC_STAMP(1);
 
   const int nblk0 = (tp.seg[0].K + kTcBK - 1) / kTcBK;
   const int nblk1 = tp.nseg > 1 ? (tp.seg[1].K + kTcBK - 1) / kTcBK : 0;
@@ -310,6 +318,7 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
     for (int c = 0; c < nchunks; ++c) {
       const int cb = c & 1;
       mbar_wait_backoff(&cfull[cb], (c >> 1) & 1);
+      if (wid == 8 && c == nchunks - 1) TC_STAMP(4);
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < kTcBN / 2; cc += 32) {
@@ -321,6 +330,7 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&cempty[cb]);
+      if (wid == 8 && c == nchunks - 1) TC_STAMP(5);
     }
   } else if (wid >= 4) {
     // ===== split workers: x -> (hi, lo), 128 threads over 2 x 4096 words =====
@@ -328,6 +338,7 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
     int st = 0, par = 0;
     for (int i = 0; i < total; ++i) {
       mbar_wait(&full[st], par);
+      if (wt == 0 && i == 0) TC_STAMP(2);
       const bool s1 = i0 + i >= nblk0;
       const TcSeg& sg = tp.seg[s1 ? 1 : 0];
       const int kb = (s1 ? i0 + i - nblk0 : i0 + i) * kTcBK;
@@ -362,6 +373,7 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
       }
       fence_async_smem();          // generic-proxy writes -> visible to the tensor core's async proxy
       __syncwarp();
+      if (wt == 0 && i == 0) TC_STAMP(3);
       if (lane == 0) mbar_arrive(&ready[st]);
       if (++st == kTcStages) { st = 0; par ^= 1; }
     }
@@ -369,21 +381,27 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
   // every role has passed its last use of the operand ring before the staging tile overwrites it
   __syncthreads();
   if (wid >= 8) {
-    float* Cs = reinterpret_cast<float*>(smem);               // [128][129] staging tile over the (now idle) operand ring
+    float* Cs = reinterpret_cast<float*>(smem);               // [128][132] staging tile over the (now idle) operand ring
     const int row = (wid & 3) * 32 + lane, col0 = ((wid - 8) >> 2) * (kTcBN / 2);
 #pragma unroll
-    for (int j = 0; j < kTcBN / 2; ++j) Cs[row * (kTcBN + 1) + col0 + j] = acc_reg[j];
+    for (int j = 0; j < kTcBN / 2; j += 4)
+      *reinterpret_cast<float4*>(Cs + row * kTcLdCs + col0 + j) = make_float4(acc_reg[j], acc_reg[j + 1], acc_reg[j + 2], acc_reg[j + 3]);
   }
   __syncthreads();
+  if (tid == 0) TC_STAMP(6);
   if constexpr (EPI == EPI_STATS) {   // row-per-warp epilogue: all 16 warps
-    gemm_epilogue<EPI, kTcBM, kTcBN, kTcThreads>(p, reinterpret_cast<const float*>(smem), kTcBN + 1, m0, c0, tid, blockIdx.x, gridDim.x);
-  } else if (tid < 256) {             // the element-wise epilogues stride by 256 threads
-    gemm_epilogue<EPI, kTcBM, kTcBN>(p, reinterpret_cast<const float*>(smem), kTcBN + 1, m0, c0, tid, blockIdx.x, gridDim.x);
+    gemm_epilogue<EPI, kTcBM, kTcBN, kTcThreads>(p, reinterpret_cast<const float*>(smem), kTcLdCs, m0, c0, tid, blockIdx.x, gridDim.x);
+  } else if constexpr (EPI == EPI_PLAIN) {   // all 16 warps
+    gemm_epilogue<EPI, kTcBM, kTcBN, kTcThreads>(p, reinterpret_cast<const float*>(smem), kTcLdCs, m0, c0, tid, blockIdx.x, gridDim.x);
+  } else if (tid < 256) {             // the other element-wise epilogues stride by 256 threads
+    gemm_epilogue<EPI, kTcBM, kTcBN>(p, reinterpret_cast<const float*>(smem), kTcLdCs, m0, c0, tid, blockIdx.x, gridDim.x);
   }
   __syncthreads();
+  if (tid == 0) TC_STAMP(7);
   if (wid == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(256));
+    TC_STAMP(8);
   }
 }
 
@@ -441,6 +459,7 @@ inline int try_launch_tc(const GemmParams& p, cudaStream_t st) {
   const int NC = p.U;
   TcParams tp{};
   tp.nseg = p.nseg;
+  tp.trace = tc_trace_ptr();
   CUtensorMap maps[4];
   memset(maps, 0, sizeof(maps));
   for (int s = 0; s < p.nseg; ++s) {
