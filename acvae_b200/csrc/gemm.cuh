@@ -55,6 +55,8 @@ struct EpiParams {
   const float* bias[kMaxGate];
   int accumulate;
   int atomic;       // split-K (tc_gemm.cuh): several CTAs add partial tiles into a pre-zeroed / accumulated C
+  int free_order;   // the caller accepts an order-dependent last bit (gradient GEMMs): any number of K splits.
+                    // Otherwise at most two partials are added onto zeros (commutative, hence bit-reproducible)
   float scale;
   // cells: precomputed input-side pre-activations (x-part incl. b_ih) or NULL
   const float* gx; long long ld_gx;

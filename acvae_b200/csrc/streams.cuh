@@ -8,7 +8,8 @@
 
 namespace acvae {
 
-constexpr int kAuxStreams = 8;      // 0,1: posterior directions; 2: prior; 3: memory backward; 4..7: weight-gradient fan
+constexpr int kAuxStreams = 9;      // 0,1: posterior directions; 2: prior; 3: memory backward; 4..7: weight-gradient fan; 8: main chain
+constexpr int kAuxMain = 8;
 constexpr int kAuxEvents = 64;
 
 struct Aux {
@@ -22,8 +23,15 @@ struct Aux {
 inline Aux* aux() {
   static Aux a;
   if (!a.ok) {
-    for (int i = 0; i < kAuxStreams; ++i)
-      if (cudaStreamCreateWithFlags(&a.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    // Priorities: the recurrent chains and the few batched kernels between them are the critical path (highest);
+    // the memory backward is next; the weight-gradient fan only fills idle SMs (lowest).  The caller's stream has
+    // the default (lowest) priority, so the critical work runs on s[kAuxMain], forked from / joined to it.
+    int lo = 0, hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) { lo = 0; hi = 0; }
+    for (int i = 0; i < kAuxStreams; ++i) {
+      const int prio = (i >= 4 && i <= 7) ? lo : (i == 3 ? (hi + lo) / 2 : hi);
+      if (cudaStreamCreateWithPriority(&a.s[i], cudaStreamNonBlocking, prio) != cudaSuccess) return nullptr;
+    }
     for (int i = 0; i < kAuxEvents; ++i)
       if (cudaEventCreateWithFlags(&a.e[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     a.ok = true;

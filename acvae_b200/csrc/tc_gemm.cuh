@@ -495,6 +495,7 @@ inline int try_launch_tc(const GemmParams& p, cudaStream_t st) {
     static int min_blk = 0;                         // k-blocks per CTA below which splitting stops paying (profiles/r1/gemm_split.log: 16 -> 11 us at 2)
     if (!min_blk) { const char* e = getenv("ACVAE_TC_MIN_KBLK"); min_blk = e ? atoi(e) : 2; if (min_blk < 1) min_blk = 1; }
     if (splits > nblk / min_blk) splits = nblk / min_blk;
+    if (!p.epi.free_order) splits = p.epi.accumulate ? 1 : (splits > 2 ? 2 : splits);   // forward / sampling: reproducible
     if (splits >= 2) {
       const int per = (nblk + splits - 1) / splits;
       splits = (nblk + per - 1) / per;              // no empty CTA

@@ -107,7 +107,7 @@ inline int linear_bwd_data(int M, int K, int Nn, const float* dy, long long lddy
   GemmSeg s{};
   s.a = dy; s.lda = lddy; s.w[0] = w; s.ldw = ldw; s.w_trans = 1; s.K = Nn;
   p.seg[0] = s;
-  p.epi.c[0] = dx; p.epi.ldc = lddx; p.epi.scale = 1.0f; p.epi.accumulate = accumulate;
+  p.epi.c[0] = dx; p.epi.ldc = lddx; p.epi.scale = 1.0f; p.epi.accumulate = accumulate; p.epi.free_order = 1;
   return launch_gemm<EPI_PLAIN>(p, st);
 }
 // dW[Nn,K] (lddw) = dY[R,Nn](lddy)^T . X[R,K](ldx)             (nn.Linear backward-weight)
@@ -121,7 +121,7 @@ inline int linear_bwd_weight(int Nn, int K, int R, const float* dy, long long ld
   s.a = dy; s.lda = lddy; s.a_trans = 1; s.w[0] = x; s.ldw = ldx; s.w_trans = 1; s.K = R;
   s.k_zero_period = k_zero_period; s.k_zero_rem = k_zero_rem; s.w_row_shift = x_row_shift;
   p.seg[0] = s;
-  p.epi.c[0] = dw; p.epi.ldc = lddw; p.epi.scale = 1.0f;
+  p.epi.c[0] = dw; p.epi.ldc = lddw; p.epi.scale = 1.0f; p.epi.free_order = 1;
   return launch_gemm<EPI_PLAIN>(p, st);
 }
 inline int colsum(long long rows, int cols, const float* x, long long ld, float* out, cudaStream_t st, int accumulate = 0) {

@@ -21,9 +21,12 @@ inline bool fast_path_ok(const acvae_dims& d, const acvae_train_io& io) {
 }
 
 inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acvae_train_io& io, void* workspace,
-                          cudaStream_t st) {
+                          cudaStream_t st_user) {
   TrainWs ws = carve_train_ws(d, workspace);
   Aux* ax = aux();
+  // the critical path runs on a high-priority stream forked from (and, at the end, joined to) the caller's
+  cudaStream_t st = ax->s[kAuxMain];
+  ACVAE_TRY(stream_dep(st_user, st, ax));
   const int N = d.N, T = d.T, E = d.E, A = d.A, Te = d.Te, NT = N * T;
   const long long s1 = T;
   cudaStream_t sq0 = ax->s[0], sq1 = ax->s[1], sp = ax->s[2];
@@ -219,15 +222,18 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   ACVAE_TRY(linear_fwd(N, 2 * E, E, ws.pool_d, E, w.g_w, E, w.g_b, io.p_means_utt, 2 * E, st));
   if (io.logits) ACVAE_TRY(linear_fwd(NT, d.V, E, io.outputs, E, w.cls_w, E, w.cls_b, io.logits, d.V, st));
   ACVAE_TRY(stream_dep(sp, st, ax));
+  ACVAE_TRY(stream_dep(st, st_user, ax));
   return 0;
 }
 
 // ===================================== backward ===================================================
 inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acvae_train_io& io,
                           const acvae_train_grads_in& gi, acvae_weight_grads& gw, float* d_audio, void* workspace,
-                          cudaStream_t st) {
+                          cudaStream_t st_user) {
   TrainWs ws = carve_train_ws(d, workspace);
   Aux* ax = aux();
+  cudaStream_t st = ax->s[kAuxMain];          // high-priority critical-path stream (see train_fwd_fast)
+  ACVAE_TRY(stream_dep(st_user, st, ax));
   const int N = d.N, T = d.T, E = d.E, A = d.A, Te = d.Te, NT = N * T, V = d.V;
   const long long s1 = T;
   cudaStream_t sp = ax->s[2], sx = ax->s[3], sq0 = ax->s[0], sq1 = ax->s[1];
@@ -295,6 +301,20 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   // decoder+prior kernel in chain mode)
   cudaEvent_t ev_prior_acc = ax->ev();      // recorded on sp once the prior's dPp / dmem are complete
   auto prior_remainders = [&]() -> int {
+    // weight / bias gradients that need only the chain's dg_p / dml_p: fanned over four streams so that they fill
+    // the SMs the decoder's persistent kernel leaves free instead of queueing behind the attention backward
+    {
+      cudaStream_t f[4] = {ax->s[4], ax->s[5], ax->s[6], ax->s[7]};
+      for (int i = 0; i < 4; ++i) ACVAE_TRY(stream_dep(sp, f[i], ax));
+      ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.xp, E, gw.p_wih, 3 * E, f[0]));
+      ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.ctx_p, E, gw.p_wih + E, 3 * E, f[1]));
+      ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, io.p_z - E, E, gw.p_wih + 2 * E, 3 * E, f[2], T, 0, -1));
+      ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.h_p - E, E, gw.p_whh, E, f[3], T, 0, -1));
+      ACVAE_TRY(linear_bwd_weight(2 * E, E, NT, ws.dml_p, 2 * E, ws.h_p, E, gw.p_head_w, E, f[0]));
+      ACVAE_TRY(colsum(NT, 4 * E, ws.dg_p, 4 * E, gw.p_bih, f[1]));
+      ACVAE_CHECK(cudaMemcpyAsync(gw.p_bhh, gw.p_bih, sizeof(float) * 4 * E, cudaMemcpyDeviceToDevice, f[1]));
+      ACVAE_TRY(colsum(NT, 2 * E, ws.dml_p, 2 * E, gw.p_head_b, f[2]));
+    }
     // critical first: d ctx -> attention backward -> per-clip accumulation (the memory backward waits for it)
     ACVAE_TRY(linear_bwd_data(NT, E, 4 * E, ws.dg_p, 4 * E, w.p_wih + E, 3 * E, ws.dctx_p, E, sp));
     {
@@ -315,20 +335,12 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
       ACVAE_TRY(launch_attn_bwd_acc(a, sp));
     }
     ACVAE_CHECK(cudaEventRecord(ev_prior_acc, sp));
-    // the rest: embedding / weight / bias gradients
+    // the rest: embedding / attention-query weight gradients (need dqp_p from the attention backward)
     ACVAE_TRY(linear_bwd_data(NT, E, 4 * E, ws.dg_p, 4 * E, w.p_wih, 3 * E, ws.dxe_p, E, sp));
     ACVAE_TRY(linear_bwd_data(NT, E, E, ws.dqp_p, E, w.p_attn_w, 2 * E, ws.dxe_p, E, sp, 1));
     ACVAE_CHECK(zero(gw.p_emb, (size_t)V * E, sp));
     ACVAE_TRY(scatter_rows(NT, E, ws.dxe_p, E, ws.words, gw.p_emb, sp));
     ACVAE_TRY(linear_bwd_weight(E, E, NT, ws.dqp_p, E, ws.xp, E, gw.p_attn_w, 2 * E, sp));
-    ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.xp, E, gw.p_wih, 3 * E, sp));
-    ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.ctx_p, E, gw.p_wih + E, 3 * E, sp));
-    ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, io.p_z - E, E, gw.p_wih + 2 * E, 3 * E, sp, T, 0, -1));
-    ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.h_p - E, E, gw.p_whh, E, sp, T, 0, -1));
-    ACVAE_TRY(colsum(NT, 4 * E, ws.dg_p, 4 * E, gw.p_bih, sp));
-    ACVAE_CHECK(cudaMemcpyAsync(gw.p_bhh, gw.p_bih, sizeof(float) * 4 * E, cudaMemcpyDeviceToDevice, sp));
-    ACVAE_TRY(linear_bwd_weight(2 * E, E, NT, ws.dml_p, 2 * E, ws.h_p, E, gw.p_head_w, E, sp));
-    ACVAE_TRY(colsum(NT, 2 * E, ws.dml_p, 2 * E, gw.p_head_b, sp));
     return 0;
   };
   ACVAE_TRY(prior_remainders());
@@ -536,6 +548,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   ACVAE_TRY(scatter_rows(NT, E, ws.dxq, E, ws.qids, gw.q_emb, st));
   ACVAE_TRY(stream_dep(sp, st, ax));
   ACVAE_TRY(stream_dep(sx, st, ax));
+  ACVAE_TRY(stream_dep(st, st_user, ax));
   return 0;
 }
 
