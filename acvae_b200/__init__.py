@@ -6,10 +6,18 @@ The public surface mirrors the reference's `models` package for this path
 callables of the runner boundary.  Importing this package does not need a GPU;
 running it does, and needs `libacvae_b200.so` (there is no fallback).
 """
+import os as _os
+
+# The train step forks up to ten concurrent streams (critical chain, posterior directions, prior, memory backward,
+# weight-gradient fan).  With the default of 8 hardware work queues several of them alias onto one queue and a
+# critical kernel can sit behind an unrelated batched GEMM (seen as 30 us gaps in profiles/r1 timelines).  Must be
+# set before the CUDA context exists, hence at import; an explicit user setting wins.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 from . import synthetic  # noqa: F401
 from .models import (CaptionModel, Hybrid_VAEModel, PosteriorRNN, PosteriorRNN_hybrid, PrecomputedEncoder,  # noqa: F401
                      PreparedBatch, PriorRNN, Seq2SeqAttention, VAEModel, VAERNNBahdanauAttnDecoder)
-from .train_util import CrossEntropyLoss, LabelSmoothingLoss, Normal_kl_loss  # noqa: F401
+from .train_util import CrossEntropyLoss, FusedVAELoss, LabelSmoothingLoss, Normal_kl_loss  # noqa: F401
 from .lazy import LazyLogits  # noqa: F401
 from .optim import FusedClipAdam  # noqa: F401
 

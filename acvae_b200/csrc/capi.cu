@@ -274,4 +274,22 @@ int acvae_clip_adam(int64_t n, float* params, float* grads, float* exp_avg, floa
   return 0;
 }
 
+int acvae_loss_combine_fwd(int64_t n, const float* q_utt, const float* p_utt, const float* ce, const float* kl, float kl_weight,
+                           float alpha, float* terms, void* stream) {
+  ACVAE_REQUIRE(ce && kl && terms, "NULL pointer");
+  ACVAE_REQUIRE((q_utt == nullptr) == (p_utt == nullptr) && (q_utt == nullptr || n > 0), "bad global-term arguments");
+  ACVAE_LAUNCH(loss_combine_kernel, 1, 1024, 0, (cudaStream_t)stream, (long long)n, q_utt, p_utt, ce, kl, kl_weight, alpha, terms);
+  return 0;
+}
+
+int acvae_loss_combine_bwd(int64_t n, const float* q_utt, const float* p_utt, const float* d_loss, float kl_weight, float alpha,
+                           float* d_q_utt, float* d_p_utt, float* scal, void* stream) {
+  ACVAE_REQUIRE(d_loss && scal, "NULL pointer");
+  ACVAE_REQUIRE(q_utt == nullptr || (p_utt && d_q_utt && d_p_utt && n > 0), "bad global-term arguments");
+  const long long cnt = q_utt ? n : 1;
+  ACVAE_LAUNCH(loss_combine_bwd_kernel, grid1d(cnt), 256, 0, (cudaStream_t)stream, (long long)n, q_utt, p_utt, d_loss, kl_weight,
+               alpha, d_q_utt, d_p_utt, scal);
+  return 0;
+}
+
 }  // extern "C"

@@ -89,4 +89,35 @@ __global__ void __launch_bounds__(kOptThreads) clip_adam_kernel(const __grid_con
 
 __global__ void step_advance_kernel(int* step) { step[0] += 1; }
 
+
+// ---- loss composition of the runner (runners/pytorch_runner_vae.py:315-320) as one node ----------------------
+// terms = {loss, ce, kl, mse}: mse = mean((a - b)^2) over n elements (nn.MSELoss, :318), loss = ce + kl_w*kl + alpha*mse.
+// One block, fixed summation order (deterministic).  a == NULL: no global-constraint term.
+__global__ void __launch_bounds__(1024) loss_combine_kernel(long long n, const float* __restrict__ a, const float* __restrict__ b,
+                                                            const float* __restrict__ ce, const float* __restrict__ kl,
+                                                            float kl_w, float alpha, float* __restrict__ terms) {
+  __shared__ float red[33];
+  float s = 0.0f;
+  if (a)
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) { const float d = a[i] - b[i]; s = fmaf(d, d, s); }
+  s = block_sum_opt(s, red);
+  if (threadIdx.x == 0) {
+    const float mse = a ? s / (float)n : 0.0f;
+    terms[1] = ce[0]; terms[2] = kl[0]; terms[3] = mse;
+    terms[0] = ce[0] + kl_w * kl[0] + alpha * mse;
+  }
+}
+// backward: d a = g*alpha*2(a-b)/n, d b = -d a; scal = {g (for the CE rows), g*kl_w (for the KL)}
+__global__ void loss_combine_bwd_kernel(long long n, const float* __restrict__ a, const float* __restrict__ b,
+                                        const float* __restrict__ g, float kl_w, float alpha, float* __restrict__ da,
+                                        float* __restrict__ db, float* __restrict__ scal) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const float gg = g[0];
+  if (i == 0) { scal[0] = gg; scal[1] = gg * kl_w; }
+  if (a && i < n) {
+    const float v = gg * alpha * 2.0f * (a[i] - b[i]) / (float)n;
+    da[i] = v; db[i] = -v;
+  }
+}
+
 }  // namespace acvae

@@ -194,6 +194,7 @@ class LatentDecodeTrainFn(torch.autograd.Function):
                  "attn_weights", "seqs", "sampled_logprobs", "logit_lse", "logit_sum", "rnn_input", "logits"]
         res = tuple(o[k] for k in order)
         ctx.mark_non_differentiable(*res[9:])
+        ctx.set_materialize_grads(False)     # outputs the loss never touches arrive as None, not as zero tensors
         # `io` holds raw pointers into these outputs; saving them keeps the storage alive for backward
         ctx.save_for_backward(*res[:9])
         return res
@@ -323,6 +324,79 @@ class VocabCEFn(torch.autograd.Function):
         if ctx.grad_sink is not None:
             return dh, None, None, None, None, None, None, None
         return dh, dw, db, None, None, None, None, None
+
+
+class VAELossFn(torch.autograd.Function):
+    """loss = CE + kl_weight*KL + alpha*MSE as ONE autograd node (runners/pytorch_runner_vae.py:315-320):
+    label-smoothed CE over packed rows from the step's vocabulary statistics (no logits), the Gaussian KL and the
+    global-constraint MSE, composed on the device.  Returns (loss, terms[4] = {loss, ce, kl, mse})."""
+
+    @staticmethod
+    def forward(ctx, hidden, cls_w, cls_b, targets, smoothing, row_lse, row_sum, grad_sink,
+                q_means, q_logs, p_means, p_logs, q_utt, p_utt, kl_weight, alpha):
+        l = _lib.lib()
+        dev = hidden.device
+        h2 = hidden.contiguous()
+        M, E = h2.shape
+        V = cls_w.shape[0]
+        w, b = cls_w.detach().contiguous(), cls_b.detach().contiguous()
+        tg = targets.to(device=dev, dtype=torch.int32).contiguous()
+        row_lse, row_sum = row_lse.contiguous(), row_sum.contiguous()
+        scal = torch.empty(4, dtype=torch.float32, device=dev)          # ce, kl | g, g*kl_w
+        terms = torch.empty(4, dtype=torch.float32, device=dev)
+        ws = _workspace(max(l.acvae_vocab_workspace_bytes(M, V, E), 1024), dev)
+        _lib.check(l.acvae_vocab_ce_fwd(M, V, E, _dev(h2), _dev(w), _dev(b), _dev(tg, torch.int32), None, float(smoothing), 1,
+                                        _dev(row_lse), _dev(row_sum), scal.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                   "acvae_vocab_ce_fwd")
+        kls = [t.contiguous() for t in (q_means, q_logs, p_means, p_logs)]
+        Ez = kls[0].shape[-1]
+        rows = kls[0].numel() // Ez
+        _lib.check(l.acvae_kl_fwd(rows, Ez, *[_dev(t) for t in kls], scal.data_ptr() + 4, ws.data_ptr(), ws.numel(), _stream()),
+                   "acvae_kl_fwd")
+        have_g = q_utt is not None and p_utt is not None and alpha
+        qu = q_utt.contiguous() if have_g else None
+        pu = p_utt.contiguous() if have_g else None
+        _lib.check(l.acvae_loss_combine_fwd(qu.numel() if have_g else 0, _opt(qu), _opt(pu), scal.data_ptr(), scal.data_ptr() + 4,
+                                            float(kl_weight), float(alpha or 0.0), terms.data_ptr(), _stream()),
+                   "acvae_loss_combine_fwd")
+        ctx.save_for_backward(h2, w, b, tg, row_lse, *kls, *([qu, pu] if have_g else []))
+        ctx.have_g, ctx.smoothing, ctx.kl_weight, ctx.alpha = bool(have_g), float(smoothing), float(kl_weight), float(alpha or 0.0)
+        ctx.ws, ctx.scal, ctx.grad_sink = ws, scal, grad_sink
+        ctx.mark_non_differentiable(terms)
+        return terms[0], terms
+
+    @staticmethod
+    def backward(ctx, g, _g_terms):
+        l = _lib.lib()
+        saved = ctx.saved_tensors
+        h2, w, b, tg, row_lse = saved[:5]
+        kls = saved[5:9]
+        qu, pu = (saved[9], saved[10]) if ctx.have_g else (None, None)
+        M, E = h2.shape
+        V = w.shape[0]
+        g = g.contiguous().to(torch.float32)
+        dqu = torch.empty_like(qu) if ctx.have_g else None
+        dpu = torch.empty_like(pu) if ctx.have_g else None
+        scal = ctx.scal
+        _lib.check(l.acvae_loss_combine_bwd(qu.numel() if ctx.have_g else 0, _opt(qu), _opt(pu), _dev(g), ctx.kl_weight, ctx.alpha,
+                                            _opt(dqu), _opt(dpu), scal.data_ptr() + 8, _stream()), "acvae_loss_combine_bwd")
+        Ez = kls[0].shape[-1]
+        rows = kls[0].numel() // Ez
+        dk = [torch.empty_like(t) for t in kls]
+        _lib.check(l.acvae_kl_bwd(rows, Ez, *[_dev(t) for t in kls], scal.data_ptr() + 12, *[_dev(t) for t in dk], _stream()),
+                   "acvae_kl_bwd")
+        dh = torch.empty_like(h2)
+        if ctx.grad_sink is not None:
+            dw, db = ctx.grad_sink
+        else:
+            dw = torch.empty_like(w)
+            db = torch.empty(V, dtype=torch.float32, device=h2.device)
+        _lib.check(l.acvae_vocab_ce_bwd(M, V, E, _dev(h2), _dev(w), _dev(b), _dev(tg, torch.int32), None, ctx.smoothing,
+                                        _dev(row_lse), scal.data_ptr() + 8, _dev(dh), _dev(dw), _dev(db),
+                                        ctx.ws.data_ptr(), ctx.ws.numel(), _stream()), "acvae_vocab_ce_bwd")
+        sink = ctx.grad_sink is not None
+        return (dh, None if sink else dw, None if sink else db, None, None, None, None, None,
+                dk[0], dk[1], dk[2], dk[3], dqu, dpu, None, None)
 
 
 class NormalKLFn(torch.autograd.Function):

@@ -112,7 +112,8 @@ def make_params(d: Dims, seed: int = 1, variant: str = "hybrid") -> Dict[str, np
 
 
 def make_batch(d: Dims, seed: int = 1, min_cap_len: Optional[int] = None,
-               sample_steps: int = 0, beam: int = 0, cap_lens_override: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
+               sample_steps: int = 0, beam: int = 0, cap_lens_override: Optional[np.ndarray] = None,
+               dbs_groups: int = 0) -> Dict[str, np.ndarray]:
     """One synthetic batch in hot-path-only form plus all injected noise.
 
     Returns float32 `audio_embeds [N,Te,Eenc]`, int64 `mem_lens [N]`,
@@ -120,7 +121,8 @@ def make_batch(d: Dims, seed: int = 1, min_cap_len: Optional[int] = None,
     `eps_q [N,T,E]`, `eps_p [T,N,E]`, `eps_q_steps [T,N,E]` (AR posterior),
     `u_tf [T]`, `u_dis [T]` (the uniforms behind the per-step teacher-forcing
     / dis_ratio decisions), and for sampling `eps_s [S,N,E]`, `u_s [S,N,V]`,
-    for beam search `eps_b [N,S,beam,E]`.
+    for beam search `eps_b [N,S,beam,E]`, for diverse beam search (`beam` hypotheses in `dbs_groups` groups)
+    `eps_dbs [N, S+G-1, G, beam//G, E]` (global step, group; only the active (t, g) pairs are consumed).
     """
     rs = np.random.RandomState(seed + 1000)
     N, Te, L, E, V = d.N, d.Te, d.L, d.E, d.V
@@ -155,4 +157,8 @@ def make_batch(d: Dims, seed: int = 1, min_cap_len: Optional[int] = None,
         out["u_s"] = rs.uniform(size=(sample_steps, N, V)).astype(np.float32)
     if beam:
         out["eps_b"] = rs.standard_normal((N, sample_steps, beam, E)).astype(np.float32)
+    if dbs_groups:
+        G = dbs_groups
+        out["eps_dbs"] = np.random.RandomState(seed + 7000).standard_normal(
+            (N, sample_steps + G - 1, G, beam // G, E)).astype(np.float32)
     return out

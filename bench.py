@@ -25,6 +25,9 @@ import sys
 import threading
 import time
 
+# more hardware work queues than the default 8: the step forks ten streams (see acvae_b200/__init__.py)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 import torch
 
@@ -141,6 +144,7 @@ def make_train_step(dev, world, rank, use_graph=True):
     crit = models.LabelSmoothingLoss(d.V, smoothing=SMOOTHING, device=dev)
     klf = models.Normal_kl_loss(device=dev)
     mse = torch.nn.MSELoss()
+    fused_loss = models.FusedVAELoss(d.V, smoothing=SMOOTHING, alpha=ALPHA)
 
     # a pool of distinct batches that share one caption-length profile (static pack indices / graph shapes)
     host = make_host_batches(d, N_BATCH_POOL, seed0=100 + 1000 * rank)
@@ -169,8 +173,8 @@ def make_train_step(dev, world, rank, use_graph=True):
         out = model.train_forward({"audio_embeds": st_audio, "audio_embeds_lens": st_mem_lens}, st_prep, None,
                                   ss_ratio=1.0, dis_ratio=0.0, tf_flags=[True] * st_prep.T, dis_flags=[False] * st_prep.T)
         packed = torch.nn.utils.rnn.pack_padded_sequence(out["logits"], lens1, batch_first=True).data
-        loss = crit(packed, st_targets) + KL_WEIGHT * klf(out["q_means"], out["q_logs"], out["p_means"], out["p_logs"]) \
-            + ALPHA * mse(out["q_means_utt"], out["p_means_utt"])
+        # criterion(packed, targets) + kl_w * kl_loss(...) + alpha * MSE(...) (pytorch_runner_vae.py:315-320) as one node
+        loss = fused_loss(out, packed, st_targets, KL_WEIGHT)
         loss.backward()
         flat.all_reduce()
         opt.step()

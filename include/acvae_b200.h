@@ -237,6 +237,16 @@ int acvae_clip_adam(int64_t n, float *params, float *grads, float *exp_avg, floa
                     int32_t *step, float *total_norm, int32_t write_clipped_grads,
                     void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- loss composition (runners/pytorch_runner_vae.py:315-320) as one node ------------------
+ * terms[4] = {loss, ce, kl, mse}; loss = ce + kl_weight*kl + alpha*mean((q_utt - p_utt)^2) (nn.MSELoss, :318).
+ * ce / kl are the device scalars of acvae_vocab_ce_fwd / acvae_kl_fwd.  q_utt == p_utt == NULL: no global term.
+ * bwd: d_q_utt / d_p_utt [n]; scal[2] = {d_loss, d_loss*kl_weight} = the device scalars acvae_vocab_ce_bwd /
+ * acvae_kl_bwd take as d_loss / d_kl.                                                                       */
+int acvae_loss_combine_fwd(int64_t n, const float *q_utt, const float *p_utt, const float *ce, const float *kl,
+                           float kl_weight, float alpha, float *terms, void *stream);
+int acvae_loss_combine_bwd(int64_t n, const float *q_utt, const float *p_utt, const float *d_loss, float kl_weight,
+                           float alpha, float *d_q_utt, float *d_p_utt, float *scal, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

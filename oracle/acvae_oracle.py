@@ -455,6 +455,82 @@ def beam_search(p: Params, audio_embeds, mem_lens, eps_beam, beam_size=3, max_le
     return {"seqs": out_seqs}
 
 
+# ----------------------------------------------------------------------------
+# diverse beam search with prior latents
+# (models/word_model.py:297-394 driven by models/vae_model.py:997-1048)
+# ----------------------------------------------------------------------------
+def diverse_beam_search(p: Params, audio_embeds, mem_lens, eps_dbs, beam_size=5, group_size=5, diversity_lambda=0.5,
+                        temperature=1.0, group_nbest=True, max_length=20):
+    """CaptionModel.diverse_beam_search with Hybrid_VAEModel.dbs_step: per clip, `group_size` groups of
+    bdash = beam_size // group_size hypotheses; group g runs g steps behind group 0 (word_model.py:333-335) and is
+    pushed away from the words the earlier groups hold at the same position (add_diversity, :298-313).  Every
+    dbs_step draws prior noise for its bdash rows: eps_dbs[i][(t, g)] is a [bdash, E] tensor, in the reference's
+    draw order (clip, global step t, group g active at t).  Returns seqs [N, beam_size | group_size, max_length]."""
+    mem_all = project_memory(p, audio_embeds)
+    V = p["decoder.classifier.weight"].shape[0]
+    E = p["pnet.mean_log_out.weight"].shape[0] // 2
+    H = p["decoder.model.weight_hh_l0"].shape[1]
+    N = mem_all.shape[0]
+    G, bdash = group_size, beam_size // group_size
+    out_seqs = torch.full((N, beam_size if group_nbest else G, max_length), END_IDX, dtype=torch.long)   # :322-327
+    for i in range(N):                                                                          # :329
+        mem = mem_all[i].unsqueeze(0).repeat(bdash, 1, 1)                                       # vae_model.py:1001
+        lens = torch.as_tensor(mem_lens)[i].repeat(bdash)
+        seq_table = [torch.zeros(bdash, 0, dtype=torch.long) for _ in range(G)]                 # :330
+        lp_table = [mem.new_zeros(bdash) for _ in range(G)]                                     # :331
+        done = [[] for _ in range(G)]
+        st = [None] * G                                                                         # (h_d, h_p, c_p, last_z)
+        nxt, prevb = [None] * G, [None] * G
+        for t in range(max_length + G - 1):                                                     # :336
+            for g in range(G):
+                if not (g <= t <= max_length + g - 1):                                          # :338
+                    continue
+                lt = t - g
+                if lt == 0:                                                                     # vae_model.py:1008-1012
+                    word = torch.full((bdash,), START_IDX, dtype=torch.long)
+                    h_d = mem.new_zeros(bdash, H); h_p = mem.new_zeros(bdash, E)
+                    c_p = mem.new_zeros(bdash, E); last_z = mem.new_zeros(bdash, E)
+                else:                                                                           # :1013-1024
+                    word = nxt[g]
+                    h_d, h_p, c_p, last_z = (x[prevb[g]] for x in st[g])
+                pr = prior_step(p, word, mem, lens, h_p, c_p, last_z, eps_dbs[i][(t, g)])
+                de = decoder_step(p, word, mem, lens, h_d, pr["z"])
+                logp = torch.log_softmax(de["logits"], dim=1)                                   # :353
+                logp = torch.log_softmax(logp / temperature, dim=1)                             # :354
+                if g > 0:                                                                       # add_diversity :302-311
+                    change = torch.zeros(V, dtype=logp.dtype)
+                    for pc in range(g):
+                        dec = seq_table[pc][..., lt]
+                        for b in range(bdash):
+                            change[dec[b]] += 1
+                    logp = logp - change.unsqueeze(0) * diversity_lambda
+                logp = lp_table[g].unsqueeze(-1) + logp                                         # :356
+                if lt == 0:
+                    top_lp, top_w = logp[0].topk(bdash, 0, True, True)                          # :358-359
+                else:
+                    top_lp, top_w = logp.view(-1).topk(bdash, 0, True, True)                    # :361-362
+                lp_table[g] = top_lp
+                prevb[g] = torch.div(top_w, V, rounding_mode="floor")                           # :365
+                nxt[g] = top_w % V                                                              # :366
+                if lt > 0:
+                    seq_table[g] = seq_table[g][prevb[g]]                                       # :368
+                seq_table[g] = torch.cat([seq_table[g], nxt[g].unsqueeze(-1)], -1)              # :369-371
+                is_end = seq_table[g][:, lt] == END_IDX                                         # :373
+                if t == max_length + g - 1:
+                    is_end = torch.ones_like(is_end)                                            # :375-376
+                for b in range(bdash):                                                          # :377-384
+                    if is_end[b]:
+                        done[g].append({"seq": seq_table[g][b].clone(), "score": lp_table[g][b].item() / (lt + 1)})
+                lp_table[g] = lp_table[g].clone()
+                lp_table[g][is_end] -= 1000                                                     # :385
+                st[g] = (de["h"], pr["h"], pr["c"], pr["z"])                                    # dbs_process_step, vae_model.py:1026-1030
+        done = [sorted(done[g], key=lambda x: -x["score"])[:bdash] for g in range(G)]           # :387
+        beams = sum(done, []) if group_nbest else [gb[0] for gb in done]                        # :388-391
+        for k, bm in enumerate(beams):
+            out_seqs[i, k, :len(bm["seq"])] = bm["seq"]                                         # :394
+    return {"seqs": out_seqs}
+
+
 def algorithmic_flops_train_fwd(N, Te, T, E, H, A, Hq, V, Eenc):
     """factorised-attention forward FLOPs of one train step."""
     f = 2 * N * Te * Eenc * E + 2 * 2 * N * Te * E * A

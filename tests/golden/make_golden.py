@@ -297,9 +297,41 @@ def run_beam_case(name, d, seed, beam, max_length, dtype=torch.float32):
         seqs=out["seqs"].numpy())
 
 
+def run_dbs_case(name, d, seed, beam, groups, max_length, lam=0.5, temperature=1.0, nbest=True, dtype=torch.float32):
+    """Diverse beam search (word_model.py:297-394 + vae_model.py:997-1048) of the reference itself."""
+    params = synthetic.make_params(d, seed, "hybrid")
+    b = synthetic.make_batch(d, seed, sample_steps=max_length, beam=beam, dbs_groups=groups)
+    m = build_reference(d, params, "hybrid", dtype)
+    m.eval()
+    feats = torch.from_numpy(b["audio_embeds"]).to(dtype)
+    eps = torch.from_numpy(b["eps_dbs"]).to(dtype)
+    active = lambda t, g: g <= t <= max_length + g - 1
+    order = [eps[i, t, g] for i in range(d.N) for t in range(max_length + groups - 1) for g in range(groups) if active(t, g)]
+    with torch.no_grad(), _Patched(randn=order):
+        out = m(feats, torch.from_numpy(b["mem_lens"].copy()), method="dbs", beam_size=beam, group_size=groups,
+                diversity_lambda=lam, temperature=temperature, group_nbest=nbest, max_length=max_length)
+    op = tparams(params, dtype)
+    eps_d = [{(t, g): eps[i, t, g] for t in range(max_length + groups - 1) for g in range(groups)} for i in range(d.N)]
+    with torch.no_grad():
+        oo = oracle.diverse_beam_search(op, feats, b["mem_lens"], eps_d, beam, groups, lam, temperature, nbest, max_length)
+    assert torch.equal(oo["seqs"], out["seqs"]), f"{name}: oracle dbs seqs != reference"
+    print(f"[{name}] oracle==reference; seqs[0]={out['seqs'][0].tolist()}")
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"),
+        meta_dims=np.array([d.N, d.Te, d.L, d.E, d.H, d.A, d.Hq, d.V, d.Eenc], dtype=np.int64),
+        meta_seed=np.array(seed), meta_max_length=np.array(max_length), meta_beam=np.array(beam),
+        meta_groups=np.array(groups), meta_lambda=np.array(lam), meta_temperature=np.array(temperature),
+        meta_nbest=np.array(int(nbest)), seqs=out["seqs"].numpy())
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     T, C0 = synthetic.TINY, synthetic.CFG0
+    only_dbs = len(sys.argv) > 1 and sys.argv[1] == "dbs"        # add the dbs fixtures without regenerating the rest
+    if only_dbs:
+        run_dbs_case("tiny_dbs", T, 1, 6, 3, 6, lam=0.5, temperature=1.0, nbest=True)
+        run_dbs_case("tiny_dbs_best", T, 2, 4, 2, 6, lam=1.5, temperature=0.7, nbest=False)
+        run_dbs_case("cfg0_dbs", C0, 1, 10, 5, 20, lam=0.5, temperature=1.0, nbest=True)
+        sys.exit(0)
     # fp64 pin of the restatement (tolerance 1e-10), nothing stored from it
     run_train_case("_pin64", T, 1, 1.0, 0.0, full=True, dtype=torch.float64)
     run_train_case("_pin64ss", T, 2, 0.5, 0.5, full=True, dtype=torch.float64)
@@ -322,3 +354,7 @@ if __name__ == "__main__":
     run_sample_case("cfg0_sample_multinomial", C0, 2, "sample", 20)
     run_beam_case("tiny_beam", T, 1, 3, 6)
     run_beam_case("cfg0_beam", C0, 1, 3, 20)
+    if True:
+        run_dbs_case("tiny_dbs", T, 1, 6, 3, 6, lam=0.5, temperature=1.0, nbest=True)
+        run_dbs_case("tiny_dbs_best", T, 2, 4, 2, 6, lam=1.5, temperature=0.7, nbest=False)
+        run_dbs_case("cfg0_dbs", C0, 1, 10, 5, 20, lam=0.5, temperature=1.0, nbest=True)

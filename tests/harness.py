@@ -83,7 +83,7 @@ def build_model(d, seed, variant="hybrid", device="cuda"):
 
 
 def run_cuda_train(d, seed, ss_ratio=1.0, dis_ratio=0.0, variant="hybrid", smoothing=0.1, kl_weight=0.5, alpha=1.0,
-                   dense_logits=False, backward=True, model=None, keep_grads=False):
+                   dense_logits=False, backward=True, model=None, keep_grads=False, fused_loss=False):
     """Runner._forward(mode="train") + loss composition + backward on the product."""
     import acvae_b200 as models
     dev = "cuda"
@@ -106,13 +106,18 @@ def run_cuda_train(d, seed, ss_ratio=1.0, dis_ratio=0.0, variant="hybrid", smoot
     packed = torch.nn.utils.rnn.pack_padded_sequence(out["logits"], lens1, batch_first=True).data      # :94-95
     crit = models.LabelSmoothingLoss(d.V, smoothing=smoothing, device=dev)
     klf = models.Normal_kl_loss(device=dev)
-    ce = crit(packed, targets)
-    kl = klf(out["q_means"], out["q_logs"], out["p_means"], out["p_logs"])
-    loss = ce + kl_weight * kl                                                                          # :315
-    g = torch.tensor(float("nan"))
-    if variant == "hybrid":
-        g = torch.nn.MSELoss()(out["q_means_utt"], out["p_means_utt"])                                 # :318
-        loss = loss + alpha * g
+    if fused_loss:       # opt-in: the same composition as one autograd node
+        fl = models.FusedVAELoss(d.V, smoothing=smoothing, alpha=alpha if variant == "hybrid" else None)
+        loss = fl(out, packed, targets, kl_weight)
+        ce, kl, g = fl.terms[1], fl.terms[2], fl.terms[3]
+    else:
+        ce = crit(packed, targets)
+        kl = klf(out["q_means"], out["q_logs"], out["p_means"], out["p_logs"])
+        loss = ce + kl_weight * kl                                                                      # :315
+        g = torch.tensor(float("nan"))
+        if variant == "hybrid":
+            g = torch.nn.MSELoss()(out["q_means_utt"], out["p_means_utt"])                             # :318
+            loss = loss + alpha * g
     grads = {}
     if backward:
         loss.backward()                                                                                # :321

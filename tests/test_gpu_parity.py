@@ -334,3 +334,19 @@ def test_fused_clip_adam_vs_torch():
             torch.testing.assert_close(p.grad, r.grad, rtol=1e-5, atol=1e-9)          # clipped gradient written back
             torch.testing.assert_close(p.data, r.data, rtol=1e-6, atol=1e-7)
     assert int(opt.step_count) == 3
+
+
+def test_fused_vae_loss_matches_separate_callables():
+    """FusedVAELoss (one autograd node) == criterion + kl_w * kl_loss + alpha * MSE of the runner boundary
+    (pytorch_runner_vae.py:315-320): same loss terms, same gradients on every parameter."""
+    _require_cuda()
+    import acvae_b200 as models
+    d = synthetic.CFG0
+    a = harness.run_cuda_train(d, 7)                      # separate callables (the drop-in composition)
+    m = harness.build_model(d, 7)
+    b = harness.run_cuda_train(d, 7, model=m, fused_loss=True)
+    for k in ("loss", "ce", "kl", "global"):
+        x, y = float(a["terms"][k]), float(b["terms"][k])
+        assert abs(x - y) <= 1e-6 * max(1.0, abs(x)), (k, x, y)
+    for k in a["grads"]:
+        assert harness.rel_err(b["grads"][k], a["grads"][k]) < 1e-5, k
