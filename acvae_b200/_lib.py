@@ -89,6 +89,8 @@ SYMBOLS = {
     "acvae_decode_sample": (C.c_int, [_DP, _WP, C.POINTER(SampleIO), _vp, _sz, _vp]),
     "acvae_beam_workspace_bytes": (_sz, [_DP, _i32]),
     "acvae_beam_search": (C.c_int, [_DP, _WP, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "acvae_dbs_workspace_bytes": (_sz, [_DP, _i32, _i32]),
+    "acvae_diverse_beam_search": (C.c_int, [_DP, _WP, _vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "acvae_loss_combine_fwd": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp]),
     "acvae_loss_combine_bwd": (C.c_int, [_i64, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
     "acvae_clip_adam_workspace_bytes": (_sz, []),

@@ -292,4 +292,23 @@ int acvae_loss_combine_bwd(int64_t n, const float* q_utt, const float* p_utt, co
   return 0;
 }
 
+size_t acvae_dbs_workspace_bytes(const acvae_dims* d, int32_t beam_size, int32_t group_size) {
+  if (check_dims(d) != 0 || group_size <= 0 || beam_size < group_size) return 0;
+  return carve_dbs_ws(*d, group_size, beam_size / group_size, nullptr).bytes;
+}
+
+int acvae_diverse_beam_search(const acvae_dims* d, const acvae_weights* w, const float* audio_embeds, const int32_t* mem_lens,
+                              const float* eps_g, int32_t beam_size, int32_t group_size, float diversity_lambda,
+                              float temperature, int32_t group_nbest, int32_t start_idx, int32_t end_idx, int64_t* seqs,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  ACVAE_TRY(check_dims(d));
+  ACVAE_REQUIRE(w && audio_embeds && mem_lens && eps_g && seqs && workspace, "NULL pointer");
+  ACVAE_REQUIRE(group_size >= 1 && beam_size >= group_size && beam_size <= kDbsMaxBeam, "need 1 <= group_size <= beam_size <= 32");
+  ACVAE_REQUIRE(temperature > 0.0f, "temperature must be positive");
+  ACVAE_REQUIRE(d->mem_rep == 1, "diverse beam search takes one row per clip (mem_rep == 1)");
+  ACVAE_REQUIRE(workspace_bytes >= carve_dbs_ws(*d, group_size, beam_size / group_size, nullptr).bytes, "workspace too small");
+  return diverse_beam_search(*d, *w, audio_embeds, mem_lens, eps_g, beam_size, group_size, diversity_lambda, temperature,
+                             group_nbest != 0, start_idx, end_idx, seqs, workspace, (cudaStream_t)stream);
+}
+
 }  // extern "C"

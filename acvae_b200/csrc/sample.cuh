@@ -371,4 +371,270 @@ inline int beam_search(const acvae_dims& d0, const acvae_weights& w, const float
   return 0;
 }
 
+// ================================ diverse beam search ============================================
+// CaptionModel.diverse_beam_search (word_model.py:297-394) with Hybrid_VAEModel.dbs_step (vae_model.py:997-1048).
+// Rows r = (clip*G + g)*bdash + k.  Group g runs g steps behind group 0; at global step t every active group
+// advances one local step.  The model step (prior, decoder, vocabulary projection) of ALL clips and groups is one
+// batched launch sequence -- it depends only on the selections of global step t-1 -- while the selection itself is
+// sequential over the groups of a clip (group g is penalised with the words groups < g hold at the same position
+// AFTER their own selection at this global step), so one CTA per clip walks its groups in order.
+struct DbsWs {
+  float *mem, *Pp, *Pd;
+  int *words, *prev, *hist;
+  float *top_lp, *logits;
+  float *qp_p, *w_p, *ctx_p, *gates_p, *c_p, *h_p, *pm, *pl, *pz, *qp_d, *w_d, *ctx_d, *gates_d, *hd;
+  double* done_score;   // [clips*G, bdash] best finished hypotheses per group, sorted by score (stable)
+  int *done_len, *done_seq, *done_cnt;
+  size_t state_off, state_bytes;   // the recurrent-state block zeroed before the first step
+  size_t bytes;
+};
+
+inline DbsWs carve_dbs_ws(const acvae_dims& d, int G, int bdash, void* base) {
+  Arena ar(base);
+  DbsWs w{};
+  const size_t clips = d.N, R = (size_t)d.N * G * bdash, Te = d.Te, E = d.E, A = d.A, T = d.T;
+  w.mem = ar.take<float>(clips * Te * E); w.Pp = ar.take<float>(clips * Te * E); w.Pd = ar.take<float>(clips * Te * A);
+  w.words = ar.take<int>(R * 2); w.prev = ar.take<int>(R); w.hist = ar.take<int>(R * T);
+  w.top_lp = ar.take<float>(R); w.logits = ar.take<float>(R * d.V);
+  w.qp_p = ar.take<float>(R * 2 * E); w.w_p = ar.take<float>(R * 2 * Te); w.ctx_p = ar.take<float>(R * 2 * E);
+  w.gates_p = ar.take<float>(R * 2 * 4 * E);
+  w.state_off = ar.off;
+  w.c_p = ar.take<float>(R * 2 * E); w.h_p = ar.take<float>(R * 2 * E); w.pz = ar.take<float>(R * 2 * E); w.hd = ar.take<float>(R * 2 * E);
+  w.state_bytes = ar.off - w.state_off;
+  w.pm = ar.take<float>(R * 2 * E); w.pl = ar.take<float>(R * 2 * E);
+  w.qp_d = ar.take<float>(R * 2 * A); w.w_d = ar.take<float>(R * 2 * Te); w.ctx_d = ar.take<float>(R * 2 * E);
+  w.gates_d = ar.take<float>(R * 2 * 4 * E);
+  w.done_score = ar.take<double>(R); w.done_len = ar.take<int>(R); w.done_seq = ar.take<int>(R * T); w.done_cnt = ar.take<int>(clips * G);
+  w.bytes = ar.off;
+  return w;
+}
+
+__global__ void dbs_init_kernel(int R, int groups, int start_idx, int* __restrict__ words, float* __restrict__ top_lp,
+                                int* __restrict__ done_cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < R) { words[i * 2] = start_idx; words[i * 2 + 1] = start_idx; top_lp[i] = 0.0f; }   // vae_model.py:1008, word_model.py:331
+  if (i < groups) done_cnt[i] = 0;
+}
+
+struct DbsParams {
+  int G, bdash, V, T, t, end_idx;
+  float temperature, lambda;
+  float* logits; float* top_lp; int* prev; int* words; int* hist;
+  double* done_score; int* done_len; int* done_seq; int* done_cnt;
+};
+
+constexpr int kDbsMaxBeam = 32;
+
+// One CTA per clip; groups in order (word_model.py:337-386).
+__global__ void __launch_bounds__(256) dbs_select_kernel(const __grid_constant__ DbsParams p) {
+  extern __shared__ int s_hist[];            // [bdash][T] staging of the group's hypotheses while they are re-ordered
+  __shared__ float red[33];
+  __shared__ float s_val[8];
+  __shared__ int s_idx[8];
+  __shared__ float s_newlp[kDbsMaxBeam];
+  __shared__ int s_newidx[kDbsMaxBeam];
+  __shared__ int s_tok[kDbsMaxBeam];
+  __shared__ float s_cnt[kDbsMaxBeam];
+  __shared__ int s_ntok;
+  const int clip = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int G = p.G, bdash = p.bdash, V = p.V, T = p.T, t = p.t;
+  for (int g = 0; g < G; ++g) {
+    if (!(g <= t && t <= T + g - 1)) continue;                 // word_model.py:338 (uniform over the CTA)
+    const int lt = t - g;
+    const int r0 = (clip * G + g) * bdash;
+    float* lg = p.logits + (long long)r0 * V;
+    const int nb = lt == 0 ? 1 : bdash;                        // first local step: all rows are equal, row 0 is used (:357-359)
+    // ---- words the earlier groups hold at this position, with multiplicities (add_diversity, :298-313) ----
+    if (tid == 0) {
+      int n = 0;
+      for (int pc = 0; pc < g; ++pc)
+        for (int k = 0; k < bdash; ++k) {
+          const int tok = p.hist[(long long)((clip * G + pc) * bdash + k) * T + lt];
+          int j = 0;
+          while (j < n && s_tok[j] != tok) ++j;
+          if (j == n) { s_tok[n] = tok; s_cnt[n] = 0.0f; ++n; }
+          s_cnt[j] += 1.0f;
+        }
+      s_ntok = n;
+    }
+    // ---- log_softmax(log_softmax(logits) / temperature) per row (:353-354), in place ----
+    for (int b = 0; b < nb; ++b) {
+      float* row = lg + (long long)b * V;
+      float mx = -INFINITY;
+      for (int v = tid; v < V; v += blockDim.x) mx = fmaxf(mx, row[v]);
+      mx = block_max(mx, red);
+      float se = 0.0f;
+      for (int v = tid; v < V; v += blockDim.x) se += expf(row[v] - mx);
+      se = block_sum(se, red);
+      const float lse = logf(se);
+      float mx2 = -INFINITY;
+      for (int v = tid; v < V; v += blockDim.x) {
+        const float x = __fdiv_rn(__fsub_rn(__fsub_rn(row[v], mx), lse), p.temperature);
+        row[v] = x;
+        mx2 = fmaxf(mx2, x);
+      }
+      mx2 = block_max(mx2, red);
+      float se2 = 0.0f;
+      for (int v = tid; v < V; v += blockDim.x) se2 += expf(row[v] - mx2);
+      se2 = block_sum(se2, red);
+      const float lse2 = logf(se2);
+      for (int v = tid; v < V; v += blockDim.x) row[v] = __fsub_rn(__fsub_rn(row[v], mx2), lse2);
+    }
+    __syncthreads();
+    // ---- diversity penalty, then the running score of the hypothesis (:355-356) ----
+    for (int i = tid; i < s_ntok * nb; i += blockDim.x) {
+      const int b = i / s_ntok, j = i % s_ntok;
+      float* x = lg + (long long)b * V + s_tok[j];
+      *x = __fsub_rn(*x, __fmul_rn(s_cnt[j], p.lambda));
+    }
+    __syncthreads();
+    for (int b = 0; b < nb; ++b) {
+      const float base = p.top_lp[r0 + b];
+      float* row = lg + (long long)b * V;
+      for (int v = tid; v < V; v += blockDim.x) row[v] = __fadd_rn(base, row[v]);
+    }
+    __syncthreads();
+    // ---- top bdash of the nb*V candidates, sorted (:357-362) ----
+    const int total = nb * V;
+    for (int k = 0; k < bdash; ++k) {
+      float best = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int i = tid; i < total; i += blockDim.x) {
+        const float x = lg[i];
+        if (x > best) { best = x; bi = i; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (lane == 0) { s_val[wid] = best; s_idx[wid] = bi; }
+      __syncthreads();
+      if (tid == 0) {
+        float bb = s_val[0]; int ii = s_idx[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+          if (s_val[w] > bb || (s_val[w] == bb && s_idx[w] < ii)) { bb = s_val[w]; ii = s_idx[w]; }
+        s_newlp[k] = bb; s_newidx[k] = ii;
+        lg[ii] = -INFINITY;   // exclude from the next pass
+      }
+      __syncthreads();
+    }
+    // ---- re-order and extend the group's hypotheses (:363-371) ----
+    for (int i = tid; i < bdash * lt; i += blockDim.x) s_hist[i] = p.hist[(long long)(r0 + i / lt) * T + i % lt];
+    __syncthreads();
+    for (int i = tid; i < bdash * (lt + 1); i += blockDim.x) {
+      const int k = i / (lt + 1), tt = i % (lt + 1);
+      const int idx = s_newidx[k];
+      p.hist[(long long)(r0 + k) * T + tt] = tt < lt ? s_hist[(idx / V) * lt + tt] : idx % V;
+    }
+    __syncthreads();
+    // ---- finished hypotheses (:373-385): kept sorted by score, ties in insertion order (== sorted(...)[:bdash], :387) ----
+    if (tid == 0) {
+      const int grp = clip * G + g;
+      int cnt = p.done_cnt[grp];
+      for (int k = 0; k < bdash; ++k) {
+        const int idx = s_newidx[k];
+        const int word = idx % V;
+        float lp = s_newlp[k];
+        const bool is_end = word == p.end_idx || t == T + g - 1;
+        if (is_end) {
+          const double score = (double)lp / (double)(lt + 1);
+          int pos = cnt < bdash ? cnt : bdash;
+          while (pos > 0 && score > p.done_score[(long long)grp * bdash + pos - 1]) --pos;
+          if (pos < bdash) {
+            const int last = cnt < bdash ? cnt : bdash - 1;
+            for (int j = last; j > pos; --j) {
+              p.done_score[(long long)grp * bdash + j] = p.done_score[(long long)grp * bdash + j - 1];
+              p.done_len[grp * bdash + j] = p.done_len[grp * bdash + j - 1];
+              for (int tt = 0; tt < T; ++tt)
+                p.done_seq[(long long)(grp * bdash + j) * T + tt] = p.done_seq[(long long)(grp * bdash + j - 1) * T + tt];
+            }
+            p.done_score[(long long)grp * bdash + pos] = score;
+            p.done_len[grp * bdash + pos] = lt + 1;
+            for (int tt = 0; tt <= lt; ++tt) p.done_seq[(long long)(grp * bdash + pos) * T + tt] = p.hist[(long long)(r0 + k) * T + tt];
+            if (cnt < bdash) ++cnt;
+          }
+          lp -= 1000.0f;                                        // :385
+        }
+        p.top_lp[r0 + k] = lp;
+        p.prev[r0 + k] = idx / V;
+        p.words[(r0 + k) * 2] = word;
+      }
+      p.done_cnt[grp] = cnt;
+    }
+    __syncthreads();
+  }
+}
+
+// state[(clip,g,k), slot 0] = state[(clip,g,prev[k]), slot 1] for the groups that stepped at global step t
+// (vae_model.py:1015-1024); groups that have not started keep their zero state and <start> word
+__global__ void dbs_reindex_kernel(int R, int G, int bdash, int T, int t, int E, const int* __restrict__ prev,
+                                   float* __restrict__ hd, float* __restrict__ h_p, float* __restrict__ c_p,
+                                   float* __restrict__ pz) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)R * E) return;
+  const int r = (int)(i / E), e = (int)(i % E);
+  const int g = (r / bdash) % G;
+  if (!(g <= t && t <= T + g - 1)) return;
+  const int src = (r / bdash) * bdash + prev[r];
+  const long long so = ((long long)src * 2 + 1) * E + e, dst_o = ((long long)r * 2) * E + e;
+  hd[dst_o] = hd[so]; h_p[dst_o] = h_p[so]; c_p[dst_o] = c_p[so]; pz[dst_o] = pz[so];
+}
+
+// seqs [clips, n_out, T] (END-filled): group_nbest -> every group's bdash best in group order (:388-389),
+// else the best of each group (:390-391)
+__global__ void dbs_final_kernel(int clips, int G, int bdash, int T, int n_out, int nbest, int end_idx,
+                                 const int* __restrict__ done_len, const int* __restrict__ done_seq,
+                                 const int* __restrict__ done_cnt, long long* __restrict__ seqs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= clips * n_out * T) return;
+  const int tt = i % T, o = (i / T) % n_out, clip = i / (T * n_out);
+  int g, j;
+  if (nbest) { g = o / bdash; j = o % bdash; } else { g = o; j = 0; }
+  long long v = end_idx;
+  if (g < G) {
+    const int grp = clip * G + g;
+    if (j < done_cnt[grp] && tt < done_len[grp * bdash + j]) v = done_seq[(long long)(grp * bdash + j) * T + tt];
+  }
+  seqs[i] = v;
+}
+
+inline int diverse_beam_search(const acvae_dims& d0, const acvae_weights& w, const float* audio, const int* mem_lens,
+                               const float* eps_g, int beam, int G, float lambda, float temperature, int nbest, int start_idx,
+                               int end_idx, int64_t* seqs, void* workspace, cudaStream_t st) {
+  const int bdash = beam / G;
+  DbsWs ws = carve_dbs_ws(d0, G, bdash, workspace);
+  const int clips = d0.N, T = d0.T, E = d0.E, V = d0.V, R = clips * G * bdash;
+  acvae_dims dm = d0;                       // memory: one row per clip
+  ACVAE_TRY(memory_prepare(dm, w, audio, ws.mem, ws.Pp, ws.Pd, st));
+  acvae_dims d = d0;
+  d.N = R; d.mem_rep = G * bdash;           // decode rows: all hypotheses of a clip share its memory
+  ACVAE_CHECK(cudaMemsetAsync(static_cast<char*>(workspace) + ws.state_off, 0, ws.state_bytes, st));
+  const int ninit = R > clips * G ? R : clips * G;
+  ACVAE_LAUNCH(dbs_init_kernel, grid1d(ninit), 256, 0, st, R, clips * G, start_idx, ws.words, ws.top_lp, ws.done_cnt);
+  StepBufs b{2, ws.qp_p, ws.w_p, ws.ctx_p, ws.gates_p, ws.c_p, ws.h_p, ws.pm, ws.pl, ws.pz,
+             ws.qp_d, ws.w_d, ws.ctx_d, ws.gates_d, ws.hd};
+  StepCtx c{d, w, st, mem_lens, ws.mem, ws.Pp, ws.Pd, nullptr};
+  DbsParams p{};
+  p.G = G; p.bdash = bdash; p.V = V; p.T = T; p.end_idx = end_idx; p.temperature = temperature; p.lambda = lambda;
+  p.logits = ws.logits; p.top_lp = ws.top_lp; p.prev = ws.prev; p.words = ws.words; p.hist = ws.hist;
+  p.done_score = ws.done_score; p.done_len = ws.done_len; p.done_seq = ws.done_seq; p.done_cnt = ws.done_cnt;
+  const size_t smem = sizeof(int) * (size_t)bdash * T;
+  for (int t = 0; t < T + G - 1; ++t) {                                   // word_model.py:336
+    // slot 0 holds the (re-indexed or initial zero) state, slot 1 receives the fresh step
+    ACVAE_TRY(prior_step(c, b, 1, 0, ws.words, 2, eps_g + (long long)t * R * E));
+    ACVAE_TRY(decoder_step(c, b, 1, 0, ws.words, 2, ws.pz + E, 2LL * E, nullptr, 0, 0));
+    ACVAE_TRY(linear_fwd(R, V, E, ws.hd + E, 2LL * E, w.cls_w, E, w.cls_b, ws.logits, V, st));
+    p.t = t;
+    ACVAE_LAUNCH(dbs_select_kernel, clips, 256, smem, st, p);
+    ACVAE_LAUNCH(dbs_reindex_kernel, grid1d((long long)R * E), 256, 0, st, R, G, bdash, T, t, E, (const int*)ws.prev, ws.hd,
+                 ws.h_p, ws.c_p, ws.pz);
+  }
+  const int n_out = nbest ? beam : G;
+  ACVAE_LAUNCH(dbs_final_kernel, grid1d((long long)clips * n_out * T), 256, 0, st, clips, G, bdash, T, n_out, nbest, end_idx,
+               (const int*)ws.done_len, (const int*)ws.done_seq, (const int*)ws.done_cnt, (long long*)seqs);
+  return 0;
+}
+
 }  // namespace acvae

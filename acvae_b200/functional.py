@@ -490,3 +490,23 @@ def beam_search(dims, weights, audio_embeds, mem_lens, eps_b, beam=3, start_idx=
                                    _dev(eps_b.contiguous()), int(beam), int(start_idx), _dev(seqs, torch.int64),
                                    ws.data_ptr(), ws.numel(), _stream()), "acvae_beam_search")
     return {"seqs": seqs}
+
+
+def diverse_beam_search(dims, weights, audio_embeds, mem_lens, eps_g, beam_size=5, group_size=5, diversity_lambda=0.5,
+                        temperature=1.0, group_nbest=True, start_idx=1, end_idx=2):
+    """Diverse beam search with prior latents (reference word_model.py:297-394, vae_model.py:997-1048).
+    eps_g: [T + group_size - 1, N*group_size*(beam_size // group_size), E]."""
+    l = _lib.lib()
+    dev = audio_embeds.device
+    n_out = int(beam_size) if group_nbest else int(group_size)
+    seqs = torch.empty(dims.N, n_out, dims.T, dtype=torch.int64, device=dev)
+    wmap = {k: v.detach().contiguous() for k, v in weights.items()}
+    wstruct = pack_weights(wmap)
+    audio_embeds = audio_embeds.contiguous()
+    ws = _workspace(l.acvae_dbs_workspace_bytes(C.byref(dims), int(beam_size), int(group_size)), dev)
+    _lib.check(l.acvae_diverse_beam_search(C.byref(dims), C.byref(wstruct), _dev(audio_embeds), _dev(mem_lens, torch.int32),
+                                           _dev(eps_g.contiguous()), int(beam_size), int(group_size), float(diversity_lambda),
+                                           float(temperature), int(bool(group_nbest)), int(start_idx), int(end_idx),
+                                           _dev(seqs, torch.int64), ws.data_ptr(), ws.numel(), _stream()),
+               "acvae_diverse_beam_search")
+    return {"seqs": seqs}

@@ -345,7 +345,21 @@ class _FusedVAEBase(CaptionModel):
                 eps_b = torch.randn(max_length, clips * beam, E, device=dev)
             return F.beam_search(dims, weights, audio, mem_lens, eps_b.to(dev), beam, self.start_idx)
         if method == "dbs":
-            raise NotImplementedError("diverse beam search (word_model.py:297-394) is not yet on the fused path")
+            # vae_model.py:887-893 (same keyword names and defaults); `eps_g` injects the prior noise
+            beam = int(kwargs.get("beam_size", 5))
+            groups = int(kwargs.get("group_size", 5))
+            lam = kwargs.get("diversity_lambda", 0.5)
+            temperature = kwargs.get("temperature", 1.0)
+            nbest = kwargs.get("group_nbest", True)
+            if groups < 1 or beam < groups:
+                raise ValueError("diverse beam search needs 1 <= group_size <= beam_size")
+            dims = self._dims(clips, Te, max_length)
+            rows = clips * groups * (beam // groups)
+            eps_g = kwargs.get("eps_g")
+            if eps_g is None:
+                eps_g = torch.randn(max_length + groups - 1, rows, E, device=dev)
+            return F.diverse_beam_search(dims, weights, audio, mem_lens, eps_g.to(dev), beam, groups, lam, temperature, nbest,
+                                         self.start_idx, self.end_idx)
         K = int(kwargs.get("n_captions", 1))
         N = clips * K
         dims = self._dims(N, Te, max_length, mem_rep=K)

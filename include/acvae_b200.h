@@ -247,6 +247,19 @@ int acvae_loss_combine_fwd(int64_t n, const float *q_utt, const float *p_utt, co
 int acvae_loss_combine_bwd(int64_t n, const float *q_utt, const float *p_utt, const float *d_loss, float kl_weight,
                            float alpha, float *d_q_utt, float *d_p_utt, float *scal, void *stream);
 
+/* ---- diverse beam search with prior latents --------------------------------------------------
+ * Replaces CaptionModel.diverse_beam_search (models/word_model.py:297-394) driven by
+ * Hybrid_VAEModel.dbs_step / prepare_dbs_decoder_input / dbs_process_step (models/vae_model.py:997-1048).
+ * N clips; group_size groups of bdash = beam_size / group_size hypotheses, group g running g steps behind
+ * group 0; d->T = max_length.  eps_g [T + group_size - 1, N*group_size*bdash, E]: prior noise of global step t
+ * for row (clip*group_size + g)*bdash + k (the caller permutes the reference's draw order; rows of groups
+ * inactive at t are ignored).  seqs [N, group_nbest ? beam_size : group_size, T], END-filled.           */
+size_t acvae_dbs_workspace_bytes(const acvae_dims *d, int32_t beam_size, int32_t group_size);
+int acvae_diverse_beam_search(const acvae_dims *d, const acvae_weights *w, const float *audio_embeds,
+                              const int32_t *mem_lens, const float *eps_g, int32_t beam_size, int32_t group_size,
+                              float diversity_lambda, float temperature, int32_t group_nbest, int32_t start_idx,
+                              int32_t end_idx, int64_t *seqs, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -245,6 +245,56 @@ def test_beam_golden(name):
     assert np.array_equal(out["seqs"].cpu().numpy(), g["seqs"])
 
 
+def _dbs_meta(g):
+    return (int(g["meta_seed"]), int(g["meta_max_length"]), int(g["meta_beam"]), int(g["meta_groups"]),
+            float(g["meta_lambda"]), float(g["meta_temperature"]), bool(int(g["meta_nbest"])))
+
+
+@pytest.mark.parametrize("name", ["tiny_dbs", "tiny_dbs_best", "cfg0_dbs"])
+def test_dbs_golden(name):
+    """Diverse beam search (word_model.py:297-394 + vae_model.py:997-1048): token ids identical to the reference's."""
+    _require_cuda()
+    g = harness.load_golden(name)
+    d = harness.dims_from_golden(g)
+    seed, ml, beam, groups, lam, temperature, nbest = _dbs_meta(g)
+    m = harness.build_model(d, seed).eval()
+    b = synthetic.make_batch(d, seed, sample_steps=ml, beam=beam, dbs_groups=groups)
+    bdash = beam // groups
+    # reference draw order (clip, global step, group) -> step-major rows (clip*G + g)*bdash + k
+    eps_g = torch.from_numpy(b["eps_dbs"]).permute(1, 0, 2, 3, 4).reshape(ml + groups - 1, d.N * groups * bdash, d.E).contiguous()
+    with torch.no_grad():
+        out = m(torch.from_numpy(b["audio_embeds"]).cuda(), torch.from_numpy(b["mem_lens"].copy()), method="dbs",
+                beam_size=beam, group_size=groups, diversity_lambda=lam, temperature=temperature, group_nbest=nbest,
+                max_length=ml, eps_g=eps_g)
+    assert out["seqs"].shape == g["seqs"].shape
+    assert np.array_equal(out["seqs"].cpu().numpy(), g["seqs"])
+
+
+def test_dbs_vs_oracle_many_clips():
+    """A wider case than the fixtures (12 clips, 3 groups x 2, lambda 0.8, temperature 1.3) against the oracle, plus a
+    property of the algorithm itself: group 0 is never penalised, so its hypotheses do not depend on lambda."""
+    _require_cuda()
+    import acvae_oracle as oracle
+    d = synthetic.Dims(N=12, Te=9, L=9, E=32, H=32, A=32, Hq=32, V=61, Eenc=40)
+    seed, ml, beam, groups = 5, 8, 6, 3
+    m = harness.build_model(d, seed).eval()
+    b = synthetic.make_batch(d, seed, sample_steps=ml, beam=beam, dbs_groups=groups)
+    bdash = beam // groups
+    eps = torch.from_numpy(b["eps_dbs"])
+    eps_g = eps.permute(1, 0, 2, 3, 4).reshape(ml + groups - 1, d.N * groups * bdash, d.E).contiguous()
+    feats, lens = torch.from_numpy(b["audio_embeds"]), torch.from_numpy(b["mem_lens"].copy())
+    outs = {}
+    for lam in (0.8, 3.0):
+        with torch.no_grad():
+            outs[lam] = m(feats.cuda(), lens.clone(), method="dbs", beam_size=beam, group_size=groups, diversity_lambda=lam,
+                          temperature=1.3, group_nbest=True, max_length=ml, eps_g=eps_g)["seqs"].cpu()
+    p = harness.oracle_params(d, seed)
+    eps_d = [{(t, gg): eps[i, t, gg] for t in range(ml + groups - 1) for gg in range(groups)} for i in range(d.N)]
+    with torch.no_grad():
+        o = oracle.diverse_beam_search(p, feats, b["mem_lens"], eps_d, beam, groups, 0.8, 1.3, True, ml)
+    assert np.array_equal(outs[0.8].numpy(), o["seqs"].numpy())
+    assert np.array_equal(outs[0.8][:, :bdash].numpy(), outs[3.0][:, :bdash].numpy())      # group 0 ignores lambda
+
 # ----------------------------------------------------------------------------- components
 def test_vocab_stats_and_ce_vs_torch():
     _require_cuda()

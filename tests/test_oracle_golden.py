@@ -73,6 +73,21 @@ def test_oracle_beam_tiny():
     assert np.array_equal(o["seqs"].numpy(), g["seqs"])
 
 
+def test_oracle_dbs_tiny():
+    """The oracle's diverse beam search reproduces the reference's token ids (fixtures made by make_golden.py dbs)."""
+    for name in ("tiny_dbs", "tiny_dbs_best"):
+        g = harness.load_golden(name)
+        d = harness.dims_from_golden(g)
+        seed, ml, beam, groups = int(g["meta_seed"]), int(g["meta_max_length"]), int(g["meta_beam"]), int(g["meta_groups"])
+        b = synthetic.make_batch(d, seed, sample_steps=ml, beam=beam, dbs_groups=groups)
+        p = harness.oracle_params(d, seed)
+        eps = torch.from_numpy(b["eps_dbs"])
+        eps_d = [{(t, gg): eps[i, t, gg] for t in range(ml + groups - 1) for gg in range(groups)} for i in range(d.N)]
+        with torch.no_grad():
+            o = oracle.diverse_beam_search(p, torch.from_numpy(b["audio_embeds"]), b["mem_lens"], eps_d, beam, groups,
+                                           float(g["meta_lambda"]), float(g["meta_temperature"]), bool(int(g["meta_nbest"])), ml)
+        assert np.array_equal(o["seqs"].numpy(), g["seqs"]), name
+
 def test_oracle_edge_min_length_and_single_frame():
     """Ragged edge cases: a caption of the minimum length (<start>,<end>) and a clip with one frame."""
     d = synthetic.Dims(N=3, Te=5, L=5, E=16, H=16, A=16, Hq=16, V=23, Eenc=20)
