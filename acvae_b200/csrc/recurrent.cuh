@@ -108,6 +108,41 @@ __device__ __forceinline__ void reduce8(float (&acc)[COLS]) {
   }
 }
 
+
+// ---- "quad" mapping (4 rows per warp, 32-way K split) ---------------------------------------------------------
+// A warp = one group of four batch rows; lane = K slice (float4s {lane, lane+32, ...} of a row).  Every weight word
+// a lane reads from shared memory is used for four rows from registers: the row-per-8-lanes mapping above re-reads
+// each weight word in all four row groups of a warp (LDS.128 is served per quarter warp), which made the phases
+// shared-memory bound: 2800 cycles of LDS for 770 cycles of FMA per posterior step (profiles/ubench_chain.cu).
+template <int K>
+__device__ __forceinline__ void quadload(const float* __restrict__ src, int lane, float4 (&a)[K / 128]) {
+#pragma unroll
+  for (int i = 0; i < K / 128; ++i) a[i] = ldcg4(src + (i * 32 + lane) * 4);
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& w, float acc) {
+  acc = fmaf(a.x, w.x, acc); acc = fmaf(a.y, w.y, acc); acc = fmaf(a.z, w.z, acc); return fmaf(a.w, w.w, acc);
+}
+// Reduce-scatter over the 32 lanes of a warp: every lane holds partial sums v[q][g] of 16 "combos" q with G_ values
+// each; afterwards lanes 2q and 2q+1 hold the full sums of combo q in v[0][*].  48 shuffles for 16 x 3 values
+// instead of 5 x 48 for a butterfly all-reduce; only static register indices.
+template <int G_>
+__device__ __forceinline__ void reduce_scatter16(float (&v)[16][G_], int lane) {
+#pragma unroll
+  for (int half = 8; half >= 1; half >>= 1) {
+    const bool hi = (lane & (half * 2)) != 0;
+#pragma unroll
+    for (int q = 0; q < half; ++q)
+#pragma unroll
+      for (int g = 0; g < G_; ++g) {
+        const float keep = hi ? v[q + half][g] : v[q][g];
+        const float send = hi ? v[q][g] : v[q + half][g];
+        v[q][g] = keep + __shfl_xor_sync(0xffffffffu, send, half * 2);
+      }
+  }
+#pragma unroll
+  for (int g = 0; g < G_; ++g) v[0][g] += __shfl_xor_sync(0xffffffffu, v[0][g], 1);
+}
+
 // =====================================================================================================
 // posterior biGRU forward, both directions in one kernel (text_encoder.py:188-191)
 // =====================================================================================================
@@ -124,8 +159,8 @@ struct PostChainFwd {
 };
 __global__ void __launch_bounds__(kChainThreads) post_chain_fwd_kernel(const __grid_constant__ PostChainFwd p) {
   constexpr int E = kChainE;
-  __shared__ __align__(16) float W[2][6][E];
-  const int tid = threadIdx.x, n = tid >> 3, kp = tid & 7;
+  __shared__ __align__(16) float W[2][6][E];            // W[dir][gate*2 + j][k] = W_hh[dir][gate*E + u0 + j][k]
+  const int tid = threadIdx.x, wq = tid >> 5, lane = tid & 31;
   const int u0 = blockIdx.x * 2;
   for (int i = tid; i < 2 * 6 * E; i += kChainThreads) {
     const int dir = i / (6 * E), r = (i / E) % 6, k = i % E;
@@ -134,58 +169,67 @@ __global__ void __launch_bounds__(kChainThreads) post_chain_fwd_kernel(const __g
   __syncthreads();
   GridBar gb{p.bar, 0u, gridDim.x};
   const int T = p.T;
-  const bool row = n < p.N;
-  const int len = row ? p.lens[n] : 0;
-  const int dir = (kp >> 1) & 1, j = kp & 1, u = u0 + j;      // epilogue role of lanes kp < 4
+  const int n0 = wq * 4;                                 // this warp's rows n0 .. n0+3
+  // epilogue role of the even lanes after the reduce-scatter: combo q = lane >> 1 = (row r, direction, unit j)
+  const int q = lane >> 1, er = q >> 2, dir = (q >> 1) & 1, j = q & 1, u = u0 + j;
+  const int n = n0 + er;
+  const bool epi = (lane & 1) == 0 && n < p.N;
+  const int len = epi ? p.lens[n] : 0;
   const float bh_r = p.bhh[dir][u], bh_z = p.bhh[dir][E + u], bh_n = p.bhh[dir][2 * E + u];
   for (int s = 0; s < T; ++s) {
-    float acc[2][6];
+    float v[16][3];                                      // v[r*4 + dir*2 + j][gate]
 #pragma unroll
-    for (int d = 0; d < 2; ++d)
-#pragma unroll
-      for (int c = 0; c < 6; ++c) acc[d][c] = 0.0f;
+    for (int c = 0; c < 16; ++c) { v[c][0] = 0.0f; v[c][1] = 0.0f; v[c][2] = 0.0f; }
     const int t = dir ? T - 1 - s : s;
     const int tp = dir ? t + 1 : t - 1;
     const bool tr = p.trace && blockIdx.x == 0 && tid == 0;
     if (tr) p.trace[s * 8 + 0] = clock64();
     float gxr = 0.f, gxz = 0.f, gxn = 0.f, hp = 0.f;
-    if (row && kp < 4) {                               // pointwise operands: issued with the row loads
+    if (epi) {                                           // pointwise operands: issued with the row loads
       const float* gx = p.gx[dir] + ((long long)n * T + t) * 3 * E + u;
       gxr = ldcg1(gx); gxz = ldcg1(gx + E); gxn = ldcg1(gx + 2 * E);
       if (s > 0) hp = ldcg1(p.ho + ((long long)n * T + tp) * 2 * E + dir * E + u);
     }
     if (s > 0) {
-      float4 a0[E / 32], a1[E / 32];
-      if (row) {
-        rowload<E>(p.ho + ((long long)n * T + (s - 1)) * 2 * E, kp, a0);
-        rowload<E>(p.ho + ((long long)n * T + (T - s)) * 2 * E + E, kp, a1);
+      float4 a[4][2][E / 128];                           // [row][dir][float4]
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (n0 + r < p.N) {
+          quadload<E>(p.ho + ((long long)(n0 + r) * T + (s - 1)) * 2 * E, lane, a[r][0]);
+          quadload<E>(p.ho + ((long long)(n0 + r) * T + (T - s)) * 2 * E + E, lane, a[r][1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < E / 128; ++i) { a[r][0][i] = make_float4(0.f, 0.f, 0.f, 0.f); a[r][1][i] = a[r][0][i]; }
+        }
       }
       __syncwarp();
-      if (tr) {                                        // stamp 5: this thread's row loads have landed
+      if (tr) {                                          // stamp 5: this thread's row loads have landed
         float chk = 0.0f;
 #pragma unroll
-        for (int i = 0; i < E / 32; ++i) chk += a0[i].x + a1[i].x;
+        for (int r = 0; r < 4; ++r) chk += a[r][0][0].x + a[r][1][0].x + a[r][0][1].x + a[r][1][1].x;
         if (chk == 1234.5f) p.trace[s * 8 + 6] = 0;
         p.trace[s * 8 + 5] = clock64();
       }
-      if (row) {
-        rowfma<6, E>(a0, &W[0][0][0], E, kp, acc[0]);
-        rowfma<6, E>(a1, &W[1][0][0], E, kp, acc[1]);
-      }
+#pragma unroll
+      for (int d = 0; d < 2; ++d)
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+#pragma unroll
+          for (int i = 0; i < E / 128; ++i) {
+            const float4 w = *(reinterpret_cast<const float4*>(&W[d][c][0]) + i * 32 + lane);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[r * 4 + d * 2 + (c & 1)][c >> 1] = dot4(a[r][d][i], w, v[r * 4 + d * 2 + (c & 1)][c >> 1]);
+          }
       if (tr) p.trace[s * 8 + 1] = clock64();
-      reduce8(acc[0]);
-      reduce8(acc[1]);
+      reduce_scatter16<3>(v, lane);
     }
     if (tr) p.trace[s * 8 + 2] = clock64();
-    if (row && kp < 4) {
-      // static register indices only (a runtime index would spill the accumulators to local memory)
-      const float hr = (dir ? (j ? acc[1][1] : acc[1][0]) : (j ? acc[0][1] : acc[0][0])) + bh_r;
-      const float hz = (dir ? (j ? acc[1][3] : acc[1][2]) : (j ? acc[0][3] : acc[0][2])) + bh_z;
-      const float hn = (dir ? (j ? acc[1][5] : acc[1][4]) : (j ? acc[0][5] : acc[0][4])) + bh_n;
+    if (epi) {
+      const float hr = v[0][0] + bh_r, hz = v[0][1] + bh_z, hn = v[0][2] + bh_n;
       const float rg = sigmoidf_(gxr + hr), zg = sigmoidf_(gxz + hz);
       const float ng = tanhf(gxn + rg * hn);
       float hnew = (1.0f - zg) * ng + zg * hp;
-      if (t >= len) hnew = 0.0f;                       // packed sequence: padded outputs are zero
+      if (t >= len) hnew = 0.0f;                         // packed sequence: padded outputs are zero
       float* gs = p.gq[dir] + ((long long)n * T + t) * 4 * E + u;
       gs[0] = rg; gs[E] = zg; gs[2 * E] = ng; gs[3 * E] = hn;
       p.ho[((long long)n * T + t) * 2 * E + dir * E + u] = hnew;
