@@ -143,6 +143,83 @@ __device__ __forceinline__ void reduce_scatter16(float (&v)[16][G_], int lane) {
   for (int g = 0; g < G_; ++g) v[0][g] += __shfl_xor_sync(0xffffffffu, v[0][g], 1);
 }
 
+// 8 combos q = (row r, unit j) x G_ values: afterwards lanes 4q .. 4q+3 hold combo q in v[0][*]
+template <int G_>
+__device__ __forceinline__ void reduce_scatter8(float (&v)[8][G_], int lane) {
+#pragma unroll
+  for (int half = 4; half >= 1; half >>= 1) {
+    const bool hi = (lane & (half * 4)) != 0;
+#pragma unroll
+    for (int q = 0; q < half; ++q)
+#pragma unroll
+      for (int g = 0; g < G_; ++g) {
+        const float keep = hi ? v[q + half][g] : v[q][g];
+        const float send = hi ? v[q][g] : v[q + half][g];
+        v[q][g] = keep + __shfl_xor_sync(0xffffffffu, send, half * 4);
+      }
+  }
+#pragma unroll
+  for (int g = 0; g < G_; ++g) {
+    v[0][g] += __shfl_xor_sync(0xffffffffu, v[0][g], 2);
+    v[0][g] += __shfl_xor_sync(0xffffffffu, v[0][g], 1);
+  }
+}
+// v[r*2 + j][g] += sum_k a_r[k] * W[g*2 + j][k] over this lane's K slice; W: shared [2*G_][ldw]
+template <int G_, int K>
+__device__ __forceinline__ void quadfma(const float4 (&a)[4][K / 128], const float* W, int ldw, int lane, float (&v)[8][G_]) {
+#pragma unroll
+  for (int c = 0; c < 2 * G_; ++c)
+#pragma unroll
+    for (int i = 0; i < K / 128; ++i) {
+      const float4 w = *(reinterpret_cast<const float4*>(W + c * ldw) + i * 32 + lane);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) v[r * 2 + (c & 1)][c >> 1] = dot4(a[r][i], w, v[r * 2 + (c & 1)][c >> 1]);
+    }
+}
+// rows n0 .. n0+3 (row stride `stride` floats, K contiguous floats each) against W; loads first, then the FMAs
+template <int K>
+__device__ __forceinline__ void quadrows(int n0, int N, const float* __restrict__ src0, long long stride, int lane, float4 (&a)[4][K / 128]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    if (n0 + r < N) quadload<K>(src0 + r * stride, lane, a[r]);
+    else {
+#pragma unroll
+      for (int i = 0; i < K / 128; ++i) a[r][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+template <int G_, int K>
+__device__ __forceinline__ void quaddot(int n0, int N, const float* __restrict__ src0, long long stride, const float* W, int ldw,
+                                        int lane, float (&v)[8][G_]) {
+  float4 a[4][K / 128];
+  quadrows<K>(n0, N, src0, stride, lane, a);
+  __syncwarp();
+  quadfma<G_, K>(a, W, ldw, lane, v);
+}
+template <int G_>
+__device__ __forceinline__ void zero8(float (&v)[8][G_]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+#pragma unroll
+    for (int g = 0; g < G_; ++g) v[q][g] = 0.0f;
+}
+// Thread roles of the quad mapping inside a chain kernel: the warp's rows, and -- for the lanes that run the
+// pointwise epilogue after reduce_scatter8 -- the (row, unit) they own for the whole kernel (so per-unit carries
+// stay in that lane's registers).
+struct QuadRole {
+  int lane, n0;     // K slice, first row of the warp
+  int n, j, u;      // epilogue row, unit index within the CTA (0/1), global unit
+  bool epi;         // this lane runs the epilogue
+};
+__device__ __forceinline__ QuadRole quad_role(int N, int u0) {
+  QuadRole q;
+  q.lane = threadIdx.x & 31; q.n0 = (threadIdx.x >> 5) * 4;
+  const int c = q.lane >> 2;
+  q.n = q.n0 + (c >> 1); q.j = c & 1; q.u = u0 + q.j;
+  q.epi = (q.lane & 3) == 0 && q.n < N;
+  return q;
+}
+
 // =====================================================================================================
 // posterior biGRU forward, both directions in one kernel (text_encoder.py:188-191)
 // =====================================================================================================
@@ -280,59 +357,53 @@ __device__ __forceinline__ void prior_fwd_setup(const PriorChainFwd& p, float* W
   r.c_prev = 0.0f; r.eps_t = 0.0f;
 }
 // LSTM cell of step t (needs z_{t-1}, h_{t-1} of all units: one barrier after the previous head phase)
-__device__ __forceinline__ void prior_fwd_lstm(const PriorChainFwd& p, const float* Wl, PriorFwdRegs& r, int t, int n, int kp,
-                                               bool row, int j, int u) {
+__device__ __forceinline__ void prior_fwd_lstm(const PriorChainFwd& p, const float* Wl, PriorFwdRegs& r, int t, const QuadRole& q) {
   constexpr int E = kChainE;
   const int T = p.T, N = p.N;
-  float acc[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) acc[c] = 0.0f;
+  float v[8][4];
+  zero8(v);
   float gxv[4] = {0.f, 0.f, 0.f, 0.f};
-  if (row && kp < 2) {
-    const float* gx = p.gx + ((long long)n * T + t) * 4 * E + u;
+  if (q.epi) {
+    const float* gx = p.gx + ((long long)q.n * T + t) * 4 * E + q.u;
 #pragma unroll
     for (int g = 0; g < 4; ++g) gxv[g] = ldcg1(gx + g * E);
-    r.eps_t = ldcg1(p.eps + ((long long)t * N + n) * E + u);
+    r.eps_t = ldcg1(p.eps + ((long long)t * N + q.n) * E + q.u);
   }
   if (t > 0) {
-    float4 a0[E / 32], a1[E / 32];
-    if (row) {
-      rowload<E>(p.pz + ((long long)n * T + t - 1) * E, kp, a0);
-      rowload<E>(p.h + ((long long)n * T + t - 1) * E, kp, a1);
-    }
+    float4 a0[4][E / 128], a1[4][E / 128];
+    quadrows<E>(q.n0, N, p.pz + ((long long)q.n0 * T + t - 1) * E, (long long)T * E, q.lane, a0);
+    quadrows<E>(q.n0, N, p.h + ((long long)q.n0 * T + t - 1) * E, (long long)T * E, q.lane, a1);
     __syncwarp();
-    if (row) {
-      rowfma<8, E>(a0, Wl, 2 * E, kp, acc);
-      rowfma<8, E>(a1, Wl + E, 2 * E, kp, acc);
-    }
-    reduce8(acc);
+    quadfma<4, E>(a0, Wl, 2 * E, q.lane, v);
+    quadfma<4, E>(a1, Wl + E, 2 * E, q.lane, v);
+    reduce_scatter8<4>(v, q.lane);
   }
-  if (row && kp < 2) {
-    const float ig = sigmoidf_((j ? acc[1] : acc[0]) + gxv[0] + r.bh[0]);
-    const float fg = sigmoidf_((j ? acc[3] : acc[2]) + gxv[1] + r.bh[1]);
-    const float gg = tanhf((j ? acc[5] : acc[4]) + gxv[2] + r.bh[2]);
-    const float og = sigmoidf_((j ? acc[7] : acc[6]) + gxv[3] + r.bh[3]);
+  if (q.epi) {
+    const float ig = sigmoidf_(v[0][0] + gxv[0] + r.bh[0]);
+    const float fg = sigmoidf_(v[0][1] + gxv[1] + r.bh[1]);
+    const float gg = tanhf(v[0][2] + gxv[2] + r.bh[2]);
+    const float og = sigmoidf_(v[0][3] + gxv[3] + r.bh[3]);
     const float cn = fg * r.c_prev + ig * gg;
     const float hn = og * tanhf(cn);
     r.c_prev = cn;
-    float* gs = p.gates + ((long long)n * T + t) * 4 * E + u;
+    float* gs = p.gates + ((long long)q.n * T + t) * 4 * E + q.u;
     gs[0] = ig; gs[E] = fg; gs[2 * E] = gg; gs[3 * E] = og;
-    p.c[((long long)n * T + t) * E + u] = cn;
-    p.h[((long long)n * T + t) * E + u] = hn;
+    p.c[((long long)q.n * T + t) * E + q.u] = cn;
+    p.h[((long long)q.n * T + t) * E + q.u] = hn;
   }
 }
 // Gaussian head + reparameterisation of step t (needs h_t of all units: one barrier after the LSTM phase)
-__device__ __forceinline__ void prior_fwd_head(const PriorChainFwd& p, const float* Wh, PriorFwdRegs& r, int t, int n, int kp,
-                                               bool row, int j, int u) {
+__device__ __forceinline__ void prior_fwd_head(const PriorChainFwd& p, const float* Wh, PriorFwdRegs& r, int t, const QuadRole& q) {
   constexpr int E = kChainE;
   const int T = p.T;
-  float hc[4] = {0.f, 0.f, 0.f, 0.f};
-  rowdot<4, E>(row, p.h + ((long long)n * T + t) * E, Wh, E, kp, hc);
-  reduce8(hc);
-  if (row && kp < 2) {
-    const float mean = (j ? hc[1] : hc[0]) + r.hb_m;
-    const float lg = (j ? hc[3] : hc[2]) + r.hb_l;
-    const long long o = ((long long)n * T + t) * E + u;
+  float v[8][2];
+  zero8(v);
+  quaddot<2, E>(q.n0, p.N, p.h + ((long long)q.n0 * T + t) * E, (long long)T * E, Wh, E, q.lane, v);
+  reduce_scatter8<2>(v, q.lane);
+  if (q.epi) {
+    const float mean = v[0][0] + r.hb_m;
+    const float lg = v[0][1] + r.hb_l;
+    const long long o = ((long long)q.n * T + t) * E + q.u;
     p.pm[o] = mean; p.pl[o] = lg; p.pz[o] = r.eps_t * expf(0.5f * lg) + mean;
   }
 }
@@ -340,17 +411,16 @@ __device__ __forceinline__ void prior_fwd_head(const PriorChainFwd& p, const flo
 __global__ void __launch_bounds__(kChainThreads) prior_chain_fwd_kernel(const __grid_constant__ PriorChainFwd p) {
   __shared__ __align__(16) float Wsm[kPriorFwdSmemFloats];
   float* Wl = Wsm; float* Wh = Wsm + 8 * 2 * kChainE;
-  const int tid = threadIdx.x, n = tid >> 3, kp = tid & 7;
-  const int u0 = blockIdx.x * 2, j = kp & 1, u = u0 + j;
+  const int u0 = blockIdx.x * 2;
+  const QuadRole q = quad_role(p.N, u0);
   PriorFwdRegs r;
-  prior_fwd_setup(p, Wl, Wh, r, u0, u);
+  prior_fwd_setup(p, Wl, Wh, r, u0, q.u);
   __syncthreads();
   GridBar gb{p.bar, 0u, gridDim.x};
-  const bool row = n < p.N;
   for (int t = 0; t < p.T; ++t) {
-    prior_fwd_lstm(p, Wl, r, t, n, kp, row, j, u);
+    prior_fwd_lstm(p, Wl, r, t, q);
     grid_sync(gb);
-    prior_fwd_head(p, Wh, r, t, n, kp, row, j, u);
+    prior_fwd_head(p, Wh, r, t, q);
     if (t + 1 < p.T) grid_sync(gb);
   }
 }
@@ -372,7 +442,7 @@ struct PostChainBwd {
 __global__ void __launch_bounds__(kChainThreads) post_chain_bwd_kernel(const __grid_constant__ PostChainBwd p) {
   constexpr int E = kChainE;
   __shared__ __align__(16) float Wt[2][2][3 * E];   // Wt[dir][j][c] = W_hh[c][u0+j]
-  const int tid = threadIdx.x, n = tid >> 3, kp = tid & 7;
+  const int tid = threadIdx.x, lane = tid & 31, n0 = (tid >> 5) * 4;
   const int u0 = blockIdx.x * 2;
   for (int i = tid; i < 2 * 2 * 3 * E; i += kChainThreads) {
     const int dir = i / (2 * 3 * E), jj = (i / (3 * E)) & 1, c = i % (3 * E);
@@ -380,29 +450,44 @@ __global__ void __launch_bounds__(kChainThreads) post_chain_bwd_kernel(const __g
   }
   __syncthreads();
   GridBar gb{p.bar, 0u, gridDim.x};
-  const int T = p.T;
-  const bool row = n < p.N;
-  const int len = row ? p.lens[n] : 0;
-  const int dir = (kp >> 1) & 1, j = kp & 1, u = u0 + j;
+  const int T = p.T, N = p.N;
+  // epilogue role after reduce_scatter16: combo = lane >> 1 = (row r, direction, unit j)
+  const int cq = lane >> 1, dir = (cq >> 1) & 1, j = cq & 1, u = u0 + j, n = n0 + (cq >> 2);
+  const bool epi = (lane & 1) == 0 && n < N;
+  const int len = epi ? p.lens[n] : 0;
   float carry = 0.0f;
   for (int s = T - 1; s >= 0; --s) {
-    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    float v[16][1];                                    // v[r*4 + dir*2 + j]
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c][0] = 0.0f;
     const int t = dir ? T - 1 - s : s;
     const int tp = dir ? t + 1 : t - 1;
     float dho = 0.f, rr = 0.f, z = 0.f, nn = 0.f, ghn = 0.f, hp = 0.f;
-    if (row && kp < 4) {                               // pointwise operands: issued with the row loads
+    if (epi) {                                         // pointwise operands: issued with the row loads
       dho = ldcg1(p.dho + ((long long)n * T + t) * 2 * E + dir * E + u);
       const float* g = p.gq[dir] + ((long long)n * T + t) * 4 * E + u;
       rr = ldcg1(g); z = ldcg1(g + E); nn = ldcg1(g + 2 * E); ghn = ldcg1(g + 3 * E);
       if (s > 0) hp = ldcg1(p.ho + ((long long)n * T + tp) * 2 * E + dir * E + u);
     }
     if (s < T - 1) {
-      rowdot<2, 3 * E>(row, p.dgh[0] + ((long long)n * T + (s + 1)) * 3 * E, &Wt[0][0][0], 3 * E, kp, acc[0]);
-      rowdot<2, 3 * E>(row, p.dgh[1] + ((long long)n * T + (T - 2 - s)) * 3 * E, &Wt[1][0][0], 3 * E, kp, acc[1]);
-      reduce8(acc[0]);
-      reduce8(acc[1]);
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        const int ts = d ? T - 2 - s : s + 1;          // the step this direction processed in the previous phase
+        float4 a[4][3 * E / 128];
+        quadrows<3 * E>(n0, N, p.dgh[d] + ((long long)n0 * T + ts) * 3 * E, (long long)T * 3 * E, lane, a);
+        __syncwarp();
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+          for (int i = 0; i < 3 * E / 128; ++i) {
+            const float4 w = *(reinterpret_cast<const float4*>(&Wt[d][jj][0]) + i * 32 + lane);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[r * 4 + d * 2 + jj][0] = dot4(a[r][i], w, v[r * 4 + d * 2 + jj][0]);
+          }
+      }
+      reduce_scatter16<1>(v, lane);
     }
-    if (row && kp < 4) {
+    if (epi) {
       float* gi = p.dgi[dir] + ((long long)n * T + t) * 3 * E + u;
       float* gh = p.dgh[dir] + ((long long)n * T + t) * 3 * E + u;
       if (t >= len) {
@@ -411,7 +496,7 @@ __global__ void __launch_bounds__(kChainThreads) post_chain_bwd_kernel(const __g
         carry = 0.0f;
       } else {
         float dh = dho;
-        if (s < T - 1) dh += carry + (dir ? (j ? acc[1][1] : acc[1][0]) : (j ? acc[0][1] : acc[0][0]));
+        if (s < T - 1) dh += carry + v[0][0];
         const float dn = dh * (1.0f - z), dz = dh * (hp - nn);
         const float dan = dn * (1.0f - nn * nn);
         const float dar = dan * ghn * rr * (1.0f - rr), daz = dz * z * (1.0f - z);
@@ -457,40 +542,40 @@ __device__ __forceinline__ void prior_bwd_setup(const PriorChainBwd& p, float* W
   r.dh_carry = 0.0f; r.dc_carry = 0.0f;
 }
 // head backward of the LAST step (no chain input): must be followed by a barrier before prior_bwd_lstm(T-1)
-__device__ __forceinline__ void prior_bwd_first(const PriorChainBwd& p, int n, int kp, bool row, int u) {
+__device__ __forceinline__ void prior_bwd_first(const PriorChainBwd& p, const QuadRole& q) {
   constexpr int E = kChainE;
   const int T = p.T, N = p.N, t = T - 1;
-  if (row && kp < 2) {
-    const long long o = ((long long)n * T + t) * E + u;
+  if (q.epi) {
+    const long long o = ((long long)q.n * T + t) * E + q.u;
     float dz = p.d_pz ? p.d_pz[o] : 0.0f;
     float dm = dz;
-    float dl = dz * p.eps[((long long)t * N + n) * E + u] * 0.5f * expf(0.5f * p.p_logs[o]);
+    float dl = dz * p.eps[((long long)t * N + q.n) * E + q.u] * 0.5f * expf(0.5f * p.p_logs[o]);
     if (p.d_pm) dm += p.d_pm[o];
     if (p.d_pl) dl += p.d_pl[o];
-    float* d = p.dml + ((long long)n * T + t) * 2 * E + u;
+    float* d = p.dml + ((long long)q.n * T + t) * 2 * E + q.u;
     d[0] = dm; d[E] = dl;
   }
 }
 // dh_t = dML_t . W_head (+ carry); LSTM pointwise backward of step t
-__device__ __forceinline__ void prior_bwd_lstm(const PriorChainBwd& p, const float* WA, PriorBwdRegs& r, int t, int n, int kp,
-                                               bool row, int j, int u) {
+__device__ __forceinline__ void prior_bwd_lstm(const PriorChainBwd& p, const float* WA, PriorBwdRegs& r, int t, const QuadRole& q) {
   constexpr int E = kChainE;
   const int T = p.T;
-  float a2[2] = {0.f, 0.f};
+  float v[8][1];
+  zero8(v);
   float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, cc = 0.f, cp = 0.f;
-  if (row && kp < 2) {
-    const float* g = p.gates + ((long long)n * T + t) * 4 * E + u;
+  if (q.epi) {
+    const float* g = p.gates + ((long long)q.n * T + t) * 4 * E + q.u;
     ig = ldcg1(g); fg = ldcg1(g + E); gg = ldcg1(g + 2 * E); og = ldcg1(g + 3 * E);
-    cc = ldcg1(p.c + ((long long)n * T + t) * E + u);
-    if (t > 0) cp = ldcg1(p.c + ((long long)n * T + t - 1) * E + u);
+    cc = ldcg1(p.c + ((long long)q.n * T + t) * E + q.u);
+    if (t > 0) cp = ldcg1(p.c + ((long long)q.n * T + t - 1) * E + q.u);
   }
-  rowdot<2, 2 * E>(row, p.dml + ((long long)n * T + t) * 2 * E, WA, 2 * E, kp, a2);
-  reduce8(a2);
-  if (row && kp < 2) {
-    const float dh = (j ? a2[1] : a2[0]) + r.dh_carry;
+  quaddot<1, 2 * E>(q.n0, p.N, p.dml + ((long long)q.n0 * T + t) * 2 * E, (long long)T * 2 * E, WA, 2 * E, q.lane, v);
+  reduce_scatter8<1>(v, q.lane);
+  if (q.epi) {
+    const float dh = v[0][0] + r.dh_carry;
     const float tc = tanhf(cc);
     const float dc = dh * og * (1.0f - tc * tc) + r.dc_carry;
-    float* dg = p.dg + ((long long)n * T + t) * 4 * E + u;
+    float* dg = p.dg + ((long long)q.n * T + t) * 4 * E + q.u;
     dg[0] = dc * gg * ig * (1.0f - ig);
     dg[E] = dc * cp * fg * (1.0f - fg);
     dg[2 * E] = dc * ig * (1.0f - gg * gg);
@@ -499,28 +584,28 @@ __device__ __forceinline__ void prior_bwd_lstm(const PriorChainBwd& p, const flo
   }
 }
 // [d last_z | d h_{t-1}] = dG_t . [W_ih[:, 2E:3E] | W_hh]; head backward of step t-1   (t > 0)
-__device__ __forceinline__ void prior_bwd_head(const PriorChainBwd& p, const float* WB, PriorBwdRegs& r, int t, int n, int kp,
-                                               bool row, int j, int u) {
+__device__ __forceinline__ void prior_bwd_head(const PriorChainBwd& p, const float* WB, PriorBwdRegs& r, int t, const QuadRole& q) {
   constexpr int E = kChainE;
   const int T = p.T, N = p.N;
-  float a4[4] = {0.f, 0.f, 0.f, 0.f};
+  float v[8][2];                                       // (d last_z, d h) per (row, unit)
+  zero8(v);
   float u_pz = 0.f, u_pm = 0.f, u_pl = 0.f, e_ = 0.f, lv = 0.f;
-  if (row && kp < 2) {
-    const long long o = ((long long)n * T + t - 1) * E + u;
+  if (q.epi) {
+    const long long o = ((long long)q.n * T + t - 1) * E + q.u;
     if (p.d_pz) u_pz = ldcg1(p.d_pz + o);
     if (p.d_pm) u_pm = ldcg1(p.d_pm + o);
     if (p.d_pl) u_pl = ldcg1(p.d_pl + o);
-    e_ = ldcg1(p.eps + ((long long)(t - 1) * N + n) * E + u);
+    e_ = ldcg1(p.eps + ((long long)(t - 1) * N + q.n) * E + q.u);
     lv = ldcg1(p.p_logs + o);
   }
-  // two halves of K = 4E: 16 instead of 32 float4 of operands in flight (register pressure of the merged kernel)
-  rowdot<4, 2 * E>(row, p.dg + ((long long)n * T + t) * 4 * E, WB, 4 * E, kp, a4);
-  rowdot<4, 2 * E>(row, p.dg + ((long long)n * T + t) * 4 * E + 2 * E, WB + 2 * E, 4 * E, kp, a4);
-  reduce8(a4);
-  if (row && kp < 2) {
-    r.dh_carry = j ? a4[3] : a4[2];
-    const float dz = (j ? a4[1] : a4[0]) + u_pz;
-    float* d = p.dml + ((long long)n * T + t - 1) * 2 * E + u;
+  // two halves of K = 4E: 16 instead of 32 float4 of operands in flight
+  quaddot<2, 2 * E>(q.n0, N, p.dg + ((long long)q.n0 * T + t) * 4 * E, (long long)T * 4 * E, WB, 4 * E, q.lane, v);
+  quaddot<2, 2 * E>(q.n0, N, p.dg + ((long long)q.n0 * T + t) * 4 * E + 2 * E, (long long)T * 4 * E, WB + 2 * E, 4 * E, q.lane, v);
+  reduce_scatter8<2>(v, q.lane);
+  if (q.epi) {
+    r.dh_carry = v[0][1];
+    const float dz = v[0][0] + u_pz;
+    float* d = p.dml + ((long long)q.n * T + t - 1) * 2 * E + q.u;
     d[0] = dz + u_pm;
     d[E] = dz * e_ * 0.5f * expf(0.5f * lv) + u_pl;
   }
@@ -529,20 +614,19 @@ __device__ __forceinline__ void prior_bwd_head(const PriorChainBwd& p, const flo
 __global__ void __launch_bounds__(kChainThreads) prior_chain_bwd_kernel(const __grid_constant__ PriorChainBwd p) {
   __shared__ __align__(16) float Wsm[kPriorBwdSmemFloats];
   float* WA = Wsm; float* WB = Wsm + 2 * 2 * kChainE;
-  const int tid = threadIdx.x, n = tid >> 3, kp = tid & 7;
-  const int u0 = blockIdx.x * 2, j = kp & 1, u = u0 + j;
+  const int u0 = blockIdx.x * 2;
+  const QuadRole q = quad_role(p.N, u0);
   PriorBwdRegs r;
   prior_bwd_setup(p, WA, WB, r, u0);
   __syncthreads();
   GridBar gb{p.bar, 0u, gridDim.x};
-  const bool row = n < p.N;
-  prior_bwd_first(p, n, kp, row, u);
+  prior_bwd_first(p, q);
   grid_sync(gb);
   for (int t = p.T - 1; t >= 0; --t) {
-    prior_bwd_lstm(p, WA, r, t, n, kp, row, j, u);
+    prior_bwd_lstm(p, WA, r, t, q);
     if (t == 0) break;
     grid_sync(gb);
-    prior_bwd_head(p, WB, r, t, n, kp, row, j, u);
+    prior_bwd_head(p, WB, r, t, q);
     grid_sync(gb);
   }
 }
@@ -584,8 +668,9 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __gr
   float* vs = qps + A;                    // [A]
   float* sc = vs + A;                     // [Te]
   float* red = sc + Te;                   // [64]
-  const int tid = threadIdx.x, n = tid >> 3, kp = tid & 7, lane = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int u0 = blockIdx.x * 2;
+  const QuadRole q = quad_role(N, u0);
   const int clip = blockIdx.x;
   const bool own_clip = clip < N;
   const int len = own_clip ? max(1, min(p.mem_lens[clip], Te)) : 0;
@@ -602,8 +687,7 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __gr
     const long long wr = (long long)((rr >> 1) * E + u0 + (rr & 1));
     Wg[i] = r < 6 ? p.wih[wr * 3 * E + E + k] : p.whh[wr * E + k];
   }
-  const bool row = n < N;
-  const int j = kp & 1, u = u0 + j;
+  const int n = q.n, u = q.u;
   PriorFwdRegs pr;
   if (prior) prior_fwd_setup(pp, Wprior, Wprior + 8 * 2 * E, pr, u0, u);
   __syncthreads();
@@ -612,14 +696,15 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __gr
   for (int t = 0; t < T; ++t) {
     // ---- P1: query projection q.Wq^T, columns {u0, u0+1} of A  [+ prior LSTM cell] ----
     if (t > 0) {
-      float a2[2] = {0.f, 0.f};
-      rowdot<2, E>(row, p.out + ((long long)n * T + t - 1) * E, Wq, E, kp, a2);
-      reduce8(a2);
-      if (row && kp < 2) p.qp[((long long)n * T + t) * A + u] = j ? a2[1] : a2[0];
-    } else if (row && kp < 2) {
+      float v1[8][1];
+      zero8(v1);
+      quaddot<1, E>(q.n0, N, p.out + ((long long)q.n0 * T + t - 1) * E, (long long)T * E, Wq, E, q.lane, v1);
+      reduce_scatter8<1>(v1, q.lane);
+      if (q.epi) p.qp[((long long)n * T + t) * A + u] = v1[0][0];
+    } else if (q.epi) {
       p.qp[((long long)n * T) * A + u] = 0.0f;     // zero query at t = 0 (decoder.py:94-98)
     }
-    if (prior) prior_fwd_lstm(pp, Wprior, pr, t, n, kp, row, j, u);
+    if (prior) prior_fwd_lstm(pp, Wprior, pr, t, q);
     if (t > 0 || prior) grid_sync(gb);
     // ---- P2: attention of clip `clip` ----
     if (own_clip) {
@@ -661,35 +746,32 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __gr
       if (jj < len) c0 = fmaf(sc[jj], Ms[(size_t)jj * E + tid], c0);
       p.ctx[((long long)clip * T + t) * E + tid] = c0 + c1;
     }
-    if (prior) prior_fwd_head(pp, Wprior + 8 * 2 * E, pr, t, n, kp, row, j, u);
+    if (prior) prior_fwd_head(pp, Wprior + 8 * 2 * E, pr, t, q);
     grid_sync(gb);
     // ---- P3: GRU cell, units {u0, u0+1} ----
-    float ax[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ah[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float vx[8][3], vh[8][3];                        // (r, z, n) pre-activations from ctx_t and from h_{t-1}
+    zero8(vx); zero8(vh);
     float gxr = 0.f, gxz = 0.f, gxn = 0.f, hp = 0.f;
-    if (row && kp < 2) {
+    if (q.epi) {
       const float* gx = p.gx + ((long long)n * T + t) * 3 * E + u;
       gxr = ldcg1(gx); gxz = ldcg1(gx + E); gxn = ldcg1(gx + 2 * E);
       if (t > 0) hp = ldcg1(p.out + ((long long)n * T + t - 1) * E + u);
     }
     {
-      float4 a0[E / 32], a1[E / 32];
-      if (row) {
-        rowload<E>(p.ctx + ((long long)n * T + t) * E, kp, a0);
-        if (t > 0) rowload<E>(p.out + ((long long)n * T + t - 1) * E, kp, a1);
-      }
+      float4 a0[4][E / 128], a1[4][E / 128];
+      quadrows<E>(q.n0, N, p.ctx + ((long long)q.n0 * T + t) * E, (long long)T * E, q.lane, a0);
+      if (t > 0) quadrows<E>(q.n0, N, p.out + ((long long)q.n0 * T + t - 1) * E, (long long)T * E, q.lane, a1);
       __syncwarp();
-      if (row) {
-        rowfma<6, E>(a0, Wg, E, kp, ax);
-        if (t > 0) rowfma<6, E>(a1, Wg + 6 * E, E, kp, ah);
-      }
+      quadfma<3, E>(a0, Wg, E, q.lane, vx);
+      if (t > 0) quadfma<3, E>(a1, Wg + 6 * E, E, q.lane, vh);
     }
-    reduce8(ax);
-    reduce8(ah);
-    if (row && kp < 2) {
-      const float hn = (j ? ah[5] : ah[4]) + bh_n;
-      const float rg = sigmoidf_((j ? ax[1] : ax[0]) + gxr + (j ? ah[1] : ah[0]) + bh_r);
-      const float zg = sigmoidf_((j ? ax[3] : ax[2]) + gxz + (j ? ah[3] : ah[2]) + bh_z);
-      const float ng = tanhf((j ? ax[5] : ax[4]) + gxn + rg * hn);
+    reduce_scatter8<3>(vx, q.lane);
+    if (t > 0) reduce_scatter8<3>(vh, q.lane);
+    if (q.epi) {
+      const float hn = vh[0][2] + bh_n;
+      const float rg = sigmoidf_(vx[0][0] + gxr + vh[0][0] + bh_r);
+      const float zg = sigmoidf_(vx[0][1] + gxz + vh[0][1] + bh_z);
+      const float ng = tanhf(vx[0][2] + gxn + rg * hn);
       float* gs = p.gates + ((long long)n * T + t) * 4 * E + u;
       gs[0] = rg; gs[E] = zg; gs[2 * E] = ng; gs[3 * E] = hn;
       p.out[((long long)n * T + t) * E + u] = (1.0f - zg) * ng + zg * hp;
@@ -737,8 +819,9 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_bwd_kernel(const __gr
   float* dcs = qps + A;                   // [E]
   float* dw = dcs + E;                    // [Te]
   float* red = dw + Te;                   // [64]
-  const int tid = threadIdx.x, n = tid >> 3, kp = tid & 7, lane = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int u0 = blockIdx.x * 2;
+  const QuadRole q = quad_role(N, u0);
   const int clip = blockIdx.x;
   const bool own_clip = clip < N;
   const int len = own_clip ? max(1, min(p.mem_lens[clip], Te)) : 0;
@@ -756,46 +839,42 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_bwd_kernel(const __gr
     const int jj = i / (3 * E), c = i % (3 * E);
     W2[i] = p.wih[(long long)c * 3 * E + E + u0 + jj];
   }
-  const bool row = n < N;
-  const int j = kp & 1, u = u0 + j;
+  const int n = q.n, u = q.u;
   PriorBwdRegs pr;
   if (prior) prior_bwd_setup(pp, Wprior, Wprior + 2 * 2 * E, pr, u0);
   __syncthreads();
   GridBar gb{p.bar, 0u, gridDim.x};
   if (prior) {
-    prior_bwd_first(pp, n, kp, row, u);
+    prior_bwd_first(pp, q);
     grid_sync(gb);
   }
   const float va = p.attn_v[tid];
   float carry = 0.0f;
   for (int t = T - 1; t >= 0; --t) {
     // ---- B1: dh_t (units u0, u0+1) and the GRU pointwise backward of step t ----
-    float a2[2] = {0.f, 0.f};
+    float va2[8][1];
+    zero8(va2);
     float dh = 0.f, rr = 0.f, z = 0.f, nn = 0.f, ghn = 0.f, hp = 0.f;
-    if (row && kp < 2) {
+    if (q.epi) {
       dh = ldcg1(p.dout + ((long long)n * T + t) * E + u);
       const float* g = p.gates + ((long long)n * T + t) * 4 * E + u;
       rr = ldcg1(g); z = ldcg1(g + E); nn = ldcg1(g + 2 * E); ghn = ldcg1(g + 3 * E);
       if (t > 0) hp = ldcg1(p.out + ((long long)n * T + t - 1) * E + u);
     }
     if (t < T - 1) {
-      rowdot<2, 2 * E>(row, p.dgh + ((long long)n * T + t + 1) * 3 * E, W1, 4 * E, kp, a2);
+      quaddot<1, 2 * E>(q.n0, N, p.dgh + ((long long)q.n0 * T + t + 1) * 3 * E, (long long)T * 3 * E, W1, 4 * E, q.lane, va2);
       {
-        float4 a0[E / 32], a1[A / 32];
-        if (row) {
-          rowload<E>(p.dgh + ((long long)n * T + t + 1) * 3 * E + 2 * E, kp, a0);
-          rowload<A>(p.dqp + ((long long)n * T + t + 1) * A, kp, a1);
-        }
+        float4 a0[4][E / 128], a1[4][A / 128];
+        quadrows<E>(q.n0, N, p.dgh + ((long long)q.n0 * T + t + 1) * 3 * E + 2 * E, (long long)T * 3 * E, q.lane, a0);
+        quadrows<A>(q.n0, N, p.dqp + ((long long)q.n0 * T + t + 1) * A, (long long)T * A, q.lane, a1);
         __syncwarp();
-        if (row) {
-          rowfma<2, E>(a0, W1 + 2 * E, 4 * E, kp, a2);
-          rowfma<2, A>(a1, W1 + 3 * E, 4 * E, kp, a2);
-        }
+        quadfma<1, E>(a0, W1 + 2 * E, 4 * E, q.lane, va2);
+        quadfma<1, A>(a1, W1 + 3 * E, 4 * E, q.lane, va2);
       }
-      reduce8(a2);
+      reduce_scatter8<1>(va2, q.lane);
     }
-    if (row && kp < 2) {
-      if (t < T - 1) dh += carry + (j ? a2[1] : a2[0]);
+    if (q.epi) {
+      if (t < T - 1) dh += carry + va2[0][0];
       const float dn = dh * (1.0f - z), dz = dh * (hp - nn);
       const float dan = dn * (1.0f - nn * nn);
       const float dar = dan * ghn * rr * (1.0f - rr), daz = dz * z * (1.0f - z);
@@ -805,15 +884,16 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_bwd_kernel(const __gr
       gh[0] = dar; gh[E] = daz; gh[2 * E] = dan * rr;
       carry = dh * z;
     }
-    if (prior) prior_bwd_lstm(pp, Wprior, pr, t, n, kp, row, j, u);
+    if (prior) prior_bwd_lstm(pp, Wprior, pr, t, q);
     grid_sync(gb);
     // ---- B1.5: d ctx_t = dGi_t . W_ih[:, E:2E], columns {u0, u0+1} ----
-    float b2[2] = {0.f, 0.f};
-    rowdot<2, 2 * E>(row, p.dgi + ((long long)n * T + t) * 3 * E, W2, 3 * E, kp, b2);
-    rowdot<2, E>(row, p.dgi + ((long long)n * T + t) * 3 * E + 2 * E, W2 + 2 * E, 3 * E, kp, b2);
-    reduce8(b2);
-    if (row && kp < 2) p.dctx[((long long)n * T + t) * E + u] = j ? b2[1] : b2[0];
-    if (prior && t > 0) prior_bwd_head(pp, Wprior + 2 * 2 * E, pr, t, n, kp, row, j, u);
+    float vb2[8][1];
+    zero8(vb2);
+    quaddot<1, 2 * E>(q.n0, N, p.dgi + ((long long)q.n0 * T + t) * 3 * E, (long long)T * 3 * E, W2, 3 * E, q.lane, vb2);
+    quaddot<1, E>(q.n0, N, p.dgi + ((long long)q.n0 * T + t) * 3 * E + 2 * E, (long long)T * 3 * E, W2 + 2 * E, 3 * E, q.lane, vb2);
+    reduce_scatter8<1>(vb2, q.lane);
+    if (q.epi) p.dctx[((long long)n * T + t) * E + u] = vb2[0][0];
+    if (prior && t > 0) prior_bwd_head(pp, Wprior + 2 * 2 * E, pr, t, q);
     grid_sync(gb);
     // ---- B2: attention backward of clip `clip` ----
     if (own_clip) {
