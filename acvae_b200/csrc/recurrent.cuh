@@ -801,8 +801,8 @@ inline size_t dec_chain_bwd_smem(int Te) { return ((size_t)Te * 2 * kChainE + 2 
 
 // `pp.N > 0`: the prior backward chain runs inside the same phases (LSTM backward next to the GRU backward, head
 // backward next to the d ctx projection).
-// (MERGE = true currently spills ~800 bytes per thread on sm_100a and is slower than the two kernels back to back;
-// train_fast.cuh launches MERGE = false plus prior_chain_bwd_kernel.)
+// (With the row-per-8-lanes mapping MERGE = true spilled ~800 bytes per thread; with the quad mapping it does not.
+// ACVAE_MERGE_BWD=0 selects MERGE = false plus prior_chain_bwd_kernel.)
 template <bool MERGE>
 __global__ void __launch_bounds__(kChainThreads) dec_chain_bwd_kernel(const __grid_constant__ DecChainBwd p,
                                                                       const __grid_constant__ PriorChainBwd pp) {
@@ -977,7 +977,8 @@ inline bool chain_supported(int N, int T, int Te, int E, int A) {
       const int dyn_max = optin - 24 * 1024;
       max_te = (int)(((size_t)dyn_max / sizeof(float) - (2 * 4 + 2 * 3 + 2 + 12 + 2) * kChainE - 256) / (2 * kChainE + 1));   // ~85 on B200
       if (cudaFuncSetAttribute(dec_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max) == cudaSuccess &&
-          cudaFuncSetAttribute(dec_chain_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max) == cudaSuccess)
+          cudaFuncSetAttribute(dec_chain_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max) == cudaSuccess &&
+          cudaFuncSetAttribute(dec_chain_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max) == cudaSuccess)
         ok = 1;
     }
   }

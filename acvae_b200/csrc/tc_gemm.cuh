@@ -57,6 +57,15 @@ struct TcParams {
   TcSeg seg[2];
   long long* trace;    // optional clock64 stamps of CTA (0,0,0) (profiles/ubench_gemm_trace.cu) or NULL
 };
+// Split-K policy of the calling thread: 0 = default (latency: as many K splits as fill the machine, >= 2 k-blocks
+// each); n > 0 = at least n k-blocks per CTA (throughput: the fixed prologue / epilogue of a CTA, ~3 us, is amortised
+// over more k-blocks -- used for the weight-gradient GEMMs that only fill idle SMs next to the persistent chains).
+inline int& tc_min_kblk_override() { thread_local int v = 0; return v; }
+struct TcThroughputScope {
+  int saved;
+  explicit TcThroughputScope(int min_kblk) : saved(tc_min_kblk_override()) { tc_min_kblk_override() = min_kblk; }
+  ~TcThroughputScope() { tc_min_kblk_override() = saved; }
+};
 // process-wide trace destination picked up by try_launch_tc (micro-benchmark only)
 inline long long*& tc_trace_ptr() { static long long* p = nullptr; return p; }
 #define TC_STAMP(slot) do { if (tr) tp.trace[slot] = clock64(); } while (0)
@@ -494,7 +503,8 @@ inline int try_launch_tc(const GemmParams& p, cudaStream_t st) {
     int splits = 148 / tiles;                       // fill the machine once
     static int min_blk = 0;                         // k-blocks per CTA below which splitting stops paying (profiles/r1/gemm_split.log: 16 -> 11 us at 2)
     if (!min_blk) { const char* e = getenv("ACVAE_TC_MIN_KBLK"); min_blk = e ? atoi(e) : 2; if (min_blk < 1) min_blk = 1; }
-    if (splits > nblk / min_blk) splits = nblk / min_blk;
+    const int mb = tc_min_kblk_override() > 0 ? tc_min_kblk_override() : min_blk;
+    if (splits > nblk / mb) splits = nblk / mb;
     if (!p.epi.free_order) splits = p.epi.accumulate ? 1 : (splits > 2 ? 2 : splits);   // forward / sampling: reproducible
     if (splits >= 2) {
       const int per = (nblk + splits - 1) / splits;

@@ -226,6 +226,13 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   return 0;
 }
 
+// k-blocks per CTA of the weight-gradient GEMMs on the fan streams (see TcThroughputScope)
+inline int fan_min_kblk() {
+  static int v = 0;
+  if (!v) { const char* e = getenv("ACVAE_FAN_MIN_KBLK"); v = e ? atoi(e) : 6; if (v < 1) v = 1; }
+  return v;
+}
+
 // ===================================== backward ===================================================
 inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acvae_train_io& io,
                           const acvae_train_grads_in& gi, acvae_weight_grads& gw, float* d_audio, void* workspace,
@@ -239,6 +246,11 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   cudaStream_t sp = ax->s[2], sx = ax->s[3], sq0 = ax->s[0], sq1 = ax->s[1];
   auto zero = [&](float* p, size_t n, cudaStream_t s) { return cudaMemsetAsync(p, 0, n * sizeof(float), s); };
   const bool chain = chain_supported(N, T, Te, E, A);   // persistent recurrent-chain kernels (recurrent.cuh)
+  // chain mode: the prior's backward chain runs inside the decoder's persistent kernel (same barriers), so the two
+  // chains cost max(...) instead of their sum (two cooperative kernels never overlap on the device)
+  static int merge_env = -1;
+  if (merge_env < 0) { const char* e = getenv("ACVAE_MERGE_BWD"); merge_env = (e && e[0] == '0') ? 0 : 1; }
+  const bool merge_bwd = chain && merge_env == 1;
   if (chain) ACVAE_CHECK(cudaMemsetAsync(ws.bars + 4 * 128, 0, 4 * 128 * sizeof(unsigned), st));
   ACVAE_TRY(stream_dep(st, sp, ax));
 
@@ -248,7 +260,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     ppc.N = N; ppc.T = T; ppc.d_pz = gi.d_p_z; ppc.d_pm = gi.d_p_means; ppc.d_pl = gi.d_p_logs; ppc.eps = io.eps_p;
     ppc.p_logs = io.p_logs; ppc.head_w = w.p_head_w; ppc.wih = w.p_wih; ppc.whh = w.p_whh; ppc.gates = ws.gates_p; ppc.c = ws.c_p;
     ppc.dml = ws.dml_p; ppc.dg = ws.dg_p; ppc.bar = ws.bars + 4 * 128;
-    ACVAE_TRY(launch_chain(prior_chain_bwd_kernel, 0, sp, "prior_chain_bwd_kernel", ppc));
+    if (!merge_bwd) ACVAE_TRY(launch_chain(prior_chain_bwd_kernel, 0, sp, "prior_chain_bwd_kernel", ppc));
   } else
   {
     // step T-1 head backward (standalone), then per step: [dh GEMM + LSTM pointwise] -> [dz|dh GEMM + head pointwise]
@@ -305,6 +317,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     // the SMs the decoder's persistent kernel leaves free instead of queueing behind the attention backward
     {
       cudaStream_t f[4] = {ax->s[4], ax->s[5], ax->s[6], ax->s[7]};
+      TcThroughputScope throughput(fan_min_kblk());
       for (int i = 0; i < 4; ++i) ACVAE_TRY(stream_dep(sp, f[i], ax));
       ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.xp, E, gw.p_wih, 3 * E, f[0]));
       ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.ctx_p, E, gw.p_wih + E, 3 * E, f[1]));
@@ -343,7 +356,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     ACVAE_TRY(linear_bwd_weight(E, E, NT, ws.dqp_p, E, ws.xp, E, gw.p_attn_w, 2 * E, sp));
     return 0;
   };
-  ACVAE_TRY(prior_remainders());
+  if (!merge_bwd) ACVAE_TRY(prior_remainders());
 
   // ================= decoder BPTT on the main stream ========================================================
   const float* dpool = nullptr;
@@ -363,8 +376,14 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     dc.whh = w.d_whh; dc.Pd = ws.Pd; dc.mem = ws.mem; dc.mem_lens = io.mem_lens; dc.qp = ws.qp_d; dc.w = ws.w_d;
     dc.gates = ws.gates_d; dc.out = io.outputs; dc.dgi = ws.dgi_d; dc.dgh = ws.dgh_d; dc.dctx = ws.dctx_d; dc.ds = ws.ds_d;
     dc.dqp = ws.dqp_d; dc.bar = ws.bars + 5 * 128;
-    PriorChainBwd none{};
-    ACVAE_TRY(launch_chain(dec_chain_bwd_kernel<false>, dec_chain_bwd_smem(Te), st, "dec_chain_bwd_kernel", dc, none));
+    if (merge_bwd) {
+      ACVAE_TRY(launch_chain(dec_chain_bwd_kernel<true>, dec_chain_bwd_smem(Te), st, "dec_chain_bwd_kernel", dc, ppc));
+      ACVAE_TRY(stream_dep(st, sp, ax));
+      ACVAE_TRY(prior_remainders());
+    } else {
+      PriorChainBwd none{};
+      ACVAE_TRY(launch_chain(dec_chain_bwd_kernel<false>, dec_chain_bwd_smem(Te), st, "dec_chain_bwd_kernel", dc, none));
+    }
   } else
   {
     GruBwdParams g{};
@@ -428,6 +447,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     // weight / bias gradients of the two memory projections need only dPp / dPd: off the memory-backward chain
     const int R = N * Te;
     cudaStream_t f0 = ax->s[4], f1 = ax->s[5];
+    TcThroughputScope throughput(fan_min_kblk());
     ACVAE_TRY(stream_dep(sx, f0, ax));
     ACVAE_TRY(stream_dep(sx, f1, ax));
     ACVAE_TRY(linear_bwd_weight(E, E, R, ws.dPp, E, ws.mem, E, gw.p_attn_w + E, 2 * E, f0));
@@ -453,6 +473,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   // out over four more streams (each GEMM is a ~10 us launch of a few dozen CTAs; in one stream they serialise)
   {
     cudaStream_t f[4] = {ax->s[4], ax->s[5], ax->s[6], ax->s[7]};
+    TcThroughputScope throughput(fan_min_kblk());
     for (int i = 0; i < 4; ++i) ACVAE_TRY(stream_dep(st, f[i], ax));
     ACVAE_TRY(linear_bwd_data(NT, E, 3 * E, ws.dgi_d, 3 * E, w.d_wih, 3 * E, ws.dxe_d, E, f[0]));
     ACVAE_CHECK(zero(gw.d_emb, (size_t)V * E, f[0]));

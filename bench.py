@@ -58,6 +58,18 @@ def chain_kernel_bytes(d):
     return 4 * (weights + memory + N * T * per_nt)
 
 
+def chain_bwd_kernel_bytes(d):
+    """Algorithmic bytes of ONE launch of dec_chain_bwd_kernel<true> (decoder + prior backward chains merged, all T steps):
+    weight slices once (decoder W_hh | Wq, W_ih ctx columns; prior head, W_ih z columns, W_hh), the clips' memory once,
+    and per (n,t) every saved activation / upstream gradient read once and every produced gradient written once.  fp32."""
+    N, Te, T, E = d.N, d.Te, d.T, d.E
+    weights = 17 * E * E
+    memory = 2 * N * Te * E
+    per_nt = 30 * E + 2 * Te     # reads: dout, gates_d 4E, out, qp, w Te | d_pm, d_pl, eps, p_logs, gates_p 4E, c;  writes: dgi 3E, dgh 3E,
+                                 # dctx, ds Te, dqp | dml 2E, dg 4E
+    return 4 * (weights + memory + N * T * per_nt)
+
+
 def probe_kernel(lib, name, run, n, flush):
     """Average duration (us) of the kernel whose name contains `name`, timed with CUDA events recorded on ITS
     launching stream inside the library (acvae_set_kernel_probe), over `n` eager runs of `run`."""
@@ -323,6 +335,7 @@ def run_ours(args):
     def eager_step():
         load_resident(0); ts.step_body()
     chain_us, chain_n = probe_kernel(lib, "dec_chain_fwd_kernel", eager_step, n_probe, lambda: flush.fill_(1.0))
+    chainb_us, chainb_n = probe_kernel(lib, "dec_chain_bwd_kernel", eager_step, n_probe, lambda: flush.fill_(1.0))
     attn_us, _ = probe_kernel(lib, "attn_fwd_kernel", eager_step, n_probe, lambda: flush.fill_(1.0))
     # the largest tcgen05 GEMM of the step (vocabulary statistics, [N*T, E] x [E, V]) on its own
     hid = torch.randn(d.N * st_prep.T, d.E, device=dev)
@@ -380,19 +393,27 @@ def run_ours(args):
             ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
         except Exception:
             pass
-        if chain_us:
-            kb = chain_kernel_bytes(d)
-            k_ach = kb / (chain_us * 1e-6) / 1e9
-            roofline = {"bound": "hbm", "achieved": round(k_ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": round(k_ach / peaks["hbm_gbs"], 4),
-                        "traffic": ncu.get("dec_chain_fwd_kernel", {}).get("dram_bytes_per_launch"),
-                        "kernel": "dec_chain_fwd_kernel: decoder + prior forward chains, all T steps in ONE persistent "
-                                  "cooperative launch (largest single kernel of the step); bound by its serial chain of "
-                                  "3 grid barriers per step, not by bandwidth (DESIGN.md 4.3)",
-                        "us_per_launch": round(chain_us, 1), "launches_timed": chain_n,
-                        "share_of_step": round(chain_us * 1e-3 / ms_resident, 3),
-                        "algorithmic_bytes_per_launch": int(kb), "peak_source": peaks["src"],
-                        "timing": "CUDA events recorded on the kernel's launching stream (acvae_set_kernel_probe), eager steps, L2 flushed"}
+        chain_entries = []
+        for kname, us_, n_, kb, what in (
+                ("dec_chain_fwd_kernel", chain_us, chain_n, chain_kernel_bytes(d) if chain_us else 0,
+                 "decoder + prior forward chains, all T steps in ONE persistent cooperative launch; 3 grid barriers per step"),
+                ("dec_chain_bwd_kernel", chainb_us, chainb_n, chain_bwd_kernel_bytes(d) if chainb_us else 0,
+                 "decoder + prior backward chains (BPTT), all T steps in ONE persistent cooperative launch; 3 grid barriers per step")):
+            if not us_:
+                continue
+            k_ach = kb / (us_ * 1e-6) / 1e9
+            chain_entries.append({
+                "bound": "hbm", "achieved": round(k_ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": round(k_ach / peaks["hbm_gbs"], 4),
+                "traffic": ncu.get(kname, {}).get("dram_bytes_per_launch"),
+                "kernel": f"{kname}: {what}; bound by that serial chain of barriers + L2 round trips, not by bandwidth "
+                          "(DESIGN.md 4.3)",
+                "us_per_launch": round(us_, 1), "launches_timed": n_, "share_of_step": round(us_ * 1e-3 / ms_resident, 3),
+                "algorithmic_bytes_per_launch": int(kb), "peak_source": peaks["src"],
+                "timing": "CUDA events recorded on the kernel's launching stream (acvae_set_kernel_probe), eager steps, L2 flushed"})
+        chain_entries.sort(key=lambda e: -e["us_per_launch"])
+        if chain_entries:
+            roofline = chain_entries[0]          # the dominant (longest) kernel of the step
         else:   # launch-per-step schedule (chain kernels unavailable for this shape): whole-step figure
             roofline = {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None,
@@ -411,6 +432,7 @@ def run_ours(args):
              "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4),
              "algorithmic_bytes_per_step": int(bytes_step)},
         ]
+        roofline_other = chain_entries[1:] + roofline_other
         if attn_us:
             ab = 4.0 * d.N * st_prep.T * d.Te * 2 * d.E          # every query row streams its clip's P and mem
             roofline_other.append(
