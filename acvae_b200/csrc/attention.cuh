@@ -162,10 +162,14 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const __grid_constant__ A
 // 10 450 rows).  tanh-bound: R * Te * A evaluations per clip.
 constexpr int kAttnMaxR = 16;
 // dynamic smem: ring + R*A (qp) + R*Te (scores) + 64
+// RT > 0: rows_per_clip known at compile time (no predicated-off iterations: at R = 10 the 16-way unrolled runtime
+// form issued 25 instructions per tanh, 130 M warp instructions per call); RT == 0: any R <= kAttnMaxR.
+template <int RT>
 __global__ void __launch_bounds__(256) attn_fwd_multi_kernel(const __grid_constant__ AttnFwdParams p) {
   extern __shared__ __align__(16) float sm[];
   if (p.live && *p.live == 0) return;
-  const int WMAX = max(p.A, p.E), R = p.rows_per_clip, A = p.A, E = p.E, Te = p.Te;
+  constexpr int RU = RT > 0 ? RT : kAttnMaxR;            // unroll bound
+  const int WMAX = max(p.A, p.E), R = RT > 0 ? RT : p.rows_per_clip, A = p.A, E = p.E, Te = p.Te;
   constexpr int NB = 2;                                  // shallow ring: 3 CTAs per SM hide the tanh latency
   float* bufs = sm;
   float* qp = bufs + (size_t)NB * kAttnJT * WMAX;        // [R][A]
@@ -178,10 +182,15 @@ __global__ void __launch_bounds__(256) attn_fwd_multi_kernel(const __grid_consta
   const int nchunk = 2 * ring.ntile;
   int issued = 0;
   for (; issued < min(nchunk, NB); ++issued) ring.issue(issued);
+  // queries pre-scaled by 2 log2(e): the score loop is then  x = P' + q' ; t = ex2(x) ; r = rcp(t + 1) ; s += (-2 v) r
+  // (tanh = 1 - 2 r, so sum_a v_a tanh = sum_a v_a + sum_a (-2 v_a) r_a): 4 instructions + 1 LDS per evaluation
   for (int i = tid; i < R * A; i += blockDim.x) {
     const int r = i / A, a = i % A;
-    qp[i] = p.qp_in ? p.qp_in[(long long)(r0 + r) * p.ld_qp_in + a] : 0.0f;
+    qp[i] = p.qp_in ? kTwoLog2e * p.qp_in[(long long)(r0 + r) * p.ld_qp_in + a] : 0.0f;
   }
+  float vsum = 0.0f;
+  for (int a = lane; a < A; a += 32) vsum += __ldg(p.v + a);
+  vsum = warp_sum(vsum);
   __syncthreads();
   // pass 1: scores; a warp owns a frame, lanes stride A, all R queries per loaded P value
   for (int c = 0; c < ring.ntile; ++c) {
@@ -191,19 +200,20 @@ __global__ void __launch_bounds__(256) attn_fwd_multi_kernel(const __grid_consta
     const int nf = min(kAttnJT, len - c * kAttnJT);
     for (int jj = wid; jj < nf; jj += nw) {
       const float* pr = tile + jj * A;
-      float s[kAttnMaxR];
+      float s[RU];
 #pragma unroll
-      for (int r = 0; r < kAttnMaxR; ++r) s[r] = 0.0f;
+      for (int r = 0; r < RU; ++r) s[r] = 0.0f;
+#pragma unroll 2
       for (int a = lane; a < A; a += 32) {
-        const float pv = pr[a], vv = __ldg(p.v + a);
+        const float pv = kTwoLog2e * pr[a], vv = -2.0f * __ldg(p.v + a);
 #pragma unroll
-        for (int r = 0; r < kAttnMaxR; ++r)
-          if (r < R) s[r] = fmaf(vv, attn_tanh(pv + qp[r * A + a]), s[r]);
+        for (int r = 0; r < RU; ++r)
+          if (RT > 0 || r < R) s[r] = fmaf(vv, rcp_approx(ex2_approx(pv + qp[r * A + a]) + 1.0f), s[r]);
       }
 #pragma unroll
-      for (int r = 0; r < kAttnMaxR; ++r)
-        if (r < R) {
-          const float t = warp_sum(s[r]);
+      for (int r = 0; r < RU; ++r)
+        if (RT > 0 || r < R) {
+          const float t = warp_sum(s[r]) + vsum;
           if (lane == 0) sc[r * Te + c * kAttnJT + jj] = t;
         }
     }
@@ -228,9 +238,9 @@ __global__ void __launch_bounds__(256) attn_fwd_multi_kernel(const __grid_consta
   }
   // pass 2: context; a thread owns features e, e + 256, ... for all R queries
   for (int e0 = 0; e0 < E; e0 += blockDim.x) {   // E <= 256 in practice: one sweep of the ring
-    float acc[kAttnMaxR];
+    float acc[RU];
 #pragma unroll
-    for (int r = 0; r < kAttnMaxR; ++r) acc[r] = 0.0f;
+    for (int r = 0; r < RU; ++r) acc[r] = 0.0f;
     const int e = e0 + tid;
     for (int c = ring.ntile; c < nchunk; ++c) {
       attn_wait_dyn(issued - 1 - c);
@@ -242,8 +252,8 @@ __global__ void __launch_bounds__(256) attn_fwd_multi_kernel(const __grid_consta
         for (int jj = 0; jj < nf; ++jj) {
           const float mv = tile[jj * E + e];
 #pragma unroll
-          for (int r = 0; r < kAttnMaxR; ++r)
-            if (r < R) acc[r] = fmaf(sc[r * Te + j0 + jj], mv, acc[r]);
+          for (int r = 0; r < RU; ++r)
+            if (RT > 0 || r < R) acc[r] = fmaf(sc[r * Te + j0 + jj], mv, acc[r]);
         }
       }
       __syncthreads();
@@ -251,8 +261,8 @@ __global__ void __launch_bounds__(256) attn_fwd_multi_kernel(const __grid_consta
     }
     if (e < E) {
 #pragma unroll
-      for (int r = 0; r < kAttnMaxR; ++r)
-        if (r < R) p.ctx[(long long)(r0 + r) * p.ld_ctx + e] = acc[r];
+      for (int r = 0; r < RU; ++r)
+        if (RT > 0 || r < R) p.ctx[(long long)(r0 + r) * p.ld_ctx + e] = acc[r];
     }
   }
 }
@@ -269,12 +279,27 @@ inline int launch_attn_fwd(const AttnFwdParams& p, cudaStream_t st) {
     const int WMAX = p.A > p.E ? p.A : p.E;
     const size_t smem_m = ((size_t)2 * kAttnJT * WMAX + (size_t)p.rows_per_clip * (p.A + p.Te) + 64) * sizeof(float);
     if (smem_m <= 227 * 1024) {
-      static size_t configured_m = 0;
-      if (smem_m > configured_m) {
-        ACVAE_CHECK(cudaFuncSetAttribute(attn_fwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
-        configured_m = smem_m;
+      // compile-time row counts for the common captions-per-clip / beam sizes, the runtime form for the rest
+#define ACVAE_ATTN_MULTI(RT)                                                                                             \
+      {                                                                                                                  \
+        static size_t configured_m = 0;                                                                                  \
+        if (smem_m > configured_m) {                                                                                     \
+          ACVAE_CHECK(cudaFuncSetAttribute(attn_fwd_multi_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m)); \
+          configured_m = smem_m;                                                                                         \
+        }                                                                                                                \
+        ACVAE_LAUNCH(attn_fwd_multi_kernel<RT>, p.rows / p.rows_per_clip, 256, smem_m, st, p);                           \
       }
-      ACVAE_LAUNCH(attn_fwd_multi_kernel, p.rows / p.rows_per_clip, 256, smem_m, st, p);
+      switch (p.rows_per_clip) {
+        case 2: ACVAE_ATTN_MULTI(2) break;
+        case 3: ACVAE_ATTN_MULTI(3) break;
+        case 4: ACVAE_ATTN_MULTI(4) break;
+        case 5: ACVAE_ATTN_MULTI(5) break;
+        case 6: ACVAE_ATTN_MULTI(6) break;
+        case 8: ACVAE_ATTN_MULTI(8) break;
+        case 10: ACVAE_ATTN_MULTI(10) break;
+        default: ACVAE_ATTN_MULTI(0) break;
+      }
+#undef ACVAE_ATTN_MULTI
       return 0;
     }
   }

@@ -61,14 +61,24 @@ inline int set_error(const char* what, const char* detail = "") {
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // tanh for the additive-attention scores (attn_model.py:32): T = Te*A evaluations per query row make the
-// attention kernels MUFU/issue bound, and libdevice tanhf costs ~100 issue slots per warp there (branchy, two
-// paths).  (e^{2x} - 1) / (e^{2x} + 1) with one ex2.approx and one rcp.approx: absolute error < 2e-7 over the
-// whole range (the subtraction only loses RELATIVE accuracy near 0, where tanh itself is ~x), clamped where
-// fp32 tanh is 1.  Used consistently by the forward, its backward and the sampling kernels.
+// attention kernels MUFU / issue bound, and libdevice tanhf costs ~100 issue slots per warp there (branchy, two
+// paths).  tanh(x) = 1 - 2 / (e^{2x} + 1) with one ex2.approx and one rcp.approx: five instructions, no clamp needed
+// (e^{2x} = inf gives 1, e^{2x} = 0 gives -1), absolute error < 2e-7 over the whole range (the final subtraction only
+// loses RELATIVE accuracy near 0, where tanh itself is ~x).  Used consistently by the forward, its backward and the
+// sampling kernels.
+constexpr float kTwoLog2e = 2.885390081777927f;      // 2 * log2(e)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float attn_tanh(float x) {
-  const float xc = fminf(fmaxf(x, -9.0f), 9.0f);
-  const float t = __expf(2.0f * xc);
-  return __fdividef(t - 1.0f, t + 1.0f);
+  return fmaf(-2.0f, rcp_approx(ex2_approx(x * kTwoLog2e) + 1.0f), 1.0f);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
