@@ -178,8 +178,18 @@ class PreparedBatch:
     the host-known step count T.  Lets a step run without any host->device copy (CUDA-graph capture,
     device-resident benchmarking); `Hybrid_VAEModel.prepare_batch` builds it."""
 
-    def __init__(self, caps_ids, cap_lens_dev, T, targets=None):
+    def __init__(self, caps_ids, cap_lens_dev, T, targets=None, flat=None):
         self.caps_ids, self.cap_lens_dev, self.T, self.targets = caps_ids, cap_lens_dev, int(T), targets
+        self.flat = flat        # the one int32 device buffer the three views above live in (prepare_batch), or None
+
+    def clone(self) -> "PreparedBatch":
+        """A copy with its own storage (static buffers of a captured step)."""
+        if self.flat is None:
+            return PreparedBatch(self.caps_ids.clone(), self.cap_lens_dev.clone(), self.T,
+                                 None if self.targets is None else self.targets.clone())
+        f = self.flat.clone()
+        N, L = self.caps_ids.shape
+        return PreparedBatch(f[:N * L].view(N, L), f[N * L:N * L + N], self.T, f[N * L + N:], f)
 
 
 class _FusedVAEBase(CaptionModel):
@@ -233,17 +243,41 @@ class _FusedVAEBase(CaptionModel):
             return self.inference_forward({"audio_embeds": audio_embeds, "audio_embeds_lens": mem_lens}, **kwargs)
         raise Exception("Number of input should be either 4 (feats, feat_lens, caps, cap_lens) or 2 (feats, feat_lens)")
 
-    def prepare_batch(self, caps, cap_lens, device) -> PreparedBatch:
-        """Host -> device staging of (caps, cap_lens) exactly as the step consumes them, plus the
-        packed CE targets of pytorch_runner_vae.py:89-90."""
-        cap_lens_np = np.asarray(cap_lens).astype(np.int64)
-        caps_t = torch.as_tensor(caps)
-        lens1 = torch.as_tensor(cap_lens_np) - 1
-        targets = torch.nn.utils.rnn.pack_padded_sequence(caps_t[:, 1:].cpu(), lens1, batch_first=True).data
-        return PreparedBatch(caps_t.to(device=device, dtype=torch.int32, non_blocking=True).contiguous(),
-                             torch.as_tensor(cap_lens_np).to(device=device, dtype=torch.int32, non_blocking=True),
-                             int(cap_lens_np.max()) - 1,
-                             targets.to(device=device, dtype=torch.int32, non_blocking=True))
+    def prepare_batch(self, caps, cap_lens, device, out: "PreparedBatch" = None) -> PreparedBatch:
+        """Host -> device staging of (caps, cap_lens) exactly as the step consumes them, plus the packed CE targets of
+        pytorch_runner_vae.py:89-90 (`pack_padded_sequence(caps[:, 1:], cap_lens - 1).data`).  Everything is converted
+        on the host into ONE pinned int32 staging buffer and crosses PCIe in ONE asynchronous copy
+        (ids [N*L] | lens [N] | targets [M]); `out` (a PreparedBatch made by an earlier call with the same caption-length
+        profile) receives the copy in place, so a captured CUDA graph keeps reading the same addresses."""
+        caps_np = caps.detach().cpu().numpy() if torch.is_tensor(caps) else np.asarray(caps)
+        lens = np.asarray(cap_lens).astype(np.int64)
+        if caps_np.ndim != 2 or lens.shape != (caps_np.shape[0],):
+            raise ValueError("caps must be [N,L] and cap_lens [N]")
+        if np.any(np.diff(lens) > 0):
+            raise RuntimeError("`lengths` array must be sorted in decreasing order when `enforce_sorted` is True.")
+        N, L = caps_np.shape
+        T = int(lens.max()) - 1
+        lens1 = lens - 1
+        M = int(lens1.sum())
+        total = N * L + N + M
+        ring = getattr(self, "_stage_ring", None)
+        if ring is None or ring[0].numel() < total:
+            ring = [torch.empty(max(total, 4096), dtype=torch.int32).pin_memory() for _ in range(4)]
+            self._stage_ring, self._stage_next = ring, 0
+        stage = ring[self._stage_next]
+        self._stage_next = (self._stage_next + 1) % len(ring)
+        sn = stage.numpy()
+        sn[:N * L] = caps_np.reshape(-1)                              # caps.long() of vae_model.py:827, as int32
+        sn[N * L:N * L + N] = lens
+        mask = lens1[None, :] > np.arange(T)[:, None]                 # time-major packing order of sorted lengths
+        sn[N * L + N:total] = caps_np[:, 1:T + 1].T[mask]
+        if out is not None:
+            if out.flat is None or out.flat.numel() != total or out.T != T or tuple(out.caps_ids.shape) != (N, L):
+                raise ValueError("`out` was prepared for a different caption-length profile")
+            out.flat.copy_(stage[:total], non_blocking=True)
+            return out
+        flat = stage[:total].to(device=device, non_blocking=True)
+        return PreparedBatch(flat[:N * L].view(N, L), flat[N * L:N * L + N], T, flat[N * L + N:], flat)
 
     # ---- training ------------------------------------------------------------------------
     def train_forward(self, encoded, caps, cap_lens, **kwargs):

@@ -400,3 +400,28 @@ def test_fused_vae_loss_matches_separate_callables():
         assert abs(x - y) <= 1e-6 * max(1.0, abs(x)), (k, x, y)
     for k in a["grads"]:
         assert harness.rel_err(b["grads"][k], a["grads"][k]) < 1e-5, k
+
+
+def test_prepare_batch_single_copy_matches_runner_packing():
+    """prepare_batch: ids / lens / packed CE targets (pytorch_runner_vae.py:89-90) through one pinned staging copy, and the
+    in-place `out=` refresh a captured step uses."""
+    _require_cuda()
+    d = synthetic.CFG0
+    m = harness.build_model(d, 1)
+    b = synthetic.make_batch(d, 21)
+    caps = torch.from_numpy(b["caps"])
+    lens1 = torch.as_tensor(b["cap_lens"]) - 1
+    want = torch.nn.utils.rnn.pack_padded_sequence(caps[:, 1:], lens1, batch_first=True).data.to(torch.int32)
+    pb = m.prepare_batch(caps, b["cap_lens"], "cuda")
+    torch.cuda.synchronize()
+    assert torch.equal(pb.targets.cpu(), want)
+    assert torch.equal(pb.caps_ids.cpu(), caps.to(torch.int32))
+    assert torch.equal(pb.cap_lens_dev.cpu(), torch.as_tensor(b["cap_lens"]).to(torch.int32))
+    assert pb.T == int(b["cap_lens"].max()) - 1
+    st = pb.clone()
+    b2 = synthetic.make_batch(d, 22, cap_lens_override=b["cap_lens"])
+    m.prepare_batch(torch.from_numpy(b2["caps"]), b2["cap_lens"], "cuda", out=st)
+    torch.cuda.synchronize()
+    assert torch.equal(st.caps_ids.cpu(), torch.from_numpy(b2["caps"]).to(torch.int32))
+    with pytest.raises(RuntimeError):
+        m.prepare_batch(caps, b["cap_lens"][::-1].copy(), "cuda")
