@@ -311,4 +311,11 @@ int acvae_diverse_beam_search(const acvae_dims* d, const acvae_weights* w, const
                              group_nbest != 0, start_idx, end_idx, seqs, workspace, (cudaStream_t)stream);
 }
 
+// profiling only (profiles/chain_trace.py): device buffer of [T][16] int64 that thread 0 of CTA 0 of the decoder
+// forward chain fills with clock64 stamps; NULL switches it off
+int acvae_debug_set_chain_trace(void* device_buffer) {
+  chain_trace_ptr() = static_cast<long long*>(device_buffer);
+  return 0;
+}
+
 }  // extern "C"

@@ -356,33 +356,43 @@ __device__ __forceinline__ void prior_fwd_setup(const PriorChainFwd& p, float* W
   r.hb_m = p.head_b[u]; r.hb_l = p.head_b[E + u];
   r.c_prev = 0.0f; r.eps_t = 0.0f;
 }
-// LSTM cell of step t (needs z_{t-1}, h_{t-1} of all units: one barrier after the previous head phase)
-__device__ __forceinline__ void prior_fwd_lstm(const PriorChainFwd& p, const float* Wl, PriorFwdRegs& r, int t, const QuadRole& q) {
+// LSTM cell of step t (needs z_{t-1}, h_{t-1} of all units: one barrier after the previous head phase).
+// Split into the operand loads and the arithmetic so that a caller can put independent work (the decoder's attention)
+// between the two: the L2 round trip of the rows then overlaps that work instead of following it.
+struct PriorLstmOps { float4 a0[4][kChainE / 128], a1[4][kChainE / 128]; float gxv[4]; };
+__device__ __forceinline__ void prior_fwd_lstm_load(const PriorChainFwd& p, PriorFwdRegs& r, int t, const QuadRole& q, PriorLstmOps& o) {
   constexpr int E = kChainE;
   const int T = p.T, N = p.N;
-  float v[8][4];
-  zero8(v);
-  float gxv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int g = 0; g < 4; ++g) o.gxv[g] = 0.0f;
   if (q.epi) {
     const float* gx = p.gx + ((long long)q.n * T + t) * 4 * E + q.u;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) gxv[g] = ldcg1(gx + g * E);
+    for (int g = 0; g < 4; ++g) o.gxv[g] = ldcg1(gx + g * E);
     r.eps_t = ldcg1(p.eps + ((long long)t * N + q.n) * E + q.u);
   }
   if (t > 0) {
-    float4 a0[4][E / 128], a1[4][E / 128];
-    quadrows<E>(q.n0, N, p.pz + ((long long)q.n0 * T + t - 1) * E, (long long)T * E, q.lane, a0);
-    quadrows<E>(q.n0, N, p.h + ((long long)q.n0 * T + t - 1) * E, (long long)T * E, q.lane, a1);
+    quadrows<E>(q.n0, N, p.pz + ((long long)q.n0 * T + t - 1) * E, (long long)T * E, q.lane, o.a0);
+    quadrows<E>(q.n0, N, p.h + ((long long)q.n0 * T + t - 1) * E, (long long)T * E, q.lane, o.a1);
+  }
+}
+__device__ __forceinline__ void prior_fwd_lstm_compute(const PriorChainFwd& p, const float* Wl, PriorFwdRegs& r, int t, const QuadRole& q,
+                                                       const PriorLstmOps& o) {
+  constexpr int E = kChainE;
+  const int T = p.T;
+  float v[8][4];
+  zero8(v);
+  if (t > 0) {
     __syncwarp();
-    quadfma<4, E>(a0, Wl, 2 * E, q.lane, v);
-    quadfma<4, E>(a1, Wl + E, 2 * E, q.lane, v);
+    quadfma<4, E>(o.a0, Wl, 2 * E, q.lane, v);
+    quadfma<4, E>(o.a1, Wl + E, 2 * E, q.lane, v);
     reduce_scatter8<4>(v, q.lane);
   }
   if (q.epi) {
-    const float ig = sigmoidf_(v[0][0] + gxv[0] + r.bh[0]);
-    const float fg = sigmoidf_(v[0][1] + gxv[1] + r.bh[1]);
-    const float gg = tanhf(v[0][2] + gxv[2] + r.bh[2]);
-    const float og = sigmoidf_(v[0][3] + gxv[3] + r.bh[3]);
+    const float ig = sigmoidf_(v[0][0] + o.gxv[0] + r.bh[0]);
+    const float fg = sigmoidf_(v[0][1] + o.gxv[1] + r.bh[1]);
+    const float gg = tanhf(v[0][2] + o.gxv[2] + r.bh[2]);
+    const float og = sigmoidf_(v[0][3] + o.gxv[3] + r.bh[3]);
     const float cn = fg * r.c_prev + ig * gg;
     const float hn = og * tanhf(cn);
     r.c_prev = cn;
@@ -392,13 +402,24 @@ __device__ __forceinline__ void prior_fwd_lstm(const PriorChainFwd& p, const flo
     p.h[((long long)q.n * T + t) * E + q.u] = hn;
   }
 }
+__device__ __forceinline__ void prior_fwd_lstm(const PriorChainFwd& p, const float* Wl, PriorFwdRegs& r, int t, const QuadRole& q) {
+  PriorLstmOps o;
+  prior_fwd_lstm_load(p, r, t, q, o);
+  prior_fwd_lstm_compute(p, Wl, r, t, q, o);
+}
 // Gaussian head + reparameterisation of step t (needs h_t of all units: one barrier after the LSTM phase)
-__device__ __forceinline__ void prior_fwd_head(const PriorChainFwd& p, const float* Wh, PriorFwdRegs& r, int t, const QuadRole& q) {
+__device__ __forceinline__ void prior_fwd_head_load(const PriorChainFwd& p, int t, const QuadRole& q, float4 (&a)[4][kChainE / 128]) {
+  constexpr int E = kChainE;
+  quadrows<E>(q.n0, p.N, p.h + ((long long)q.n0 * p.T + t) * E, (long long)p.T * E, q.lane, a);
+}
+__device__ __forceinline__ void prior_fwd_head_compute(const PriorChainFwd& p, const float* Wh, PriorFwdRegs& r, int t, const QuadRole& q,
+                                                       const float4 (&a)[4][kChainE / 128]) {
   constexpr int E = kChainE;
   const int T = p.T;
   float v[8][2];
   zero8(v);
-  quaddot<2, E>(q.n0, p.N, p.h + ((long long)q.n0 * T + t) * E, (long long)T * E, Wh, E, q.lane, v);
+  __syncwarp();
+  quadfma<2, E>(a, Wh, E, q.lane, v);
   reduce_scatter8<2>(v, q.lane);
   if (q.epi) {
     const float mean = v[0][0] + r.hb_m;
@@ -406,6 +427,11 @@ __device__ __forceinline__ void prior_fwd_head(const PriorChainFwd& p, const flo
     const long long o = ((long long)q.n * T + t) * E + q.u;
     p.pm[o] = mean; p.pl[o] = lg; p.pz[o] = r.eps_t * expf(0.5f * lg) + mean;
   }
+}
+__device__ __forceinline__ void prior_fwd_head(const PriorChainFwd& p, const float* Wh, PriorFwdRegs& r, int t, const QuadRole& q) {
+  float4 a[4][kChainE / 128];
+  prior_fwd_head_load(p, t, q, a);
+  prior_fwd_head_compute(p, Wh, r, t, q, a);
 }
 
 __global__ void __launch_bounds__(kChainThreads) prior_chain_fwd_kernel(const __grid_constant__ PriorChainFwd p) {
@@ -647,12 +673,23 @@ struct DecChainFwd {
   const int* mem_lens;
   float *qp, *w, *ctx, *gates, *out;   // [N,T,A], [N,T,Te], [N,T,E], [N,T,4E], [N,T,E]
   float* aw;              // [N,Te,T] user-visible attention weights or NULL
+  float* part;            // [N, kChainCtas, A] per-CTA partial query projections of the step in flight
   unsigned* bar;
+  long long* trace;       // optional [T][16] clock64 stamps of thread 0 of CTA 0 (profiles/chain_trace.py) or NULL
 };
-inline size_t dec_chain_fwd_smem(int Te) { return ((size_t)Te * 2 * kChainE + 2 * kChainE + 12 * kChainE + 2 * kChainE + Te + 64) * sizeof(float); }
+// process-wide trace destination picked up by train_fast.cuh (profiling only)
+inline long long*& chain_trace_ptr() { static long long* p = nullptr; return p; }
+inline size_t dec_chain_fwd_smem(int Te) { return ((size_t)Te * 2 * kChainE + 2 * kChainE + 12 * kChainE + 2 * kChainE + Te + 64 + 4 * kChainE) * sizeof(float); }
 
-// `pp.N > 0`: the (independent) prior chain of the same step count is run inside the same phases: LSTM next to the
-// query projection, Gaussian head next to the attention; its barriers are the decoder's.
+// Two phases (grid barriers) per step:
+//   A (clip CTAs): query projection of the clip = sum of the 128 per-CTA partials written by phase G of the previous
+//     step, additive attention, context;                                  [+ prior LSTM cell of the step, all CTAs]
+//   G (all CTAs): GRU cell of units {u0, u0+1} for all rows, then THIS CTA's partial of the next step's query
+//     projection, q.Wq^T restricted to k in {u0, u0+1} for all A outputs  [+ prior Gaussian head of the step].
+// The partial-sum form removes the separate query-projection phase (one barrier + one state broadcast per step):
+// a unit-partitioned product needs every unit of h_t, the partials need only the two this CTA has just computed,
+// and the clip's CTA adds them in a fixed order (deterministic).
+// `pp.N > 0`: the (independent) prior chain of the same step count runs inside the same phases.
 __global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __grid_constant__ DecChainFwd p,
                                                                       const __grid_constant__ PriorChainFwd pp) {
   constexpr int E = kChainE, A = kChainE;
@@ -662,11 +699,12 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __gr
   const int Te = p.Te, T = p.T, N = p.N;
   float* Ps = dsm;                        // [Te][A]   clip blockIdx.x
   float* Ms = Ps + (size_t)Te * A;        // [Te][E]
-  float* Wq = Ms + (size_t)Te * E;        // [2][E]
-  float* Wg = Wq + 2 * E;                 // [12][E]: rows 0..5 (r,z,n)x2 on ctx, rows 6..11 on h
+  float* hs = Ms + (size_t)Te * E;        // [N][2] h_t of this CTA's two units (+ padding up to 2E floats)
+  float* Wg = hs + 2 * E;                 // [12][E]: rows 0..5 (r,z,n)x2 on ctx, rows 6..11 on h
   float* qps = Wg + 12 * E;               // [A]
   float* vs = qps + A;                    // [A]
-  float* sc = vs + A;                     // [Te]
+  float* psum = vs + A;                   // [4][A] partial query projections, one row per quarter of the CTAs (16-byte aligned)
+  float* sc = psum + 4 * A;               // [Te]
   float* red = sc + Te;                   // [64]
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int u0 = blockIdx.x * 2;
@@ -675,13 +713,24 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __gr
   const bool own_clip = clip < N;
   const int len = own_clip ? max(1, min(p.mem_lens[clip], Te)) : 0;
   if (own_clip) {
+    // P_d is kept pre-scaled by 2 log2(e): the score loop is  t = ex2(P' + q') ; r = rcp(t + 1) ; s += (-2 v) r
+    // (tanh(x) = 1 - 2 / (e^{2x} + 1), so  sum_a v_a tanh(x_a) = sum_a v_a + sum_a (-2 v_a) r_a)
     const float4* sp = reinterpret_cast<const float4*>(p.Pd + (long long)clip * Te * A);
     const float4* sm_ = reinterpret_cast<const float4*>(p.mem + (long long)clip * Te * E);
-    for (int i = tid; i < len * A / 4; i += kChainThreads) reinterpret_cast<float4*>(Ps)[i] = sp[i];
+    for (int i = tid; i < len * A / 4; i += kChainThreads) {
+      float4 v = sp[i];
+      v.x *= kTwoLog2e; v.y *= kTwoLog2e; v.z *= kTwoLog2e; v.w *= kTwoLog2e;
+      reinterpret_cast<float4*>(Ps)[i] = v;
+    }
     for (int i = tid; i < len * E / 4; i += kChainThreads) reinterpret_cast<float4*>(Ms)[i] = sm_[i];
   }
   vs[tid] = p.attn_v[tid];                 // blockDim == A
-  for (int i = tid; i < 2 * E; i += kChainThreads) Wq[i] = p.attn_w[(long long)(u0 + i / E) * 2 * E + (i % E)];
+  float v2[A / 32], vsum = 0.0f;           // this lane's slice of -2 v, and sum_a v_a
+#pragma unroll
+  for (int i = 0; i < A / 32; ++i) { const float x = p.attn_v[lane + 32 * i]; v2[i] = -2.0f * x; vsum += x; }
+  vsum = warp_sum(vsum);
+  // query-projection weights of output a = tid for this CTA's two input units (attn_model.py:31: query columns first)
+  const float wq0 = p.attn_w[(long long)tid * 2 * E + u0], wq1 = p.attn_w[(long long)tid * 2 * E + u0 + 1];
   for (int i = tid; i < 12 * E; i += kChainThreads) {
     const int r = i / E, k = i % E, rr = r % 6;
     const long long wr = (long long)((rr >> 1) * E + u0 + (rr & 1));
@@ -694,47 +743,67 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __gr
   GridBar gb{p.bar, 0u, gridDim.x};
   const float bh_r = p.bhh[u], bh_z = p.bhh[E + u], bh_n = p.bhh[2 * E + u];
   for (int t = 0; t < T; ++t) {
-    // ---- P1: query projection q.Wq^T, columns {u0, u0+1} of A  [+ prior LSTM cell] ----
-    if (t > 0) {
-      float v1[8][1];
-      zero8(v1);
-      quaddot<1, E>(q.n0, N, p.out + ((long long)q.n0 * T + t - 1) * E, (long long)T * E, Wq, E, q.lane, v1);
-      reduce_scatter8<1>(v1, q.lane);
-      if (q.epi) p.qp[((long long)n * T + t) * A + u] = v1[0][0];
-    } else if (q.epi) {
-      p.qp[((long long)n * T) * A + u] = 0.0f;     // zero query at t = 0 (decoder.py:94-98)
-    }
-    if (prior) prior_fwd_lstm(pp, Wprior, pr, t, q);
-    if (t > 0 || prior) grid_sync(gb);
-    // ---- P2: attention of clip `clip` ----
+    // the prior LSTM's operand rows are requested first: their L2 round trip overlaps the attention below
+    const bool tr = p.trace && blockIdx.x == 0 && tid == 0;
+    if (tr) p.trace[t * 16 + 0] = clock64();
+    PriorLstmOps lops;
+    if (prior) prior_fwd_lstm_load(pp, pr, t, q, lops);
+    // ---- A: attention of clip `clip` (query projection = sum of the partials; zero query at t = 0, decoder.py:94-98) ----
     if (own_clip) {
-      qps[tid] = t > 0 ? ldcg1(p.qp + ((long long)clip * T + t) * A + tid) : 0.0f;
+      // query projection of the clip: 128 partial rows of A floats, summed in a fixed order (deterministic): thread
+      // (quarter bq, columns 4*aq..4*aq+3) adds 32 rows with 16-byte loads, the four quarters meet in shared memory
+      if (t > 0) {
+        const int aq = tid & 63, bq = tid >> 6;
+        const float4* pq = reinterpret_cast<const float4*>(p.part + ((long long)clip * kChainCtas + bq * 32) * A) + aq;
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+#pragma unroll 4
+        for (int b = 0; b < 32; b += 2) {
+          const float4 x0 = ldcg4(reinterpret_cast<const float*>(pq + (long long)b * (A / 4)));
+          const float4 x1 = ldcg4(reinterpret_cast<const float*>(pq + (long long)(b + 1) * (A / 4)));
+          s0.x += x0.x; s0.y += x0.y; s0.z += x0.z; s0.w += x0.w;
+          s1.x += x1.x; s1.y += x1.y; s1.z += x1.z; s1.w += x1.w;
+        }
+        reinterpret_cast<float4*>(psum + bq * A)[aq] = make_float4(s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w);
+        __syncthreads();
+      }
+      const float qv = t > 0 ? (psum[tid] + psum[A + tid]) + (psum[2 * A + tid] + psum[3 * A + tid]) : 0.0f;
+      qps[tid] = qv;
+      p.qp[((long long)clip * T + t) * A + tid] = qv;          // saved for the backward
       __syncthreads();
-      for (int jj = wid; jj < len; jj += kChainThreads / 32) {
-        const float* pr = Ps + (size_t)jj * A;
-        float s = 0.0f;
+      if (tr) p.trace[t * 16 + 1] = clock64();
+      {
+        float qreg[A / 32];
 #pragma unroll
-        for (int a = lane; a < A; a += 32) s = fmaf(vs[a], attn_tanh(pr[a] + qps[a]), s);
-        s = warp_sum(s);
-        if (lane == 0) sc[jj] = s;
+        for (int i = 0; i < A / 32; ++i) qreg[i] = kTwoLog2e * qps[lane + 32 * i];
+        for (int jj = wid; jj < len; jj += 2 * (kChainThreads / 32)) {     // two frames per pass: 16 independent chains
+          const int j2 = jj + kChainThreads / 32;
+          const float* pr0 = Ps + (size_t)jj * A + lane;
+          const float* pr1 = Ps + (size_t)(j2 < len ? j2 : jj) * A + lane;
+          float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+          for (int i = 0; i < A / 32; ++i) {
+            s0 = fmaf(v2[i], rcp_approx(ex2_approx(pr0[32 * i] + qreg[i]) + 1.0f), s0);
+            s1 = fmaf(v2[i], rcp_approx(ex2_approx(pr1[32 * i] + qreg[i]) + 1.0f), s1);
+          }
+          s0 = warp_sum(s0); s1 = warp_sum(s1);
+          if (lane == 0) { sc[jj] = s0 + vsum; if (j2 < len) sc[j2] = s1 + vsum; }
+        }
       }
       __syncthreads();
-      float mx = -INFINITY;
-      for (int jj = tid; jj < len; jj += kChainThreads) mx = fmaxf(mx, sc[jj]);
-      mx = block_max(mx, red);
-      float sum = 0.0f;
-      for (int jj = tid; jj < len; jj += kChainThreads) {
-        const float e = expf(sc[jj] - mx);
-        sc[jj] = e;
-        sum += e;
-      }
-      sum = block_sum(sum, red);
-      const float inv = 1.0f / sum;
-      for (int jj = tid; jj < Te; jj += kChainThreads) {
-        const float wv = jj < len ? sc[jj] * inv : 0.0f;
-        if (jj < len) sc[jj] = wv;
-        p.w[((long long)clip * T + t) * Te + jj] = wv;
-        if (p.aw) p.aw[((long long)clip * Te + jj) * T + t] = wv;
+      if (wid == 0) {                                        // masked softmax over <= Te frames by one warp (no block reductions)
+        float mx = -INFINITY;
+        for (int jj = lane; jj < len; jj += 32) mx = fmaxf(mx, sc[jj]);
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        for (int jj = lane; jj < len; jj += 32) { const float e = expf(sc[jj] - mx); sc[jj] = e; sum += e; }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        for (int jj = lane; jj < Te; jj += 32) {
+          const float wv = jj < len ? sc[jj] * inv : 0.0f;
+          if (jj < len) sc[jj] = wv;
+          p.w[((long long)clip * T + t) * Te + jj] = wv;
+          if (p.aw) p.aw[((long long)clip * Te + jj) * T + t] = wv;
+        }
       }
       __syncthreads();
       float c0 = 0.f, c1 = 0.f;
@@ -746,9 +815,12 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __gr
       if (jj < len) c0 = fmaf(sc[jj], Ms[(size_t)jj * E + tid], c0);
       p.ctx[((long long)clip * T + t) * E + tid] = c0 + c1;
     }
-    if (prior) prior_fwd_head(pp, Wprior + 8 * 2 * E, pr, t, q);
+    if (tr) p.trace[t * 16 + 2] = clock64();
+    if (prior) prior_fwd_lstm_compute(pp, Wprior, pr, t, q, lops);
+    if (tr) p.trace[t * 16 + 3] = clock64();
     grid_sync(gb);
-    // ---- P3: GRU cell, units {u0, u0+1} ----
+    if (tr) p.trace[t * 16 + 4] = clock64();
+    // ---- G: GRU cell, units {u0, u0+1} ----
     float vx[8][3], vh[8][3];                        // (r, z, n) pre-activations from ctx_t and from h_{t-1}
     zero8(vx); zero8(vh);
     float gxr = 0.f, gxz = 0.f, gxn = 0.f, hp = 0.f;
@@ -757,16 +829,19 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __gr
       gxr = ldcg1(gx); gxz = ldcg1(gx + E); gxn = ldcg1(gx + 2 * E);
       if (t > 0) hp = ldcg1(p.out + ((long long)n * T + t - 1) * E + u);
     }
+    float4 hrow[4][E / 128];                          // the prior head's operand rows, requested with the GRU's
     {
       float4 a0[4][E / 128], a1[4][E / 128];
       quadrows<E>(q.n0, N, p.ctx + ((long long)q.n0 * T + t) * E, (long long)T * E, q.lane, a0);
       if (t > 0) quadrows<E>(q.n0, N, p.out + ((long long)q.n0 * T + t - 1) * E, (long long)T * E, q.lane, a1);
+      if (prior) prior_fwd_head_load(pp, t, q, hrow);
       __syncwarp();
       quadfma<3, E>(a0, Wg, E, q.lane, vx);
       if (t > 0) quadfma<3, E>(a1, Wg + 6 * E, E, q.lane, vh);
     }
     reduce_scatter8<3>(vx, q.lane);
     if (t > 0) reduce_scatter8<3>(vh, q.lane);
+    if (tr) p.trace[t * 16 + 5] = clock64();
     if (q.epi) {
       const float hn = vh[0][2] + bh_n;
       const float rg = sigmoidf_(vx[0][0] + gxr + vh[0][0] + bh_r);
@@ -774,9 +849,22 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __gr
       const float ng = tanhf(vx[0][2] + gxn + rg * hn);
       float* gs = p.gates + ((long long)n * T + t) * 4 * E + u;
       gs[0] = rg; gs[E] = zg; gs[2 * E] = ng; gs[3 * E] = hn;
-      p.out[((long long)n * T + t) * E + u] = (1.0f - zg) * ng + zg * hp;
+      const float hnew = (1.0f - zg) * ng + zg * hp;
+      p.out[((long long)n * T + t) * E + u] = hnew;
+      hs[n * 2 + q.j] = hnew;
     }
-    if (t + 1 < T) grid_sync(gb);
+    if (prior) prior_fwd_head_compute(pp, Wprior + 8 * 2 * E, pr, t, q, hrow);
+    if (tr) p.trace[t * 16 + 6] = clock64();
+    if (t + 1 < T) {
+      // this CTA's partial of the next step's query projection: part[n][b][a] = Wq[a][u0] h[n][u0] + Wq[a][u0+1] h[n][u0+1]
+      __syncthreads();
+      float* dst = p.part + (long long)blockIdx.x * A + tid;
+      for (int r = 0; r < N; ++r)
+        dst[(long long)r * kChainCtas * A] = fmaf(wq1, hs[r * 2 + 1], wq0 * hs[r * 2]);
+      if (tr) p.trace[t * 16 + 7] = clock64();
+      grid_sync(gb);
+      if (tr) p.trace[t * 16 + 8] = clock64();
+    }
   }
 }
 
@@ -975,7 +1063,7 @@ inline bool chain_supported(int N, int T, int Te, int E, int A) {
       // largest Te whose resident clip fits next to the weight slices (the merged prior phases keep 20 KB of
       // weights in static shared memory)
       const int dyn_max = optin - 24 * 1024;
-      max_te = (int)(((size_t)dyn_max / sizeof(float) - (2 * 4 + 2 * 3 + 2 + 12 + 2) * kChainE - 256) / (2 * kChainE + 1));   // ~85 on B200
+      max_te = (int)(((size_t)dyn_max / sizeof(float) - (2 * 4 + 2 * 3 + 2 + 12 + 2 + 4) * kChainE - 256) / (2 * kChainE + 1));   // ~83 on B200
       if (cudaFuncSetAttribute(dec_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max) == cudaSuccess &&
           cudaFuncSetAttribute(dec_chain_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max) == cudaSuccess &&
           cudaFuncSetAttribute(dec_chain_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max) == cudaSuccess)

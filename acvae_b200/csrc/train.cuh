@@ -27,6 +27,7 @@ struct TrainWs {
   float *qp_p, *w_p, *ctx_p, *gates_p, *c_p, *h_p;
   // decoder
   float *qp_d, *w_d, *ctx_d, *gates_d, *pool_d; int* amax_d;
+  float* part_d;    // [min(N,32), 128, max(A,E)] per-CTA partial projections of the persistent decoder chains (recurrent.cuh)
   // vocab partials
   float *pmax, *pexp, *psum, *pbest; int* parg;
   // backward scratch
@@ -52,6 +53,7 @@ inline TrainWs carve_train_ws(const acvae_dims& d, void* base) {
   w.qp_p = ar.take<float>(NT * E); w.w_p = ar.take<float>(NT * Te); w.ctx_p = ar.take<float>(NT * E);
   w.gates_p = ar.take<float>(NT * 4 * E); w.c_p = ar.take<float>(NT * E); w.h_p = ar.take<float>(NT * E);
   w.qp_d = ar.take<float>(NT * A); w.w_d = ar.take<float>(NT * Te); w.ctx_d = ar.take<float>(NT * E);
+  w.part_d = ar.take<float>((N < 32 ? N : 32) * 128 * (A > E ? A : E));
   w.gates_d = ar.take<float>(NT * 4 * E); w.pool_d = ar.take<float>(N * E); w.amax_d = ar.take<int>(N * E);
   w.pmax = ar.take<float>(NT * ntiles); w.pexp = ar.take<float>(NT * ntiles); w.psum = ar.take<float>(NT * ntiles);
   w.pbest = ar.take<float>(NT * ntiles * 2); w.parg = ar.take<int>(NT * ntiles);

@@ -166,7 +166,7 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     dc.N = N; dc.T = T; dc.Te = Te; dc.gx = ws.dgi_d; dc.attn_w = w.d_attn_w; dc.attn_v = w.d_attn_v;
     dc.wih = w.d_wih; dc.whh = w.d_whh; dc.bhh = w.d_bhh; dc.Pd = ws.Pd; dc.mem = ws.mem; dc.mem_lens = io.mem_lens;
     dc.qp = ws.qp_d; dc.w = ws.w_d; dc.ctx = ws.ctx_d; dc.gates = ws.gates_d; dc.out = io.outputs; dc.aw = io.attn_weights;
-    dc.bar = ws.bars + 2 * 128;
+    dc.bar = ws.bars + 2 * 128; dc.part = ws.part_d; dc.trace = chain_trace_ptr();
     ACVAE_TRY(stream_dep(sp, st, ax));      // the prior's hoisted inputs (gx_p) are produced on sp
     ACVAE_TRY(launch_chain(dec_chain_fwd_kernel, dec_chain_fwd_smem(Te), st, "dec_chain_fwd_kernel", dc, ppc));
   }

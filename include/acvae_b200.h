@@ -260,6 +260,9 @@ int acvae_diverse_beam_search(const acvae_dims *d, const acvae_weights *w, const
                               float diversity_lambda, float temperature, int32_t group_nbest, int32_t start_idx,
                               int32_t end_idx, int64_t *seqs, void *workspace, size_t workspace_bytes, void *stream);
 
+/* profiling only: [T][16] int64 device buffer for clock64 stamps of the decoder forward chain (CTA 0), or NULL */
+int acvae_debug_set_chain_trace(void *device_buffer);
+
 #ifdef __cplusplus
 }
 #endif
