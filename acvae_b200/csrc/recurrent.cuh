@@ -746,26 +746,29 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __gr
     // the prior LSTM's operand rows are requested first: their L2 round trip overlaps the attention below
     const bool tr = p.trace && blockIdx.x == 0 && tid == 0;
     if (tr) p.trace[t * 16 + 0] = clock64();
+    // ---- A: attention of clip `clip` (query projection = sum of the partials; zero query at t = 0, decoder.py:94-98) ----
+    // query projection of the clip: 128 partial rows of A floats, summed in a fixed order (deterministic): thread
+    // (quarter bq, columns 4*aq..4*aq+3) adds 32 rows with 16-byte loads -- ALL 32 requested before the first add, one
+    // L2 round trip (8 in flight cost four: 4500 cycles, profiles/chain_trace.py) -- the four quarters meet in shared memory
+    if (own_clip && t > 0) {
+      const int aq = tid & 63, bq = tid >> 6;
+      const float4* pq = reinterpret_cast<const float4*>(p.part + ((long long)clip * kChainCtas + bq * 32) * A) + aq;
+      float4 x[32];
+#pragma unroll
+      for (int b = 0; b < 32; ++b) x[b] = ldcg4(reinterpret_cast<const float*>(pq + (long long)b * (A / 4)));
+      float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+#pragma unroll
+      for (int b = 0; b < 32; b += 2) {
+        s0.x += x[b].x; s0.y += x[b].y; s0.z += x[b].z; s0.w += x[b].w;
+        s1.x += x[b + 1].x; s1.y += x[b + 1].y; s1.z += x[b + 1].z; s1.w += x[b + 1].w;
+      }
+      reinterpret_cast<float4*>(psum + bq * A)[aq] = make_float4(s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w);
+    }
+    // the prior LSTM's operand rows are requested next: their L2 round trip overlaps the attention below
     PriorLstmOps lops;
     if (prior) prior_fwd_lstm_load(pp, pr, t, q, lops);
-    // ---- A: attention of clip `clip` (query projection = sum of the partials; zero query at t = 0, decoder.py:94-98) ----
     if (own_clip) {
-      // query projection of the clip: 128 partial rows of A floats, summed in a fixed order (deterministic): thread
-      // (quarter bq, columns 4*aq..4*aq+3) adds 32 rows with 16-byte loads, the four quarters meet in shared memory
-      if (t > 0) {
-        const int aq = tid & 63, bq = tid >> 6;
-        const float4* pq = reinterpret_cast<const float4*>(p.part + ((long long)clip * kChainCtas + bq * 32) * A) + aq;
-        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-#pragma unroll 4
-        for (int b = 0; b < 32; b += 2) {
-          const float4 x0 = ldcg4(reinterpret_cast<const float*>(pq + (long long)b * (A / 4)));
-          const float4 x1 = ldcg4(reinterpret_cast<const float*>(pq + (long long)(b + 1) * (A / 4)));
-          s0.x += x0.x; s0.y += x0.y; s0.z += x0.z; s0.w += x0.w;
-          s1.x += x1.x; s1.y += x1.y; s1.z += x1.z; s1.w += x1.w;
-        }
-        reinterpret_cast<float4*>(psum + bq * A)[aq] = make_float4(s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w);
-        __syncthreads();
-      }
+      if (t > 0) __syncthreads();
       const float qv = t > 0 ? (psum[tid] + psum[A + tid]) + (psum[2 * A + tid] + psum[3 * A + tid]) : 0.0f;
       qps[tid] = qv;
       p.qp[((long long)clip * T + t) * A + tid] = qv;          // saved for the backward
@@ -790,6 +793,7 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __gr
         }
       }
       __syncthreads();
+      if (tr) p.trace[t * 16 + 9] = clock64();
       if (wid == 0) {                                        // masked softmax over <= Te frames by one warp (no block reductions)
         float mx = -INFINITY;
         for (int jj = lane; jj < len; jj += 32) mx = fmaxf(mx, sc[jj]);
@@ -798,22 +802,26 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_fwd_kernel(const __gr
         for (int jj = lane; jj < len; jj += 32) { const float e = expf(sc[jj] - mx); sc[jj] = e; sum += e; }
         sum = warp_sum(sum);
         const float inv = 1.0f / sum;
-        for (int jj = lane; jj < Te; jj += 32) {
-          const float wv = jj < len ? sc[jj] * inv : 0.0f;
-          if (jj < len) sc[jj] = wv;
-          p.w[((long long)clip * T + t) * Te + jj] = wv;
-          if (p.aw) p.aw[((long long)clip * Te + jj) * T + t] = wv;
-        }
+        for (int jj = lane; jj < len; jj += 32) sc[jj] *= inv;
       }
       __syncthreads();
-      float c0 = 0.f, c1 = 0.f;
+      if (tr) p.trace[t * 16 + 10] = clock64();
+      float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
       int jj = 0;
-      for (; jj + 2 <= len; jj += 2) {
+      for (; jj + 4 <= len; jj += 4) {
         c0 = fmaf(sc[jj], Ms[(size_t)jj * E + tid], c0);
         c1 = fmaf(sc[jj + 1], Ms[(size_t)(jj + 1) * E + tid], c1);
+        c2 = fmaf(sc[jj + 2], Ms[(size_t)(jj + 2) * E + tid], c2);
+        c3 = fmaf(sc[jj + 3], Ms[(size_t)(jj + 3) * E + tid], c3);
       }
-      if (jj < len) c0 = fmaf(sc[jj], Ms[(size_t)jj * E + tid], c0);
-      p.ctx[((long long)clip * T + t) * E + tid] = c0 + c1;
+      for (; jj < len; ++jj) c0 = fmaf(sc[jj], Ms[(size_t)jj * E + tid], c0);
+      p.ctx[((long long)clip * T + t) * E + tid] = (c0 + c1) + (c2 + c3);
+      // the saved / user-visible attention weights leave the chip off the critical path (sc is read-only until the next step)
+      for (int j2 = tid; j2 < Te; j2 += kChainThreads) {
+        const float wv = j2 < len ? sc[j2] : 0.0f;
+        p.w[((long long)clip * T + t) * Te + j2] = wv;
+        if (p.aw) p.aw[((long long)clip * Te + j2) * T + t] = wv;
+      }
     }
     if (tr) p.trace[t * 16 + 2] = clock64();
     if (prior) prior_fwd_lstm_compute(pp, Wprior, pr, t, q, lops);

@@ -27,4 +27,5 @@ names = ["partials summed", "attention", "prior LSTM", "barrier A", "GRU product
 print("step  " + "  ".join(f"{n:>18s}" for n in names) + "   total (cycles, thread 0 of CTA 0)")
 for t in range(1, T - 1):
     d = [int(tr[t, k + 1] - tr[t, k]) for k in range(8)]
-    print(f"{t:4d}  " + "  ".join(f"{x:18d}" for x in d) + f"   {int(tr[t, 8] - tr[t, 0])}")
+    print(f"{t:4d}  " + "  ".join(f"{x:18d}" for x in d) + f"   {int(tr[t, 8] - tr[t, 0])}"
+          f"   [attention: scores {int(tr[t, 9] - tr[t, 1])}, softmax {int(tr[t, 10] - tr[t, 9])}, context {int(tr[t, 2] - tr[t, 10])}]")
