@@ -892,6 +892,7 @@ struct DecChainBwd {
   float *dgi, *dgh;       // [N,T,3E]
   float *dctx, *ds, *dqp; // [N,T,E], [N,T,Te], [N,T,A]
   unsigned* bar;
+  long long* trace;       // optional [T][16] clock64 stamps of thread 0 of CTA 0 or NULL (profiles/chain_trace.py)
 };
 inline size_t dec_chain_bwd_smem(int Te) { return ((size_t)Te * 2 * kChainE + 2 * 4 * kChainE + 2 * 3 * kChainE + 2 * kChainE + Te + 64) * sizeof(float); }
 
@@ -924,7 +925,12 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_bwd_kernel(const __gr
   if (own_clip) {
     const float4* sp = reinterpret_cast<const float4*>(p.Pd + (long long)clip * Te * A);
     const float4* sm_ = reinterpret_cast<const float4*>(p.mem + (long long)clip * Te * E);
-    for (int i = tid; i < len * A / 4; i += kChainThreads) reinterpret_cast<float4*>(Ps)[i] = sp[i];
+    // P_d pre-scaled by 2 log2(e) (see the forward kernel): r = 1 / (e^{2x} + 1) = rcp(ex2(P' + q') + 1), 1 - tanh^2 = 4 r (1 - r)
+    for (int i = tid; i < len * A / 4; i += kChainThreads) {
+      float4 v = sp[i];
+      v.x *= kTwoLog2e; v.y *= kTwoLog2e; v.z *= kTwoLog2e; v.w *= kTwoLog2e;
+      reinterpret_cast<float4*>(Ps)[i] = v;
+    }
     for (int i = tid; i < len * E / 4; i += kChainThreads) reinterpret_cast<float4*>(Ms)[i] = sm_[i];
   }
   for (int i = tid; i < 2 * 4 * E; i += kChainThreads) {
@@ -947,7 +953,12 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_bwd_kernel(const __gr
   const float va = p.attn_v[tid];
   float carry = 0.0f;
   for (int t = T - 1; t >= 0; --t) {
+    const bool tr = p.trace && blockIdx.x == 0 && tid == 0;
+    if (tr) p.trace[t * 16 + 0] = clock64();
     // ---- B1: dh_t (units u0, u0+1) and the GRU pointwise backward of step t ----
+    // (requesting all 6E floats of row operands of this phase at once was tried: the backward phases are L2-bandwidth
+    // bound -- every CTA reads every row, 130-230 KB per CTA and phase, 25 MB per phase over all CTAs -- and the chunked
+    // form below overlaps one chunk's FMAs with the next chunk's loads: 5500 vs 7000 cycles, profiles/chain_trace.py)
     float va2[8][1];
     zero8(va2);
     float dh = 0.f, rr = 0.f, z = 0.f, nn = 0.f, ghn = 0.f, hp = 0.f;
@@ -980,8 +991,11 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_bwd_kernel(const __gr
       gh[0] = dar; gh[E] = daz; gh[2 * E] = dan * rr;
       carry = dh * z;
     }
+    if (tr) p.trace[t * 16 + 1] = clock64();
     if (prior) prior_bwd_lstm(pp, Wprior, pr, t, q);
+    if (tr) p.trace[t * 16 + 2] = clock64();
     grid_sync(gb);
+    if (tr) p.trace[t * 16 + 3] = clock64();
     // ---- B1.5: d ctx_t = dGi_t . W_ih[:, E:2E], columns {u0, u0+1} ----
     float vb2[8][1];
     zero8(vb2);
@@ -989,40 +1003,68 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_bwd_kernel(const __gr
     quaddot<1, E>(q.n0, N, p.dgi + ((long long)q.n0 * T + t) * 3 * E + 2 * E, (long long)T * 3 * E, W2 + 2 * E, 3 * E, q.lane, vb2);
     reduce_scatter8<1>(vb2, q.lane);
     if (q.epi) p.dctx[((long long)n * T + t) * E + u] = vb2[0][0];
+    if (tr) p.trace[t * 16 + 4] = clock64();
     if (prior && t > 0) prior_bwd_head(pp, Wprior + 2 * 2 * E, pr, t, q);
+    if (tr) p.trace[t * 16 + 5] = clock64();
     grid_sync(gb);
+    if (tr) p.trace[t * 16 + 6] = clock64();
     // ---- B2: attention backward of clip `clip` ----
     if (own_clip) {
-      dcs[tid] = ldcg1(p.dctx + ((long long)clip * T + t) * E + tid);
-      qps[tid] = p.qp[((long long)clip * T + t) * A + tid];
+      // all global operands of the phase in one round trip: d ctx, the saved query projection, the saved weights
+      const float dcv = ldcg1(p.dctx + ((long long)clip * T + t) * E + tid);
+      const float qa = kTwoLog2e * p.qp[((long long)clip * T + t) * A + tid];
+      const float wreg = tid < len ? p.w[((long long)clip * T + t) * Te + tid] : 0.0f;      // Te <= 83 < blockDim
+      dcs[tid] = dcv;
+      if (tid < len) qps[tid] = wreg;          // the weights, staged for the dot product below (qps is free: q lives in qa)
       __syncthreads();
-      for (int jj = wid; jj < len; jj += kChainThreads / 32) {
-        float s = 0.0f;
+      {
+        float dreg[E / 32];
 #pragma unroll
-        for (int e = lane; e < E; e += 32) s = fmaf(dcs[e], Ms[(size_t)jj * E + e], s);
-        s = warp_sum(s);
-        if (lane == 0) dw[jj] = s;
+        for (int i = 0; i < E / 32; ++i) dreg[i] = dcs[lane + 32 * i];
+        for (int jj = wid; jj < len; jj += 2 * (kChainThreads / 32)) {       // d w_j = d ctx . mem_j, two frames per pass
+          const int j2 = jj + kChainThreads / 32;
+          const float* m0 = Ms + (size_t)jj * E + lane;
+          const float* m1 = Ms + (size_t)(j2 < len ? j2 : jj) * E + lane;
+          float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+          for (int i = 0; i < E / 32; ++i) { s0 = fmaf(dreg[i], m0[32 * i], s0); s1 = fmaf(dreg[i], m1[32 * i], s1); }
+          s0 = warp_sum(s0); s1 = warp_sum(s1);
+          if (lane == 0) { dw[jj] = s0; if (j2 < len) dw[j2] = s1; }
+        }
       }
       __syncthreads();
-      const float* wr = p.w + ((long long)clip * T + t) * Te;
+      // softmax backward d s_j = w_j (d w_j - sum_k w_k d w_k): the dot product by every warp for itself (<= 3 terms a lane)
       float dot = 0.0f;
-      for (int jj = tid; jj < len; jj += kChainThreads) dot = fmaf(wr[jj], dw[jj], dot);
-      dot = block_sum(dot, red);
-      for (int jj = tid; jj < Te; jj += kChainThreads) {
-        const float d = jj < len ? wr[jj] * (dw[jj] - dot) : 0.0f;
-        if (jj < len) dw[jj] = d;
-        p.ds[((long long)clip * T + t) * Te + jj] = d;
-      }
+      for (int jj = lane; jj < len; jj += 32) dot = fmaf(qps[jj], dw[jj], dot);
+      dot = warp_sum(dot);
       __syncthreads();
-      const float qa = qps[tid];
-      float s = 0.0f;
-      for (int jj = 0; jj < len; ++jj) {
-        const float th = attn_tanh(Ps[(size_t)jj * A + tid] + qa);
-        s = fmaf(dw[jj] * va, 1.0f - th * th, s);
+      float dsv = 0.0f;
+      if (tid < len) { dsv = wreg * (dw[tid] - dot); dw[tid] = 4.0f * dsv; }          // dw := 4 d s (the factor of 4 r (1 - r))
+      if (tid < Te) p.ds[((long long)clip * T + t) * Te + tid] = dsv;
+      __syncthreads();
+      // d qp_a = v_a sum_j d s_j (1 - tanh^2(P_ja + q_a)), four independent chains
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      const float* pc = Ps + tid;
+      int jj = 0;
+      for (; jj + 4 <= len; jj += 4) {
+        const float r0 = rcp_approx(ex2_approx(pc[(size_t)jj * A] + qa) + 1.0f);
+        const float r1 = rcp_approx(ex2_approx(pc[(size_t)(jj + 1) * A] + qa) + 1.0f);
+        const float r2 = rcp_approx(ex2_approx(pc[(size_t)(jj + 2) * A] + qa) + 1.0f);
+        const float r3 = rcp_approx(ex2_approx(pc[(size_t)(jj + 3) * A] + qa) + 1.0f);
+        s0 = fmaf(dw[jj], fmaf(-r0, r0, r0), s0);
+        s1 = fmaf(dw[jj + 1], fmaf(-r1, r1, r1), s1);
+        s2 = fmaf(dw[jj + 2], fmaf(-r2, r2, r2), s2);
+        s3 = fmaf(dw[jj + 3], fmaf(-r3, r3, r3), s3);
       }
-      p.dqp[((long long)clip * T + t) * A + tid] = s;
+      for (; jj < len; ++jj) {
+        const float r0 = rcp_approx(ex2_approx(pc[(size_t)jj * A] + qa) + 1.0f);
+        s0 = fmaf(dw[jj], fmaf(-r0, r0, r0), s0);
+      }
+      p.dqp[((long long)clip * T + t) * A + tid] = va * ((s0 + s1) + (s2 + s3));
     }
+    if (tr) p.trace[t * 16 + 7] = clock64();
     if (t > 0) grid_sync(gb);
+    if (tr) p.trace[t * 16 + 8] = clock64();
   }
 }
 

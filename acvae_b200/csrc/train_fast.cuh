@@ -376,6 +376,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     dc.whh = w.d_whh; dc.Pd = ws.Pd; dc.mem = ws.mem; dc.mem_lens = io.mem_lens; dc.qp = ws.qp_d; dc.w = ws.w_d;
     dc.gates = ws.gates_d; dc.out = io.outputs; dc.dgi = ws.dgi_d; dc.dgh = ws.dgh_d; dc.dctx = ws.dctx_d; dc.ds = ws.ds_d;
     dc.dqp = ws.dqp_d; dc.bar = ws.bars + 5 * 128;
+    dc.trace = chain_trace_ptr() ? chain_trace_ptr() + (long long)T * 16 : nullptr;
     if (merge_bwd) {
       ACVAE_TRY(launch_chain(dec_chain_bwd_kernel<true>, dec_chain_bwd_smem(Te), st, "dec_chain_bwd_kernel", dc, ppc));
       ACVAE_TRY(stream_dep(st, sp, ax));
