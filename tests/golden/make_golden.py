@@ -354,7 +354,6 @@ if __name__ == "__main__":
     run_sample_case("cfg0_sample_multinomial", C0, 2, "sample", 20)
     run_beam_case("tiny_beam", T, 1, 3, 6)
     run_beam_case("cfg0_beam", C0, 1, 3, 20)
-    if True:
-        run_dbs_case("tiny_dbs", T, 1, 6, 3, 6, lam=0.5, temperature=1.0, nbest=True)
-        run_dbs_case("tiny_dbs_best", T, 2, 4, 2, 6, lam=1.5, temperature=0.7, nbest=False)
-        run_dbs_case("cfg0_dbs", C0, 1, 10, 5, 20, lam=0.5, temperature=1.0, nbest=True)
+    run_dbs_case("tiny_dbs", T, 1, 6, 3, 6, lam=0.5, temperature=1.0, nbest=True)
+    run_dbs_case("tiny_dbs_best", T, 2, 4, 2, 6, lam=1.5, temperature=0.7, nbest=False)
+    run_dbs_case("cfg0_dbs", C0, 1, 10, 5, 20, lam=0.5, temperature=1.0, nbest=True)
