@@ -8,9 +8,10 @@
 
 namespace acvae {
 
-constexpr int kAuxStreams = 9;      // 0,1: posterior directions; 2: prior; 3: memory backward; 4..7: weight-gradient fan; 8: main chain
-constexpr int kAuxMain = 8;
-constexpr int kAuxEvents = 64;
+constexpr int kAuxStreams = 13;     // 0,1: posterior directions; 2: prior; 3: memory backward; 4..11: weight-gradient fan; 12: main chain
+constexpr int kAuxMain = 12;
+constexpr int kAuxFan0 = 4, kAuxFanN = 8;
+constexpr int kAuxEvents = 128;
 
 struct Aux {
   cudaStream_t s[kAuxStreams];
@@ -29,7 +30,7 @@ inline Aux* aux() {
     int lo = 0, hi = 0;
     if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) { lo = 0; hi = 0; }
     for (int i = 0; i < kAuxStreams; ++i) {
-      const int prio = (i >= 4 && i <= 7) ? lo : (i == 3 ? (hi + lo) / 2 : hi);
+      const int prio = (i >= kAuxFan0 && i < kAuxFan0 + kAuxFanN) ? lo : (i == 3 ? (hi + lo) / 2 : hi);
       if (cudaStreamCreateWithPriority(&a.s[i], cudaStreamNonBlocking, prio) != cudaSuccess) return nullptr;
     }
     for (int i = 0; i < kAuxEvents; ++i)

@@ -116,14 +116,14 @@ inline int linear_bwd_data(int M, int K, int Nn, const float* dy, long long lddy
 // k_zero_period/rem: rows r with r % period == rem are skipped (shifted recurrent operands).
 inline int linear_bwd_weight(int Nn, int K, int R, const float* dy, long long lddy, const float* x, long long ldx,
                              float* dw, long long lddw, cudaStream_t st, int k_zero_period = 0, int k_zero_rem = 0,
-                             int x_row_shift = 0) {
+                             int x_row_shift = 0, int accumulate = 0) {
   GemmParams p{};
   p.M = Nn; p.U = K; p.G = 1; p.nseg = 1;
   GemmSeg s{};
   s.a = dy; s.lda = lddy; s.a_trans = 1; s.w[0] = x; s.ldw = ldx; s.w_trans = 1; s.K = R;
   s.k_zero_period = k_zero_period; s.k_zero_rem = k_zero_rem; s.w_row_shift = x_row_shift;
   p.seg[0] = s;
-  p.epi.c[0] = dw; p.epi.ldc = lddw; p.epi.scale = 1.0f; p.epi.free_order = 1;
+  p.epi.c[0] = dw; p.epi.ldc = lddw; p.epi.scale = 1.0f; p.epi.free_order = 1; p.epi.accumulate = accumulate;
   return launch_gemm<EPI_PLAIN>(p, st);
 }
 inline int colsum(long long rows, int cols, const float* x, long long ld, float* out, cudaStream_t st, int accumulate = 0) {

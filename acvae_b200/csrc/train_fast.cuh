@@ -311,22 +311,22 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   }
   // prior batched remainders (after the prior chain: at once in the launch-per-step schedule, after the merged
   // decoder+prior kernel in chain mode)
-  cudaEvent_t ev_prior_acc = ax->ev();      // recorded on sp once the prior's dPp / dmem are complete
+  cudaEvent_t ev_dec_mem = ax->ev();        // recorded on sx once the decoder's half of the memory backward is complete
   auto prior_remainders = [&]() -> int {
     // weight / bias gradients that need only the chain's dg_p / dml_p: fanned over four streams so that they fill
     // the SMs the decoder's persistent kernel leaves free instead of queueing behind the attention backward
     {
-      cudaStream_t f[4] = {ax->s[4], ax->s[5], ax->s[6], ax->s[7]};
+      cudaStream_t* f = &ax->s[kAuxFan0];
       TcThroughputScope throughput(fan_min_kblk());
-      for (int i = 0; i < 4; ++i) ACVAE_TRY(stream_dep(sp, f[i], ax));
+      for (int i = 0; i < 6; ++i) ACVAE_TRY(stream_dep(sp, f[i], ax));
       ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.xp, E, gw.p_wih, 3 * E, f[0]));
       ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.ctx_p, E, gw.p_wih + E, 3 * E, f[1]));
       ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, io.p_z - E, E, gw.p_wih + 2 * E, 3 * E, f[2], T, 0, -1));
       ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.h_p - E, E, gw.p_whh, E, f[3], T, 0, -1));
-      ACVAE_TRY(linear_bwd_weight(2 * E, E, NT, ws.dml_p, 2 * E, ws.h_p, E, gw.p_head_w, E, f[0]));
-      ACVAE_TRY(colsum(NT, 4 * E, ws.dg_p, 4 * E, gw.p_bih, f[1]));
-      ACVAE_CHECK(cudaMemcpyAsync(gw.p_bhh, gw.p_bih, sizeof(float) * 4 * E, cudaMemcpyDeviceToDevice, f[1]));
-      ACVAE_TRY(colsum(NT, 2 * E, ws.dml_p, 2 * E, gw.p_head_b, f[2]));
+      ACVAE_TRY(linear_bwd_weight(2 * E, E, NT, ws.dml_p, 2 * E, ws.h_p, E, gw.p_head_w, E, f[4]));
+      ACVAE_TRY(colsum(NT, 4 * E, ws.dg_p, 4 * E, gw.p_bih, f[5]));
+      ACVAE_CHECK(cudaMemcpyAsync(gw.p_bhh, gw.p_bih, sizeof(float) * 4 * E, cudaMemcpyDeviceToDevice, f[5]));
+      ACVAE_TRY(colsum(NT, 2 * E, ws.dml_p, 2 * E, gw.p_head_b, f[5]));
     }
     // critical first: d ctx -> attention backward -> per-clip accumulation (the memory backward waits for it)
     ACVAE_TRY(linear_bwd_data(NT, E, 4 * E, ws.dg_p, 4 * E, w.p_wih + E, 3 * E, ws.dctx_p, E, sp));
@@ -347,13 +347,18 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
       a.dP = ws.dPp; a.dmem = ws.dmem; a.dmem_accumulate = 0; a.dv = gw.p_attn_v;
       ACVAE_TRY(launch_attn_bwd_acc(a, sp));
     }
-    ACVAE_CHECK(cudaEventRecord(ev_prior_acc, sp));
-    // the rest: embedding / attention-query weight gradients (need dqp_p from the attention backward)
-    ACVAE_TRY(linear_bwd_data(NT, E, 4 * E, ws.dg_p, 4 * E, w.p_wih, 3 * E, ws.dxe_p, E, sp));
-    ACVAE_TRY(linear_bwd_data(NT, E, E, ws.dqp_p, E, w.p_attn_w, 2 * E, ws.dxe_p, E, sp, 1));
-    ACVAE_CHECK(zero(gw.p_emb, (size_t)V * E, sp));
-    ACVAE_TRY(scatter_rows(NT, E, ws.dxe_p, E, ws.words, gw.p_emb, sp));
-    ACVAE_TRY(linear_bwd_weight(E, E, NT, ws.dqp_p, E, ws.xp, E, gw.p_attn_w, 2 * E, sp));
+    // the rest: embedding / attention-query weight gradients (need dqp_p from the attention backward); off sp, which
+    // carries the prior's half of the memory backward next (the step's last dependency chain)
+    {
+      cudaStream_t f3 = ax->s[kAuxFan0 + 7];
+      TcThroughputScope throughput(fan_min_kblk());
+      ACVAE_TRY(stream_dep(sp, f3, ax));
+      ACVAE_TRY(linear_bwd_data(NT, E, 4 * E, ws.dg_p, 4 * E, w.p_wih, 3 * E, ws.dxe_p, E, f3));
+      ACVAE_TRY(linear_bwd_data(NT, E, E, ws.dqp_p, E, w.p_attn_w, 2 * E, ws.dxe_p, E, f3, 1));
+      ACVAE_CHECK(zero(gw.p_emb, (size_t)V * E, f3));
+      ACVAE_TRY(scatter_rows(NT, E, ws.dxe_p, E, ws.words, gw.p_emb, f3));
+      ACVAE_TRY(linear_bwd_weight(E, E, NT, ws.dqp_p, E, ws.xp, E, gw.p_attn_w, 2 * E, f3));
+    }
     return 0;
   };
   if (!merge_bwd) ACVAE_TRY(prior_remainders());
@@ -443,50 +448,64 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     a.dP = ws.dPd; a.dmem = ws.dmem2; a.dmem_accumulate = 0; a.dv = gw.d_attn_v;
     ACVAE_TRY(launch_attn_bwd_acc(a, sx));
   }
-  ACVAE_CHECK(cudaStreamWaitEvent(sx, ev_prior_acc, 0));
-  {
-    // weight / bias gradients of the two memory projections need only dPp / dPd: off the memory-backward chain
-    const int R = N * Te;
-    cudaStream_t f0 = ax->s[4], f1 = ax->s[5];
-    TcThroughputScope throughput(fan_min_kblk());
-    ACVAE_TRY(stream_dep(sx, f0, ax));
-    ACVAE_TRY(stream_dep(sx, f1, ax));
-    ACVAE_TRY(linear_bwd_weight(E, E, R, ws.dPp, E, ws.mem, E, gw.p_attn_w + E, 2 * E, f0));
-    ACVAE_TRY(colsum(R, E, ws.dPp, E, gw.p_attn_b, f0));
-    ACVAE_TRY(linear_bwd_weight(A, E, R, ws.dPd, A, ws.mem, E, gw.d_attn_w + E, 2 * E, f1));
-    ACVAE_TRY(colsum(R, A, ws.dPd, A, gw.d_attn_b, f1));
-  }
-  // memory backward: attention memory halves, ln (vae_model.py:743-744)
+  // Memory backward (attention memory halves, ln: vae_model.py:743-744), split by linearity into the decoder's and the
+  // prior's contribution: d mem = (d mem_dec + dP_d.W_d) + (d mem_prior + dP_p.W_p), and d ln.weight, d ln.bias, d audio are
+  // linear in d mem.  The decoder's half is complete ~150 us before the prior's (whose attention backward is a batched
+  // kernel AFTER the chain), so the step's last dependency chain is one accumulating pass over the prior's half instead
+  // of the whole memory backward.
   {
     const int R = N * Te;
-    ACVAE_LAUNCH(add_inplace_kernel, grid1d((long long)R * E), 256, 0, sx, (long long)R * E, ws.dmem, (const float*)ws.dmem2);
-    ACVAE_TRY(linear_bwd_data(R, E, E, ws.dPp, E, w.p_attn_w + E, 2 * E, ws.dmem, E, sx, 1));
-    ACVAE_TRY(linear_bwd_data(R, E, A, ws.dPd, A, w.d_attn_w + E, 2 * E, ws.dmem, E, sx, 1));
+    {
+      cudaStream_t f1 = ax->s[kAuxFan0 + 6];
+      TcThroughputScope throughput(fan_min_kblk());
+      ACVAE_TRY(stream_dep(sx, f1, ax));
+      ACVAE_TRY(linear_bwd_weight(A, E, R, ws.dPd, A, ws.mem, E, gw.d_attn_w + E, 2 * E, f1));
+      ACVAE_TRY(colsum(R, A, ws.dPd, A, gw.d_attn_b, f1));
+    }
+    ACVAE_TRY(linear_bwd_data(R, E, A, ws.dPd, A, w.d_attn_w + E, 2 * E, ws.dmem2, E, sx, 1));
     if (w.ln_w) {
-      if (d_audio) ACVAE_TRY(linear_bwd_data(R, d.Eenc, E, ws.dmem, E, w.ln_w, d.Eenc, d_audio, d.Eenc, sx));
-      ACVAE_TRY(linear_bwd_weight(E, d.Eenc, R, ws.dmem, E, io.audio_embeds, d.Eenc, gw.ln_w, d.Eenc, sx));
-      ACVAE_TRY(colsum(R, E, ws.dmem, E, gw.ln_b, sx));
+      if (d_audio) ACVAE_TRY(linear_bwd_data(R, d.Eenc, E, ws.dmem2, E, w.ln_w, d.Eenc, d_audio, d.Eenc, sx));
+      ACVAE_TRY(linear_bwd_weight(E, d.Eenc, R, ws.dmem2, E, io.audio_embeds, d.Eenc, gw.ln_w, d.Eenc, sx));
+      ACVAE_TRY(colsum(R, E, ws.dmem2, E, gw.ln_b, sx));
     } else if (d_audio) {
-      ACVAE_CHECK(cudaMemcpyAsync(d_audio, ws.dmem, sizeof(float) * (size_t)R * E, cudaMemcpyDeviceToDevice, sx));
+      ACVAE_CHECK(cudaMemcpyAsync(d_audio, ws.dmem2, sizeof(float) * (size_t)R * E, cudaMemcpyDeviceToDevice, sx));
+    }
+    ACVAE_CHECK(cudaEventRecord(ev_dec_mem, sx));
+    // the prior's half, on its own stream behind its attention accumulation
+    {
+      cudaStream_t f0 = ax->s[kAuxFan0 + 6];
+      TcThroughputScope throughput(fan_min_kblk());
+      ACVAE_TRY(stream_dep(sp, f0, ax));
+      ACVAE_TRY(linear_bwd_weight(E, E, R, ws.dPp, E, ws.mem, E, gw.p_attn_w + E, 2 * E, f0));
+      ACVAE_TRY(colsum(R, E, ws.dPp, E, gw.p_attn_b, f0));
+    }
+    ACVAE_TRY(linear_bwd_data(R, E, E, ws.dPp, E, w.p_attn_w + E, 2 * E, ws.dmem, E, sp, 1));
+    ACVAE_CHECK(cudaStreamWaitEvent(sp, ev_dec_mem, 0));
+    if (w.ln_w) {
+      if (d_audio) ACVAE_TRY(linear_bwd_data(R, d.Eenc, E, ws.dmem, E, w.ln_w, d.Eenc, d_audio, d.Eenc, sp, 1));
+      ACVAE_TRY(linear_bwd_weight(E, d.Eenc, R, ws.dmem, E, io.audio_embeds, d.Eenc, gw.ln_w, d.Eenc, sp, 0, 0, 0, 1));
+      ACVAE_TRY(colsum(R, E, ws.dmem, E, gw.ln_b, sp, 1));
+    } else if (d_audio) {
+      ACVAE_LAUNCH(add_inplace_kernel, grid1d((long long)R * E), 256, 0, sp, (long long)R * E, d_audio, (const float*)ws.dmem);
     }
   }
   // decoder embedding / weight / bias gradients: independent of each other and of the memory backward, so they fan
   // out over four more streams (each GEMM is a ~10 us launch of a few dozen CTAs; in one stream they serialise)
   {
-    cudaStream_t f[4] = {ax->s[4], ax->s[5], ax->s[6], ax->s[7]};
+    cudaStream_t* f = &ax->s[kAuxFan0];
     TcThroughputScope throughput(fan_min_kblk());
-    for (int i = 0; i < 4; ++i) ACVAE_TRY(stream_dep(st, f[i], ax));
+    for (int i = 0; i < 6; ++i) ACVAE_TRY(stream_dep(st, f[i], ax));
     ACVAE_TRY(linear_bwd_data(NT, E, 3 * E, ws.dgi_d, 3 * E, w.d_wih, 3 * E, ws.dxe_d, E, f[0]));
     ACVAE_CHECK(zero(gw.d_emb, (size_t)V * E, f[0]));
     ACVAE_TRY(scatter_rows(NT, E, ws.dxe_d, E, ws.words, gw.d_emb, f[0]));
     ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_d, 3 * E, ws.xd, E, gw.d_wih, 3 * E, f[1]));
     ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_d, 3 * E, ws.ctx_d, E, gw.d_wih + E, 3 * E, f[2]));
     ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_d, 3 * E, io.q_z, E, gw.d_wih + 2 * E, 3 * E, f[3]));
-    ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgh_d, 3 * E, io.outputs - E, E, gw.d_whh, E, f[1], T, 0, -1));
-    ACVAE_TRY(linear_bwd_weight(A, E, NT, ws.dqp_d, A, io.outputs - E, E, gw.d_attn_w, 2 * E, f[2], T, 0, -1));
-    ACVAE_TRY(colsum(NT, 3 * E, ws.dgi_d, 3 * E, gw.d_bih, f[3]));
-    ACVAE_TRY(colsum(NT, 3 * E, ws.dgh_d, 3 * E, gw.d_bhh, f[3]));
-    for (int i = 0; i < 4; ++i) ACVAE_TRY(stream_dep(f[i], sx, ax));
+    ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgh_d, 3 * E, io.outputs - E, E, gw.d_whh, E, f[4], T, 0, -1));
+    ACVAE_TRY(linear_bwd_weight(A, E, NT, ws.dqp_d, A, io.outputs - E, E, gw.d_attn_w, 2 * E, f[5], T, 0, -1));
+    ACVAE_TRY(colsum(NT, 3 * E, ws.dgi_d, 3 * E, gw.d_bih, f[5]));
+    ACVAE_TRY(colsum(NT, 3 * E, ws.dgh_d, 3 * E, gw.d_bhh, f[4]));
+    for (int i = 0; i < kAuxFanN; ++i) ACVAE_TRY(stream_dep(f[i], sx, ax));
   }
 
   // ================= posterior backward (main + one side stream per direction) ==============================
