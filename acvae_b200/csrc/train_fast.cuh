@@ -573,20 +573,38 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
       p.epi.y2 = carry[dir];
       ACVAE_TRY(launch_gemm<EPI_GRU_BWD>(p, s_));
     }
-    ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_q[dir], 3 * E, ws.xq, E, gw.q_wih[dir], E, s_));
-    ACVAE_TRY(colsum(NT, 3 * E, ws.dgi_q[dir], 3 * E, gw.q_bih[dir], s_));
-    ACVAE_TRY(colsum(NT, 3 * E, ws.dgh_q[dir], 3 * E, gw.q_bhh[dir], s_));
+    // weight / bias gradients of this direction: in chain mode each on its own fan stream (nothing but the embedding
+    // gradient below is left on the critical stream after the last chain), otherwise behind the direction's BPTT
+    cudaStream_t* f = &ax->s[kAuxFan0];
+    cudaStream_t s_wih = chain ? f[dir * 3] : s_, s_whh = chain ? f[dir * 3 + 1] : s_, s_b = chain ? f[dir * 3 + 2] : s_;
+    if (chain)
+      for (int i = 0; i < 3; ++i) ACVAE_TRY(stream_dep(sq0, f[dir * 3 + i], ax));
+    ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_q[dir], 3 * E, ws.xq, E, gw.q_wih[dir], E, s_wih));
+    ACVAE_TRY(colsum(NT, 3 * E, ws.dgi_q[dir], 3 * E, gw.q_bih[dir], s_b));
+    ACVAE_TRY(colsum(NT, 3 * E, ws.dgh_q[dir], 3 * E, gw.q_bhh[dir], s_b));
     if (dir == 0)
-      ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgh_q[0], 3 * E, ws.ho - 2 * E, 2 * E, gw.q_whh[0], E, s_, T, 0, -1));
+      ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgh_q[0], 3 * E, ws.ho - 2 * E, 2 * E, gw.q_whh[0], E, s_whh, T, 0, -1));
     else
-      ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgh_q[1], 3 * E, ws.ho + 2 * E + E, 2 * E, gw.q_whh[1], E, s_, T, T - 1, 1));
+      ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgh_q[1], 3 * E, ws.ho + 2 * E + E, 2 * E, gw.q_whh[1], E, s_whh, T, T - 1, 1));
   }
   ACVAE_TRY(stream_dep(sq0, st, ax));
   ACVAE_TRY(stream_dep(sq1, st, ax));
-  ACVAE_TRY(linear_bwd_data(NT, E, 3 * E, ws.dgi_q[0], 3 * E, w.q_wih[0], E, ws.dxq, E, st, 0));
-  ACVAE_TRY(linear_bwd_data(NT, E, 3 * E, ws.dgi_q[1], 3 * E, w.q_wih[1], E, ws.dxq, E, st, 1));
+  {
+    // d x_q = d gi_fwd . W_ih_fwd + d gi_bwd . W_ih_bwd as ONE two-segment contraction (K = 3E + 3E)
+    GemmParams g{};
+    g.M = NT; g.U = E; g.G = 1; g.nseg = 2;
+    for (int dir = 0; dir < 2; ++dir) {
+      GemmSeg sg{};
+      sg.a = ws.dgi_q[dir]; sg.lda = 3 * E; sg.w[0] = w.q_wih[dir]; sg.ldw = E; sg.w_trans = 1; sg.K = 3 * E;
+      g.seg[dir] = sg;
+    }
+    g.epi.c[0] = ws.dxq; g.epi.ldc = E; g.epi.scale = 1.0f; g.epi.free_order = 1;
+    ACVAE_TRY(launch_gemm<EPI_PLAIN>(g, st));
+  }
   ACVAE_CHECK(zero(gw.q_emb, (size_t)V * E, st));
   ACVAE_TRY(scatter_rows(NT, E, ws.dxq, E, ws.qids, gw.q_emb, st));
+  if (chain)
+    for (int i = 0; i < 6; ++i) ACVAE_TRY(stream_dep(ax->s[kAuxFan0 + i], st, ax));
   ACVAE_TRY(stream_dep(sp, st, ax));
   ACVAE_TRY(stream_dep(sx, st, ax));
   ACVAE_TRY(stream_dep(st, st_user, ax));
