@@ -96,24 +96,52 @@ def algorithmic_bytes_train(d, n_params):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML in-process
+    (nvidia_ml_py) when available -- a query costs ~0.1 ms and takes no driver-wide lock for long -- else the
+    `nvidia-smi` command line of the recipe.  Only rank 0 samples: eight ranks each spawning nvidia-smi (which
+    enumerates all eight GPUs) every 0.2 s stalled kernel launches of the timed loop on an 8-GPU box."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:        # NVML ignores CUDA_VISIBLE_DEVICES: address the device by the UUID torch reports for this rank's GPU
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nvml = (pynvml, h)
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        nv, h = self._nvml
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        bit = lambda name: "Active" if (r & getattr(nv, name, 0)) else "Not Active"
+        return [str(sm), str(mx), bit("nvmlClocksThrottleReasonHwSlowdown"), bit("nvmlClocksThrottleReasonHwThermalSlowdown"),
+                bit("nvmlClocksThrottleReasonSwThermalSlowdown"), bit("nvmlClocksThrottleReasonSwPowerCap")]
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                if self._nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.01 if self._nvml is not None else 0.2)
 
     def stop(self):
         self._stop_evt.set()
@@ -125,7 +153,15 @@ class ClockSampler(threading.Thread):
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
                 "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
-                "reasons": reasons}
+                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
+
+
+class _NoSampler:
+    def start(self):
+        pass
+
+    def stop(self):
+        return None
 
 
 def make_host_batches(d, n, seed0):
@@ -292,7 +328,7 @@ def run_ours(args):
 
     for i in range(max(args.warmup, 3)):
         load_resident(i); run_step()
-    clocks = ClockSampler(local); clocks.start()
+    clocks = ClockSampler(local) if rank == 0 else _NoSampler(); clocks.start()
     ms_resident = timed(args.steps, load_resident)
 
     # ---- e2e: HOST inputs through the public API, H2D + loss D2H inside the timed region -------
