@@ -281,6 +281,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        torch.set_num_threads(max(1, (os.cpu_count() or 8) // world))     # one node: do not oversubscribe the host cores
         # keep stdout to the ONE JSON line: NCCL prints its version banner / debug log there
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
