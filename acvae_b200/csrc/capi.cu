@@ -318,4 +318,14 @@ int acvae_debug_set_chain_trace(void* device_buffer) {
   return 0;
 }
 
+// Arithmetic of the batched contractions, process-wide: 0 = fp32-grade (3xTF32, default), 1 = single-pass TF32
+// (reduced precision: products with 10-bit mantissas, fp32 accumulation -- the "bf16" tolerance class of BASELINE.json).
+// The recurrent chains, attention and all pointwise arithmetic stay fp32 in both modes.
+int acvae_set_precision(int32_t mode) {
+  ACVAE_REQUIRE(mode == 0 || mode == 1, "precision mode must be 0 (fp32-grade) or 1 (single-pass tf32)");
+  tc_precision_mode() = mode;
+  return 0;
+}
+int acvae_get_precision(void) { return tc_precision_mode(); }
+
 }  // extern "C"

@@ -56,7 +56,11 @@ struct TcParams {
   int nseg;
   TcSeg seg[2];
   long long* trace;    // optional clock64 stamps of CTA (0,0,0) (profiles/ubench_gemm_trace.cu) or NULL
+  int single_pass;     // reduced precision (acvae_set_precision(1)): ONE kind::tf32 MMA per k-step on the raw fp32 words,
+                       // no hi/lo split pass (10-bit mantissa products, fp32 accumulation; within the 2e-2 bf16 tolerance)
 };
+// process-wide arithmetic mode of the batched contractions: 0 = fp32-grade 3xTF32 (default), 1 = single-pass TF32
+inline int& tc_precision_mode() { static int m = 0; return m; }
 // Split-K policy of the calling thread: 0 = default (latency: as many K splits as fill the machine, >= 2 k-blocks
 // each); n > 0 = at least n k-blocks per CTA (throughput: the fixed prologue / epilogue of a CTA, ~3 us, is amortised
 // over more k-blocks -- used for the weight-gradient GEMMs that only fill idle SMs next to the persistent chains).
@@ -299,16 +303,23 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
         const uint64_t dbl = dbh + (kTcTileBytes >> 4);
         const uint32_t tmem_c = tmem_d + (uint32_t)cb * kTcBN;
         const uint32_t as = a_step[s], bs = b_step[s], id = idesc[s];
-        // small terms first, the dominant hi*hi product last
-        if (in_chunk == 0) tc_mma_tf32_c<0>(tmem_c, dal, dbh, id);
-        else tc_mma_tf32_c<1>(tmem_c, dal, dbh, id);
-        tc_mma_tf32_c<1>(tmem_c, dah, dbl, id);
-        tc_mma_tf32_c<1>(tmem_c, dah, dbh, id);
+        if (tp.single_pass) {
+          if (in_chunk == 0) tc_mma_tf32_c<0>(tmem_c, dah, dbh, id);
+          else tc_mma_tf32_c<1>(tmem_c, dah, dbh, id);
 #pragma unroll
-        for (int j = 1; j < kTcBK / 8; ++j) {
-          tc_mma_tf32_c<1>(tmem_c, dal + j * as, dbh + j * bs, id);
-          tc_mma_tf32_c<1>(tmem_c, dah + j * as, dbl + j * bs, id);
-          tc_mma_tf32_c<1>(tmem_c, dah + j * as, dbh + j * bs, id);
+          for (int j = 1; j < kTcBK / 8; ++j) tc_mma_tf32_c<1>(tmem_c, dah + j * as, dbh + j * bs, id);
+        } else {
+          // small terms first, the dominant hi*hi product last
+          if (in_chunk == 0) tc_mma_tf32_c<0>(tmem_c, dal, dbh, id);
+          else tc_mma_tf32_c<1>(tmem_c, dal, dbh, id);
+          tc_mma_tf32_c<1>(tmem_c, dah, dbl, id);
+          tc_mma_tf32_c<1>(tmem_c, dah, dbh, id);
+#pragma unroll
+          for (int j = 1; j < kTcBK / 8; ++j) {
+            tc_mma_tf32_c<1>(tmem_c, dal + j * as, dbh + j * bs, id);
+            tc_mma_tf32_c<1>(tmem_c, dah + j * as, dbl + j * bs, id);
+            tc_mma_tf32_c<1>(tmem_c, dah + j * as, dbh + j * bs, id);
+          }
         }
         tc_commit(&empty[st]);
         if (in_chunk == kTcChunk - 1 || i == total - 1) tc_commit(&cfull[cb]);
@@ -355,18 +366,26 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
       uint4* loA = hiA + kTcTileBytes / 16;
       uint4* hiB = loA + kTcTileBytes / 16;
       uint4* loB = hiB + kTcTileBytes / 16;
-#pragma unroll
-      for (int q0 = 0; q0 < kTcTileBytes / 16; q0 += 128 * 4) {
-        uint4 x[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) x[u] = hiA[q0 + u * 128 + wt];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          loA[q0 + u * 128 + wt] = make_uint4(tc_lo(x[u].x), tc_lo(x[u].y), tc_lo(x[u].z), tc_lo(x[u].w));
-      }
       const bool kmask = sg.k_zero_period > 0 && sg.b_mn_major;
+      if (!tp.single_pass) {
 #pragma unroll
-      for (int q0 = 0; q0 < kTcTileBytes / 16; q0 += 128 * 4) {
+        for (int q0 = 0; q0 < kTcTileBytes / 16; q0 += 128 * 4) {
+          uint4 x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) x[u] = hiA[q0 + u * 128 + wt];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            loA[q0 + u * 128 + wt] = make_uint4(tc_lo(x[u].x), tc_lo(x[u].y), tc_lo(x[u].z), tc_lo(x[u].w));
+        }
+      }
+      if (tp.single_pass && kmask) {                   // only the masked K rows of B have to be cleared
+        for (int q = wt; q < kTcTileBytes / 16; q += 128) {
+          const int krow = kb + ((q >> 3) & 31);
+          if (krow % sg.k_zero_period == sg.k_zero_rem) hiB[q] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+#pragma unroll
+      for (int q0 = 0; !tp.single_pass && q0 < kTcTileBytes / 16; q0 += 128 * 4) {
         uint4 x[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) x[u] = hiB[q0 + u * 128 + wt];
@@ -469,6 +488,7 @@ inline int try_launch_tc(const GemmParams& p, cudaStream_t st) {
   TcParams tp{};
   tp.nseg = p.nseg;
   tp.trace = tc_trace_ptr();
+  tp.single_pass = tc_precision_mode() == 1;
   CUtensorMap maps[4];
   memset(maps, 0, sizeof(maps));
   for (int s = 0; s < p.nseg; ++s) {

@@ -510,3 +510,17 @@ def diverse_beam_search(dims, weights, audio_embeds, mem_lens, eps_g, beam_size=
                                            _dev(seqs, torch.int64), ws.data_ptr(), ws.numel(), _stream()),
                "acvae_diverse_beam_search")
     return {"seqs": seqs}
+
+
+def set_precision(mode: str) -> None:
+    """Arithmetic of the batched contractions: "fp32" (default; 3xTF32 on the tensor cores, the 1e-4 parity mode) or
+    "tf32" (single-pass TF32 products, fp32 accumulation: the reduced-precision class BASELINE.json calls bf16, 2e-2).
+    Process-wide; CUDA graphs captured before the switch keep the mode they were captured with."""
+    modes = {"fp32": 0, "tf32": 1}
+    if mode not in modes:
+        raise ValueError(f"precision must be one of {sorted(modes)}")
+    _lib.check(_lib.lib().acvae_set_precision(modes[mode]), "acvae_set_precision")
+
+
+def get_precision() -> str:
+    return {0: "fp32", 1: "tf32"}[_lib.lib().acvae_get_precision()]

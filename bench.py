@@ -424,6 +424,39 @@ def run_ours(args):
         dist.all_reduce(ms_s, op=dist.ReduceOp.MAX)
     ms_sample = float(ms_s)
 
+    # ---- the same sampling loop with single-pass TF32 contractions (the reduced-precision class of BASELINE.json), and
+    #      the largest contraction of a decode step ([sequences, 4E] LSTM gates, K = 3E + E) alone in both modes ----
+    import acvae_b200 as models_pkg
+    models_pkg.set_precision("tf32")
+    torch.manual_seed(1234 + rank); sample_once(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); a.record()
+    for _ in range(n_rep):
+        torch.manual_seed(1234 + rank)
+        o_fast = sample_once()
+    b.record(); barrier()
+    ms_f = torch.tensor([a.elapsed_time(b) / n_rep], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_f, op=dist.ReduceOp.MAX)
+    ms_sample_fast = float(ms_f)
+    gemm_modes = {}
+    if rank == 0:
+        Mg, Ng, Kg = (hi - lo) * SAMPLE_K, 4 * d.E, 4 * d.E
+        Ag = torch.randn(Mg, Kg, device=dev); Bg = torch.randn(Ng, Kg, device=dev); Cg = torch.empty(Mg, Ng, device=dev)
+        for mode in ("tf32", "fp32"):
+            models_pkg.set_precision(mode)
+            for _ in range(3):
+                F.gemm(Ag, Bg, False, False, out=Cg)
+            torch.cuda.synchronize()
+            us = []
+            for _ in range(5):
+                flush.fill_(3.0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); F.gemm(Ag, Bg, False, False, out=Cg); e1.record(); torch.cuda.synchronize()
+                us.append(e0.elapsed_time(e1) * 1e3)
+            gemm_modes[mode] = (sum(us) / len(us), 2.0 * Mg * Ng * Kg)
+    models_pkg.set_precision("fp32")
+
     if rank == 0:
         peaks = load_peaks()
         clips = d.N * world
@@ -476,6 +509,13 @@ def run_ours(args):
              "algorithmic_bytes_per_step": int(bytes_step)},
         ]
         roofline_other = chain_entries[1:] + roofline_other
+        for mode, (us_, fl_) in gemm_modes.items():
+            roofline_other.append(
+                {"kernel": f"tc_gemm_kernel<EPI_PLAIN>, sampling LSTM gates [{(hi - lo) * SAMPLE_K} x {4 * d.E}] . [{4 * d.E} x {4 * d.E}], "
+                           + ("3xTF32 (fp32-grade: 3 MMAs per product)" if mode == "fp32" else "single-pass TF32 (acvae_set_precision(1))"),
+                 "bound": "tensor", "achieved": round(fl_ / (us_ * 1e-6) / 1e12, 1), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                 "frac": round(fl_ / (us_ * 1e-6) / 1e12 / peaks["bf16_tflops"], 4), "us_per_launch": round(us_, 1),
+                 "flops_per_launch": int(fl_), "note": "peak is the measured bf16 figure; dense TF32 peak is half of it"})
         if attn_us:
             ab = 4.0 * d.N * st_prep.T * d.Te * 2 * d.E          # every query row streams its clip's P and mem
             roofline_other.append(
@@ -506,6 +546,10 @@ def run_ours(args):
                          "max_length": SAMPLE_LEN, "method": "sample", "launches": int(sample_launches),
                          "n_steps_executed": int(o["n_steps"]),
                          "ms_per_decode_step": round(ms_sample / max(1, int(o["n_steps"])), 4)},
+            "sampling_tf32": {"metric": "sampled_captions_per_s", "value": round(SAMPLE_CLIPS * SAMPLE_K / (ms_sample_fast * 1e-3), 1),
+                              "unit": "captions/s", "ms": round(ms_sample_fast, 3), "n_steps_executed": int(o_fast["n_steps"]),
+                              "ms_per_decode_step": round(ms_sample_fast / max(1, int(o_fast["n_steps"])), 4),
+                              "precision": "single-pass TF32 contractions (acvae_b200.set_precision('tf32')), rest fp32"},
             "final_loss": host_losses[-1] if host_losses else None,
         }
         if world == 1 and not args.no_cpu_baseline:

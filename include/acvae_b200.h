@@ -263,6 +263,14 @@ int acvae_diverse_beam_search(const acvae_dims *d, const acvae_weights *w, const
 /* profiling only: [T][16] int64 device buffer for clock64 stamps of the decoder forward chain (CTA 0), or NULL */
 int acvae_debug_set_chain_trace(void *device_buffer);
 
+/* ---- arithmetic mode of the batched contractions (process-wide) ------------------------------
+ * 0 (default): fp32-grade products on the tensor cores (three kind::tf32 MMAs per k-step, chunked fp32
+ * accumulation) -- the mode of the 1e-4 parity tests.  1: single-pass TF32 (one MMA per k-step, no operand split):
+ * the reduced-precision class BASELINE.json quotes as "bf16" (2e-2).  Recurrent chains, attention and pointwise
+ * arithmetic are fp32 in both modes. */
+int acvae_set_precision(int32_t mode);
+int acvae_get_precision(void);
+
 #ifdef __cplusplus
 }
 #endif

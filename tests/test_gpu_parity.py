@@ -425,3 +425,44 @@ def test_prepare_batch_single_copy_matches_runner_packing():
     assert torch.equal(st.caps_ids.cpu(), torch.from_numpy(b2["caps"]).to(torch.int32))
     with pytest.raises(RuntimeError):
         m.prepare_batch(caps, b["cap_lens"][::-1].copy(), "cuda")
+
+
+@pytest.fixture
+def tf32_mode():
+    """Single-pass TF32 products for the batched contractions (process-wide switch), restored afterwards."""
+    import acvae_b200 as models
+    models.set_precision("tf32")
+    try:
+        yield
+    finally:
+        models.set_precision("fp32")
+
+
+def test_reduced_precision_gemm_error_class(tf32_mode):
+    """acvae_set_precision(1): one kind::tf32 MMA per k-step.  Error vs fp64 is in the 1e-3 class (10-bit mantissas),
+    far above the 3xTF32 mode's 5e-7 and far inside the 2e-2 tolerance BASELINE.json gives reduced precision."""
+    _require_cuda()
+    from acvae_b200 import functional as F
+    import acvae_b200 as models
+    torch.manual_seed(0)
+    A = torch.randn(1000, 512, device="cuda"); B = torch.randn(384, 512, device="cuda")
+    ref = (A.double() @ B.double().t())
+    C, used = F.gemm(A, B, False, False)
+    assert used
+    err_fast = float((C.double() - ref).norm() / ref.norm())
+    models.set_precision("fp32")
+    C2, _ = F.gemm(A, B, False, False)
+    err_full = float((C2.double() - ref).norm() / ref.norm())
+    assert err_full < 5e-6 < err_fast < 2e-3, (err_full, err_fast)
+
+
+def test_reduced_precision_train_step_within_bf16_tolerance(tf32_mode):
+    """BASELINE.json: loss, KL and gradients within 2e-2 relative in reduced precision (CFG1 shape, vs oracle autograd)."""
+    _require_cuda()
+    d = synthetic.CFG1
+    r = harness.run_cuda_train(d, 11)
+    o = harness.run_oracle_train(d, 11)
+    for k in ("loss", "ce", "kl", "global"):
+        a, b = float(r["terms"][k]), float(o["terms"][k])
+        assert abs(a - b) <= 2e-2 * max(1.0, abs(b)), (k, a, b)
+    assert harness.max_grad_rel_err(r["grads"], o["grads"]) < 2e-2
