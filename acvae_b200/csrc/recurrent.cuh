@@ -6,8 +6,8 @@
 //   * the weight matrix is COLUMN-partitioned: CTA b owns hidden units {2b, 2b+1} (all their gates) and keeps
 //     that weight slice resident in shared memory for all T steps -- weights are read from L2 exactly once;
 //   * per step a CTA reads the [N, K] state rows written by all CTAs in the previous phase (L2, ld.cg),
-//     computes its columns for all N rows (8-way K split inside a row group, shuffle-reduced), applies the
-//     cell arithmetic in registers and writes its units;
+//     computes its columns for all N rows (a warp owns four rows, a lane a 1/32 slice of K; reduce-scatter over the
+//     warp), applies the cell arithmetic in registers and writes its units;
 //   * phases are separated by a grid barrier (one global atomic counter);
 //   * per-unit carries (dh*z, dc*f, ...) never leave registers: the unit partition is the same in every phase.
 // The decoder chains add a per-clip phase: CTA c keeps clip c's projected memory P_d[c] and memory mem[c]
@@ -23,7 +23,7 @@ namespace acvae {
 
 constexpr int kChainE = 256;                 // E == H == Hq == A handled by the persistent kernels
 constexpr int kChainCtas = kChainE / 2;      // 2 hidden units per CTA
-constexpr int kChainThreads = 256;           // thread = (row n = tid / 8, K-slice kp = tid % 8)
+constexpr int kChainThreads = 256;           // 8 warps: warp = rows 4w .. 4w+3, lane = K slice (quad mapping below)
 constexpr int kChainMaxN = kChainThreads / 8;
 
 struct GridBar {
@@ -66,49 +66,6 @@ __device__ __forceinline__ float ldcg1(const float* p) {
   asm volatile("ld.global.cg.f32 %0, [%1];\n" : "=f"(v) : "l"(p));
   return v;
 }
-// src: one global row (K floats, 16-byte aligned).  Lane kp of the 8-lane row group takes the float4s
-// {kp, kp+8, ...}: a row group reads 128 contiguous bytes per iteration.
-template <int K>
-__device__ __forceinline__ void rowload(const float* __restrict__ src, int kp, float4 (&a)[K / 32]) {
-#pragma unroll
-  for (int i = 0; i < K / 32; ++i) a[i] = ldcg4(src + (i * 8 + kp) * 4);
-}
-// acc[c] += sum over this lane's K slice of a[k] * W[c][k];  W: shared [COLS][ldw] (conflict-free: 8 lanes read
-// 128 contiguous bytes, the 4 row groups of a warp read the same addresses).
-template <int COLS, int K>
-__device__ __forceinline__ void rowfma(const float4 (&a)[K / 32], const float* W, int ldw, int kp, float (&acc)[COLS]) {
-#pragma unroll
-  for (int i = 0; i < K / 32; ++i) {
-#pragma unroll
-    for (int c = 0; c < COLS; ++c) {
-      const float4 w = *(reinterpret_cast<const float4*>(W + c * ldw) + i * 8 + kp);
-      acc[c] = fmaf(a[i].x, w.x, acc[c]);
-      acc[c] = fmaf(a[i].y, w.y, acc[c]);
-      acc[c] = fmaf(a[i].z, w.z, acc[c]);
-      acc[c] = fmaf(a[i].w, w.w, acc[c]);
-    }
-  }
-}
-// load block | __syncwarp (a scheduling fence for ptxas: every load is issued before the first FMA) | FMA block
-template <int COLS, int K>
-__device__ __forceinline__ void rowdot(bool row, const float* __restrict__ src, const float* W, int ldw, int kp, float (&acc)[COLS]) {
-  float4 a[K / 32];
-  if (row) rowload<K>(src, kp, a);
-  __syncwarp();
-  if (row) rowfma<COLS, K>(a, W, ldw, kp, acc);
-}
-// butterfly over the 8 lanes of a row group: every lane ends with the full sum
-template <int COLS>
-__device__ __forceinline__ void reduce8(float (&acc)[COLS]) {
-#pragma unroll
-  for (int c = 0; c < COLS; ++c) {
-    acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 4);
-    acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
-    acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
-  }
-}
-
-
 // ---- "quad" mapping (4 rows per warp, 32-way K split) ---------------------------------------------------------
 // A warp = one group of four batch rows; lane = K slice (float4s {lane, lane+32, ...} of a row).  Every weight word
 // a lane reads from shared memory is used for four rows from registers: the row-per-8-lanes mapping above re-reads
