@@ -77,3 +77,19 @@ def test_dense_label_smoothing_matches_oracle():
     a = LabelSmoothingLoss(13, smoothing=0.1, device="cpu")(x, y)
     b = oracle.label_smoothing_loss(x, y, 13, 0.1)
     assert torch.allclose(a, b, atol=1e-6)
+
+
+def test_bench_reference_arm_runs_without_gpu():
+    """`bench.py --impl reference` (the reference algorithm's CPU path, oracle port) prints one JSON line with the
+    contract's keys and needs no GPU."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "train_clips_per_s" and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
