@@ -20,6 +20,7 @@ from .models import (CaptionModel, Hybrid_VAEModel, PosteriorRNN, PosteriorRNN_h
 from .train_util import CrossEntropyLoss, FusedVAELoss, LabelSmoothingLoss, Normal_kl_loss  # noqa: F401
 from .lazy import LazyLogits  # noqa: F401
 from .optim import FusedClipAdam  # noqa: F401
+from .metrics import diversity_stats  # noqa: F401
 from .functional import get_precision, set_precision  # noqa: F401
 
 # the reference resolves decoders as getattr(models.decoder, name) and posteriors/priors as

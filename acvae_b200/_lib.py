@@ -93,6 +93,7 @@ SYMBOLS = {
     "acvae_diverse_beam_search": (C.c_int, [_DP, _WP, _vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "acvae_loss_combine_fwd": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp]),
     "acvae_loss_combine_bwd": (C.c_int, [_i64, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
+    "acvae_diversity_stats": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "acvae_debug_set_chain_trace": (C.c_int, [_vp]),
     "acvae_set_precision": (C.c_int, [_i32]),
     "acvae_get_precision": (C.c_int, []),

@@ -328,4 +328,14 @@ int acvae_set_precision(int32_t mode) {
 }
 int acvae_get_precision(void) { return tc_precision_mode(); }
 
+int acvae_diversity_stats(int32_t clips, int32_t K, int32_t L, int32_t V, const int64_t* seqs, int32_t start_idx, int32_t end_idx,
+                          double* div1, double* div2, int32_t* vocab_flags, void* stream) {
+  ACVAE_REQUIRE(clips > 0 && K > 0 && L > 0 && V > 0 && seqs && div1 && div2, "bad argument");
+  const size_t smem = sizeof(int) * 2 * (size_t)K * L;
+  ACVAE_REQUIRE(smem <= 48 * 1024, "K * L too large for the per-clip shared-memory table (<= 6144 tokens)");
+  ACVAE_LAUNCH(diversity_stats_kernel, clips, 256, smem, (cudaStream_t)stream, K, L, V, start_idx, end_idx, (const long long*)seqs,
+               div1, div2, vocab_flags);
+  return 0;
+}
+
 }  // extern "C"

@@ -637,4 +637,54 @@ inline int diverse_beam_search(const acvae_dims& d0, const acvae_weights& w, con
   return 0;
 }
 
+// ================================ diversity statistics ===========================================
+// Div-1 / Div-2 of the K captions decoded per clip (utils/div_utils.py:11-29: distinct n-grams over the clip's captions
+// divided by its token count) and the presence flags behind the global distinct-word count gDiv-1 (:31-44, n = 1),
+// straight from the id tensor the sampling loop leaves on the device.  A caption is the ids up to the first <end>,
+// <start> skipped (runners/base_runner.py:146-157).  One CTA per clip; the K*L tokens live in shared memory and an
+// n-gram counts when no earlier position of the clip holds the same one (quadratic in K*L <= a few hundred).
+__global__ void __launch_bounds__(256) diversity_stats_kernel(int K, int L, int V, int start_idx, int end_idx,
+                                                             const long long* __restrict__ seqs, double* __restrict__ div1,
+                                                             double* __restrict__ div2, int* __restrict__ vocab_flags) {
+  extern __shared__ int dsm_i[];
+  int* tok = dsm_i;                 // [K*L] compacted tokens of the clip, caption after caption
+  int* cap = tok + K * L;           // [K*L] caption index of each compacted token
+  __shared__ int s_n, s_uni, s_bi;
+  const int clip = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) {
+    int n = 0;
+    for (int k = 0; k < K; ++k)
+      for (int l = 0; l < L; ++l) {
+        const int w = (int)seqs[((long long)clip * K + k) * L + l];
+        if (w == end_idx) break;
+        if (w == start_idx) continue;
+        tok[n] = w; cap[n] = k; ++n;
+      }
+    s_n = n; s_uni = 0; s_bi = 0;
+  }
+  __syncthreads();
+  const int n = s_n;
+  int uni = 0, bi = 0;
+  for (int p = tid; p < n; p += blockDim.x) {
+    const int w = tok[p];
+    if (vocab_flags && w >= 0 && w < V) vocab_flags[w] = 1;
+    bool first = true;
+    for (int q = 0; q < p && first; ++q) first = tok[q] != w;
+    uni += first;
+    if (p + 1 < n && cap[p + 1] == cap[p]) {          // a bigram never crosses captions
+      const int w2 = tok[p + 1];
+      bool f2 = true;
+      for (int q = 0; q < p && f2; ++q) f2 = !(tok[q] == w && q + 1 < n && cap[q + 1] == cap[q] && tok[q + 1] == w2);
+      bi += f2;
+    }
+  }
+  atomicAdd(&s_uni, uni);
+  atomicAdd(&s_bi, bi);
+  __syncthreads();
+  if (tid == 0) {
+    div1[clip] = (double)s_uni / (1e-6 + (double)n);
+    div2[clip] = (double)s_bi / (1e-6 + (double)n);
+  }
+}
+
 }  // namespace acvae

@@ -260,6 +260,15 @@ int acvae_diverse_beam_search(const acvae_dims *d, const acvae_weights *w, const
                               float diversity_lambda, float temperature, int32_t group_nbest, int32_t start_idx,
                               int32_t end_idx, int64_t *seqs, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- diversity statistics of the decoded captions -------------------------
+ * Replaces utils/div_utils.py:11-44 (compute_div_n for n = 1, 2; compute_global_div_n for n = 1) as used by
+ * utils/diverse_mutil.py:25-29, on the id tensor seqs [clips, K, L] of the sampling loop (a caption = ids up to the
+ * first <end>, <start> skipped: runners/base_runner.py:146-157).  div1 / div2 [clips] (fp64, as numpy computes them):
+ * distinct uni- / bigrams of the clip's K captions over its token count; vocab_flags [V] (may be NULL; zeroed by the
+ * caller): set to 1 for every word that occurs -- their sum is gDiv-1. */
+int acvae_diversity_stats(int32_t clips, int32_t K, int32_t L, int32_t V, const int64_t *seqs, int32_t start_idx,
+                          int32_t end_idx, double *div1, double *div2, int32_t *vocab_flags, void *stream);
+
 /* profiling only: [T][16] int64 device buffer for clock64 stamps of the decoder forward chain (CTA 0), or NULL */
 int acvae_debug_set_chain_trace(void *device_buffer);
 

@@ -323,9 +323,41 @@ def run_dbs_case(name, d, seed, beam, groups, max_length, lam=0.5, temperature=1
         meta_groups=np.array(groups), meta_lambda=np.array(lam), meta_temperature=np.array(temperature),
         meta_nbest=np.array(int(nbest)), seqs=out["seqs"].numpy())
 
+def run_div_case(name="div_stats", clips=9, K=5, L=12, V=40, seed=3):
+    """Diversity statistics of the reference itself (utils/div_utils.py, imported from /root/reference/utils) on synthetic
+    id sequences rendered as words, against the id-based oracle restatement."""
+    sys.path.insert(0, os.path.join("/root/reference", "utils"))
+    import div_utils as ref_div                      # numpy-only module of the reference
+    import diversity_oracle as dorc
+    rs = np.random.RandomState(seed)
+    seqs = rs.randint(3, V, size=(clips, K, L)).astype(np.int64)
+    for c in range(clips):                           # ragged ends, an empty caption, a <start> inside, repeated captions
+        for k in range(K):
+            e = rs.randint(0, L + 1)
+            if e < L:
+                seqs[c, k, e:] = 2
+    seqs[0, 0, 0] = 2
+    seqs[1, 1, 0] = 1
+    seqs[2, 2] = seqs[2, 1]
+    def words(row):
+        return " ".join(f"w{t}" for t in dorc.caption_tokens(row))
+    caps = {c: [words(seqs[c, k]) for k in range(K)] for c in range(clips)}
+    d1, a1 = ref_div.compute_div_n(caps, 1)
+    d2, a2 = ref_div.compute_div_n(caps, 2)
+    g1, _ = ref_div.compute_global_div_n(caps, 1)
+    o = dorc.diversity_stats(seqs)
+    assert o["Div1"] == d1 and o["Div2"] == d2 and o["gDiv1"] == g1, (o, d1, d2, g1)
+    assert np.array_equal(o["div1"], a1) and np.array_equal(o["div2"], a2)
+    print(f"[{name}] oracle==reference; Div1={d1:.6f} Div2={d2:.6f} gDiv1={g1}")
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), seqs=seqs, div1=a1, div2=a2, Div1=np.array(d1), Div2=np.array(d2),
+                        gDiv1=np.array(g1), meta_V=np.array(V))
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     T, C0 = synthetic.TINY, synthetic.CFG0
+    if len(sys.argv) > 1 and sys.argv[1] == "div":               # diversity-statistics fixture only
+        run_div_case()
+        sys.exit(0)
     only_dbs = len(sys.argv) > 1 and sys.argv[1] == "dbs"        # add the dbs fixtures without regenerating the rest
     if only_dbs:
         run_dbs_case("tiny_dbs", T, 1, 6, 3, 6, lam=0.5, temperature=1.0, nbest=True)
@@ -357,3 +389,4 @@ if __name__ == "__main__":
     run_dbs_case("tiny_dbs", T, 1, 6, 3, 6, lam=0.5, temperature=1.0, nbest=True)
     run_dbs_case("tiny_dbs_best", T, 2, 4, 2, 6, lam=1.5, temperature=0.7, nbest=False)
     run_dbs_case("cfg0_dbs", C0, 1, 10, 5, 20, lam=0.5, temperature=1.0, nbest=True)
+    run_div_case()

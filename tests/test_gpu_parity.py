@@ -466,3 +466,27 @@ def test_reduced_precision_train_step_within_bf16_tolerance(tf32_mode):
         a, b = float(r["terms"][k]), float(o["terms"][k])
         assert abs(a - b) <= 2e-2 * max(1.0, abs(b)), (k, a, b)
     assert harness.max_grad_rel_err(r["grads"], o["grads"]) < 2e-2
+
+
+def test_diversity_stats_golden_and_oracle():
+    """Div-1 / Div-2 / gDiv-1 (utils/div_utils.py:11-44) on the device: bit-equal (fp64) to the reference's numbers on the
+    committed fixture, and to the oracle on a larger ragged case with empty captions and a single caption per clip."""
+    _require_cuda()
+    import acvae_b200 as models
+    import diversity_oracle as dorc
+    g = harness.load_golden("div_stats")
+    out = models.diversity_stats(torch.from_numpy(g["seqs"]).cuda(), int(g["meta_V"]))
+    assert np.array_equal(out["div1"].cpu().numpy(), g["div1"]) and np.array_equal(out["div2"].cpu().numpy(), g["div2"])
+    assert out["gDiv1"] == float(g["gDiv1"])
+    assert abs(out["Div1"] - float(g["Div1"])) < 1e-12 and abs(out["Div2"] - float(g["Div2"])) < 1e-12
+    rs = np.random.RandomState(5)
+    for clips, K, L, V in ((64, 10, 20, 4400), (7, 1, 20, 50), (3, 16, 30, 9)):
+        seqs = rs.randint(3, V, size=(clips, K, L)).astype(np.int64)
+        ends = rs.randint(0, L + 1, size=(clips, K))
+        for c in range(clips):
+            for k in range(K):
+                seqs[c, k, ends[c, k]:] = 2
+        o = dorc.diversity_stats(seqs)
+        got = models.diversity_stats(torch.from_numpy(seqs).cuda(), V)
+        assert np.array_equal(got["div1"].cpu().numpy(), o["div1"]) and np.array_equal(got["div2"].cpu().numpy(), o["div2"])
+        assert got["gDiv1"] == o["gDiv1"]

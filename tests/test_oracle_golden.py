@@ -103,3 +103,13 @@ def test_oracle_edge_min_length_and_single_frame():
     assert torch.isfinite(terms["loss"])
     # padded posterior positions see ho = 0 => head = bias
     assert torch.allclose(out["q_means"][-1, 1:], p["qnet.token_mean_log.bias"][:d.E].expand(T - 1, d.E), atol=1e-6)
+
+
+def test_oracle_diversity_stats_golden():
+    """The id-based restatement of utils/div_utils.py reproduces the reference's Div-1 / Div-2 / gDiv-1 (fixture made by
+    `make_golden.py div` from the reference functions themselves)."""
+    import diversity_oracle as dorc
+    g = harness.load_golden("div_stats")
+    o = dorc.diversity_stats(g["seqs"])
+    assert np.array_equal(o["div1"], g["div1"]) and np.array_equal(o["div2"], g["div2"])
+    assert o["Div1"] == float(g["Div1"]) and o["Div2"] == float(g["Div2"]) and o["gDiv1"] == float(g["gDiv1"])
