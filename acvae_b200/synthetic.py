@@ -133,7 +133,7 @@ def make_batch(d: Dims, seed: int = 1, min_cap_len: Optional[int] = None,
     mem_lens = rs.randint(lo, Te + 1, size=N).astype(np.int64)
     mem_lens[rs.randint(0, N)] = Te
     out["mem_lens"] = mem_lens
-    lo_c = min_cap_len if min_cap_len is not None else min(8, max(3, L // 2))
+    lo_c = min(L, min_cap_len if min_cap_len is not None else min(8, max(3, L // 2)))
     cap_lens = rs.randint(lo_c, L + 1, size=N).astype(np.int64)
     cap_lens[0] = L
     cap_lens = np.sort(cap_lens)[::-1].copy()

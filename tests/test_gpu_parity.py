@@ -490,3 +490,22 @@ def test_diversity_stats_golden_and_oracle():
         got = models.diversity_stats(torch.from_numpy(seqs).cuda(), V)
         assert np.array_equal(got["div1"].cpu().numpy(), o["div1"]) and np.array_equal(got["div2"].cpu().numpy(), o["div2"])
         assert got["gDiv1"] == o["gDiv1"]
+
+
+@pytest.mark.parametrize("dims", [
+    dict(N=1, Te=1, L=2, E=256, H=256, A=256, Hq=256, V=11, Eenc=48),     # persistent chains at their smallest: one row, one step, one frame
+    dict(N=3, Te=83, L=4, E=256, H=256, A=256, Hq=256, V=29, Eenc=64),      # the largest clip the resident attention holds (Te = 83)
+    dict(N=2, Te=84, L=3, E=256, H=256, A=256, Hq=256, V=29, Eenc=64),      # one frame more: launch-per-step schedule
+    dict(N=33, Te=5, L=3, E=256, H=256, A=256, Hq=256, V=17, Eenc=32),      # one row more than the chains take
+    dict(N=1, Te=1, L=2, E=16, H=16, A=16, Hq=16, V=5, Eenc=20),            # the same extremes on the general path
+])
+def test_train_extreme_shapes_vs_oracle(dims):
+    """Smallest / boundary shapes of both schedules (a hang here would be a grid-barrier protocol bug: the barrier traps
+    instead of spinning forever) against oracle autograd."""
+    _require_cuda()
+    d = synthetic.Dims(**dims)
+    r = harness.run_cuda_train(d, 13)
+    o = harness.run_oracle_train(d, 13)
+    for k in ("loss", "ce", "kl", "global"):
+        assert abs(float(r["terms"][k]) - float(o["terms"][k])) <= TOL * max(1.0, abs(float(o["terms"][k]))), k
+    assert harness.max_grad_rel_err(r["grads"], o["grads"]) < 2 * TOL
