@@ -338,4 +338,12 @@ int acvae_diversity_stats(int32_t clips, int32_t K, int32_t L, int32_t V, const 
   return 0;
 }
 
+// Optional: a CUDA event the caller records after the host-to-device copy of the next step's audio embeddings (on any
+// stream).  acvae_train_fwd (hoisted schedule) then waits for it only where the audio is first read, so the copy overlaps
+// the posterior chain; NULL (default) restores plain stream order.  The event must outlive every captured graph.
+int acvae_set_input_event(void* cuda_event) {
+  input_ready_event() = static_cast<cudaEvent_t>(cuda_event);
+  return 0;
+}
+
 }  // extern "C"

@@ -40,6 +40,12 @@ inline Aux* aux() {
   return &a;
 }
 
+// Optional "inputs ready" event of the caller (acvae_set_input_event): recorded by the caller on whatever stream carries
+// the host-to-device copy of the step's audio embeddings.  The forward waits for it right before the first kernel that
+// reads them, with cudaEventWaitExternal -- legal inside stream capture, where it becomes an external event-wait node --
+// so the copy runs under the posterior chain (which does not read the audio) instead of in front of the step.
+inline cudaEvent_t& input_ready_event() { static cudaEvent_t e = nullptr; return e; }
+
 // `to` waits for everything enqueued so far on `from`
 inline int stream_dep(cudaStream_t from, cudaStream_t to, Aux* a) {
   cudaEvent_t e = a->ev();

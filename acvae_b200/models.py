@@ -249,16 +249,28 @@ class _FusedVAEBase(CaptionModel):
         on the host into ONE pinned int32 staging buffer and crosses PCIe in ONE asynchronous copy
         (ids [N*L] | lens [N] | targets [M]); `out` (a PreparedBatch made by an earlier call with the same caption-length
         profile) receives the copy in place, so a captured CUDA graph keeps reading the same addresses."""
-        caps_np = caps.detach().cpu().numpy() if torch.is_tensor(caps) else np.asarray(caps)
-        lens = np.asarray(cap_lens).astype(np.int64)
+        caps_np = caps.detach().cpu().numpy() if torch.is_tensor(caps) else np.asarray(caps)   # the collate_fn's CPU output
+        lens = np.asarray(cap_lens)
         if caps_np.ndim != 2 or lens.shape != (caps_np.shape[0],):
             raise ValueError("caps must be [N,L] and cap_lens [N]")
-        if np.any(np.diff(lens) > 0):
-            raise RuntimeError("`lengths` array must be sorted in decreasing order when `enforce_sorted` is True.")
         N, L = caps_np.shape
-        T = int(lens.max()) - 1
-        lens1 = lens - 1
-        M = int(lens1.sum())
+        # everything that depends only on the length profile is cached (a training run sees few distinct profiles)
+        key = (L, lens.tobytes())
+        prof = getattr(self, "_len_profiles", None)
+        if prof is None:
+            prof = self._len_profiles = {}
+        ent = prof.get(key)
+        if ent is None:
+            lens64 = lens.astype(np.int64)
+            if np.any(np.diff(lens64) > 0):
+                raise RuntimeError("`lengths` array must be sorted in decreasing order when `enforce_sorted` is True.")
+            T_ = int(lens64.max()) - 1
+            lens1 = lens64 - 1
+            mask_ = lens1[None, :] > np.arange(T_)[:, None]           # time-major packing order of sorted lengths
+            if len(prof) > 256:
+                prof.clear()
+            ent = prof[key] = (T_, int(lens1.sum()), mask_, lens64.astype(np.int32))
+        T, M, mask, lens32 = ent
         total = N * L + N + M
         ring = getattr(self, "_stage_ring", None)
         if ring is None or ring[0].numel() < total:
@@ -268,8 +280,7 @@ class _FusedVAEBase(CaptionModel):
         self._stage_next = (self._stage_next + 1) % len(ring)
         sn = stage.numpy()
         sn[:N * L] = caps_np.reshape(-1)                              # caps.long() of vae_model.py:827, as int32
-        sn[N * L:N * L + N] = lens
-        mask = lens1[None, :] > np.arange(T)[:, None]                 # time-major packing order of sorted lengths
+        sn[N * L:N * L + N] = lens32
         sn[N * L + N:total] = caps_np[:, 1:T + 1].T[mask]
         if out is not None:
             if out.flat is None or out.flat.numel() != total or out.T != T or tuple(out.caps_ids.shape) != (N, L):

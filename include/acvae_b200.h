@@ -269,6 +269,13 @@ int acvae_diverse_beam_search(const acvae_dims *d, const acvae_weights *w, const
 int acvae_diversity_stats(int32_t clips, int32_t K, int32_t L, int32_t V, const int64_t *seqs, int32_t start_idx,
                           int32_t end_idx, double *div1, double *div2, int32_t *vocab_flags, void *stream);
 
+/* ---- overlapping the input copy --------------------------------------------------------------
+ * `cuda_event` (a cudaEvent_t, or NULL to switch off): recorded by the caller after the host-to-device copy of a step's
+ * audio embeddings, on whatever stream carries it.  acvae_train_fwd waits for it (cudaEventWaitExternal: an external
+ * event-wait node under stream capture) right before the first kernel that reads the audio, so the copy runs under the
+ * posterior chain, which does not.  The caller keeps the usual WAR discipline on the audio buffer. */
+int acvae_set_input_event(void *cuda_event);
+
 /* profiling only: [T][16] int64 device buffer for clock64 stamps of the decoder forward chain (CTA 0), or NULL */
 int acvae_debug_set_chain_trace(void *device_buffer);
 
