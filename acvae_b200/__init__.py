@@ -21,7 +21,7 @@ from .train_util import CrossEntropyLoss, FusedVAELoss, LabelSmoothingLoss, Norm
 from .lazy import LazyLogits  # noqa: F401
 from .optim import FusedClipAdam  # noqa: F401
 from .metrics import diversity_stats  # noqa: F401
-from .functional import get_precision, set_precision  # noqa: F401
+from .functional import get_precision, set_input_event, set_precision  # noqa: F401
 
 # the reference resolves decoders as getattr(models.decoder, name) and posteriors/priors as
 # getattr(text_encoder, name) (pytorch_runner_vae.py:44, vae_model.py:678-691): same attribute paths

@@ -524,3 +524,21 @@ def set_precision(mode: str) -> None:
 
 def get_precision() -> str:
     return {0: "fp32", 1: "tf32"}[_lib.lib().acvae_get_precision()]
+
+
+_input_event_keepalive = None
+
+
+def set_input_event(event: Optional[torch.cuda.Event]) -> None:
+    """Let the host-to-device copy of a step's audio embeddings overlap the posterior chain: record `event` after that
+    copy (on whatever stream carries it) before every call of the training forward; the forward waits for it only where
+    the audio is first read (an external event-wait node when the step is captured in a CUDA graph).  `None` restores
+    plain stream order.  The caller still orders the copy after the previous step's last read of the buffer."""
+    global _input_event_keepalive
+    if event is None:
+        _lib.check(_lib.lib().acvae_set_input_event(None), "acvae_set_input_event")
+        _input_event_keepalive = None
+        return
+    event.record()                              # materialises the cudaEvent_t; a complete event is a no-op to wait for
+    _lib.check(_lib.lib().acvae_set_input_event(event.cuda_event), "acvae_set_input_event")
+    _input_event_keepalive = event              # the library keeps the raw handle: keep the Python owner alive

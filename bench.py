@@ -235,12 +235,11 @@ def make_train_step(dev, world, rank, use_graph=True):
 
     # the audio's host-to-device copy travels on its own stream; the step waits for `audio_ready` only where the audio is
     # first read (acvae_set_input_event), so the copy overlaps the posterior chain
-    from acvae_b200 import _lib as _l
     copy_stream = torch.cuda.Stream()
     audio_ready = torch.cuda.Event()
     audio_ready.record()
     if os.environ.get("ACVAE_BENCH_NO_INPUT_EVENT") is None:
-        _l.check(_l.lib().acvae_set_input_event(audio_ready.cuda_event), "acvae_set_input_event")
+        models.set_input_event(audio_ready)
     # ---- warm-up (eager) and optional whole-step CUDA graph ---------------------------------
     load_resident(0)
     l0 = F.launch_count()
