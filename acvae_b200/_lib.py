@@ -100,6 +100,7 @@ SYMBOLS = {
     "acvae_get_precision": (C.c_int, []),
     "acvae_clip_adam_workspace_bytes": (_sz, []),
     "acvae_clip_adam": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "acvae_clip_adam_dev": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
 }
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -282,7 +282,8 @@ inline int launch_attn_fwd(const AttnFwdParams& p, cudaStream_t st) {
       // compile-time row counts for the common captions-per-clip / beam sizes, the runtime form for the rest
 #define ACVAE_ATTN_MULTI(RT)                                                                                             \
       {                                                                                                                  \
-        static size_t configured_m = 0;                                                                                  \
+        static size_t configured_dev[kMaxDevices] = {0};                                                                 \
+        size_t& configured_m = configured_dev[current_device()];                                                         \
         if (smem_m > configured_m) {                                                                                     \
           ACVAE_CHECK(cudaFuncSetAttribute(attn_fwd_multi_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m)); \
           configured_m = smem_m;                                                                                         \
@@ -305,7 +306,8 @@ inline int launch_attn_fwd(const AttnFwdParams& p, cudaStream_t st) {
   }
   const size_t smem = attn_smem_bytes(p.A, p.E, p.Te, 0);
   ACVAE_REQUIRE(smem <= 227 * 1024, "attention tile ring exceeds shared memory");
-  static size_t configured = 0;
+  static size_t configured_dev[kMaxDevices] = {0};
+  size_t& configured = configured_dev[current_device()];
   if (smem > configured) {
     ACVAE_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
@@ -405,7 +407,8 @@ inline int launch_attn_bwd_q(const AttnBwdQParams& p, cudaStream_t st) {
   ACVAE_REQUIRE(p.E <= 1024 && p.A <= 1024 && p.A % 4 == 0 && p.E % 4 == 0, "attention: A, E <= 1024, multiples of 4");
   const size_t smem = attn_smem_bytes(p.A, p.E, p.Te, p.E);
   ACVAE_REQUIRE(smem <= 227 * 1024, "attention tile ring exceeds shared memory");
-  static size_t configured = 0;
+  static size_t configured_dev[kMaxDevices] = {0};
+  size_t& configured = configured_dev[current_device()];
   if (smem > configured) {
     ACVAE_CHECK(cudaFuncSetAttribute(attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

@@ -75,6 +75,7 @@ int acvae_memory_prepare(const acvae_dims* d, const acvae_weights* w, const floa
                          float* Pd, void* stream) {
   ACVAE_TRY(check_dims(d));
   ACVAE_REQUIRE(w && audio_embeds && mem && Pp && Pd, "NULL pointer");
+  ACVAE_TRY(wait_input_event((cudaStream_t)stream));
   return memory_prepare(*d, *w, audio_embeds, mem, Pp, Pd, (cudaStream_t)stream);
 }
 
@@ -252,14 +253,13 @@ int acvae_beam_search(const acvae_dims* d, const acvae_weights* w, const float* 
 
 size_t acvae_clip_adam_workspace_bytes(void) { return sizeof(float) * kOptBlocks; }
 
-int acvae_clip_adam(int64_t n, float* params, float* grads, float* exp_avg, float* exp_avg_sq, float max_norm, float lr,
-                    float beta1, float beta2, float eps, float weight_decay, int32_t* step, float* total_norm,
-                    int32_t write_clipped_grads, void* workspace, size_t workspace_bytes, void* stream) {
+static int clip_adam_impl(int64_t n, float* params, float* grads, float* exp_avg, float* exp_avg_sq, float max_norm, float lr,
+                          float beta1, float beta2, float eps, float weight_decay, const float* hyper, int32_t* step,
+                          float* total_norm, int32_t write_clipped_grads, void* workspace, size_t workspace_bytes, void* stream) {
   ACVAE_REQUIRE(n > 0 && n % 4 == 0, "n must be a positive multiple of 4 (pad the flat buffers)");
   ACVAE_REQUIRE(params && grads && exp_avg && exp_avg_sq && step && workspace, "NULL pointer");
   ACVAE_REQUIRE(aligned16(params) && aligned16(grads) && aligned16(exp_avg) && aligned16(exp_avg_sq), "flat buffers must be 16-byte aligned");
   ACVAE_REQUIRE(workspace_bytes >= sizeof(float) * kOptBlocks, "workspace too small");
-  ACVAE_REQUIRE(lr >= 0.0f && beta1 >= 0.0f && beta1 < 1.0f && beta2 >= 0.0f && beta2 < 1.0f && eps >= 0.0f, "bad hyper-parameter");
   const long long n4 = n / 4;
   int blocks = (int)((n4 + kOptThreads - 1) / kOptThreads);
   blocks = blocks < 1 ? 1 : (blocks > kOptBlocks ? kOptBlocks : blocks);
@@ -268,10 +268,31 @@ int acvae_clip_adam(int64_t n, float* params, float* grads, float* exp_avg, floa
   ClipAdamParams a{};
   a.n4 = n4; a.p = (float4*)params; a.g = (float4*)grads; a.m = (float4*)exp_avg; a.v = (float4*)exp_avg_sq;
   a.partial = (const float*)workspace; a.npartial = blocks; a.max_norm = max_norm; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2;
-  a.eps = eps; a.weight_decay = weight_decay; a.step = step; a.total_norm = total_norm; a.write_grad = write_clipped_grads;
+  a.eps = eps; a.weight_decay = weight_decay; a.hyper = hyper; a.step = step; a.total_norm = total_norm;
+  a.write_grad = write_clipped_grads;
   ACVAE_LAUNCH(clip_adam_kernel, blocks, kOptThreads, 0, st, a);
   ACVAE_LAUNCH(step_advance_kernel, 1, 1, 0, st, step);
   return 0;
+}
+
+int acvae_clip_adam(int64_t n, float* params, float* grads, float* exp_avg, float* exp_avg_sq, float max_norm, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int32_t* step, float* total_norm,
+                    int32_t write_clipped_grads, void* workspace, size_t workspace_bytes, void* stream) {
+  ACVAE_REQUIRE(lr >= 0.0f && beta1 >= 0.0f && beta1 < 1.0f && beta2 >= 0.0f && beta2 < 1.0f && eps >= 0.0f, "bad hyper-parameter");
+  return clip_adam_impl(n, params, grads, exp_avg, exp_avg_sq, max_norm, lr, beta1, beta2, eps, weight_decay, nullptr, step,
+                        total_norm, write_clipped_grads, workspace, workspace_bytes, stream);
+}
+
+// The same update with every hyper-parameter read from DEVICE memory at run time: hyper[6] = {max_norm, lr, beta1, beta2,
+// eps, weight_decay}.  A captured CUDA graph of the step then follows an LR schedule (utils/lr_scheduler.py:5-86, stepped
+// every iteration by the runner, pytorch_runner_vae.py:241-257, 305) without re-capture: the host only rewrites the
+// (pinned) source of the 24-byte copy that feeds `hyper`.
+int acvae_clip_adam_dev(int64_t n, float* params, float* grads, float* exp_avg, float* exp_avg_sq, const float* hyper,
+                        int32_t* step, float* total_norm, int32_t write_clipped_grads, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  ACVAE_REQUIRE(hyper, "hyper (device vector of 6 floats) is NULL");
+  return clip_adam_impl(n, params, grads, exp_avg, exp_avg_sq, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, hyper, step, total_norm,
+                        write_clipped_grads, workspace, workspace_bytes, stream);
 }
 
 int acvae_loss_combine_fwd(int64_t n, const float* q_utt, const float* p_utt, const float* ce, const float* kl, float kl_weight,
@@ -338,9 +359,11 @@ int acvae_diversity_stats(int32_t clips, int32_t K, int32_t L, int32_t V, const 
   return 0;
 }
 
-// Optional: a CUDA event the caller records after the host-to-device copy of the next step's audio embeddings (on any
-// stream).  acvae_train_fwd (hoisted schedule) then waits for it only where the audio is first read, so the copy overlaps
-// the posterior chain; NULL (default) restores plain stream order.  The event must outlive every captured graph.
+// Optional: a CUDA event the caller records after the host-to-device copy of the next call's audio embeddings (on any
+// stream).  Every entry point that reads audio_embeds (acvae_train_fwd in both schedules, acvae_memory_prepare,
+// acvae_decode_sample, acvae_beam_search, acvae_diverse_beam_search) waits for it right before its first read -- the
+// hoisted training schedule only after the posterior chain, so the copy overlaps it; NULL (default) restores plain
+// stream order.  The event must outlive every captured graph.
 int acvae_set_input_event(void* cuda_event) {
   input_ready_event() = static_cast<cudaEvent_t>(cuda_event);
   return 0;

@@ -123,6 +123,15 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   return red[32];
 }
 
+// Per-device caches: function attributes (cudaFuncSetAttribute), side streams and capability probes belong to the device
+// that was current when they were set; every such cache in the library is an array indexed by the current device.
+constexpr int kMaxDevices = 16;
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 // Bump allocator over the caller-supplied workspace.

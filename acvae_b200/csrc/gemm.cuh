@@ -559,7 +559,8 @@ inline int launch_skinny(const GemmParams& p, int NC, cudaStream_t st) {
   for (int s = 0; s < p.nseg; ++s) nchunk += (p.seg[s].K + kSkinnyKC - 1) / kSkinnyKC;
   int nstages = nchunk < 2 ? 2 : (nchunk > kSkinnyMaxStages ? kSkinnyMaxStages : nchunk);
   const size_t smem = (size_t)nstages * (32 + BN) * kSkinnyLD * sizeof(float);
-  static size_t configured = 0;
+  static size_t configured_dev[kMaxDevices] = {0};
+  size_t& configured = configured_dev[current_device()];
   if (smem > configured) {
     ACVAE_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

@@ -48,6 +48,8 @@ struct ClipAdamParams {
   const float* partial; int npartial;
   float max_norm;          // <= 0: no clipping
   float lr, beta1, beta2, eps, weight_decay;
+  const float* hyper;      // optional DEVICE vector {max_norm, lr, beta1, beta2, eps, weight_decay}: overrides the by-value
+                           // fields, so an LR scheduler can change them between replays of a captured CUDA graph
   int* step;               // device step counter (incremented by block 0 AFTER every block has read it: see below)
   float* total_norm;       // device scalar out (may be NULL)
   int write_grad;          // store the clipped gradient back (clip_grad_norm_ semantics)
@@ -60,16 +62,19 @@ __global__ void __launch_bounds__(kOptThreads) clip_adam_kernel(const __grid_con
   s = block_sum_opt(s, red);
   const float norm = sqrtf(s);
   float coef = 1.0f;
-  if (a.max_norm > 0.0f) coef = fminf(a.max_norm / (norm + 1e-6f), 1.0f);       // torch: clamp(max_norm / (total + 1e-6), max=1)
+  const float max_norm = a.hyper ? a.hyper[0] : a.max_norm;
+  if (max_norm > 0.0f) coef = fminf(max_norm / (norm + 1e-6f), 1.0f);           // torch: clamp(max_norm / (total + 1e-6), max=1)
   // the counter holds the number of COMPLETED steps; this launch performs step t = counter + 1.  It is advanced by
   // a separate one-thread kernel after this one (no block of this grid may see the new value).
   const int t = a.step[0] + 1;
   if (blockIdx.x == 0 && threadIdx.x == 0 && a.total_norm) a.total_norm[0] = norm;
-  const float bc1 = 1.0f - powf(a.beta1, (float)t);
-  const float bc2 = 1.0f - powf(a.beta2, (float)t);
-  const float step_size = a.lr / bc1;
+  const float lr = a.hyper ? a.hyper[1] : a.lr;
+  const float b1 = a.hyper ? a.hyper[2] : a.beta1, b2 = a.hyper ? a.hyper[3] : a.beta2;
+  const float eps = a.hyper ? a.hyper[4] : a.eps, wd = a.hyper ? a.hyper[5] : a.weight_decay;
+  const float bc1 = 1.0f - powf(b1, (float)t);
+  const float bc2 = 1.0f - powf(b2, (float)t);
+  const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = 1.0f / sqrtf(bc2);
-  const float b1 = a.beta1, b2 = a.beta2, eps = a.eps, wd = a.weight_decay;
   auto upd = [&](float& p, float& g, float& m, float& v) {
     g *= coef;
     float gg = g;

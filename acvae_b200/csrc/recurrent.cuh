@@ -26,17 +26,22 @@ constexpr int kChainCtas = kChainE / 2;      // 2 hidden units per CTA
 constexpr int kChainThreads = 256;           // 8 warps: warp = rows 4w .. 4w+3, lane = K slice (quad mapping below)
 constexpr int kChainMaxN = kChainThreads / 8;
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 struct GridBar {
   unsigned* counter;  // one arrival counter (zeroed before the launch); the target grows by nctas per barrier
   unsigned target;
   unsigned nctas;
 };
 // Barrier over all CTAs of the (cooperatively launched, hence co-resident) grid: bar.sync; thread 0: release
-// increment of one counter, volatile polling of the counter; bar.sync.  Measured on B200 with 128 CTAs
-// (profiles/ubench_gridbar.cu): 2500 cycles for this form, 5200 for per-CTA flags polled by every CTA (hot L2
-// lines), 8800 with a store before / loads after it.  Writes made by any thread of a CTA before the barrier are
-// visible to every thread of every CTA after it; cross-CTA data is read with ld.global.cg (L1 is not coherent).
-// A protocol bug traps instead of hanging the GPU.
+// increment of one counter, acquire polling of the counter; bar.sync.  Measured on B200 with 128 CTAs
+// (profiles/ubench_gridbar.cu): 2400-2500 cycles for this form, 5200 for per-CTA flags polled by every CTA (hot L2
+// lines), 8800 with a store before / loads after it.  Writes made by any thread of a CTA before the barrier
+// happen-before every thread of every CTA after it (release / acquire on the counter, bar.sync on both sides).
+// A protocol bug traps (after 10 s of wall clock) instead of hanging the GPU.
 __device__ __forceinline__ void grid_sync(GridBar& gb) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -44,11 +49,17 @@ __device__ __forceinline__ void grid_sync(GridBar& gb) {
     // release-increment without a return value: orders the CTA's earlier writes (bar.sync makes them
     // happen-before this thread) and does not wait for the atomic's round trip
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(gb.counter) : "memory");
-    long long spin = 0;
-    while (*reinterpret_cast<volatile unsigned*>(gb.counter) < gb.target)
-      if (++spin > (1ll << 26)) __trap();
-    // no trailing fence: every cross-CTA read after the barrier is an ld.global.cg (served by L2, where the
-    // producers' writes were performed before their release-increment), so there is no stale L1 line to invalidate
+    // acquire poll: pairs with the producers' release-increments, so the CTA's later reads of their data are ordered by
+    // the memory model (the ld.global.cg data loads below stay as an optimisation -- L2 hits, no L1 pollution -- and are
+    // no longer what correctness rests on).  Same cost as the volatile poll (profiles/r1/ubench_gridbar.log: 2430 vs 2400).
+    unsigned seen;
+    const unsigned long long t0 = globaltimer_ns();
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(gb.counter) : "memory");
+      // a protocol bug must abort instead of hanging the GPU; the limit is wall-clock (10 s), so preemption, MPS
+      // time-slicing or a debugger do not trip it
+      if (seen < gb.target && globaltimer_ns() - t0 > 10000000000ull) __trap();
+    } while (seen < gb.target);
   }
   __syncthreads();
 }
@@ -1057,8 +1068,12 @@ inline int launch_chain(Kern kern, size_t smem, cudaStream_t st, const char* nam
 // and memory fit in shared memory, and all kChainCtas CTAs are co-resident.)
 inline bool chain_supported(int N, int T, int Te, int E, int A) {
   if (E != kChainE || A != kChainE || N > kChainMaxN || N > kChainCtas || T < 1) return false;
-  static int ok = -1;
-  static int max_te = 0;
+  static int ok_dev[kMaxDevices], max_te_dev[kMaxDevices];
+  static bool probed[kMaxDevices] = {false};
+  const int cur = current_device();
+  int& ok = ok_dev[cur];
+  int& max_te = max_te_dev[cur];
+  if (!probed[cur]) { probed[cur] = true; ok = -1; max_te = 0; }
   if (ok < 0) {
     ok = 0;
     const char* env = getenv("ACVAE_DISABLE_CHAIN");

@@ -169,6 +169,7 @@ inline int decode_sample(const acvae_dims& d, const acvae_weights& w, const acva
                          cudaStream_t st) {
   SampleWs ws = carve_sample_ws(d, workspace);
   const int N = d.N, T = d.T, E = d.E;
+  ACVAE_TRY(wait_input_event(st));
   ACVAE_TRY(memory_prepare(d, w, io.audio_embeds, ws.mem, ws.Pp, ws.Pd, st));
   ACVAE_LAUNCH(sample_init_kernel, grid1d((long long)N * T + T + 1), 256, 0, st, N, T, io.start_idx, io.end_idx, ws.words,
                ws.unfinished, ws.active, (long long*)io.seqs, io.sampled_logprobs);
@@ -349,6 +350,7 @@ inline int beam_search(const acvae_dims& d0, const acvae_weights& w, const float
   BeamWs ws = carve_beam_ws(d0, beam, workspace);
   const int clips = d0.N, T = d0.T, E = d0.E, V = d0.V, R = clips * beam;
   acvae_dims dm = d0;                       // memory: one row per clip
+  ACVAE_TRY(wait_input_event(st));
   ACVAE_TRY(memory_prepare(dm, w, audio, ws.mem, ws.Pp, ws.Pd, st));
   acvae_dims d = d0;
   d.N = R; d.mem_rep = beam;                // decode rows: beam hypotheses per clip share its memory
@@ -607,6 +609,7 @@ inline int diverse_beam_search(const acvae_dims& d0, const acvae_weights& w, con
   DbsWs ws = carve_dbs_ws(d0, G, bdash, workspace);
   const int clips = d0.N, T = d0.T, E = d0.E, V = d0.V, R = clips * G * bdash;
   acvae_dims dm = d0;                       // memory: one row per clip
+  ACVAE_TRY(wait_input_event(st));
   ACVAE_TRY(memory_prepare(dm, w, audio, ws.mem, ws.Pp, ws.Pd, st));
   acvae_dims d = d0;
   d.N = R; d.mem_rep = G * bdash;           // decode rows: all hypotheses of a clip share its memory

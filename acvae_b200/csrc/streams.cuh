@@ -4,6 +4,8 @@
 // events, so it is legal under CUDA-graph stream capture (the side streams join the capture).
 // Created once per process on first use (the device current at that time).
 #pragma once
+#include <mutex>
+
 #include "common.cuh"
 
 namespace acvae {
@@ -18,11 +20,17 @@ struct Aux {
   cudaEvent_t e[kAuxEvents];
   int next_event = 0;
   bool ok = false;
-  cudaEvent_t ev() { cudaEvent_t r = e[next_event]; next_event = (next_event + 1) % kAuxEvents; return r; }
+  std::mutex mu;      // the event ring is shared by every host thread that drives this device
+  cudaEvent_t ev() { std::lock_guard<std::mutex> g(mu); cudaEvent_t r = e[next_event]; next_event = (next_event + 1) % kAuxEvents; return r; }
 };
 
+// One set of side streams / events per device, created on first use with that device current (streams and events belong
+// to the context they were created in).
 inline Aux* aux() {
-  static Aux a;
+  static Aux all[kMaxDevices];
+  static std::mutex init_mu;
+  Aux& a = all[current_device()];
+  std::lock_guard<std::mutex> g(init_mu);
   if (!a.ok) {
     // Priorities: the recurrent chains and the few batched kernels between them are the critical path (highest);
     // the memory backward is next; the weight-gradient fan only fills idle SMs (lowest).  The caller's stream has
@@ -45,6 +53,18 @@ inline Aux* aux() {
 // reads them, with cudaEventWaitExternal -- legal inside stream capture, where it becomes an external event-wait node --
 // so the copy runs under the posterior chain (which does not read the audio) instead of in front of the step.
 inline cudaEvent_t& input_ready_event() { static cudaEvent_t e = nullptr; return e; }
+
+// Make `st` wait for the caller's "inputs ready" event, if one is set: called by EVERY entry point right before its first
+// kernel that reads audio_embeds (both training schedules, the sampling / beam / diverse-beam loops, acvae_memory_prepare).
+inline int wait_input_event(cudaStream_t st) {
+  if (!input_ready_event()) return 0;
+  // under stream capture the wait must be an EXTERNAL event-wait node (the event is recorded outside the graph, before
+  // each replay); outside capture that flag is invalid and a plain wait does the same
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  ACVAE_CHECK(cudaStreamIsCapturing(st, &cs));
+  ACVAE_CHECK(cudaStreamWaitEvent(st, input_ready_event(), cs == cudaStreamCaptureStatusActive ? cudaEventWaitExternal : 0));
+  return 0;
+}
 
 // `to` waits for everything enqueued so far on `from`
 inline int stream_dep(cudaStream_t from, cudaStream_t to, Aux* a) {

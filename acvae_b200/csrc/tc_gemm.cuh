@@ -509,7 +509,8 @@ inline int try_launch_tc(const GemmParams& p, cudaStream_t st) {
     if (!ok) return 0;
   }
   if (p.nseg == 1) { maps[2] = maps[0]; maps[3] = maps[1]; }
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {false};
+  bool& configured = configured_dev[current_device()];
   if (!configured) {
     ACVAE_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     configured = true;

@@ -7,6 +7,7 @@
 #include "attention.cuh"
 #include "tc_gemm.cuh"
 #include "pointwise.cuh"
+#include "streams.cuh"
 
 namespace acvae {
 
@@ -377,6 +378,7 @@ inline int train_fwd(const acvae_dims& d, const acvae_weights& w, const acvae_tr
   // words for teacher-forced steps and a free step 0 (vae_model.py:826-832)
   ACVAE_LAUNCH(words_init_kernel, grid1d(NT), 256, 0, st, N, T, d.L, io.caps_ids, flag_mask(io.tf_flags, T), kStartIdx,
                ws.words);
+  ACVAE_TRY(wait_input_event(st));
   ACVAE_TRY(memory_prepare(d, w, io.audio_embeds, ws.mem, ws.Pp, ws.Pd, st));
   ACVAE_TRY(posterior_fwd(d, w, io, ws, st));
 

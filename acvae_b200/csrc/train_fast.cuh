@@ -96,13 +96,7 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   }
 
   // ---- memory (vae_model.py:743-744 + factorised attention halves) -------------------------------------
-  if (input_ready_event()) {
-    // under stream capture the wait must be an EXTERNAL event-wait node (the event is recorded outside the graph, before
-    // each replay); outside capture the flag is invalid and a plain wait does the same
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    ACVAE_CHECK(cudaStreamIsCapturing(st, &cs));
-    ACVAE_CHECK(cudaStreamWaitEvent(st, input_ready_event(), cs == cudaStreamCaptureStatusActive ? cudaEventWaitExternal : 0));
-  }
+  ACVAE_TRY(wait_input_event(st));       // the audio copy overlaps the posterior chain, which does not read it
   ACVAE_TRY(memory_prepare(d, w, io.audio_embeds, ws.mem, ws.Pp, ws.Pd, st));
   ACVAE_TRY(stream_dep(st, sp, ax));
 

@@ -7,6 +7,7 @@ autograd tape.  All arithmetic of the hot path happens inside
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -74,7 +75,49 @@ def _opt(t: Optional[torch.Tensor], dtype=torch.float32):
 
 
 def _stream() -> int:
+    """The current stream of the CURRENT device.  Every C-ABI call is made inside `_on(tensor)` below, which makes the
+    tensors' device current first: the library's per-process helpers (side streams, events, kernel attributes) are keyed
+    by the current device, so a model on cuda:1 while cuda:0 is current must not launch on cuda:0's stream."""
     return torch.cuda.current_stream().cuda_stream
+
+
+def _on(t: torch.Tensor):
+    """Context manager: the device of `t` is current (so `_stream()` and the library's device-keyed state match it)."""
+    if not t.is_cuda:
+        raise RuntimeError("acvae_b200 runs on CUDA tensors only (no CPU path)")
+    return torch.cuda.device(t.device)
+
+
+def _guard(fn):
+    """Run `fn` with the device of its first CUDA tensor argument current (autograd backward: the device its forward ran
+    on).  See `_stream`."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kw):
+        dev = None
+        for a in args:
+            if torch.is_tensor(a):
+                if a.is_cuda:
+                    dev = a.device
+                    break
+                continue
+            if isinstance(a, dict):
+                cands = [v.device for v in a.values() if torch.is_tensor(v) and v.is_cuda]
+                if cands:
+                    dev = cands[0]
+                    break
+                continue
+            tagged = getattr(a, "_acvae_dev", None)
+            if tagged is not None:
+                dev = tagged
+                break
+        if dev is None:
+            return fn(*args, **kw)
+        with torch.cuda.device(dev):
+            out = fn(*args, **kw)
+        if args and hasattr(args[0], "save_for_backward"):
+            args[0]._acvae_dev = dev          # autograd ctx: the backward runs on the same device
+        return out
+    return wrapped
 
 
 def pack_weights(weights: Dict[str, torch.Tensor], struct_cls=_lib.Weights):
@@ -102,6 +145,7 @@ def launch_count() -> int:
     return int(_lib.lib().acvae_launch_count())
 
 
+@_guard
 def gemm(a, b, a_trans=False, b_trans=False, bias=None, out=None, accumulate=False):
     """C = op(A) . op(B)^T (+bias) through `acvae_gemm`; returns (C, used_tensor_cores)."""
     l = _lib.lib()
@@ -145,6 +189,7 @@ class LatentDecodeTrainFn(torch.autograd.Function):
     """
 
     @staticmethod
+    @_guard
     def forward(ctx, meta: TrainMeta, audio_embeds: torch.Tensor, *weights: torch.Tensor):
         l = _lib.lib()
         d = meta.dims
@@ -200,6 +245,7 @@ class LatentDecodeTrainFn(torch.autograd.Function):
         return res
 
     @staticmethod
+    @_guard
     def backward(ctx, *g):
         l = _lib.lib()
         meta, d = ctx.meta, ctx.meta.dims
@@ -246,6 +292,7 @@ class VocabLogitsFn(torch.autograd.Function):
     """logits = hidden @ W^T + b  (reference models/decoder.py:199), materialised."""
 
     @staticmethod
+    @_guard
     def forward(ctx, hidden, cls_w, cls_b):
         l = _lib.lib()
         shp = hidden.shape
@@ -260,6 +307,7 @@ class VocabLogitsFn(torch.autograd.Function):
         return out.view(*shp[:-1], V)
 
     @staticmethod
+    @_guard
     def backward(ctx, g):
         l = _lib.lib()
         h2, w = ctx.saved_tensors
@@ -281,6 +329,7 @@ class VocabCEFn(torch.autograd.Function):
     """
 
     @staticmethod
+    @_guard
     def forward(ctx, hidden, cls_w, cls_b, targets, smoothing, row_lse, row_sum, grad_sink=None):
         l = _lib.lib()
         ctx.grad_sink = grad_sink     # optional (dW, db) tensors written in place (see TrainMeta.grad_sink)
@@ -306,6 +355,7 @@ class VocabCEFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @_guard
     def backward(ctx, g):
         l = _lib.lib()
         h2, w, b, tg, row_lse = ctx.saved_tensors
@@ -332,6 +382,7 @@ class VAELossFn(torch.autograd.Function):
     global-constraint MSE, composed on the device.  Returns (loss, terms[4] = {loss, ce, kl, mse})."""
 
     @staticmethod
+    @_guard
     def forward(ctx, hidden, cls_w, cls_b, targets, smoothing, row_lse, row_sum, grad_sink,
                 q_means, q_logs, p_means, p_logs, q_utt, p_utt, kl_weight, alpha):
         l = _lib.lib()
@@ -366,6 +417,7 @@ class VAELossFn(torch.autograd.Function):
         return terms[0], terms
 
     @staticmethod
+    @_guard
     def backward(ctx, g, _g_terms):
         l = _lib.lib()
         saved = ctx.saved_tensors
@@ -403,6 +455,7 @@ class NormalKLFn(torch.autograd.Function):
     """KL(q||p) summed over d, mean over all positions (utils/train_util.py:259-266)."""
 
     @staticmethod
+    @_guard
     def forward(ctx, mu1, lv1, mu2, lv2):
         l = _lib.lib()
         ts = [t.contiguous() for t in (mu1, lv1, mu2, lv2)]
@@ -416,6 +469,7 @@ class NormalKLFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_guard
     def backward(ctx, g):
         l = _lib.lib()
         ts = ctx.saved_tensors
@@ -428,6 +482,7 @@ class NormalKLFn(torch.autograd.Function):
         return tuple(outs)
 
 
+@_guard
 def vocab_stats(hidden, cls_w, cls_b):
     """(lse, sum, argmax, logprob_of_argmax) per row of hidden [M,E]; no logits stored."""
     l = _lib.lib()
@@ -444,6 +499,7 @@ def vocab_stats(hidden, cls_w, cls_b):
     return lse, ssum, arg, lp
 
 
+@_guard
 def decode_sample(dims, weights: Dict[str, torch.Tensor], audio_embeds, mem_lens, eps_p, u=None, method="greedy",
                   temp=1.0, start_idx=1, end_idx=2, keep_latents=False):
     """Prior-latent stepwise decoding (reference vae_model.py:880-894, 700-720)."""
@@ -476,6 +532,7 @@ def decode_sample(dims, weights: Dict[str, torch.Tensor], audio_embeds, mem_lens
     return out
 
 
+@_guard
 def beam_search(dims, weights, audio_embeds, mem_lens, eps_b, beam=3, start_idx=1):
     """Beam search with per-beam prior noise (reference vae_model.py:896-995).
     eps_b: [T, N*beam, E]."""
@@ -492,6 +549,7 @@ def beam_search(dims, weights, audio_embeds, mem_lens, eps_b, beam=3, start_idx=
     return {"seqs": seqs}
 
 
+@_guard
 def diverse_beam_search(dims, weights, audio_embeds, mem_lens, eps_g, beam_size=5, group_size=5, diversity_lambda=0.5,
                         temperature=1.0, group_nbest=True, start_idx=1, end_idx=2):
     """Diverse beam search with prior latents (reference word_model.py:297-394, vae_model.py:997-1048).

@@ -273,11 +273,15 @@ class _FusedVAEBase(CaptionModel):
         T, M, mask, lens32 = ent
         total = N * L + N + M
         ring = getattr(self, "_stage_ring", None)
-        if ring is None or ring[0].numel() < total:
-            ring = [torch.empty(max(total, 4096), dtype=torch.int32).pin_memory() for _ in range(4)]
+        if ring is None or ring[0][0].numel() < total:
+            # [pinned staging tensor, CUDA event recorded right after the last asynchronous copy OUT of it]
+            ring = [[torch.empty(max(total, 4096), dtype=torch.int32).pin_memory(), None] for _ in range(4)]
             self._stage_ring, self._stage_next = ring, 0
-        stage = ring[self._stage_next]
+        slot = ring[self._stage_next]
         self._stage_next = (self._stage_next + 1) % len(ring)
+        stage = slot[0]
+        if slot[1] is not None:
+            slot[1].synchronize()     # the host may run >= 4 calls ahead of the stream: never rewrite a slot whose copy is pending
         sn = stage.numpy()
         sn[:N * L] = caps_np.reshape(-1)                              # caps.long() of vae_model.py:827, as int32
         sn[N * L:N * L + N] = lens32
@@ -285,9 +289,15 @@ class _FusedVAEBase(CaptionModel):
         if out is not None:
             if out.flat is None or out.flat.numel() != total or out.T != T or tuple(out.caps_ids.shape) != (N, L):
                 raise ValueError("`out` was prepared for a different caption-length profile")
-            out.flat.copy_(stage[:total], non_blocking=True)
+            with torch.cuda.device(out.flat.device):
+                out.flat.copy_(stage[:total], non_blocking=True)
+                slot[1] = slot[1] or torch.cuda.Event()
+                slot[1].record()
             return out
-        flat = stage[:total].to(device=device, non_blocking=True)
+        with torch.cuda.device(device):
+            flat = stage[:total].to(device=device, non_blocking=True)
+            slot[1] = slot[1] or torch.cuda.Event()
+            slot[1].record()
         return PreparedBatch(flat[:N * L].view(N, L), flat[N * L:N * L + N], T, flat[N * L + N:], flat)
 
     # ---- training ------------------------------------------------------------------------

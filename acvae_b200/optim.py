@@ -1,17 +1,30 @@
 """Fused optimizer tail of the training step: global-norm gradient clipping
 (`runners/pytorch_runner_vae.py:322`, `torch.nn.utils.clip_grad_norm_`) chained with the Adam update
 (`:324`; the runner builds `getattr(torch.optim, config["optimizer"])(model.parameters(),
-**config["optimizer_args"])` at `:219-220`) in two launches over flat buffers.
+**config["optimizer_args"])` at `:219-220`) in two launches over flat buffers, driven by the reference's LR schedules
+(`utils/lr_scheduler.py:5-86`, `scheduler.step()` every iteration, `pytorch_runner_vae.py:239-257, 305`).
 
 `FusedClipAdam(flat_grads, lr=..., max_grad_norm=...)` takes the `parallel.FlatGradBuffer` that already holds
 every `param.grad`; it moves the parameters themselves into one flat buffer too (`param.data` become views, so
 modules, `state_dict()` and the C-ABI calls see the same storage) and keeps both Adam moments flat.
-`step()` = `clip_grad_norm_` + `optimizer.step()` of the reference loop, CUDA-graph capturable (the step
-counter lives on the device).  No fallback: CPU parameters raise.
+
+It IS a `torch.optim.Optimizer`: one `param_groups` entry with `lr`, `betas`, `eps`, `weight_decay` and
+`max_grad_norm`, so `torch.optim.lr_scheduler.*` and the reference's `ExponentialDecayScheduler` / `NoamScheduler` /
+`WarmupLinearSchedule` attach unchanged, and `state_dict()` / `load_state_dict()` use torch.optim.Adam's layout
+(`state[i] = {step, exp_avg, exp_avg_sq}`, the runner's `"optimizer"` checkpoint entry, `:382`).
+
+The hyper-parameters are NOT baked into the launch: every assignment to the group (what a scheduler does) lands in a
+pinned host vector, `step()` enqueues its 24-byte copy to the device and `clip_adam_kernel` reads the device copy.
+`step()` = `clip_grad_norm_` + `optimizer.step()` of the reference loop and is CUDA-graph capturable: the step counter
+lives on the device, and a replayed graph re-reads the pinned vector, so a schedule keeps working without re-capture.
+
+Semantics notes.  (1) Every parameter of the flat buffer is updated every step; a parameter whose gradient was not
+produced this step sees a ZERO gradient (its moments decay, weight decay applies), whereas torch.optim.Adam skips
+`grad is None` parameters -- the hot path produces every gradient every step, frozen parameters are not in the buffer.
+(2) No fallback: CPU parameters raise.
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Optional
 
 import torch
@@ -19,17 +32,40 @@ import torch
 from . import _lib
 from .parallel import FlatGradBuffer
 
+_HYPER_KEYS = ("max_grad_norm", "lr", "betas", "eps", "weight_decay")
 
-class FusedClipAdam:
+
+class _HyperGroup(dict):
+    """The optimizer's param group: a dict whose hyper-parameter writes are mirrored into the pinned host vector the
+    device copy is fed from (an LR scheduler only ever does `group["lr"] = value`)."""
+
+    _owner = None
+
+    def __setitem__(self, key, value):
+        super().__setitem__(key, value)
+        if self._owner is not None and key in _HYPER_KEYS:
+            self._owner._push_hyper()
+
+    def update(self, *a, **k):
+        super().update(*a, **k)
+        if self._owner is not None:
+            self._owner._push_hyper()
+
+
+class FusedClipAdam(torch.optim.Optimizer):
     def __init__(self, flat_grads: FlatGradBuffer, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, max_grad_norm: Optional[float] = None, write_clipped_grads: bool = True):
         g = flat_grads
         if g.flat.device.type != "cuda" or g.flat.dtype != torch.float32:
             raise RuntimeError("FusedClipAdam needs fp32 CUDA parameters (no CPU fallback)")
+        if not (lr >= 0 and 0 <= betas[0] < 1 and 0 <= betas[1] < 1 and eps >= 0):
+            raise ValueError("bad hyper-parameter")
         self.grads = g
-        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
-        self.max_grad_norm = float(max_grad_norm) if max_grad_norm else 0.0
         self.write_clipped_grads = bool(write_clipped_grads)
+        self._hyper_host = None
+        defaults = dict(lr=float(lr), betas=(float(betas[0]), float(betas[1])), eps=float(eps),
+                        weight_decay=float(weight_decay), max_grad_norm=float(max_grad_norm) if max_grad_norm else 0.0)
+        super().__init__(g.params, defaults)
         dev = g.flat.device
         # parameters: one flat buffer with the SAME offsets as the gradients; param.data become views
         self.flat_params = torch.zeros_like(g.flat)
@@ -43,25 +79,93 @@ class FusedClipAdam:
         self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.total_norm = torch.zeros((), dtype=torch.float32, device=dev)
         self._ws = torch.empty(_lib.lib().acvae_clip_adam_workspace_bytes() // 4, dtype=torch.float32, device=dev)
+        # hyper-parameters: pinned host vector -> device vector {max_norm, lr, beta1, beta2, eps, weight_decay}
+        self._hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self._hyper_dev = torch.zeros(8, dtype=torch.float32, device=dev)
+        grp = _HyperGroup(self.param_groups[0])
+        grp._owner = self
+        self.param_groups[0] = grp
+        self._push_hyper()
+        self._bind_state()
+
+    # ---- hyper-parameters -------------------------------------------------------------------------
+    def _push_hyper(self) -> None:
+        if self._hyper_host is None:
+            return
+        g = self.param_groups[0]
+        lr = g["lr"]
+        h = self._hyper_host
+        h[0] = float(g.get("max_grad_norm") or 0.0)
+        h[1] = float(lr)                      # a tensor lr (torch's capturable mode) is read here, on the host
+        h[2], h[3] = float(g["betas"][0]), float(g["betas"][1])
+        h[4], h[5] = float(g["eps"]), float(g["weight_decay"])
+
+    # convenience accessors kept from the first version of this class
+    @property
+    def lr(self) -> float:
+        return float(self.param_groups[0]["lr"])
+
+    @lr.setter
+    def lr(self, v: float) -> None:
+        self.param_groups[0]["lr"] = float(v)
+
+    @property
+    def max_grad_norm(self) -> float:
+        return float(self.param_groups[0]["max_grad_norm"])
+
+    # ---- torch.optim.Optimizer state in torch.optim.Adam's layout (views of the flat moments) ---------------------
+    def _bind_state(self) -> None:
+        for p, o in zip(self.grads.params, self.grads.offsets):
+            self.state[p] = {"step": self.step_count.view(()),
+                             "exp_avg": self.exp_avg[o:o + p.numel()].view_as(p),
+                             "exp_avg_sq": self.exp_avg_sq[o:o + p.numel()].view_as(p)}
 
     def zero_grad(self, set_to_none: bool = False) -> None:
+        """Zeroes the flat buffer (param.grad stay views of it; `set_to_none` is ignored on purpose)."""
         self.grads.zero()
 
     @torch.no_grad()
-    def step(self) -> torch.Tensor:
+    def step(self, closure=None) -> torch.Tensor:
         """clip_grad_norm_(params, max_grad_norm) + Adam step; returns the pre-clip global norm (device scalar)."""
+        if closure is not None:
+            raise RuntimeError("FusedClipAdam.step does not take a closure")
         g = self.grads.flat
-        _lib.check(_lib.lib().acvae_clip_adam(
-            g.numel(), self.flat_params.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-            self.max_grad_norm, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-            self.step_count.data_ptr(), self.total_norm.data_ptr(), int(self.write_clipped_grads),
-            self._ws.data_ptr(), self._ws.numel() * 4, torch.cuda.current_stream(g.device).cuda_stream), "clip_adam")
+        with torch.cuda.device(g.device):
+            self._hyper_dev.copy_(self._hyper_host, non_blocking=True)     # 32 bytes; re-read from pinned memory on every graph replay
+            _lib.check(_lib.lib().acvae_clip_adam_dev(
+                g.numel(), self.flat_params.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                self._hyper_dev.data_ptr(), self.step_count.data_ptr(), self.total_norm.data_ptr(),
+                int(self.write_clipped_grads), self._ws.data_ptr(), self._ws.numel() * 4,
+                torch.cuda.current_stream(g.device).cuda_stream), "clip_adam")
         return self.total_norm
 
     def state_dict(self):
-        return {"step": self.step_count.clone(), "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
-                "lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay}
+        sd = super().state_dict()
+        sd["param_groups"] = [dict(gr) for gr in sd["param_groups"]]
+        return sd
 
     def load_state_dict(self, sd) -> None:
-        self.step_count.copy_(sd["step"]); self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"])
-        self.lr, self.betas, self.eps, self.weight_decay = sd["lr"], tuple(sd["betas"]), sd["eps"], sd["weight_decay"]
+        """Accepts a torch.optim.Adam-layout checkpoint (this class's own `state_dict()` or stock Adam's over the same
+        parameters in the same order): moments are copied INTO the flat buffers, hyper-parameters into the group."""
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.grads.params):
+            raise ValueError("checkpoint does not match this optimizer's single parameter group")
+        step = None
+        with torch.no_grad():
+            for idx, (p, o) in zip(groups[0]["params"], zip(self.grads.params, self.grads.offsets)):
+                st = sd["state"].get(idx)
+                if st is None:
+                    continue
+                self.exp_avg[o:o + p.numel()].view_as(p).copy_(st["exp_avg"])
+                self.exp_avg_sq[o:o + p.numel()].view_as(p).copy_(st["exp_avg_sq"])
+                step = int(st["step"]) if step is None else max(step, int(st["step"]))
+            if step is not None:
+                self.step_count.fill_(step)
+        grp = self.param_groups[0]
+        for k in _HYPER_KEYS:
+            if k in groups[0]:
+                grp[k] = tuple(groups[0][k]) if k == "betas" else groups[0][k]
+        for k, v in groups[0].items():      # scheduler bookkeeping such as initial_lr
+            if k not in _HYPER_KEYS and k != "params":
+                dict.__setitem__(grp, k, v)
+        self._bind_state()

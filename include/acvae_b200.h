@@ -236,6 +236,14 @@ int acvae_clip_adam(int64_t n, float *params, float *grads, float *exp_avg, floa
                     float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
                     int32_t *step, float *total_norm, int32_t write_clipped_grads,
                     void *workspace, size_t workspace_bytes, void *stream);
+/* The same update with every hyper-parameter read from DEVICE memory when the kernel runs:
+ * hyper[6] = {max_norm, lr, beta1, beta2, eps, weight_decay}.  Replaces the reference's per-iteration
+ * `scheduler.step()` -> `optimizer.param_groups[i]["lr"]` path (utils/lr_scheduler.py:5-86,
+ * runners/pytorch_runner_vae.py:239-257, 305) for a step that is replayed as a CUDA graph: the schedule only
+ * rewrites the 24 bytes behind `hyper`, nothing is re-captured.                                            */
+int acvae_clip_adam_dev(int64_t n, float *params, float *grads, float *exp_avg, float *exp_avg_sq,
+                        const float *hyper, int32_t *step, float *total_norm, int32_t write_clipped_grads,
+                        void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- loss composition (runners/pytorch_runner_vae.py:315-320) as one node ------------------
  * terms[4] = {loss, ce, kl, mse}; loss = ce + kl_weight*kl + alpha*mean((q_utt - p_utt)^2) (nn.MSELoss, :318).

@@ -129,9 +129,38 @@ def run_cuda_train(d, seed, ss_ratio=1.0, dis_ratio=0.0, variant="hybrid", smoot
 
 
 def rel_err(a, b):
-    a = torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a).double().cpu()
-    b = torch.as_tensor(np.asarray(b) if not torch.is_tensor(b) else b).double().cpu()
+    a, b = _as_double(a), _as_double(b)
     return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _as_double(x):
+    return torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).detach().double().cpu()
+
+
+def linf_rel_err(a, b):
+    """max |a - b| / max |b|: one wrong ELEMENT of typical size shows up here even when the Frobenius error of a
+    4400 x 256 gradient hides it."""
+    a, b = _as_double(a), _as_double(b)
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def rowwise_rel_err(a, b):
+    """max over rows (last dimension = a row) of |a_r - b_r| / (|b_r| + floor), floor = 1e-3 of the RMS row norm: a wrong
+    ROW (one clip, one vocabulary entry, one hidden unit) cannot hide behind the other rows."""
+    a, b = _as_double(a), _as_double(b)
+    if a.dim() < 2:
+        a, b = a.reshape(1, -1), b.reshape(1, -1)
+    a, b = a.reshape(-1, a.shape[-1]), b.reshape(-1, b.shape[-1])
+    rn = b.norm(dim=1)
+    floor = 1e-3 * float(rn.pow(2).mean().sqrt()) + 1e-30
+    return float(((a - b).norm(dim=1) / (rn + floor)).max())
+
+
+def assert_close(a, b, tol, what=""):
+    """The parity bar three ways: norm-wise (Frobenius) < tol, element-wise (infinity norm, relative to the largest entry)
+    < tol, and row-wise < 10 tol (rows whose own norm is tiny are measured against 1e-3 of the RMS row norm)."""
+    e_f, e_inf, e_row = rel_err(a, b), linf_rel_err(a, b), rowwise_rel_err(a, b)
+    assert e_f < tol and e_inf < tol and e_row < 10 * tol, (what, "fro", e_f, "linf", e_inf, "row", e_row)
 
 
 def max_grad_rel_err(got, ref):

@@ -1,0 +1,102 @@
+"""GPU (-m gpu), needs >= 2 GPUs (skipped otherwise): data-parallel parity of BASELINE configs[2] over real NCCL.
+
+Two ranks (one process per GPU, `torch.distributed` / NCCL, rendezvous on 127.0.0.1) each run the fused train step on
+their OWN batch of the real model (N = 32, E = 256, V = 4400) with the fused backward writing into the flat all-reduce
+buffer, then `FlatGradBuffer.all_reduce()`.  The reference semantics (DDP,
+runners/pytorch_runner_vae.py:204-207, 321) are: every rank's loss is the mean over ITS batch and the gradients are
+averaged over ranks -- so the oracle is run rank by rank on the same batches and its gradients are averaged on the host.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import harness
+from harness import synthetic
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+SEEDS = (21, 22)        # model weights: seed 21 on both ranks; batch of rank r: seed SEEDS[r]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from acvae_b200 import parallel
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    d = synthetic.CFG1
+    m = harness.build_model(d, SEEDS[0], device=f"cuda:{rank}")
+    flat = parallel.FlatGradBuffer(m.parameters())
+    m.grad_sink = flat
+    with torch.cuda.device(rank):
+        r = _run_rank(d, m, SEEDS[rank])
+    local = flat.flat.clone()
+    flat.all_reduce()
+    torch.cuda.synchronize()
+    views = {k: v.detach().cpu().numpy() for k, v in flat.views_for(m).items()}
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), loss=float(r["terms"]["loss"]), local_norm=float(local.norm()), **views)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_rank(d, m, batch_seed):
+    """harness.run_cuda_train with the model's weights from one seed and the batch from another."""
+    import acvae_b200 as models
+    dev = next(m.parameters()).device
+    b = synthetic.make_batch(d, batch_seed)
+    T = int(b["cap_lens"].max()) - 1
+    m.train()
+    caps = torch.from_numpy(b["caps"])
+    lens1 = torch.as_tensor(b["cap_lens"]) - 1
+    targets = torch.nn.utils.rnn.pack_padded_sequence(caps[:, 1:], lens1, batch_first=True).data
+    out = m(torch.from_numpy(b["audio_embeds"]).to(dev), torch.from_numpy(b["mem_lens"].copy()), caps, b["cap_lens"].copy(),
+            ss_ratio=1.0, dis_ratio=0.0, eps_q=torch.from_numpy(b["eps_q"][:, :T].copy()),
+            eps_p=torch.from_numpy(b["eps_p"][:T].copy()), tf_flags=[True] * T, dis_flags=[False] * T)
+    packed = torch.nn.utils.rnn.pack_padded_sequence(out["logits"], lens1, batch_first=True).data
+    fl = models.FusedVAELoss(d.V, smoothing=0.1, alpha=1.0)
+    loss = fl(out, packed, targets, 0.5)
+    loss.backward()
+    return {"terms": {"loss": loss.detach().cpu()}}
+
+
+def _oracle_rank(d, weight_seed, batch_seed):
+    import acvae_oracle as oracle
+    b = synthetic.make_batch(d, batch_seed)
+    T = int(b["cap_lens"].max()) - 1
+    p = harness.oracle_params(d, weight_seed, grad=True)
+    caps = torch.from_numpy(b["caps"])
+    out = oracle.train_forward(p, torch.from_numpy(b["audio_embeds"]), b["mem_lens"], caps, b["cap_lens"],
+                               torch.from_numpy(b["eps_q"][:, :T]), torch.from_numpy(b["eps_p"][:T]), [True] * T, [False] * T,
+                               variant="hybrid", eps_q_steps=torch.from_numpy(b["eps_q_steps"][:T]))
+    terms = oracle.train_loss(out, caps, b["cap_lens"], d.V, 0.1, 0.5, 1.0, "MSE")
+    terms["loss"].backward()
+    return float(terms["loss"]), {k: v.grad.detach().numpy() for k, v in p.items() if v.grad is not None}
+
+
+def test_two_rank_nccl_gradient_average_vs_oracle(tmp_path):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = [dict(np.load(tmp_path / f"rank{r}.npz")) for r in range(world)]
+    d = synthetic.CFG1
+    ref = [_oracle_rank(d, SEEDS[0], SEEDS[r]) for r in range(world)]
+    for r in range(world):
+        assert abs(float(got[r]["loss"]) - ref[r][0]) <= TOL * max(1.0, abs(ref[r][0])), ("per-rank loss", r)
+    for k in ref[0][1]:
+        avg = (ref[0][1][k] + ref[1][1][k]) / world
+        for r in range(world):                                # every rank holds the same averaged gradient
+            harness.assert_close(got[r][k], avg, TOL, ("rank", r, k))
+    for k in got[0]:
+        if k not in ("loss", "local_norm"):
+            assert np.array_equal(got[0][k], got[1][k]), ("ranks disagree after the all-reduce", k)
