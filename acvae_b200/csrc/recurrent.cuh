@@ -402,7 +402,8 @@ __device__ __forceinline__ void prior_fwd_head(const PriorChainFwd& p, const flo
   prior_fwd_head_compute(p, Wh, r, t, q, a);
 }
 
-__global__ void __launch_bounds__(kChainThreads) prior_chain_fwd_kernel(const __grid_constant__ PriorChainFwd p) {
+// two CTAs per SM (<= 128 registers): next to the cluster decoder chain (64 whole SMs) the 128 CTAs fit on the other 84 SMs
+__global__ void __launch_bounds__(kChainThreads, 2) prior_chain_fwd_kernel(const __grid_constant__ PriorChainFwd p) {
   __shared__ __align__(16) float Wsm[kPriorFwdSmemFloats];
   float* Wl = Wsm; float* Wh = Wsm + 8 * 2 * kChainE;
   const int u0 = blockIdx.x * 2;
@@ -605,7 +606,7 @@ __device__ __forceinline__ void prior_bwd_head(const PriorChainBwd& p, const flo
   }
 }
 
-__global__ void __launch_bounds__(kChainThreads) prior_chain_bwd_kernel(const __grid_constant__ PriorChainBwd p) {
+__global__ void __launch_bounds__(kChainThreads, 2) prior_chain_bwd_kernel(const __grid_constant__ PriorChainBwd p) {
   __shared__ __align__(16) float Wsm[kPriorBwdSmemFloats];
   float* WA = Wsm; float* WB = Wsm + 2 * 2 * kChainE;
   const int u0 = blockIdx.x * 2;
@@ -1034,6 +1035,13 @@ __global__ void __launch_bounds__(kChainThreads) dec_chain_bwd_kernel(const __gr
     if (t > 0) grid_sync(gb);
     if (tr) p.trace[t * 16 + 8] = clock64();
   }
+}
+
+// Holds a stream for `ns` nanoseconds (one thread): used to give the decoder's cluster chain a head start over the
+// prior's cooperative chain, see train_fast.cuh.
+__global__ void stream_delay_kernel(unsigned ns) {
+  const unsigned long long t0 = globaltimer_ns();
+  while (globaltimer_ns() - t0 < ns) __nanosleep(200);
 }
 
 // ---- host side -------------------------------------------------------------------------------------

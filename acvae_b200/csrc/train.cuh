@@ -29,6 +29,7 @@ struct TrainWs {
   // decoder
   float *qp_d, *w_d, *ctx_d, *gates_d, *pool_d; int* amax_d;
   float* part_d;    // [min(N,32), 128, max(A,E)] per-CTA partial projections of the persistent decoder chains (recurrent.cuh)
+  float* Mg;        // [N,Te,3E] mem . W_ih[:, E:2E]^T: per-frame context share of the decoder's gate pre-activations (cluster_chain.cuh)
   // vocab partials
   float *pmax, *pexp, *psum, *pbest; int* parg;
   // backward scratch
@@ -55,6 +56,7 @@ inline TrainWs carve_train_ws(const acvae_dims& d, void* base) {
   w.gates_p = ar.take<float>(NT * 4 * E); w.c_p = ar.take<float>(NT * E); w.h_p = ar.take<float>(NT * E);
   w.qp_d = ar.take<float>(NT * A); w.w_d = ar.take<float>(NT * Te); w.ctx_d = ar.take<float>(NT * E);
   w.part_d = ar.take<float>((N < 32 ? N : 32) * 128 * (A > E ? A : E));
+  w.Mg = ar.take<float>(Te <= 96 ? N * Te * 3 * E : 0);
   w.gates_d = ar.take<float>(NT * 4 * E); w.pool_d = ar.take<float>(N * E); w.amax_d = ar.take<int>(N * E);
   w.pmax = ar.take<float>(NT * ntiles); w.pexp = ar.take<float>(NT * ntiles); w.psum = ar.take<float>(NT * ntiles);
   w.pbest = ar.take<float>(NT * ntiles * 2); w.parg = ar.take<int>(NT * ntiles);

@@ -7,7 +7,7 @@
 //   * pointwise backward steps are fused into the epilogue of the GEMM that produces their input, so
 //     a reverse step is 3 launches (decoder), 2 (prior) or 1 per direction (posterior).
 #pragma once
-#include "recurrent.cuh"
+#include "cluster_chain.cuh"
 #include "streams.cuh"
 #include "train.cuh"
 
@@ -31,8 +31,13 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   const long long s1 = T;
   cudaStream_t sq0 = ax->s[0], sq1 = ax->s[1], sp = ax->s[2];
 
-  const bool chain = chain_supported(N, T, Te, E, A);   // persistent recurrent-chain kernels (recurrent.cuh)
-  if (chain) ACVAE_CHECK(cudaMemsetAsync(ws.bars, 0, 8 * 128 * sizeof(unsigned), st));
+  // Persistent recurrent-chain kernels.  `cl`: posterior and decoder chains on thread-block clusters (cluster_chain.cuh,
+  // state exchange through distributed shared memory); `coop`: the cooperative-grid chains of recurrent.cuh (exchange
+  // through L2) -- used for the prior next to the cluster chains, and for every chain where the cluster form does not apply.
+  const bool cl = cluster_chain_supported(N, T, Te, E, A);
+  const bool coop = chain_supported(N, T, Te, E, A);
+  const bool post_chain = cl || coop, prior_chain = coop, dec_chain = cl || coop;
+  if (coop) ACVAE_CHECK(cudaMemsetAsync(ws.bars, 0, 8 * 128 * sizeof(unsigned), st));
   ACVAE_LAUNCH(steplens_kernel, grid1d(N), 256, 0, st, N, io.cap_lens, ws.steplens);
   ACVAE_LAUNCH(qids_kernel, grid1d(NT), 256, 0, st, N, T, d.L, io.caps_ids, ws.qids);
   ACVAE_LAUNCH(words_init_kernel, grid1d(NT), 256, 0, st, N, T, d.L, io.caps_ids, flag_mask(io.tf_flags, T), kStartIdx,
@@ -46,7 +51,7 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   cudaStream_t sq[2] = {sq0, sq1};
   for (int dir = 0; dir < 2; ++dir) {
     ACVAE_TRY(linear_fwd(NT, 3 * E, E, ws.xq, E, w.q_wih[dir], E, w.q_bih[dir], ws.gxq[dir], 3 * E, sq[dir]));
-    if (chain) continue;
+    if (post_chain) continue;
     for (int s = 0; s < T; ++s) {
       const int t = dir == 0 ? s : T - 1 - s;
       const int tp = dir == 0 ? t - 1 : t + 1;
@@ -68,11 +73,13 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     }
   }
   ACVAE_TRY(stream_dep(sq1, sq0, ax));
-  if (chain) {
+  if (post_chain) {
     PostChainFwd pc{};
     pc.N = N; pc.T = T; pc.lens = ws.steplens; pc.ho = ws.ho; pc.bar = ws.bars + 0 * 128;
     for (int dir = 0; dir < 2; ++dir) { pc.gx[dir] = ws.gxq[dir]; pc.whh[dir] = w.q_whh[dir]; pc.bhh[dir] = w.q_bhh[dir]; pc.gq[dir] = ws.gq[dir]; }
-    ACVAE_TRY(launch_chain(post_chain_fwd_kernel, 0, sq0, "post_chain_fwd_kernel", pc));
+    if (cl) pc.trace = chain_trace_ptr() ? chain_trace_ptr() + 2LL * T * 16 : nullptr;
+    if (cl) ACVAE_TRY(launch_cluster_chain(post_cl_fwd_kernel, post_cl_clusters(N), 0, sq0, "post_cl_fwd_kernel", pc));
+    else ACVAE_TRY(launch_chain(post_chain_fwd_kernel, 0, sq0, "post_chain_fwd_kernel", pc));
   }
   {
     GemmParams h{};
@@ -99,6 +106,9 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   ACVAE_TRY(wait_input_event(st));       // the audio copy overlaps the posterior chain, which does not read it
   ACVAE_TRY(memory_prepare(d, w, io.audio_embeds, ws.mem, ws.Pp, ws.Pd, st));
   ACVAE_TRY(stream_dep(st, sp, ax));
+  // cluster decoder chain: the context's share of the gate pre-activations per FRAME, Mg = mem . W_ih[:, E:2E]^T, so that
+  // the chain needs neither the K = E context product nor an exchange of the context (cluster_chain.cuh)
+  if (cl) ACVAE_TRY(linear_fwd(N * Te, 3 * E, E, ws.mem, E, w.d_wih + E, 3 * E, nullptr, ws.Mg, 3 * E, st));
 
   // ---- prior (text_encoder.py:247-268): word attention and input-side gates batched over (n,t) ---------
   ACVAE_TRY(gather_rows(NT, E, w.p_emb, ws.words, ws.xp, sp));
@@ -118,13 +128,16 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     g.epi.c[0] = ws.dg_p; g.epi.ldc = 4 * E; g.epi.bias[0] = w.p_bih; g.epi.scale = 1.0f;   // dg_p doubles as gx_p in the forward
     ACVAE_TRY(launch_gemm<EPI_PLAIN>(g, sp));
   }
-  PriorChainFwd ppc{};      // chain mode: the prior chain runs inside the decoder's persistent kernel (same barriers)
-  if (chain) {
+  PriorChainFwd ppc{};      // cooperative chains: the prior chain runs inside the decoder's persistent kernel (same barriers)
+  if (prior_chain) {
     ppc.N = N; ppc.T = T; ppc.gx = ws.dg_p; ppc.wih = w.p_wih; ppc.whh = w.p_whh; ppc.bhh = w.p_bhh;
     ppc.head_w = w.p_head_w; ppc.head_b = w.p_head_b; ppc.eps = io.eps_p;
     ppc.gates = ws.gates_p; ppc.c = ws.c_p; ppc.h = ws.h_p; ppc.pm = io.p_means; ppc.pl = io.p_logs; ppc.pz = io.p_z;
+    // next to the cluster decoder chain the prior is its own (cooperative, 128-CTA) kernel, launched below right AFTER
+    // the decoder's chain
+    if (cl) ppc.bar = ws.bars + 1 * 128;
   }
-  for (int t = 0; t < T && !chain; ++t) {
+  for (int t = 0; t < T && !prior_chain; ++t) {
     GemmParams g{};
     g.M = N; g.U = E; g.G = 4; g.nseg = 0;
     if (t > 0) {
@@ -162,7 +175,26 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     g.epi.c[0] = ws.dgi_d; g.epi.ldc = 3 * E; g.epi.bias[0] = w.d_bih; g.epi.scale = 1.0f;
     ACVAE_TRY(launch_gemm<EPI_PLAIN>(g, st));
   }
-  if (chain) {
+  if (cl) {
+    DecClFwd dc{};
+    dc.N = N; dc.T = T; dc.Te = Te; dc.gx = ws.dgi_d; dc.attn_w = w.d_attn_w; dc.attn_v = w.d_attn_v; dc.whh = w.d_whh; dc.bhh = w.d_bhh;
+    dc.Pd = ws.Pd; dc.Mg = ws.Mg; dc.mem_lens = io.mem_lens; dc.qp = ws.qp_d; dc.w = ws.w_d; dc.gates = ws.gates_d; dc.out = io.outputs;
+    dc.aw = io.attn_weights; dc.trace = chain_trace_ptr();
+    // The two chains are independent (dis_ratio == 0) and share the machine: a cluster-chain CTA needs a WHOLE SM (255
+    // registers, 180 KB), a prior CTA half of one.  Order matters: when the prior's 128 CTAs come first they take one SM
+    // each and the decoder's clusters trickle in two at a time on the 20 SMs left (214 instead of 108 us); when the
+    // decoder's 8 clusters come first they take 64 SMs and the prior packs two CTAs per SM onto the other 84.  So the
+    // prior waits for the decoder's inputs and is held back a few microseconds behind the decoder's launch.
+    if (prior_chain) ACVAE_TRY(stream_dep(st, sp, ax));
+    ACVAE_TRY(launch_cluster_chain(dec_cl_fwd_kernel, dec_cl_clusters(N), dec_cl_fwd_smem(Te), st, "dec_cl_fwd_kernel", dc));
+    if (prior_chain) {
+      ACVAE_LAUNCH(stream_delay_kernel, 1, 1, 0, sp, 8000u);
+      ACVAE_TRY(launch_chain(prior_chain_fwd_kernel, 0, sp, "prior_chain_fwd_kernel", ppc));
+    }
+    // the context itself (weight gradients, rnn_input) from the saved weights, off the critical stream
+    ACVAE_TRY(stream_dep(st, sq1, ax));
+    ACVAE_LAUNCH(attn_ctx_kernel, dim3(N, T), 256, 0, sq1, T, Te, E, (const float*)ws.w_d, (const float*)ws.mem, io.mem_lens, ws.ctx_d);
+  } else if (coop) {
     DecChainFwd dc{};
     dc.N = N; dc.T = T; dc.Te = Te; dc.gx = ws.dgi_d; dc.attn_w = w.d_attn_w; dc.attn_v = w.d_attn_v;
     dc.wih = w.d_wih; dc.whh = w.d_whh; dc.bhh = w.d_bhh; dc.Pd = ws.Pd; dc.mem = ws.mem; dc.mem_lens = io.mem_lens;
@@ -171,7 +203,7 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     ACVAE_TRY(stream_dep(sp, st, ax));      // the prior's hoisted inputs (gx_p) are produced on sp
     ACVAE_TRY(launch_chain(dec_chain_fwd_kernel, dec_chain_fwd_smem(Te), st, "dec_chain_fwd_kernel", dc, ppc));
   }
-  for (int t = 0; t < T && !chain; ++t) {
+  for (int t = 0; t < T && !dec_chain; ++t) {
     const float* hprev = t > 0 ? io.outputs + (long long)(t - 1) * E : nullptr;
     GemmParams qg{};
     qg.M = N; qg.U = A; qg.G = 1; qg.nseg = hprev ? 1 : 0;
@@ -223,6 +255,7 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   ACVAE_TRY(linear_fwd(N, 2 * E, E, ws.pool_d, E, w.g_w, E, w.g_b, io.p_means_utt, 2 * E, st));
   if (io.logits) ACVAE_TRY(linear_fwd(NT, d.V, E, io.outputs, E, w.cls_w, E, w.cls_b, io.logits, d.V, st));
   ACVAE_TRY(stream_dep(sp, st, ax));
+  if (cl) ACVAE_TRY(stream_dep(sq1, st, ax));
   ACVAE_TRY(stream_dep(st, st_user, ax));
   return 0;
 }
@@ -246,22 +279,28 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   const long long s1 = T;
   cudaStream_t sp = ax->s[2], sx = ax->s[3], sq0 = ax->s[0], sq1 = ax->s[1];
   auto zero = [&](float* p, size_t n, cudaStream_t s) { return cudaMemsetAsync(p, 0, n * sizeof(float), s); };
-  const bool chain = chain_supported(N, T, Te, E, A);   // persistent recurrent-chain kernels (recurrent.cuh)
-  // chain mode: the prior's backward chain runs inside the decoder's persistent kernel (same barriers), so the two
-  // chains cost max(...) instead of their sum (two cooperative kernels never overlap on the device)
+  const bool cl = cluster_chain_supported(N, T, Te, E, A);   // posterior / decoder chains on clusters (cluster_chain.cuh)
+  const bool coop = chain_supported(N, T, Te, E, A);         // cooperative-grid chains (recurrent.cuh)
+  const bool post_chain = cl || coop, dec_chain = cl || coop;
+  // cooperative chains only: the prior's backward chain runs inside the decoder's persistent kernel (same barriers), so
+  // the two chains cost max(...) instead of their sum (two cooperative kernels never overlap on the device).  Next to the
+  // cluster decoder chain the prior is its own kernel on its own stream.
   static int merge_env = -1;
   if (merge_env < 0) { const char* e = getenv("ACVAE_MERGE_BWD"); merge_env = (e && e[0] == '0') ? 0 : 1; }
-  const bool merge_bwd = chain && merge_env == 1;
-  if (chain) ACVAE_CHECK(cudaMemsetAsync(ws.bars + 4 * 128, 0, 4 * 128 * sizeof(unsigned), st));
+  const bool merge_bwd = !cl && coop && merge_env == 1;
+  if (coop) ACVAE_CHECK(cudaMemsetAsync(ws.bars + 4 * 128, 0, 4 * 128 * sizeof(unsigned), st));
+  // (Starting the prior's backward chain earlier -- right behind the KL gradients, under the cross-entropy gradient GEMMs --
+  // was tried: the cooperative kernel holds all 148 SMs, the GEMMs it overlaps take 130 instead of 27 us and the step gets
+  // 30 us longer, gpurun_out r2f timeline.)
   ACVAE_TRY(stream_dep(st, sp, ax));
 
   // ================= prior BPTT on its own stream (KL gradients only: dis_ratio == 0) ====================
-  PriorChainBwd ppc{};      // chain mode: the prior chain runs inside the decoder's persistent kernel (same barriers)
-  if (chain) {
+  PriorChainBwd ppc{};
+  if (coop) {
     ppc.N = N; ppc.T = T; ppc.d_pz = gi.d_p_z; ppc.d_pm = gi.d_p_means; ppc.d_pl = gi.d_p_logs; ppc.eps = io.eps_p;
     ppc.p_logs = io.p_logs; ppc.head_w = w.p_head_w; ppc.wih = w.p_wih; ppc.whh = w.p_whh; ppc.gates = ws.gates_p; ppc.c = ws.c_p;
     ppc.dml = ws.dml_p; ppc.dg = ws.dg_p; ppc.bar = ws.bars + 4 * 128;
-    if (!merge_bwd) ACVAE_TRY(launch_chain(prior_chain_bwd_kernel, 0, sp, "prior_chain_bwd_kernel", ppc));
+    if (!merge_bwd && !cl) ACVAE_TRY(launch_chain(prior_chain_bwd_kernel, 0, sp, "prior_chain_bwd_kernel", ppc));
   } else
   {
     // step T-1 head backward (standalone), then per step: [dh GEMM + LSTM pointwise] -> [dz|dh GEMM + head pointwise]
@@ -276,7 +315,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     h.dml = ws.dml_p + (long long)t * 2 * E; h.ld_dml = s1 * 2 * E;
     ACVAE_LAUNCH(head_bwd_kernel, grid1d((long long)N * E), 256, 0, sp, h);
   }
-  for (int t = T - 1; t >= 0 && !chain; --t) {
+  for (int t = T - 1; t >= 0 && !coop; --t) {
     GemmParams p{};
     p.M = N; p.U = E; p.G = 1; p.nseg = 1;
     GemmSeg s{};
@@ -362,7 +401,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     }
     return 0;
   };
-  if (!merge_bwd) ACVAE_TRY(prior_remainders());
+  if (!merge_bwd && !cl) ACVAE_TRY(prior_remainders());
 
   // ================= decoder BPTT on the main stream ========================================================
   const float* dpool = nullptr;
@@ -376,7 +415,20 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   }
   ACVAE_LAUNCH(pool_bwd_kernel, grid1d((long long)NT * E), 256, 0, st, N, T, E, dpool, ws.steplens, 0, ws.amax_d,
                gi.d_outputs, ws.dout);
-  if (chain) {
+  if (cl) {
+    DecClBwd dc{};
+    dc.N = N; dc.T = T; dc.Te = Te; dc.dout = ws.dout; dc.attn_w = w.d_attn_w; dc.attn_v = w.d_attn_v; dc.whh = w.d_whh;
+    dc.Pd = ws.Pd; dc.Mg = ws.Mg; dc.mem_lens = io.mem_lens; dc.qp = ws.qp_d; dc.w = ws.w_d; dc.gates = ws.gates_d; dc.out = io.outputs;
+    dc.dgi = ws.dgi_d; dc.dgh = ws.dgh_d; dc.ds = ws.ds_d; dc.dqp = ws.dqp_d;
+    // decoder first, the prior's cooperative chain a few microseconds behind it on its own stream (see train_fwd_fast)
+    if (coop) ACVAE_TRY(stream_dep(st, sp, ax));
+    ACVAE_TRY(launch_cluster_chain(dec_cl_bwd_kernel, dec_cl_clusters(N), dec_cl_bwd_smem(Te), st, "dec_cl_bwd_kernel", dc));
+    if (coop) {
+      ACVAE_LAUNCH(stream_delay_kernel, 1, 1, 0, sp, 8000u);
+      ACVAE_TRY(launch_chain(prior_chain_bwd_kernel, 0, sp, "prior_chain_bwd_kernel", ppc));
+    }
+    ACVAE_TRY(prior_remainders());
+  } else if (coop) {
     DecChainBwd dc{};
     dc.N = N; dc.T = T; dc.Te = Te; dc.dout = ws.dout; dc.attn_w = w.d_attn_w; dc.attn_v = w.d_attn_v; dc.wih = w.d_wih;
     dc.whh = w.d_whh; dc.Pd = ws.Pd; dc.mem = ws.mem; dc.mem_lens = io.mem_lens; dc.qp = ws.qp_d; dc.w = ws.w_d;
@@ -404,7 +456,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     g.dh_out = ws.dh_carry;
     ACVAE_LAUNCH(gru_bwd_kernel, grid1d((long long)N * E), 256, 0, st, g);
   }
-  for (int t = T - 1; t >= 0 && !chain; --t) {
+  for (int t = T - 1; t >= 0 && !dec_chain; --t) {
     ACVAE_TRY(linear_bwd_data(N, E, 3 * E, ws.dgi_d + (long long)t * 3 * E, s1 * 3 * E, w.d_wih + E, 3 * E,
                               ws.dctx_d + (long long)t * E, s1 * E, st));
     AttnBwdQParams a{};
@@ -440,6 +492,8 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   // ---- side stream sx (overlaps the posterior chains) ----
   // critical first: the decoder's per-clip attention accumulation (into its own buffer: no ordering against the
   // prior's), then the memory backward as soon as the prior's accumulation is done too
+  // cluster chain: d ctx of all steps in one batched contraction (the chain itself works on d alpha directly)
+  if (cl) ACVAE_TRY(linear_bwd_data(NT, E, 3 * E, ws.dgi_d, 3 * E, w.d_wih + E, 3 * E, ws.dctx_d, E, sx));
   ACVAE_CHECK(zero(gw.d_attn_v, A, sx));
   {
     AttnBwdAccParams a{};
@@ -530,16 +584,17 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   ACVAE_TRY(colsum(NT, 2 * E, ws.dml_q, 2 * E, gw.q_head_b, st));
   cudaStream_t sq[2] = {sq0, sq1};
   float* carry[2] = {ws.dhq_carry, ws.dzq_carry};   // one carry buffer per direction
-  if (chain) {
+  if (post_chain) {
     PostChainBwd pc{};
     pc.N = N; pc.T = T; pc.dho = ws.dho; pc.ho = ws.ho; pc.lens = ws.steplens; pc.bar = ws.bars + 6 * 128;
     for (int dir = 0; dir < 2; ++dir) { pc.whh[dir] = w.q_whh[dir]; pc.gq[dir] = ws.gq[dir]; pc.dgi[dir] = ws.dgi_q[dir]; pc.dgh[dir] = ws.dgh_q[dir]; }
-    ACVAE_TRY(launch_chain(post_chain_bwd_kernel, 0, sq0, "post_chain_bwd_kernel", pc));
+    if (cl) ACVAE_TRY(launch_cluster_chain(post_cl_bwd_kernel, post_cl_clusters(N), 0, sq0, "post_cl_bwd_kernel", pc));
+    else ACVAE_TRY(launch_chain(post_chain_bwd_kernel, 0, sq0, "post_chain_bwd_kernel", pc));
     ACVAE_TRY(stream_dep(sq0, sq1, ax));
   }
   for (int dir = 0; dir < 2; ++dir) {
     cudaStream_t s_ = sq[dir];
-    if (!chain) {
+    if (!post_chain) {
       const int s = T - 1;
       const int t = dir == 0 ? s : T - 1 - s;
       const int tp = dir == 0 ? t - 1 : t + 1;
@@ -554,7 +609,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
       g.dh_out = carry[dir];
       ACVAE_LAUNCH(gru_bwd_kernel, grid1d((long long)N * E), 256, 0, s_, g);
     }
-    for (int s = T - 1; s > 0 && !chain; --s) {
+    for (int s = T - 1; s > 0 && !post_chain; --s) {
       const int t = dir == 0 ? s : T - 1 - s;            // step whose dGh is propagated
       const int tm = dir == 0 ? t - 1 : t + 1;            // the step before it in this direction's forward order
       const int sm = s - 1;                               // its position in forward order
@@ -577,8 +632,8 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     // weight / bias gradients of this direction: in chain mode each on its own fan stream (nothing but the embedding
     // gradient below is left on the critical stream after the last chain), otherwise behind the direction's BPTT
     cudaStream_t* f = &ax->s[kAuxFan0];
-    cudaStream_t s_wih = chain ? f[dir * 3] : s_, s_whh = chain ? f[dir * 3 + 1] : s_, s_b = chain ? f[dir * 3 + 2] : s_;
-    if (chain)
+    cudaStream_t s_wih = post_chain ? f[dir * 3] : s_, s_whh = post_chain ? f[dir * 3 + 1] : s_, s_b = post_chain ? f[dir * 3 + 2] : s_;
+    if (post_chain)
       for (int i = 0; i < 3; ++i) ACVAE_TRY(stream_dep(sq0, f[dir * 3 + i], ax));
     ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_q[dir], 3 * E, ws.xq, E, gw.q_wih[dir], E, s_wih));
     ACVAE_TRY(colsum(NT, 3 * E, ws.dgi_q[dir], 3 * E, gw.q_bih[dir], s_b));
@@ -604,7 +659,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   }
   ACVAE_CHECK(zero(gw.q_emb, (size_t)V * E, st));
   ACVAE_TRY(scatter_rows(NT, E, ws.dxq, E, ws.qids, gw.q_emb, st));
-  if (chain)
+  if (post_chain)
     for (int i = 0; i < 6; ++i) ACVAE_TRY(stream_dep(ax->s[kAuxFan0 + i], st, ax));
   ACVAE_TRY(stream_dep(sp, st, ax));
   ACVAE_TRY(stream_dep(sx, st, ax));

@@ -47,27 +47,29 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback (B200_PROFILING.md)"}
 
 
-def chain_kernel_bytes(d):
-    """Algorithmic bytes of ONE launch of dec_chain_fwd_kernel (decoder + prior forward chains, all T steps;
-    DESIGN.md section 4.3): the weight slices and the clips' memory read once, the per-step inputs read once and
-    every saved activation / output written once.  fp32."""
+def chain_kernels(d):
+    """The persistent recurrent-chain kernels of the step: name -> (algorithmic fp32 bytes of ONE launch, description).
+    Algorithmic bytes: the weight slices and the clips' attention operands read once, every per-(n,t)
+    input read once and every saved activation / gradient written once."""
     N, Te, T, E = d.N, d.Te, d.T, d.E
-    weights = 17 * E * E            # Wq, W_ih[:,E:2E], W_hh (decoder); W_ih[:,2E:3E], W_hh, head (prior)
-    memory = 2 * N * Te * E         # P_d, mem
-    per_nt = 24 * E + Te            # gx_d 3E, gx_p 4E, eps E | qp, ctx, out E each, gates_d 4E, w Te | gates_p 4E, c, h, pm, pl, pz
-    return 4 * (weights + memory + N * T * per_nt)
-
-
-def chain_bwd_kernel_bytes(d):
-    """Algorithmic bytes of ONE launch of dec_chain_bwd_kernel<true> (decoder + prior backward chains merged, all T steps):
-    weight slices once (decoder W_hh | Wq, W_ih ctx columns; prior head, W_ih z columns, W_hh), the clips' memory once,
-    and per (n,t) every saved activation / upstream gradient read once and every produced gradient written once.  fp32."""
-    N, Te, T, E = d.N, d.Te, d.T, d.E
-    weights = 17 * E * E
-    memory = 2 * N * Te * E
-    per_nt = 30 * E + 2 * Te     # reads: dout, gates_d 4E, out, qp, w Te | d_pm, d_pl, eps, p_logs, gates_p 4E, c;  writes: dgi 3E, dgh 3E,
-                                 # dctx, ds Te, dqp | dml 2E, dg 4E
-    return 4 * (weights + memory + N * T * per_nt)
+    NT = N * T
+    tiles = 4 * N * Te * E                  # Mg [N,Te,3E] + P_d [N,Te,E] (cluster decoder chains)
+    return {
+        "dec_cl_fwd_kernel": (4 * (4 * E * E + tiles + NT * (9 * E + Te)),
+                              "decoder forward chain, all T steps in ONE launch of 8-CTA clusters (4 rows each); state exchange "
+                              "through distributed shared memory (st.async + mbarrier), 3 hops per step"),
+        "dec_cl_bwd_kernel": (4 * (4 * E * E + tiles + NT * (14 * E + 2 * Te)),
+                              "decoder backward chain (BPTT), 8-CTA clusters, 3 DSMEM hops per step"),
+        "post_cl_fwd_kernel": (4 * (6 * E * E + NT * 16 * E), "posterior biGRU forward, clusters = (direction, 8 rows), 1 DSMEM hop per step"),
+        "post_cl_bwd_kernel": (4 * (6 * E * E + NT * 24 * E), "posterior biGRU backward, split-K + DSMEM reduce-scatter, 1 hop per step"),
+        "prior_chain_fwd_kernel": (4 * (10 * E * E + NT * 14 * E), "prior LSTM + Gaussian head forward chain, cooperative grid, 2 grid barriers per step"),
+        "prior_chain_bwd_kernel": (4 * (10 * E * E + NT * 16 * E), "prior backward chain, cooperative grid, 2 grid barriers per step"),
+        # cooperative-grid decoder chains (prior merged), used where the cluster form does not apply
+        "dec_chain_fwd_kernel": (4 * (17 * E * E + 2 * N * Te * E + NT * (24 * E + Te)),
+                                 "decoder + prior forward chains, cooperative grid, 2 grid barriers per step"),
+        "dec_chain_bwd_kernel": (4 * (17 * E * E + 2 * N * Te * E + NT * (30 * E + 2 * Te)),
+                                 "decoder + prior backward chains, cooperative grid, 3 grid barriers per step"),
+    }
 
 
 def probe_kernel(lib, name, run, n, flush):
@@ -246,13 +248,16 @@ def make_train_step(dev, world, rank, use_graph=True):
         opt.step()
         loss_buf.copy_(loss.detach())
 
-    # the audio's host-to-device copy travels on its own stream; the step waits for `audio_ready` only where the audio is
-    # first read (acvae_set_input_event), so the copy overlaps the posterior chain
+    # e2e input pipeline: the 4 MB audio copy of step i+1 crosses PCIe on its own stream WHILE step i computes (two device
+    # staging buffers); step i+1 then starts with a device-to-device copy into the static buffer the captured graph reads.
+    # (An event-wait node inside the graph -- acvae_set_input_event -- would overlap the copy with the step's own posterior
+    # chain instead, but external event-wait nodes add ~65 us of latency before their successors: measured, DESIGN.md.)
     copy_stream = torch.cuda.Stream()
-    audio_ready = torch.cuda.Event()
-    audio_ready.record()
-    if os.environ.get("ACVAE_BENCH_NO_INPUT_EVENT") is None:
-        models.set_input_event(audio_ready)
+    staging = [torch.empty_like(resident[0]["audio"]) for _ in range(2)]
+    copy_done = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    for e in copy_done + consumed:
+        e.record()
     # ---- warm-up (eager) and optional whole-step CUDA graph ---------------------------------
     load_resident(0)
     l0 = F.launch_count()
@@ -288,7 +293,8 @@ def make_train_step(dev, world, rank, use_graph=True):
     ts.__dict__.update(dict(model=model, d=d, n_params=n_params, run_step=run_step, load_resident=load_resident,
                             pinned=pinned, resident=resident, st_audio=st_audio, st_mem_lens=st_mem_lens, st_prep=st_prep,
                             st_targets=st_targets, loss_buf=loss_buf, M=M, graph=graph, launches_per_step=launches_per_step,
-                            step_body=step_body, copy_stream=copy_stream, audio_ready=audio_ready))
+                            step_body=step_body, copy_stream=copy_stream, staging=staging, copy_done=copy_done,
+                            consumed=consumed))
     return ts
 
 
@@ -354,17 +360,26 @@ def run_ours(args):
     h2d_bytes = (pinned[0]["audio"].numel() * 4 + pinned[0]["caps"].numel() * 4 + pinned[0]["mem_lens"].numel() * 4 + d.N * 4 + M * 4)
     host_losses = []
 
+    def prefetch(i):
+        """H2D copy of step i's audio embeddings (pinned host -> device staging) on the copy stream."""
+        s_ = i % 2
+        ts.copy_stream.wait_event(ts.consumed[s_])               # WAR: step i-2 has moved staging[s_] into the static buffer
+        with torch.cuda.stream(ts.copy_stream):
+            ts.staging[s_].copy_(pinned[i % N_BATCH_POOL]["audio"], non_blocking=True)
+            ts.copy_done[s_].record()
+
     def feed_host(i):
         p = pinned[i % N_BATCH_POOL]
-        r = resident[i % N_BATCH_POOL]
-        ts.copy_stream.wait_stream(torch.cuda.current_stream())    # WAR: the previous step still reads the audio buffer
-        with torch.cuda.stream(ts.copy_stream):                # 4 MB of audio embeddings: overlaps the posterior chain
-            st_audio.copy_(p["audio"], non_blocking=True)
-            ts.audio_ready.record()
+        s_ = i % 2
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ts.copy_done[s_])                         # step i's audio has landed (copied during step i-1)
+        st_audio.copy_(ts.staging[s_], non_blocking=True)        # device-to-device, 4 MB
+        ts.consumed[s_].record()
+        prefetch(i + 1)                                          # step i+1's audio crosses PCIe while step i computes
         st_mem_lens.copy_(p["mem_lens"], non_blocking=True)
         model.prepare_batch(p["caps"], p["cap_lens"], dev, out=st_prep)  # caps float32 host -> ids | lens | targets, one H2D copy
 
-    def timed_e2e(n_steps):
+    def timed_e2e(n_steps, first=0):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
         barrier()
         wall = 0.0
@@ -373,7 +388,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             a.record()
-            feed_host(i)
+            feed_host(first + i)
             run_step()
             b.record()
             host_losses.append(float(loss_buf))        # D2H read of the step's loss (synchronises)
@@ -384,9 +399,10 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / n_steps
 
+    prefetch(0)
     for i in range(3):
         feed_host(i); run_step()
-    ms_e2e = timed_e2e(args.steps)
+    ms_e2e = timed_e2e(args.steps, first=3)
     clk = clocks.stop()
 
     # ---- dominant kernel, timed live with CUDA events on its own launching stream (eager steps, L2 flushed) ----
@@ -396,8 +412,11 @@ def run_ours(args):
 
     def eager_step():
         load_resident(0); ts.step_body()
-    chain_us, chain_n = probe_kernel(lib, "dec_chain_fwd_kernel", eager_step, n_probe, lambda: flush.fill_(1.0))
-    chainb_us, chainb_n = probe_kernel(lib, "dec_chain_bwd_kernel", eager_step, n_probe, lambda: flush.fill_(1.0))
+    chain_timing = {}
+    for kname in chain_kernels(d):
+        us_, n_ = probe_kernel(lib, kname, eager_step, n_probe, lambda: flush.fill_(1.0))
+        if us_:
+            chain_timing[kname] = (us_, n_)
     attn_us, _ = probe_kernel(lib, "attn_fwd_kernel", eager_step, n_probe, lambda: flush.fill_(1.0))
     # the largest tcgen05 GEMM of the step (vocabulary statistics, [N*T, E] x [E, V]) on its own
     hid = torch.randn(d.N * st_prep.T, d.E, device=dev)
@@ -491,20 +510,15 @@ def run_ours(args):
         except Exception:
             pass
         chain_entries = []
-        for kname, us_, n_, kb, what in (
-                ("dec_chain_fwd_kernel", chain_us, chain_n, chain_kernel_bytes(d) if chain_us else 0,
-                 "decoder + prior forward chains, all T steps in ONE persistent cooperative launch; 3 grid barriers per step"),
-                ("dec_chain_bwd_kernel", chainb_us, chainb_n, chain_bwd_kernel_bytes(d) if chainb_us else 0,
-                 "decoder + prior backward chains (BPTT), all T steps in ONE persistent cooperative launch; 3 grid barriers per step")):
-            if not us_:
-                continue
+        for kname, (us_, n_) in chain_timing.items():
+            kb, what = chain_kernels(d)[kname]
             k_ach = kb / (us_ * 1e-6) / 1e9
             chain_entries.append({
                 "bound": "hbm", "achieved": round(k_ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": round(k_ach / peaks["hbm_gbs"], 4),
                 "traffic": ncu.get(kname, {}).get("dram_bytes_per_launch"),
-                "kernel": f"{kname}: {what}; bound by that serial chain of barriers + L2 round trips, not by bandwidth "
-                          "(DESIGN.md 4.3)",
+                "kernel": f"{kname}: {what}; bound by the serial chain of T dependent steps (exchange latency + the step's "
+                          "FFMA / MUFU work on the SMs of one cluster), not by bandwidth (DESIGN.md 4.3)",
                 "us_per_launch": round(us_, 1), "launches_timed": n_, "share_of_step": round(us_ * 1e-3 / ms_resident, 3),
                 "algorithmic_bytes_per_launch": int(kb), "peak_source": peaks["src"],
                 "timing": "CUDA events recorded on the kernel's launching stream (acvae_set_kernel_probe), eager steps, L2 flushed"})
@@ -556,8 +570,9 @@ def run_ours(args):
             "config": workload_config(d, world, graph is not None),
             "e2e": {"value": round(e2e, 1), "unit": "clips/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
                     "ms_per_step": round(ms_e2e, 4),
-                    "note": "host buffers -> prepare_batch (one pinned staging copy) + audio copy on a side stream that the step "
-                            "waits for where the audio is first read (acvae_set_input_event) -> graph replay -> loss read back"},
+                    "note": "host buffers -> prepare_batch (one pinned staging copy of ids | lens | targets) + the audio copy of the NEXT "
+                            "step on a side stream (double-buffered device staging; every timed step issues one 4 MB audio copy) "
+                            "-> graph replay -> loss read back"},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "clocks": clk,
