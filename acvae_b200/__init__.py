@@ -20,8 +20,9 @@ from .models import (CaptionModel, Hybrid_VAEModel, PosteriorRNN, PosteriorRNN_h
 from .train_util import CrossEntropyLoss, FusedVAELoss, LabelSmoothingLoss, Normal_kl_loss  # noqa: F401
 from .lazy import LazyLogits  # noqa: F401
 from .optim import FusedClipAdam  # noqa: F401
-from .metrics import diversity_stats  # noqa: F401
-from .functional import get_precision, set_input_event, set_precision  # noqa: F401
+from .metrics import diversity_stats, ids_to_sentences, mbleu, predictions_json  # noqa: F401
+from .sampler import GraphSampler, gather_captions  # noqa: F401
+from .functional import encoder_handoff, get_precision, set_input_event, set_precision  # noqa: F401
 
 # the reference resolves decoders as getattr(models.decoder, name) and posteriors/priors as
 # getattr(text_encoder, name) (pytorch_runner_vae.py:44, vae_model.py:678-691): same attribute paths

@@ -3,6 +3,7 @@
 #include "../../include/acvae_b200.h"
 #include <stdlib.h>
 
+#include "handoff.cuh"
 #include "optim.cuh"
 #include "sample.cuh"
 #include "train_fast.cuh"
@@ -332,6 +333,17 @@ int acvae_diverse_beam_search(const acvae_dims* d, const acvae_weights* w, const
                              group_nbest != 0, start_idx, end_idx, seqs, workspace, (cudaStream_t)stream);
 }
 
+int acvae_encoder_handoff_fwd(int32_t N, int32_t C, int32_t Te, int32_t F, const float* fmap, float* audio_embeds, float* pooled,
+                              void* stream) {
+  ACVAE_REQUIRE(N > 0 && C > 0 && Te > 0 && F > 0 && fmap && audio_embeds, "bad argument");
+  return encoder_handoff_fwd(N, C, Te, F, fmap, audio_embeds, pooled, (cudaStream_t)stream);
+}
+
+int acvae_encoder_handoff_bwd(int32_t N, int32_t C, int32_t Te, int32_t F, const float* d_audio_embeds, float* d_fmap, void* stream) {
+  ACVAE_REQUIRE(N > 0 && C > 0 && Te > 0 && F > 0 && d_audio_embeds && d_fmap, "bad argument");
+  return encoder_handoff_bwd(N, C, Te, F, d_audio_embeds, d_fmap, (cudaStream_t)stream);
+}
+
 // profiling only (profiles/chain_trace.py): device buffer of [T][16] int64 that thread 0 of CTA 0 of the decoder
 // forward chain fills with clock64 stamps; NULL switches it off
 int acvae_debug_set_chain_trace(void* device_buffer) {
@@ -356,6 +368,15 @@ int acvae_diversity_stats(int32_t clips, int32_t K, int32_t L, int32_t V, const 
   ACVAE_REQUIRE(smem <= 48 * 1024, "K * L too large for the per-clip shared-memory table (<= 6144 tokens)");
   ACVAE_LAUNCH(diversity_stats_kernel, clips, 256, smem, (cudaStream_t)stream, K, L, V, start_idx, end_idx, (const long long*)seqs,
                div1, div2, vocab_flags);
+  return 0;
+}
+
+int acvae_mbleu_stats(int32_t clips, int32_t K, int32_t L, const int64_t* seqs, int32_t start_idx, int32_t end_idx, int32_t* stats,
+                      void* stream) {
+  ACVAE_REQUIRE(clips > 0 && K >= 2 && L > 0 && seqs && stats, "bad argument (mBLEU needs K >= 2 captions per clip)");
+  const size_t smem = sizeof(int) * ((size_t)K * L + K + 1 + (size_t)K * 4);
+  ACVAE_REQUIRE(smem <= 48 * 1024, "K * L too large for the per-clip shared-memory table");
+  ACVAE_LAUNCH(mbleu_stats_kernel, clips, 256, smem, (cudaStream_t)stream, K, L, start_idx, end_idx, (const long long*)seqs, stats);
   return 0;
 }
 

@@ -690,4 +690,67 @@ __global__ void __launch_bounds__(256) diversity_stats_kernel(int K, int L, int 
   }
 }
 
+// mBLEU statistics of the K captions decoded per clip (utils/diverse_mutil.py:35-51, eval_div_stats): for every caption i
+// of a clip the sufficient statistics of BLEU-1..4 with caption i as the candidate and the clip's other K-1 captions as
+// the references -- out[clip][i] = {testlen, reflen (closest reference length), guess[4], correct[4]} (pycocoevalcap
+// BleuScorer: cook_test / cook_refs with clipped counts).  The corpus sums over clips and the BLEU formula (40 numbers)
+// are left to the caller.  One CTA per clip; an n-gram of the candidate is "correct" when it is at most the m-th
+// occurrence of that n-gram in the candidate, m = the largest count of the n-gram in any single reference.
+__global__ void __launch_bounds__(256) mbleu_stats_kernel(int K, int L, int start_idx, int end_idx, const long long* __restrict__ seqs,
+                                                          int* __restrict__ out) {
+  extern __shared__ int msm[];
+  int* tok = msm;                    // [K*L] compacted tokens, caption after caption
+  int* off = tok + K * L;            // [K+1] first token of caption k
+  int* corr = off + K + 1;           // [K][4]
+  const int clip = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) {
+    int n = 0;
+    for (int k = 0; k < K; ++k) {
+      off[k] = n;
+      for (int l = 0; l < L; ++l) {
+        const int w = (int)seqs[((long long)clip * K + k) * L + l];
+        if (w == end_idx) break;
+        if (w == start_idx) continue;
+        tok[n++] = w;
+      }
+    }
+    off[K] = n;
+  }
+  for (int i = tid; i < K * 4; i += blockDim.x) corr[i] = 0;
+  __syncthreads();
+  const int items = K * 4 * L;       // (candidate i, order n - 1, position p)
+  for (int it = tid; it < items; it += blockDim.x) {
+    const int p = it % L, n = (it / L) % 4 + 1, i = it / (4 * L);
+    const int len = off[i + 1] - off[i];
+    if (p + n > len) continue;
+    const int* g = tok + off[i] + p;
+    auto same = [&](const int* a) { bool eq = true; for (int x = 0; x < n; ++x) eq = eq && a[x] == g[x]; return eq; };
+    int occ = 1;
+    for (int q = 0; q < p; ++q) occ += same(tok + off[i] + q) ? 1 : 0;
+    int maxref = 0;
+    for (int r = 0; r < K; ++r) {
+      if (r == i) continue;
+      const int lr = off[r + 1] - off[r];
+      int c = 0;
+      for (int q = 0; q + n <= lr; ++q) c += same(tok + off[r] + q) ? 1 : 0;
+      maxref = c > maxref ? c : maxref;
+    }
+    if (occ <= maxref) atomicAdd(&corr[i * 4 + n - 1], 1);
+  }
+  __syncthreads();
+  for (int i = tid; i < K; i += blockDim.x) {
+    const int len = off[i + 1] - off[i];
+    int best_d = 0x7fffffff, best_l = 0x7fffffff;       // closest reference length, ties to the shorter (min of (|l - len|, l))
+    for (int r = 0; r < K; ++r) {
+      if (r == i) continue;
+      const int lr = off[r + 1] - off[r];
+      const int dd = lr > len ? lr - len : len - lr;
+      if (dd < best_d || (dd == best_d && lr < best_l)) { best_d = dd; best_l = lr; }
+    }
+    int* o = out + ((long long)clip * K + i) * 10;
+    o[0] = len; o[1] = best_l;
+    for (int n = 1; n <= 4; ++n) { o[1 + n] = len - n + 1 > 0 ? len - n + 1 : 0; o[5 + n] = corr[i * 4 + n - 1]; }
+  }
+}
+
 }  // namespace acvae

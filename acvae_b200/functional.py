@@ -570,6 +570,46 @@ def diverse_beam_search(dims, weights, audio_embeds, mem_lens, eps_g, beam_size=
     return {"seqs": seqs}
 
 
+class EncoderHandoffFn(torch.autograd.Function):
+    """audio_embeds [N,Te,C] (+ pooled [N,C]) from the last convolution block's output [N,C,Te,F] in one pass: replaces
+    `torch.mean(x, dim=3)` + `x.transpose(1, 2).contiguous()` of Cnn10.forward (models/encoder.py:691-700)."""
+
+    @staticmethod
+    @_guard
+    def forward(ctx, fmap, want_pooled):
+        l = _lib.lib()
+        fmap = fmap.contiguous()
+        N, Cc, Te, Fq = fmap.shape
+        out = torch.empty(N, Te, Cc, dtype=torch.float32, device=fmap.device)
+        pooled = torch.empty(N, Cc, dtype=torch.float32, device=fmap.device) if want_pooled else None
+        _lib.check(l.acvae_encoder_handoff_fwd(N, Cc, Te, Fq, _dev(fmap), _dev(out), _opt(pooled), _stream()),
+                   "acvae_encoder_handoff_fwd")
+        ctx.shape = (N, Cc, Te, Fq)
+        if want_pooled:
+            ctx.mark_non_differentiable(pooled)      # the VAE decoder ignores the pooled embedding (decoder.py:175-180)
+            return out, pooled
+        return out, None
+
+    @staticmethod
+    @_guard
+    def backward(ctx, g, _gp):
+        l = _lib.lib()
+        N, Cc, Te, Fq = ctx.shape
+        g = g.contiguous()
+        d = torch.empty(N, Cc, Te, Fq, dtype=torch.float32, device=g.device)
+        _lib.check(l.acvae_encoder_handoff_bwd(N, Cc, Te, Fq, _dev(g), _dev(d), _stream()), "acvae_encoder_handoff_bwd")
+        return d, None
+
+
+def encoder_handoff(fmap: torch.Tensor, lens, want_pooled: bool = False):
+    """The output contract of the reference's encoders (models/encoder.py:702-707) from the feature map of the last
+    convolution block: {'audio_embeds' [N,Te,C], 'audio_embeds_pooled' (max + mean over frames of the frame means, BEFORE
+    the reference's dropout / embed_pooled / relu, or None), 'state': None, 'audio_embeds_lens'}.  `lens` must already be
+    in frames (the reference divides by 16 in place, :677-678)."""
+    out, pooled = EncoderHandoffFn.apply(fmap, bool(want_pooled))
+    return {"audio_embeds": out, "audio_embeds_pooled": pooled, "state": None, "audio_embeds_lens": lens}
+
+
 def set_precision(mode: str) -> None:
     """Arithmetic of the batched contractions: "fp32" (default; 3xTF32 on the tensor cores, the 1e-4 parity mode) or
     "tf32" (single-pass TF32 products, fp32 accumulation: the reduced-precision class BASELINE.json calls bf16, 2e-2).

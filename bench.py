@@ -464,6 +464,38 @@ def run_ours(args):
         dist.all_reduce(ms_s, op=dist.ReduceOp.MAX)
     ms_sample = float(ms_s)
 
+    # ---- the same loop as ONE CUDA graph (acvae_b200.GraphSampler), device-resident and end to end: host clip memory
+    #      (pinned) -> H2D -> decode loop -> ids D2H, per rank; then the ids of all ranks gathered on rank 0 ----
+    from acvae_b200 import GraphSampler, gather_captions
+    gs = GraphSampler(model, clips=hi - lo, Te=d.Te, n_captions=SAMPLE_K, max_length=SAMPLE_LEN, method="sample")
+    h_audio = torch.from_numpy(sb["audio_embeds"]).pin_memory()
+    h_lens = torch.from_numpy(sb["mem_lens"].astype(np.int32)).pin_memory()
+    h_ids = torch.empty(hi - lo, SAMPLE_K, SAMPLE_LEN, dtype=torch.int64).pin_memory()
+    for _ in range(2):
+        gs(s_audio, s_lens)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); a.record()
+    for _ in range(n_rep):
+        gs(s_audio, s_lens)
+    b.record(); barrier()
+    ms_g = torch.tensor([a.elapsed_time(b) / n_rep], device=dev, dtype=torch.float64)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_rep):
+        h_ids.copy_(gs(h_audio, h_lens), non_blocking=True)      # H2D of the clip memory, replay, D2H of the ids
+        torch.cuda.synchronize()
+    ms_ge = torch.tensor([(time.perf_counter() - t0) * 1e3 / n_rep], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_g, op=dist.ReduceOp.MAX); dist.all_reduce(ms_ge, op=dist.ReduceOp.MAX)
+    ms_sample_graph, ms_sample_e2e = float(ms_g), float(ms_ge)
+    t0 = time.perf_counter()
+    all_ids = gather_captions(gs.out["seqs"], SAMPLE_CLIPS)       # rank 0: [1045, K, L] on the host
+    ms_gather = (time.perf_counter() - t0) * 1e3
+    if rank == 0:
+        assert tuple(all_ids.shape) == (SAMPLE_CLIPS, SAMPLE_K, SAMPLE_LEN)
+    sample_bytes = (h_audio.numel() * 4 + h_lens.numel() * 4, h_ids.numel() * 8)
+
     # ---- the same sampling loop with single-pass TF32 contractions (the reduced-precision class of BASELINE.json), and
     #      the largest contraction of a decode step ([sequences, 4E] LSTM gates, K = 3E + E) alone in both modes ----
     import acvae_b200 as models_pkg
@@ -582,7 +614,15 @@ def run_ours(args):
                          "unit": "captions/s", "ms": round(ms_sample, 3), "clips": SAMPLE_CLIPS, "captions_per_clip": SAMPLE_K,
                          "max_length": SAMPLE_LEN, "method": "sample", "launches": int(sample_launches),
                          "n_steps_executed": int(o["n_steps"]),
-                         "ms_per_decode_step": round(ms_sample / max(1, int(o["n_steps"])), 4)},
+                         "ms_per_decode_step": round(ms_sample / max(1, int(o["n_steps"])), 4),
+                         "graph": {"value": round(SAMPLE_CLIPS * SAMPLE_K / (ms_sample_graph * 1e-3), 1), "ms": round(ms_sample_graph, 3),
+                                   "note": "the whole decode loop replayed as one CUDA graph (GraphSampler), clip memory resident"},
+                         "e2e": {"value": round(SAMPLE_CLIPS * SAMPLE_K / (ms_sample_e2e * 1e-3), 1), "unit": "captions/s",
+                                 "ms": round(ms_sample_e2e, 3), "h2d_bytes_per_call": int(sample_bytes[0]),
+                                 "d2h_bytes_per_call": int(sample_bytes[1]),
+                                 "note": "per rank: pinned host clip memory -> device, graph replay, token ids -> pinned host; "
+                                         "wall clock, max over ranks"},
+                         "gather_ids_to_rank0_ms": round(ms_gather, 3)},
             "sampling_tf32": {"metric": "sampled_captions_per_s", "value": round(SAMPLE_CLIPS * SAMPLE_K / (ms_sample_fast * 1e-3), 1),
                               "unit": "captions/s", "ms": round(ms_sample_fast, 3), "n_steps_executed": int(o_fast["n_steps"]),
                               "ms_per_decode_step": round(ms_sample_fast / max(1, int(o_fast["n_steps"])), 4),

@@ -245,6 +245,26 @@ int acvae_clip_adam_dev(int64_t n, float *params, float *grads, float *exp_avg, 
                         const float *hyper, int32_t *step, float *total_norm, int32_t write_clipped_grads,
                         void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- mBLEU sufficient statistics (utils/diverse_mutil.py:35-51, eval_div_stats) --------------------
+ * For every caption i of a clip, BLEU-1..4 statistics with caption i as the candidate and the clip's other
+ * K-1 captions as the references (pycocoevalcap BleuScorer with option "closest"):
+ * stats[clip][i][10] = {testlen, reflen, guess[4], correct[4]}.  Captions are the ids up to the first
+ * <end>, <start> skipped (runners/base_runner.py:146-157).  seqs [clips, K, L] int64, K >= 2.           */
+int acvae_mbleu_stats(int32_t clips, int32_t K, int32_t L, const int64_t *seqs, int32_t start_idx,
+                      int32_t end_idx, int32_t *stats, void *stream);
+
+/* ---- encoder hand-off -------------------------------------------------------
+ * Replaces the tail of Cnn10.forward, models/encoder.py:691 `x = torch.mean(x, dim=3)` and :700
+ * `x = x.transpose(1, 2).contiguous()`, by ONE pass over the last convolution block's output
+ * fmap [N, C, Te, F] (contiguous) that writes audio_embeds [N, Te, C] -- the row-major frame memory
+ * acvae_memory_prepare / acvae_train_fwd / acvae_decode_sample read through TMA.  pooled (optional,
+ * [N, C]) = max over frames + mean over frames of the same means (:693-695, the operand of
+ * `embed_pooled`; the VAE decoder ignores it).  bwd: d_fmap[n,c,j,f] = d_audio_embeds[n,j,c] / F.     */
+int acvae_encoder_handoff_fwd(int32_t N, int32_t C, int32_t Te, int32_t F, const float *fmap,
+                              float *audio_embeds, float *pooled, void *stream);
+int acvae_encoder_handoff_bwd(int32_t N, int32_t C, int32_t Te, int32_t F, const float *d_audio_embeds,
+                              float *d_fmap, void *stream);
+
 /* ---- loss composition (runners/pytorch_runner_vae.py:315-320) as one node ------------------
  * terms[4] = {loss, ce, kl, mse}; loss = ce + kl_weight*kl + alpha*mean((q_utt - p_utt)^2) (nn.MSELoss, :318).
  * ce / kl are the device scalars of acvae_vocab_ce_fwd / acvae_kl_fwd.  q_utt == p_utt == NULL: no global term.

@@ -248,6 +248,38 @@ def test_sampling_large_batch_tensor_core_step_vs_oracle():
     assert np.array_equal(out["seqs"].cpu().numpy().reshape(d.N * K, ml), o["seqs"].numpy())
 
 
+def test_graph_sampler_matches_eager_and_oracle():
+    """The whole sampling loop as one CUDA graph (GraphSampler): same ids as the eager call and as the oracle under the same
+    injected noise, on two different clip batches replayed through ONE capture (262 sequences: the tensor-core decode step)."""
+    _require_cuda()
+    import acvae_oracle as oracle
+    from acvae_b200 import GraphSampler
+    d, seed, ml, K = synthetic.Dims(N=26, Te=62, L=9), 8, 8, 10
+    m = harness.build_model(d, seed).eval()
+    gs = GraphSampler(m, clips=d.N, Te=d.Te, n_captions=K, max_length=ml, method="sample", inject_noise=True)
+    p = harness.oracle_params(d, seed)
+    for bseed in (8, 9):
+        b = synthetic.make_batch(d, bseed)
+        rs = np.random.RandomState(bseed)
+        eps = torch.from_numpy(rs.standard_normal((ml, d.N * K, d.E)).astype(np.float32))
+        u = torch.from_numpy(rs.uniform(size=(ml, d.N * K, d.V)).astype(np.float32))
+        gs.eps_p.copy_(eps); gs.u.copy_(u)
+        seqs = gs(torch.from_numpy(b["audio_embeds"]).pin_memory(), b["mem_lens"]).cpu().numpy()
+        with torch.no_grad():
+            eager = m(torch.from_numpy(b["audio_embeds"]).cuda(), torch.from_numpy(b["mem_lens"].copy()), method="sample",
+                      max_length=ml, n_captions=K, eps_p=eps, u=u)["seqs"].cpu().numpy()
+            o = oracle.inference_forward(p, torch.from_numpy(b["audio_embeds"]).repeat_interleave(K, 0),
+                                         np.repeat(b["mem_lens"], K), eps, "sample", ml, 1.0, u)
+        assert seqs.shape == (d.N, K, ml)
+        assert np.array_equal(seqs, eager), "graph replay differs from the eager loop"
+        assert np.array_equal(seqs.reshape(d.N * K, ml), o["seqs"].numpy()), "graph replay differs from the oracle"
+    # own noise (the product path): replays draw fresh noise
+    gs2 = GraphSampler(m, clips=d.N, Te=d.Te, n_captions=K, max_length=ml, method="sample")
+    a1 = gs2(torch.from_numpy(b["audio_embeds"]), b["mem_lens"]).clone()
+    a2 = gs2(torch.from_numpy(b["audio_embeds"]), b["mem_lens"]).clone()
+    assert not torch.equal(a1, a2), "two replays must not reuse the same noise"
+
+
 def test_sampling_full_size_first_and_last_clips_vs_oracle():
     """BASELINE configs[3] at full size: 1045 clips x 10 captions = 10 450 sequences, max_length 20, multinomial sampling.
     The oracle decodes the first and the last clip (20 sequences) under the SAME prior noise and the SAME uniforms (the rows
@@ -514,6 +546,96 @@ def test_fused_clip_adam_follows_lr_schedule_inside_cuda_graph():
     opt2.load_state_dict(rsd)                                    # a STOCK Adam checkpoint loads
     assert int(opt2.step_count) == 8 and abs(opt2.lr - ropt.param_groups[0]["lr"]) < 1e-12
     torch.testing.assert_close(opt2.exp_avg[:300 * 256].view(300, 256), rsd["state"][0]["exp_avg"])
+
+
+def test_mbleu_vs_oracle():
+    """(f4) mBLEU-1..4 of eval_div_stats (utils/diverse_mutil.py:35-51) on the device == the CPU restatement of
+    pycocoevalcap's scorer: random captions with repeated words, early <end>, empty captions and full-length ones; and on
+    real sampler output (ids of 40 clips x 10 captions)."""
+    _require_cuda()
+    import diversity_oracle as dv
+    from acvae_b200 import metrics
+    rs = np.random.RandomState(4)
+    clips, K, L, V = 37, 6, 12, 15                       # tiny vocabulary: many repeated n-grams
+    seqs = rs.randint(2, V, size=(clips, K, L)).astype(np.int64)
+    seqs[:, :, 0] = 1                                    # <start>
+    seqs[0, 0, 1] = 2                                    # an empty caption
+    seqs[3, 2, :] = rs.randint(4, V, size=L)             # never ends
+    got = metrics.mbleu(torch.from_numpy(seqs).cuda())
+    want, per = dv.mbleu(seqs)
+    for n in range(1, 5):
+        assert abs(got[f"mBLeu_{n}"] - want[f"mBLeu_{n}"]) <= 1e-12 + 1e-9 * want[f"mBLeu_{n}"], (n, got, want)
+    for i in range(K):
+        assert np.allclose(got["per_candidate"][i], per[i], rtol=1e-9, atol=1e-15)
+    d = synthetic.Dims(N=40, Te=9, L=13, E=32, H=32, A=32, Hq=32, V=80, Eenc=48)
+    m = harness.build_model(d, 3).eval()
+    b = synthetic.make_batch(d, 3)
+    with torch.no_grad():
+        out = m(torch.from_numpy(b["audio_embeds"]).cuda(), torch.from_numpy(b["mem_lens"].copy()), method="sample",
+                max_length=12, n_captions=10)
+    got = metrics.mbleu(out["seqs"])
+    want, _ = dv.mbleu(out["seqs"].cpu().numpy())
+    assert abs(got["mBLeu_4"] - want["mBLeu_4"]) <= 1e-12 + 1e-9 * want["mBLeu_4"]
+    assert 0.0 <= got["mBLeu_4"] <= got["mBLeu_1"] <= 1.0
+
+
+@pytest.mark.parametrize("shape", [(32, 512, 62, 4), (3, 70, 9, 4), (2, 48, 187, 2), (1, 33, 5, 3)])
+def test_encoder_handoff_matches_cnn10_tail(shape):
+    """(f3) encoder hand-off: one pass == `torch.mean(x, dim=3)`, `(max + mean)(dim=2)`, `x.transpose(1, 2).contiguous()`
+    of Cnn10.forward (models/encoder.py:691-700), forward and backward, and its output drives the step unchanged."""
+    _require_cuda()
+    import acvae_b200 as models
+    torch.manual_seed(2)
+    N, C, Te, Fq = shape
+    fmap = torch.randn(N, C, Te, Fq, device="cuda").abs_().requires_grad_(True)
+    enc = models.encoder_handoff(fmap, torch.full((N,), Te), want_pooled=True)
+    x = torch.mean(fmap.detach().double(), dim=3)                      # :691
+    ref_pooled = x.max(dim=2)[0] + x.mean(dim=2)                       # :693-695
+    ref = x.transpose(1, 2).contiguous()                               # :700
+    assert enc["audio_embeds"].shape == (N, Te, C) and enc["audio_embeds"].is_contiguous()
+    assert harness.rel_err(enc["audio_embeds"], ref) < 1e-6
+    assert harness.rel_err(enc["audio_embeds_pooled"], ref_pooled) < 1e-6
+    g = torch.randn(N, Te, C, device="cuda")
+    enc["audio_embeds"].backward(g)
+    want = (g.double().transpose(1, 2) / Fq).unsqueeze(3).expand(N, C, Te, Fq)
+    assert harness.rel_err(fmap.grad, want) < 1e-6
+
+
+def test_encoder_handoff_feeds_the_train_step():
+    """The hand-off output is the step's `audio_embeds`: loss and the gradient w.r.t. the convolution feature map equal the
+    reference composition (mean, transpose, then the step) on the oracle."""
+    _require_cuda()
+    import acvae_b200 as models
+    d, seed, Fq = synthetic.CFG0, 6, 4
+    b = synthetic.make_batch(d, seed)
+    rs = np.random.RandomState(3)
+    # a feature map whose frequency mean is the batch's audio_embeds (so the oracle run of harness applies unchanged)
+    noise = rs.standard_normal((d.N, d.Eenc, d.Te, Fq)).astype(np.float32)
+    noise -= noise.mean(axis=3, keepdims=True)
+    fmap_np = np.transpose(b["audio_embeds"], (0, 2, 1))[..., None] + noise
+    fmap = torch.from_numpy(fmap_np).cuda().requires_grad_(True)
+
+    class Tail(torch.nn.Module):                    # an encoder whose forward ends in the fused hand-off
+        embed_size = d.Eenc
+
+        def forward(self, feats, lens):
+            return models.encoder_handoff(feats, lens)
+    m = harness.build_model(d, seed)
+    m.encoder = Tail()
+    T = int(b["cap_lens"].max()) - 1
+    caps = torch.from_numpy(b["caps"])
+    lens1 = torch.as_tensor(b["cap_lens"]) - 1
+    out = m(fmap, torch.from_numpy(b["mem_lens"].copy()), caps, b["cap_lens"].copy(), ss_ratio=1.0, dis_ratio=0.0,
+            eps_q=torch.from_numpy(b["eps_q"][:, :T].copy()), eps_p=torch.from_numpy(b["eps_p"][:T].copy()),
+            tf_flags=[True] * T, dis_flags=[False] * T)
+    packed = torch.nn.utils.rnn.pack_padded_sequence(out["logits"], lens1, batch_first=True).data
+    targets = torch.nn.utils.rnn.pack_padded_sequence(caps[:, 1:], lens1, batch_first=True).data
+    loss = models.FusedVAELoss(d.V, smoothing=0.1, alpha=1.0)(out, packed, targets, 0.5)
+    loss.backward()
+    o = harness.run_oracle_train(d, seed)
+    assert abs(float(loss) - float(o["terms"]["loss"])) <= TOL * abs(float(o["terms"]["loss"]))
+    want = (o["grads"]["audio_embeds"].double().transpose(1, 2) / Fq).unsqueeze(3).expand(d.N, d.Eenc, d.Te, Fq)
+    harness.assert_close(fmap.grad.reshape(d.N * d.Eenc, -1), want.reshape(d.N * d.Eenc, -1), TOL, "d feature map")   # rows = (clip, channel)
 
 
 def test_fused_vae_loss_matches_separate_callables():

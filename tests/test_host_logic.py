@@ -93,3 +93,39 @@ def test_bench_reference_arm_runs_without_gpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "train_clips_per_s" and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+
+
+def test_ids_to_sentences_and_prediction_file(tmp_path):
+    """runners/base_runner.py:146-157 (`_convert_idx2sentence`: stop at <end>, skip <start>) and :243-293 (prediction file)."""
+    import json
+    from acvae_b200 import metrics
+    idx2word = {0: "<pad>", 1: "<start>", 2: "<end>", 3: "<unk>", 4: "a", 5: "dog", 6: "barks", 7: "loudly"}
+    seqs = [[1, 4, 5, 6, 2, 2], [4, 5, 6, 7, 5, 6]]                     # second caption never emits <end>
+    assert metrics.ids_to_sentences(seqs, idx2word) == ["a dog barks", "a dog barks loudly dog barks"]
+    assert metrics.ids_to_sentences(seqs, idx2word, zh=True)[0] == ["a", "dog", "barks"]
+    single = metrics.predictions_json(["x.wav", "y.wav"], seqs, idx2word)
+    assert single == {"predictions": [{"filename": "x.wav", "caption": "a dog barks", "tokens": "a dog barks"},
+                                      {"filename": "y.wav", "caption": "a dog barks loudly dog barks",
+                                       "tokens": "a dog barks loudly dog barks"}]}
+    multi = metrics.predictions_json(["x.wav"], [[[4, 5, 2, 0], [5, 6, 7, 2]]], idx2word, path=str(tmp_path / "p.json"))
+    assert multi["predictions"][0]["captions"] == [{"caption": "a dog", "cap_id": 0, "tokens": "a dog"},
+                                                   {"caption": "dog barks loudly", "cap_id": 1, "tokens": "dog barks loudly"}]
+    assert json.load(open(tmp_path / "p.json")) == multi
+    zh = metrics.predictions_json(["x.wav"], [[4, 5, 2]], idx2word, zh=True)
+    assert zh["predictions"][0] == {"filename": "x.wav", "caption": "adog", "tokens": "a dog"}
+
+
+def test_bleu_oracle_hand_worked_case():
+    """The BLEU restatement (oracle/diversity_oracle.py, pycocoevalcap BleuScorer) on a case small enough to do by hand:
+    candidate `a b a b`, references `a b c` and `a a`: unigram matches clip at max-per-reference counts (a: 2, b: 1)."""
+    import math
+    import diversity_oracle as dv
+    from acvae_b200 import metrics
+    testlen, reflen, guess, correct = dv.bleu_stats([4, 5, 4, 5], [[4, 5, 6], [4, 4]])
+    assert (testlen, reflen, guess, correct) == (4, 3, [4, 3, 2, 1], [3, 1, 0, 0])
+    b = dv.corpus_bleu([(testlen, reflen, guess, correct)])
+    assert abs(b[0] - 0.75) < 1e-9 and abs(b[1] - math.sqrt(0.75 / 3)) < 1e-9 and b[3] < 1e-3
+    assert metrics.bleu_from_stats(testlen, reflen, guess, correct) == b
+    # brevity penalty: candidate shorter than the closest reference
+    t2 = dv.bleu_stats([4, 5], [[4, 5, 6, 7]])
+    assert abs(dv.corpus_bleu([t2])[0] - math.exp(1 - 4 / 2)) < 1e-6

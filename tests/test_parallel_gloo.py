@@ -51,6 +51,17 @@ def _worker(rank, world, port, out):
         assert spans[0][0] == 0 and spans[-1][1] == 1045
         for a, b in zip(spans[:-1], spans[1:]):
             assert a[1] == b[0]
+        # ... and the optional gather of the ids at the end: rank 0 gets every clip's captions in clip order
+        from acvae_b200 import sampler
+        total_clips = 11                                   # 6 + 5: ragged shards
+        lo, hi = parallel.shard_range(total_clips, rank, world)
+        mine = (torch.arange(lo, hi).view(-1, 1, 1) * 100 + torch.arange(3).view(1, 3, 1) * 10 + torch.arange(4).view(1, 1, 4)).long()
+        got = sampler.gather_captions(mine, total_clips)
+        if rank == 0:
+            want = (torch.arange(total_clips).view(-1, 1, 1) * 100 + torch.arange(3).view(1, 3, 1) * 10 + torch.arange(4).view(1, 1, 4)).long()
+            assert got.shape == (total_clips, 3, 4) and torch.equal(got, want)
+        else:
+            assert got is None
         out.put((rank, "ok"))
     finally:
         dist.destroy_process_group()
