@@ -486,4 +486,187 @@ inline int launch_attn_bwd_acc(const AttnBwdAccParams& p, cudaStream_t st) {
   return 0;
 }
 
+// ---- backward of ALL rows of a clip together (hoisted schedule) -------------------------------------------------------
+// attn_bwd_q_kernel (one CTA per query row) + attn_bwd_acc_kernel (one CTA per clip and frame chunk) evaluate the same
+// 1 - tanh^2(P[j,a] + q[t,a]) terms twice and re-stream the clip's P / mem once per row: 46 + 42 us for the prior's
+// 608 rows at CFG1, on the critical tail of the backward.  Here a clip's rows are handled together, in two launches:
+//   attn_dalpha_kernel    d alpha[t,j] = d ctx[t,:] . mem[n,j,:]        grid (Te/8, clips), a warp per frame
+//                         (skipped when `ds_in` is given: the decoder's chain kernels have produced d s and d qp already)
+//   attn_bwd_clip_kernel  grid (4, clips); CTA (s, n) owns attention columns / memory columns [s*A/4, (s+1)*A/4):
+//     softmax backward d s[t,j] = w (d alpha - sum w d alpha) (every CTA of the clip, redundantly: T x Te values);
+//     ONE evaluation of g = 1 - tanh^2 per (t, j, a) feeds d qp[t,a] = v_a sum_j d s g, d P[j,a] = v_a sum_t d s g and
+//     d v[a] = sum d s tanh;   d mem[n,j,e] (+)= sum_t w[t,j] d ctx[t,e]
+struct AttnBwdClipParams {
+  int clips, T, Te, A, E;
+  const float* dctx;        // [clips*T, E]
+  const float* w;           // [clips*T, Te] saved softmax weights
+  const float* qp;          // [clips*T, A]  saved query projections
+  const float *P, *mem, *v; // [clips,Te,A], [clips,Te,E], [A]
+  const int* mem_lens;
+  const float* ds_in;       // optional [clips*T, Te]: d score already known
+  float* ds_out;            // [clips*T, Te]: scratch that carries d alpha between the two launches (used when ds_in == NULL)
+  float* dqp;               // [clips*T, A]  (written when ds_in == NULL)
+  float* dP;                // [clips,Te,A] (overwritten)
+  float* dmem; int dmem_accumulate;   // [clips,Te,E]
+  float* dv;                // [A], atomically accumulated (zeroed by the caller)
+};
+constexpr int kAbcSplit = 4;
+constexpr int kAbcMaxFr = 24;             // frames per thread in the tanh pass: Te <= 4 * 24
+inline size_t attn_bwd_clip_smem(int T, int Te, int A, int E) {
+  const int ld = Te + 1, AS = A / kAbcSplit;
+  return ((size_t)2 * T * ld + (size_t)T * E + (size_t)T * AS + (size_t)4 * T * AS + (size_t)Te * AS + 64) * sizeof(float);
+}
+
+// d alpha[t, j] for one clip and 8 frames: warp = frame, lanes over E (E <= 256), four rows' shuffle trees in flight at once
+__global__ void __launch_bounds__(256) attn_dalpha_kernel(int T, int Te, int E, const float* __restrict__ dctx, const float* __restrict__ mem,
+                                                          const int* __restrict__ mem_lens, float* __restrict__ dalpha) {
+  extern __shared__ __align__(16) float sm[];              // [T][E] d ctx rows of the clip
+  const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, j = blockIdx.x * 8 + (tid >> 5);
+  const int len = max(1, min(mem_lens[n], Te));
+  const long long r0 = (long long)n * T;
+  for (int i = tid; i < T * E; i += 256) sm[i] = dctx[r0 * E + i];
+  __syncthreads();
+  if (j >= Te) return;
+  if (j >= len) {
+    for (int t = lane; t < T; t += 32) dalpha[(r0 + t) * Te + j] = 0.0f;
+    return;
+  }
+  float m[8];
+  const float* mr = mem + ((long long)n * Te + j) * E;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m[k] = lane + 32 * k < E ? __ldg(mr + lane + 32 * k) : 0.0f;
+  for (int t0 = 0; t0 < T; t0 += 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = t0 + q < T ? t0 + q : T - 1;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (lane + 32 * k < E) acc[q] = fmaf(sm[t * E + lane + 32 * k], m[k], acc[q]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    if (lane < 4 && t0 + lane < T) dalpha[(r0 + t0 + lane) * Te + j] = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+  }
+}
+
+__global__ void __launch_bounds__(256) attn_bwd_clip_kernel(const __grid_constant__ AttnBwdClipParams p) {
+  extern __shared__ __align__(16) float sm[];
+  const int T = p.T, Te = p.Te, A = p.A, E = p.E, AS = A / kAbcSplit, ES = E / kAbcSplit, ld = Te + 1;
+  float* dss = sm;                        // [T][ld]  d alpha, then d score
+  float* ws = dss + T * ld;               // [T][ld]  softmax weights
+  float* dcs = ws + T * ld;               // [T][E]   d ctx rows of the clip
+  float* qs = dcs + T * E;                // [T][AS]  2 log2 e * q[t, my columns]
+  float* red = qs + T * AS;               // [4][T][AS] partial d qp per frame group
+  float* Pss = red + 4 * T * AS;          // [Te][AS] 2 log2 e * P[n, :, my columns]
+  const int s = blockIdx.x, n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int len = max(1, min(p.mem_lens[n], Te));
+  const long long r0 = (long long)n * T;
+  const float* dsrc = p.ds_in ? p.ds_in : p.ds_out;           // d score, or d alpha left by attn_dalpha_kernel
+  for (int i = tid; i < T * E; i += 256) dcs[i] = p.dctx[r0 * E + i];
+  for (int i = tid; i < T * Te; i += 256) {
+    const int t = i / Te, j = i % Te;
+    ws[t * ld + j] = j < len ? p.w[(r0 + t) * Te + j] : 0.0f;
+    dss[t * ld + j] = j < len ? dsrc[(r0 + t) * Te + j] : 0.0f;
+  }
+  for (int i = tid; i < T * AS; i += 256) { const int t = i / AS, a = i % AS; qs[i] = kTwoLog2e * p.qp[(r0 + t) * A + s * AS + a]; }
+  for (int i = tid; i < len * AS; i += 256) { const int j = i / AS, a = i % AS; Pss[i] = kTwoLog2e * __ldg(p.P + ((long long)n * Te + j) * A + s * AS + a); }
+  __syncthreads();
+  if (!p.ds_in) {
+    // softmax backward per row (a warp per row)
+    for (int t = wid; t < T; t += 8) {
+      float dot = 0.0f;
+      for (int j = lane; j < len; j += 32) dot = fmaf(ws[t * ld + j], dss[t * ld + j], dot);
+      dot = warp_sum(dot);
+      for (int j = lane; j < Te; j += 32) {
+        const float d = j < len ? ws[t * ld + j] * (dss[t * ld + j] - dot) : 0.0f;
+        dss[t * ld + j] = d;
+      }
+    }
+    __syncthreads();     // (d score stays on chip: the four CTAs of a clip all read d alpha from the scratch, nobody may overwrite it)
+  }
+  // ---- tanh pass: thread = (column a of my slice, frame group jq): frames j = jq + G*f, f < kAbcMaxFr; rows t in the outer loop ----
+  {
+    const int G = 256 / AS;                                    // frame groups (4 at A = 256)
+    const int a = tid % AS, jq = tid / AS, ag = s * AS + a;
+    const float va = __ldg(p.v + ag);
+    float dvacc = 0.0f;
+    float accP[kAbcMaxFr], pj[kAbcMaxFr];
+#pragma unroll
+    for (int f = 0; f < kAbcMaxFr; ++f) { accP[f] = 0.0f; const int j = jq + G * f; pj[f] = j < len ? Pss[j * AS + a] : 0.0f; }
+    for (int t = 0; t < T; ++t) {
+      const float qv = qs[t * AS + a];
+      const float* dr = dss + t * ld + jq;
+      float dq = 0.0f;
+#pragma unroll
+      for (int f = 0; f < kAbcMaxFr; ++f) {
+        if (jq + G * f < len) {
+          const float r = rcp_approx(ex2_approx(pj[f] + qv) + 1.0f);     // tanh = 1 - 2 r, 1 - tanh^2 = 4 r (1 - r)
+          const float d = dr[G * f];
+          const float g = 4.0f * d * fmaf(-r, r, r);
+          accP[f] += g; dq += g;
+          dvacc = fmaf(d, fmaf(-2.0f, r, 1.0f), dvacc);
+        }
+      }
+      if (!p.ds_in && jq < 4) red[(jq * T + t) * AS + a] = dq;
+    }
+#pragma unroll
+    for (int f = 0; f < kAbcMaxFr; ++f) {
+      const int j = jq + G * f;
+      if (j < Te) p.dP[((long long)n * Te + j) * A + ag] = j < len ? va * accP[f] : 0.0f;
+    }
+    atomicAdd(p.dv + ag, dvacc);
+    if (!p.ds_in) {
+      __syncthreads();
+      for (int i = tid; i < T * AS; i += 256) {
+        const int t = i / AS, aa = i % AS;
+        float sum = 0.0f;
+        for (int g2 = 0; g2 < G; ++g2) sum += red[(g2 * T + t) * AS + aa];
+        p.dqp[(r0 + t) * A + s * AS + aa] = __ldg(p.v + s * AS + aa) * sum;
+      }
+    }
+  }
+  // ---- d mem[n, j, my e slice] (+)= sum_t w[t,j] d ctx[t,e] ----
+  {
+    const int G = 256 / ES;
+    const int e = tid % ES, jq = tid / ES, eg = s * ES + e;
+    for (int j = jq; j < Te; j += G) {
+      float acc = 0.0f;
+      if (j < len)
+        for (int t = 0; t < T; ++t) acc = fmaf(ws[t * ld + j], dcs[t * E + eg], acc);
+      float* dst = p.dmem + ((long long)n * Te + j) * E + eg;
+      *dst = p.dmem_accumulate ? *dst + acc : acc;
+    }
+  }
+}
+// returns 1 if launched, 0 if the shape is not covered (caller falls back to attn_bwd_q + attn_bwd_acc)
+inline int launch_attn_bwd_clip(const AttnBwdClipParams& p, cudaStream_t st) {
+  if (p.clips <= 0) return 1;
+  const int AS = p.A / kAbcSplit, ES = p.E / kAbcSplit;
+  if (p.A % (4 * kAbcSplit) || p.E % (4 * kAbcSplit) || AS > 256 || ES > 256 || 256 % AS || 256 % ES || 256 / AS > 4 || p.E > 256 ||
+      p.Te > (256 / AS) * kAbcMaxFr)
+    return 0;
+  const size_t smem = attn_bwd_clip_smem(p.T, p.Te, p.A, p.E);
+  const size_t smem_a = (size_t)p.T * p.E * sizeof(float);
+  if (smem > 200 * 1024 || smem_a > 200 * 1024) return 0;
+  static size_t configured_dev[kMaxDevices] = {0}, configured_a[kMaxDevices] = {0};
+  size_t& configured = configured_dev[current_device()];
+  if (smem > configured) {
+    ACVAE_CHECK(cudaFuncSetAttribute(attn_bwd_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  if (!p.ds_in) {
+    size_t& conf_a = configured_a[current_device()];
+    if (smem_a > conf_a) {
+      ACVAE_CHECK(cudaFuncSetAttribute(attn_dalpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+      conf_a = smem_a;
+    }
+    ACVAE_LAUNCH(attn_dalpha_kernel, dim3((p.Te + 7) / 8, p.clips), 256, smem_a, st, p.T, p.Te, p.E, p.dctx, p.mem, p.mem_lens, p.ds_out);
+  }
+  ACVAE_LAUNCH(attn_bwd_clip_kernel, dim3(kAbcSplit, p.clips), 256, smem, st, p);
+  return 1;
+}
+
 }  // namespace acvae

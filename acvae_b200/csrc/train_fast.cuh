@@ -370,22 +370,30 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     }
     // critical first: d ctx -> attention backward -> per-clip accumulation (the memory backward waits for it)
     ACVAE_TRY(linear_bwd_data(NT, E, 4 * E, ws.dg_p, 4 * E, w.p_wih + E, 3 * E, ws.dctx_p, E, sp));
-    {
-      AttnBwdQParams a{};
-      a.rows = NT; a.Te = Te; a.A = E; a.E = E; a.rows_per_clip = T;
-      a.dctx = ws.dctx_p; a.ld_dctx = E; a.w = ws.w_p; a.ld_w = Te; a.qp = ws.qp_p; a.ld_qp = E;
-      a.P = ws.Pp; a.mem = ws.mem; a.v = w.p_attn_v; a.mem_lens = io.mem_lens;
-      a.ds = ws.ds_p; a.ld_ds = Te; a.dqp = ws.dqp_p; a.ld_dqp = E;
-      ACVAE_TRY(launch_attn_bwd_q(a, sp));
-    }
     ACVAE_CHECK(zero(gw.p_attn_v, E, sp));
     {
-      AttnBwdAccParams a{};
-      a.clips = N; a.Te = Te; a.A = E; a.E = E; a.rows_per_clip = T;
-      a.ds = ws.ds_p; a.ld_ds = Te; a.w = ws.w_p; a.ld_w = Te; a.qp = ws.qp_p; a.ld_qp = E;
-      a.dctx = ws.dctx_p; a.ld_dctx = E; a.P = ws.Pp; a.v = w.p_attn_v; a.mem_lens = io.mem_lens;
-      a.dP = ws.dPp; a.dmem = ws.dmem; a.dmem_accumulate = 0; a.dv = gw.p_attn_v;
-      ACVAE_TRY(launch_attn_bwd_acc(a, sp));
+      // all T rows of a clip in one pass (d score, d qp, d P, d mem, d v); the row-per-CTA + per-clip-accumulation pair
+      // for the shapes the fused kernel does not cover
+      AttnBwdClipParams c{};
+      c.clips = N; c.T = T; c.Te = Te; c.A = E; c.E = E; c.dctx = ws.dctx_p; c.w = ws.w_p; c.qp = ws.qp_p; c.P = ws.Pp; c.mem = ws.mem;
+      c.v = w.p_attn_v; c.mem_lens = io.mem_lens; c.ds_out = ws.ds_p; c.dqp = ws.dqp_p; c.dP = ws.dPp; c.dmem = ws.dmem;
+      c.dmem_accumulate = 0; c.dv = gw.p_attn_v;
+      const int fused = launch_attn_bwd_clip(c, sp);
+      if (fused < 0) return fused;
+      if (!fused) {
+        AttnBwdQParams a{};
+        a.rows = NT; a.Te = Te; a.A = E; a.E = E; a.rows_per_clip = T;
+        a.dctx = ws.dctx_p; a.ld_dctx = E; a.w = ws.w_p; a.ld_w = Te; a.qp = ws.qp_p; a.ld_qp = E;
+        a.P = ws.Pp; a.mem = ws.mem; a.v = w.p_attn_v; a.mem_lens = io.mem_lens;
+        a.ds = ws.ds_p; a.ld_ds = Te; a.dqp = ws.dqp_p; a.ld_dqp = E;
+        ACVAE_TRY(launch_attn_bwd_q(a, sp));
+        AttnBwdAccParams b{};
+        b.clips = N; b.Te = Te; b.A = E; b.E = E; b.rows_per_clip = T;
+        b.ds = ws.ds_p; b.ld_ds = Te; b.w = ws.w_p; b.ld_w = Te; b.qp = ws.qp_p; b.ld_qp = E;
+        b.dctx = ws.dctx_p; b.ld_dctx = E; b.P = ws.Pp; b.v = w.p_attn_v; b.mem_lens = io.mem_lens;
+        b.dP = ws.dPp; b.dmem = ws.dmem; b.dmem_accumulate = 0; b.dv = gw.p_attn_v;
+        ACVAE_TRY(launch_attn_bwd_acc(b, sp));
+      }
     }
     // the rest: embedding / attention-query weight gradients (need dqp_p from the attention backward); off sp, which
     // carries the prior's half of the memory backward next (the step's last dependency chain)
@@ -496,12 +504,19 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   if (cl) ACVAE_TRY(linear_bwd_data(NT, E, 3 * E, ws.dgi_d, 3 * E, w.d_wih + E, 3 * E, ws.dctx_d, E, sx));
   ACVAE_CHECK(zero(gw.d_attn_v, A, sx));
   {
-    AttnBwdAccParams a{};
-    a.clips = N; a.Te = Te; a.A = A; a.E = E; a.rows_per_clip = T;
-    a.ds = ws.ds_d; a.ld_ds = Te; a.w = ws.w_d; a.ld_w = Te; a.qp = ws.qp_d; a.ld_qp = A;
-    a.dctx = ws.dctx_d; a.ld_dctx = E; a.P = ws.Pd; a.v = w.d_attn_v; a.mem_lens = io.mem_lens;
-    a.dP = ws.dPd; a.dmem = ws.dmem2; a.dmem_accumulate = 0; a.dv = gw.d_attn_v;
-    ACVAE_TRY(launch_attn_bwd_acc(a, sx));
+    AttnBwdClipParams c{};
+    c.clips = N; c.T = T; c.Te = Te; c.A = A; c.E = E; c.dctx = ws.dctx_d; c.w = ws.w_d; c.qp = ws.qp_d; c.P = ws.Pd; c.mem = ws.mem;
+    c.v = w.d_attn_v; c.mem_lens = io.mem_lens; c.ds_in = ws.ds_d; c.dP = ws.dPd; c.dmem = ws.dmem2; c.dmem_accumulate = 0; c.dv = gw.d_attn_v;
+    const int fused = launch_attn_bwd_clip(c, sx);
+    if (fused < 0) return fused;
+    if (!fused) {
+      AttnBwdAccParams a{};
+      a.clips = N; a.Te = Te; a.A = A; a.E = E; a.rows_per_clip = T;
+      a.ds = ws.ds_d; a.ld_ds = Te; a.w = ws.w_d; a.ld_w = Te; a.qp = ws.qp_d; a.ld_qp = A;
+      a.dctx = ws.dctx_d; a.ld_dctx = E; a.P = ws.Pd; a.v = w.d_attn_v; a.mem_lens = io.mem_lens;
+      a.dP = ws.dPd; a.dmem = ws.dmem2; a.dmem_accumulate = 0; a.dv = gw.d_attn_v;
+      ACVAE_TRY(launch_attn_bwd_acc(a, sx));
+    }
   }
   // Memory backward (attention memory halves, ln: vae_model.py:743-744), split by linearity into the decoder's and the
   // prior's contribution: d mem = (d mem_dec + dP_d.W_d) + (d mem_prior + dP_p.W_p), and d ln.weight, d ln.bias, d audio are
