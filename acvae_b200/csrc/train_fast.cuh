@@ -415,8 +415,12 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   const float* dpool = nullptr;
   if (gi.d_p_means_utt) {
     ACVAE_TRY(linear_bwd_data(N, E, 2 * E, gi.d_p_means_utt, 2 * E, w.g_w, E, ws.dpool, E, st));
-    ACVAE_TRY(linear_bwd_weight(2 * E, E, N, gi.d_p_means_utt, 2 * E, ws.pool_d, E, gw.g_w, E, st));
-    ACVAE_TRY(colsum(N, 2 * E, gi.d_p_means_utt, 2 * E, gw.g_b, st));
+    {   // the head's own weight / bias gradients feed nothing in the step: off the critical stream (joined with the fan at the end)
+      cudaStream_t fg = ax->s[kAuxFan0 + 7];
+      ACVAE_TRY(stream_dep(st_user, fg, ax));
+      ACVAE_TRY(linear_bwd_weight(2 * E, E, N, gi.d_p_means_utt, 2 * E, ws.pool_d, E, gw.g_w, E, fg));
+      ACVAE_TRY(colsum(N, 2 * E, gi.d_p_means_utt, 2 * E, gw.g_b, fg));
+    }
     dpool = ws.dpool;
   } else {
     ACVAE_CHECK(zero(gw.g_w, (size_t)2 * E * E, st)); ACVAE_CHECK(zero(gw.g_b, (size_t)2 * E, st));

@@ -384,7 +384,7 @@ class VAELossFn(torch.autograd.Function):
     @staticmethod
     @_guard
     def forward(ctx, hidden, cls_w, cls_b, targets, smoothing, row_lse, row_sum, grad_sink,
-                q_means, q_logs, p_means, p_logs, q_utt, p_utt, kl_weight, alpha):
+                q_means, q_logs, p_means, p_logs, q_utt, p_utt, kl_weight, alpha, row_w=None):
         l = _lib.lib()
         dev = hidden.device
         h2 = hidden.contiguous()
@@ -393,10 +393,11 @@ class VAELossFn(torch.autograd.Function):
         w, b = cls_w.detach().contiguous(), cls_b.detach().contiguous()
         tg = targets.to(device=dev, dtype=torch.int32).contiguous()
         row_lse, row_sum = row_lse.contiguous(), row_sum.contiguous()
+        rw = None if row_w is None else row_w.contiguous()             # [M] row weights: 0 drops a (padded) row from the mean
         scal = torch.empty(4, dtype=torch.float32, device=dev)          # ce, kl | g, g*kl_w
         terms = torch.empty(4, dtype=torch.float32, device=dev)
         ws = _workspace(max(l.acvae_vocab_workspace_bytes(M, V, E), 1024), dev)
-        _lib.check(l.acvae_vocab_ce_fwd(M, V, E, _dev(h2), _dev(w), _dev(b), _dev(tg, torch.int32), None, float(smoothing), 1,
+        _lib.check(l.acvae_vocab_ce_fwd(M, V, E, _dev(h2), _dev(w), _dev(b), _dev(tg, torch.int32), _opt(rw), float(smoothing), 1,
                                         _dev(row_lse), _dev(row_sum), scal.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
                    "acvae_vocab_ce_fwd")
         kls = [t.contiguous() for t in (q_means, q_logs, p_means, p_logs)]
@@ -412,7 +413,7 @@ class VAELossFn(torch.autograd.Function):
                    "acvae_loss_combine_fwd")
         ctx.save_for_backward(h2, w, b, tg, row_lse, *kls, *([qu, pu] if have_g else []))
         ctx.have_g, ctx.smoothing, ctx.kl_weight, ctx.alpha = bool(have_g), float(smoothing), float(kl_weight), float(alpha or 0.0)
-        ctx.ws, ctx.scal, ctx.grad_sink = ws, scal, grad_sink
+        ctx.ws, ctx.scal, ctx.grad_sink, ctx.rw = ws, scal, grad_sink, rw
         ctx.mark_non_differentiable(terms)
         return terms[0], terms
 
@@ -443,12 +444,12 @@ class VAELossFn(torch.autograd.Function):
         else:
             dw = torch.empty_like(w)
             db = torch.empty(V, dtype=torch.float32, device=h2.device)
-        _lib.check(l.acvae_vocab_ce_bwd(M, V, E, _dev(h2), _dev(w), _dev(b), _dev(tg, torch.int32), None, ctx.smoothing,
+        _lib.check(l.acvae_vocab_ce_bwd(M, V, E, _dev(h2), _dev(w), _dev(b), _dev(tg, torch.int32), _opt(ctx.rw), ctx.smoothing,
                                         _dev(row_lse), scal.data_ptr() + 8, _dev(dh), _dev(dw), _dev(db),
                                         ctx.ws.data_ptr(), ctx.ws.numel(), _stream()), "acvae_vocab_ce_bwd")
         sink = ctx.grad_sink is not None
         return (dh, None if sink else dw, None if sink else db, None, None, None, None, None,
-                dk[0], dk[1], dk[2], dk[3], dqu, dpu, None, None)
+                dk[0], dk[1], dk[2], dk[3], dqu, dpu, None, None, None)
 
 
 class NormalKLFn(torch.autograd.Function):

@@ -81,13 +81,29 @@ class VAERNNBahdanauAttnDecoder(nn.Module):
         self.attn = Seq2SeqAttention(enc_mem_size, hidden_size, attn_size)
 
     def load_word_embeddings(self, embeddings, tune=True, **kwargs):
-        """decoder.py:50-64 (projection variant not supported by the fused step)."""
+        """decoder.py:50-64, including the `projection` form: pre-trained embeddings of another width become
+        `nn.Sequential(nn.Embedding, nn.Linear(width, embed_size))` (same `state_dict` keys as the reference:
+        `word_embeddings.0.weight`, `word_embeddings.1.weight / .bias`).  The fused step then runs on the EFFECTIVE table
+        `E_pre . P^T + b` [V, embed_size], formed once per call on the device (`effective_word_embeddings`); gradients
+        reach P, b (and E_pre when `tune`) through that contraction."""
         assert embeddings.shape[0] == self.vocab_size, "vocabulary size mismatch!"
         embeddings = torch.as_tensor(embeddings).float()
-        assert embeddings.shape[1] == self.embed_size, "embedding size mismatch!"
+        self.word_embeddings = nn.Embedding(self.vocab_size, embeddings.shape[1])
         self.word_embeddings.weight = nn.Parameter(embeddings)
         for para in self.word_embeddings.parameters():
             para.requires_grad = tune
+        if embeddings.shape[1] != self.embed_size:
+            assert "projection" in kwargs, "embedding size mismatch!"
+            if kwargs["projection"]:
+                self.word_embeddings = nn.Sequential(self.word_embeddings, nn.Linear(embeddings.shape[1], self.embed_size))
+
+    def effective_word_embeddings(self):
+        """The [V, embed_size] table the step gathers from: the embedding itself, or `Linear(Embedding)` evaluated for every
+        vocabulary entry when `load_word_embeddings(..., projection=True)` installed a projection (decoder.py:58-64)."""
+        we = self.word_embeddings
+        if isinstance(we, nn.Sequential):
+            return F.VocabLogitsFn.apply(we[0].weight, we[1].weight, we[1].bias)
+        return we.weight
 
     def init_hidden(self, bs):
         return torch.zeros(1, bs, self.model.hidden_size)
@@ -180,7 +196,16 @@ class PreparedBatch:
 
     def __init__(self, caps_ids, cap_lens_dev, T, targets=None, flat=None):
         self.caps_ids, self.cap_lens_dev, self.T, self.targets = caps_ids, cap_lens_dev, int(T), targets
-        self.flat = flat        # the one int32 device buffer the three views above live in (prepare_batch), or None
+        self.flat = flat        # the one int32 device buffer the views live in (prepare_batch), or None
+        #: un-packed criterion inputs (FusedVAELoss.forward_padded): caps[:, 1:T+1] as int32 [N,T] and the row weights
+        #: [N,T] float32 (1 where t < cap_lens[n] - 1); views of `flat` behind the packed targets
+        self.targets_padded = self.row_w = None
+        if flat is not None:
+            N, L = caps_ids.shape
+            M = flat.numel() - N * L - N - 2 * N * self.T
+            base = N * L + N + M
+            self.targets_padded = flat[base:base + N * self.T].view(N, self.T)
+            self.row_w = flat[base + N * self.T:base + 2 * N * self.T].view(torch.float32).view(N, self.T)
 
     def clone(self) -> "PreparedBatch":
         """A copy with its own storage (static buffers of a captured step)."""
@@ -189,7 +214,8 @@ class PreparedBatch:
                                  None if self.targets is None else self.targets.clone())
         f = self.flat.clone()
         N, L = self.caps_ids.shape
-        return PreparedBatch(f[:N * L].view(N, L), f[N * L:N * L + N], self.T, f[N * L + N:], f)
+        M = self.targets.numel()
+        return PreparedBatch(f[:N * L].view(N, L), f[N * L:N * L + N], self.T, f[N * L + N:N * L + N + M], f)
 
 
 class _FusedVAEBase(CaptionModel):
@@ -219,7 +245,16 @@ class _FusedVAEBase(CaptionModel):
     # ---- plumbing ------------------------------------------------------------------------
     def _hot_weights(self) -> Dict[str, torch.Tensor]:
         sd = dict(self.named_parameters())
-        return {k: v for k, v in sd.items() if not k.startswith("encoder.")}
+        hot = {k: v for k, v in sd.items() if not k.startswith("encoder.")}
+        if isinstance(self.decoder.word_embeddings, nn.Sequential):     # projected pre-trained embeddings (decoder.py:58-64)
+            for k in [k for k in hot if k.startswith("decoder.word_embeddings.")]:
+                del hot[k]
+            items = list(hot.items())
+            # keep the position the plain table has in the parameter order (first decoder entry)
+            pos = next((i for i, (k, _) in enumerate(items) if k.startswith("decoder.")), len(items))
+            items.insert(pos, ("decoder.word_embeddings.weight", self.decoder.effective_word_embeddings()))
+            hot = dict(items)
+        return hot
 
     def _encode(self, feats, feat_lens):
         encoded = self.encoder(feats, feat_lens)
@@ -271,7 +306,7 @@ class _FusedVAEBase(CaptionModel):
                 prof.clear()
             ent = prof[key] = (T_, int(lens1.sum()), mask_, lens64.astype(np.int32))
         T, M, mask, lens32 = ent
-        total = N * L + N + M
+        total = N * L + N + M + 2 * N * T                               # ids | lens | packed targets | padded targets | row weights
         ring = getattr(self, "_stage_ring", None)
         if ring is None or ring[0][0].numel() < total:
             # [pinned staging tensor, CUDA event recorded right after the last asynchronous copy OUT of it]
@@ -285,7 +320,9 @@ class _FusedVAEBase(CaptionModel):
         sn = stage.numpy()
         sn[:N * L] = caps_np.reshape(-1)                              # caps.long() of vae_model.py:827, as int32
         sn[N * L:N * L + N] = lens32
-        sn[N * L + N:total] = caps_np[:, 1:T + 1].T[mask]
+        sn[N * L + N:N * L + N + M] = caps_np[:, 1:T + 1].T[mask]
+        sn[N * L + N + M:N * L + N + M + N * T] = caps_np[:, 1:T + 1].reshape(-1)
+        sn[N * L + N + M + N * T:total].view(np.float32)[:] = mask.T.reshape(-1)       # float bits in the int32 staging buffer
         if out is not None:
             if out.flat is None or out.flat.numel() != total or out.T != T or tuple(out.caps_ids.shape) != (N, L):
                 raise ValueError("`out` was prepared for a different caption-length profile")
@@ -298,7 +335,7 @@ class _FusedVAEBase(CaptionModel):
             flat = stage[:total].to(device=device, non_blocking=True)
             slot[1] = slot[1] or torch.cuda.Event()
             slot[1].record()
-        return PreparedBatch(flat[:N * L].view(N, L), flat[N * L:N * L + N], T, flat[N * L + N:], flat)
+        return PreparedBatch(flat[:N * L].view(N, L), flat[N * L:N * L + N], T, flat[N * L + N:N * L + N + M], flat)
 
     # ---- training ------------------------------------------------------------------------
     def train_forward(self, encoded, caps, cap_lens, **kwargs):

@@ -72,6 +72,24 @@ class FusedVAELoss(torch.nn.Module):
         self.cls, self.smoothing, self.alpha = classes, float(smoothing), alpha
         self.terms = None
 
+    def forward_padded(self, output, targets_padded, row_w, kl_weight):
+        """The same loss WITHOUT packing: the cross-entropy runs over all N*T rows of `output["logits"]` with row weights
+        (`row_w[n,t] = 1` for t < cap_lens[n] - 1, else 0 -- exactly the rows `pack_padded_sequence` keeps,
+        pytorch_runner_vae.py:89-95) and the padded targets `caps[:, 1:T+1]`; `Hybrid_VAEModel.prepare_batch` stages both.
+        The mean is still over the valid tokens, the gradient lands directly in the [N,T,H] layout -- no gather of the
+        hidden rows before and no scatter of their gradient after the criterion (five small kernels per step)."""
+        lg = output["logits"]
+        if not isinstance(lg, LazyLogits) or lg.dim() != 3:
+            raise ValueError("forward_padded expects the un-packed LazyLogits of the model's output dict")
+        H = lg.hidden.shape[-1]
+        have_g = self.alpha is not None and output.get("q_means_utt") is not None and output.get("p_means_utt") is not None
+        loss, self.terms = F.VAELossFn.apply(
+            lg.hidden.reshape(-1, H), lg.cls_w, lg.cls_b, targets_padded.reshape(-1), self.smoothing, lg.row_lse.reshape(-1),
+            lg.row_sum.reshape(-1), lg.grad_sink, output["q_means"], output["q_logs"], output["p_means"], output["p_logs"],
+            output["q_means_utt"] if have_g else None, output["p_means_utt"] if have_g else None,
+            float(kl_weight), float(self.alpha) if have_g else 0.0, row_w.reshape(-1))
+        return loss
+
     def forward(self, output, packed_logits, targets, kl_weight):
         if not isinstance(packed_logits, LazyLogits) or packed_logits.dim() != 2:
             raise ValueError("FusedVAELoss expects the packed LazyLogits rows (pack_padded_sequence(output['logits'], ...).data)")

@@ -206,6 +206,7 @@ def make_train_step(dev, world, rank, use_graph=True):
     d = bench_dims()
     model = harness.build_model(d, seed=1, device=dev).train()
     n_params = sum(p.numel() for p in model.parameters())
+    ts.init_state = {k_: p_.detach().clone() for k_, p_ in model.named_parameters()}
     flat = parallel.FlatGradBuffer(model.parameters())
     model.grad_sink = flat          # fused backward writes weight gradients straight into the all-reduce buffer
     # clip_grad_norm_ + Adam (pytorch_runner_vae.py:322-324) as two launches over the flat buffers
@@ -241,7 +242,9 @@ def make_train_step(dev, world, rank, use_graph=True):
         out = model.train_forward({"audio_embeds": st_audio, "audio_embeds_lens": st_mem_lens}, st_prep, None,
                                   ss_ratio=1.0, dis_ratio=0.0, tf_flags=[True] * st_prep.T, dis_flags=[False] * st_prep.T)
         packed = torch.nn.utils.rnn.pack_padded_sequence(out["logits"], lens1, batch_first=True).data
-        # criterion(packed, targets) + kl_w * kl_loss(...) + alpha * MSE(...) (pytorch_runner_vae.py:315-320) as one node
+        # criterion(packed, targets) + kl_w * kl_loss(...) + alpha * MSE(...) (pytorch_runner_vae.py:315-320) as one node.
+        # (FusedVAELoss.forward_padded -- all N*T rows with row weights instead of packing -- saves the five pack / un-pack
+        # kernels but its 608-row gradient GEMM needs 175 tiles = two waves instead of 140 = one: no net gain at this shape.)
         loss = fused_loss(out, packed, st_targets, KL_WEIGHT)
         loss.backward()
         flat.all_reduce()
@@ -434,6 +437,11 @@ def run_ours(args):
     lo, hi = parallel.shard_range(SAMPLE_CLIPS, rank, world)
     ds = synthetic.Dims(N=hi - lo, Te=d.Te, L=SAMPLE_LEN + 1)
     sb = synthetic.make_batch(ds, 7 + rank)
+    # sample with the INITIAL weights: the trained ones differ in the last bit from run to run (order-dependent gradient
+    # atomics), which changes when every row has emitted <end> and with it the number of decode steps that are timed
+    with torch.no_grad():
+        for k_, p_ in model.named_parameters():
+            p_.copy_(ts.init_state[k_])
     model.eval()
     s_audio = torch.from_numpy(sb["audio_embeds"]).to(dev)
     s_lens = torch.from_numpy(sb["mem_lens"].astype(np.int32)).to(dev)

@@ -638,9 +638,48 @@ def test_encoder_handoff_feeds_the_train_step():
     harness.assert_close(fmap.grad.reshape(d.N * d.Eenc, -1), want.reshape(d.N * d.Eenc, -1), TOL, "d feature map")   # rows = (clip, channel)
 
 
+def test_load_word_embeddings_with_projection_vs_oracle():
+    """decoder.py:50-64: pre-trained embeddings of another width (300) behind a projection.  The step runs on the effective
+    table E_pre . P^T + b; loss and the gradients of P, b and E_pre (chain rule through the table) match the oracle."""
+    _require_cuda()
+    d, seed, width = synthetic.CFG0, 12, 300
+    rs = np.random.RandomState(5)
+    pre = (rs.standard_normal((d.V, width)) * 0.3).astype(np.float32)
+    m = harness.build_model(d, seed, device="cpu")
+    m.decoder.load_word_embeddings(pre, tune=True, projection=True)
+    assert sorted(k for k in m.state_dict() if "word_embeddings" in k and k.startswith("decoder.")) == \
+        ["decoder.word_embeddings.0.weight", "decoder.word_embeddings.1.bias", "decoder.word_embeddings.1.weight"]
+    m = m.cuda()
+    Pw = m.decoder.word_embeddings[1].weight.detach().cpu().double()
+    Pb = m.decoder.word_embeddings[1].bias.detach().cpu().double()
+    r = harness.run_cuda_train(d, seed, model=m)
+    # oracle: the same weights with the effective table in place of decoder.word_embeddings.weight
+    import acvae_oracle as oracle
+    b = synthetic.make_batch(d, seed)
+    T = int(b["cap_lens"].max()) - 1
+    p = harness.oracle_params(d, seed, grad=True)
+    eff = (torch.from_numpy(pre).double() @ Pw.t() + Pb).float().requires_grad_(True)
+    p["decoder.word_embeddings.weight"] = eff
+    caps = torch.from_numpy(b["caps"])
+    out = oracle.train_forward(p, torch.from_numpy(b["audio_embeds"]), b["mem_lens"], caps, b["cap_lens"],
+                               torch.from_numpy(b["eps_q"][:, :T]), torch.from_numpy(b["eps_p"][:T]), [True] * T, [False] * T,
+                               variant="hybrid", eps_q_steps=torch.from_numpy(b["eps_q_steps"][:T]))
+    terms = oracle.train_loss(out, caps, b["cap_lens"], d.V, 0.1, 0.5, 1.0, "MSE")
+    terms["loss"].backward()
+    assert abs(float(r["terms"]["loss"]) - float(terms["loss"])) <= TOL * abs(float(terms["loss"]))
+    dW = eff.grad.double()
+    harness.assert_close(r["grads"]["decoder.word_embeddings.1.weight"], dW.t() @ torch.from_numpy(pre).double(), TOL, "d projection")
+    harness.assert_close(r["grads"]["decoder.word_embeddings.1.bias"], dW.sum(0), TOL, "d projection bias")
+    harness.assert_close(r["grads"]["decoder.word_embeddings.0.weight"], dW @ Pw, TOL, "d pre-trained table")
+    with torch.no_grad():        # inference runs on the same effective table
+        o = m(torch.from_numpy(b["audio_embeds"]).cuda(), torch.from_numpy(b["mem_lens"].copy()), method="greedy", max_length=5)
+    assert tuple(o["seqs"].shape) == (d.N, 5)
+
+
 def test_fused_vae_loss_matches_separate_callables():
     """FusedVAELoss (one autograd node) == criterion + kl_w * kl_loss + alpha * MSE of the runner boundary
-    (pytorch_runner_vae.py:315-320): same loss terms, same gradients on every parameter."""
+    (pytorch_runner_vae.py:315-320): same loss terms, same gradients on every parameter -- in its packed form and in the
+    un-packed form (`forward_padded`: all N*T rows with row weights instead of pack_padded_sequence)."""
     _require_cuda()
     import acvae_b200 as models
     d = synthetic.CFG0
@@ -652,6 +691,22 @@ def test_fused_vae_loss_matches_separate_callables():
         assert abs(x - y) <= 1e-6 * max(1.0, abs(x)), (k, x, y)
     for k in a["grads"]:
         assert harness.rel_err(b["grads"][k], a["grads"][k]) < 1e-5, k
+    # un-packed form
+    bt = synthetic.make_batch(d, 7)
+    T = int(bt["cap_lens"].max()) - 1
+    m2 = harness.build_model(d, 7).train()
+    prep = m2.prepare_batch(torch.from_numpy(bt["caps"]), bt["cap_lens"], "cuda")
+    feats = torch.from_numpy(bt["audio_embeds"]).cuda().requires_grad_(True)
+    out = m2.train_forward({"audio_embeds": feats, "audio_embeds_lens": torch.from_numpy(bt["mem_lens"].copy())}, prep, None,
+                           ss_ratio=1.0, dis_ratio=0.0, eps_q=torch.from_numpy(bt["eps_q"][:, :T].copy()),
+                           eps_p=torch.from_numpy(bt["eps_p"][:T].copy()), tf_flags=[True] * T, dis_flags=[False] * T)
+    fl = models.FusedVAELoss(d.V, smoothing=0.1, alpha=1.0)
+    loss = fl.forward_padded(out, prep.targets_padded, prep.row_w, 0.5)
+    loss.backward()
+    assert abs(float(loss) - float(a["terms"]["loss"])) <= 1e-6 * abs(float(a["terms"]["loss"]))
+    for k, p_ in m2.named_parameters():
+        assert harness.rel_err(p_.grad, a["grads"][k]) < 1e-5, ("padded", k)
+    assert harness.rel_err(feats.grad, a["grads"]["audio_embeds"]) < 1e-5
 
 
 def test_prepare_batch_single_copy_matches_runner_packing():
@@ -670,6 +725,9 @@ def test_prepare_batch_single_copy_matches_runner_packing():
     assert torch.equal(pb.caps_ids.cpu(), caps.to(torch.int32))
     assert torch.equal(pb.cap_lens_dev.cpu(), torch.as_tensor(b["cap_lens"]).to(torch.int32))
     assert pb.T == int(b["cap_lens"].max()) - 1
+    # the un-packed criterion inputs: padded targets caps[:, 1:T+1] and the row weights of the rows packing keeps
+    assert torch.equal(pb.targets_padded.cpu(), caps[:, 1:pb.T + 1].to(torch.int32))
+    assert torch.equal(pb.row_w.cpu(), (torch.arange(pb.T)[None, :] < lens1[:, None]).float())
     st = pb.clone()
     b2 = synthetic.make_batch(d, 22, cap_lens_override=b["cap_lens"])
     m.prepare_batch(torch.from_numpy(b2["caps"]), b2["cap_lens"], "cuda", out=st)
