@@ -95,6 +95,7 @@ SYMBOLS = {
     "acvae_loss_combine_bwd": (C.c_int, [_i64, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
     "acvae_diversity_stats": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "acvae_set_input_event": (C.c_int, [_vp]),
+    "acvae_set_bucket_event": (C.c_int, [_vp]),
     "acvae_mbleu_stats": (C.c_int, [_i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp]),
     "acvae_encoder_handoff_fwd": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "acvae_encoder_handoff_bwd": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp]),

@@ -107,7 +107,9 @@ int acvae_train_bwd(const acvae_dims* d, const acvae_weights* w, const acvae_tra
   ACVAE_REQUIRE(io->tf_flags && io->dis_flags, "tf_flags / dis_flags are required");
   if (!getenv("ACVAE_DISABLE_FAST") && fast_path_ok(*d, *io))
     return train_bwd_fast(*d, *w, *io, *gin, *gw, d_audio_embeds, workspace, (cudaStream_t)stream);
-  return train_bwd(*d, *w, *io, *gin, *gw, d_audio_embeds, workspace, (cudaStream_t)stream);
+  ACVAE_TRY(train_bwd(*d, *w, *io, *gin, *gw, d_audio_embeds, workspace, (cudaStream_t)stream));
+  if (bucket_event()) ACVAE_CHECK(cudaEventRecord(bucket_event(), (cudaStream_t)stream));
+  return 0;
 }
 
 size_t acvae_vocab_workspace_bytes(int32_t M, int32_t V, int32_t E) {
@@ -385,6 +387,13 @@ int acvae_mbleu_stats(int32_t clips, int32_t K, int32_t L, const int64_t* seqs, 
 // acvae_decode_sample, acvae_beam_search, acvae_diverse_beam_search) waits for it right before its first read -- the
 // hoisted training schedule only after the posterior chain, so the copy overlaps it; NULL (default) restores plain
 // stream order.  The event must outlive every captured graph.
+// Optional: an event every acvae_train_bwd records once all decoder.* weight gradients are final (see streams.cuh);
+// NULL (default) switches it off.  The step-by-step schedule records it at its end.
+int acvae_set_bucket_event(void* cuda_event) {
+  bucket_event() = static_cast<cudaEvent_t>(cuda_event);
+  return 0;
+}
+
 int acvae_set_input_event(void* cuda_event) {
   input_ready_event() = static_cast<cudaEvent_t>(cuda_event);
   return 0;

@@ -54,6 +54,11 @@ inline Aux* aux() {
 // so the copy runs under the posterior chain (which does not read the audio) instead of in front of the step.
 inline cudaEvent_t& input_ready_event() { static cudaEvent_t e = nullptr; return e; }
 
+// Optional "decoder gradients final" event (acvae_set_bucket_event): recorded by every acvae_train_bwd at the point where all
+// decoder.* weight gradients (and, before it in the caller's stream, the classifier's) are final -- ~0.2 ms before the end of
+// the backward.  A data-parallel caller starts the all-reduce of that bucket behind it, under the rest of the backward.
+inline cudaEvent_t& bucket_event() { static cudaEvent_t e = nullptr; return e; }
+
 // Make `st` wait for the caller's "inputs ready" event, if one is set: called by EVERY entry point right before its first
 // kernel that reads audio_embeds (both training schedules, the sampling / beam / diverse-beam loops, acvae_memory_prepare).
 inline int wait_input_event(cudaStream_t st) {

@@ -579,6 +579,14 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     ACVAE_TRY(linear_bwd_weight(A, E, NT, ws.dqp_d, A, io.outputs - E, E, gw.d_attn_w, 2 * E, f[5], T, 0, -1));
     ACVAE_TRY(colsum(NT, 3 * E, ws.dgi_d, 3 * E, gw.d_bih, f[5]));
     ACVAE_TRY(colsum(NT, 3 * E, ws.dgh_d, 3 * E, gw.d_bhh, f[4]));
+    if (bucket_event()) {
+      // every decoder.* gradient is final once fan streams 0..6 and sx (attention v / bias / memory-side weights) get here;
+      // fan 7 also carries late prior work and must not hold the bucket back
+      for (int i = 0; i < 6; ++i) ACVAE_TRY(stream_dep(f[i], f[6], ax));
+      ACVAE_TRY(stream_dep(sx, f[6], ax));
+      ACVAE_TRY(stream_dep(st_user, f[6], ax));       // the classifier's gradients (loss backward, caller's stream)
+      ACVAE_CHECK(cudaEventRecord(bucket_event(), f[6]));
+    }
     for (int i = 0; i < kAuxFanN; ++i) ACVAE_TRY(stream_dep(f[i], sx, ax));
   }
 

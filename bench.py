@@ -209,6 +209,8 @@ def make_train_step(dev, world, rank, use_graph=True):
     ts.init_state = {k_: p_.detach().clone() for k_, p_ in model.named_parameters()}
     flat = parallel.FlatGradBuffer(model.parameters())
     model.grad_sink = flat          # fused backward writes weight gradients straight into the all-reduce buffer
+    if world > 1 and os.environ.get("ACVAE_BENCH_NO_BUCKETS") is None:
+        flat.enable_bucketing(model)    # the decoder's 12.7 MB are reduced under the tail of the backward
     # clip_grad_norm_ + Adam (pytorch_runner_vae.py:322-324) as two launches over the flat buffers
     opt = models.FusedClipAdam(flat, lr=LR, max_grad_norm=MAX_GRAD_NORM)
     crit = models.LabelSmoothingLoss(d.V, smoothing=SMOOTHING, device=dev)
@@ -313,6 +315,9 @@ def run_ours(args):
         torch.set_num_threads(max(1, (os.cpu_count() or 8) // world))     # one node: do not oversubscribe the host cores
         # keep stdout to the ONE JSON line: NCCL's debug log (whatever level the caller asked for) goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # the early gradient bucket is reduced UNDER the tail of the backward: its NCCL kernels must not queue behind the
+        # swarm of low-priority weight-gradient GEMMs
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=dev)
     ts = make_train_step(dev, world, rank, use_graph=not args.no_graph)
     model, d, n_params, run_step, load_resident = ts.model, ts.d, ts.n_params, ts.run_step, ts.load_resident

@@ -303,6 +303,11 @@ int acvae_diversity_stats(int32_t clips, int32_t K, int32_t L, int32_t V, const 
  * event-wait node under stream capture) right before the first kernel that reads the audio, so the copy runs under the
  * posterior chain, which does not.  The caller keeps the usual WAR discipline on the audio buffer. */
 int acvae_set_input_event(void *cuda_event);
+/* Data-parallel overlap (reference: DistributedDataParallel's bucketed all-reduce inside loss.backward(),
+ * runners/pytorch_runner_vae.py:204-207, 321): an event every acvae_train_bwd records at the point where all
+ * decoder.* weight gradients (word embeddings, GRU, attention; the classifier's are final before the call)
+ * are final, so their all-reduce can run under the rest of the backward.  NULL switches it off.          */
+int acvae_set_bucket_event(void *cuda_event);
 
 /* profiling only: [T][16] int64 device buffer for clock64 stamps of the decoder forward chain (CTA 0), or NULL */
 int acvae_debug_set_chain_trace(void *device_buffer);

@@ -27,7 +27,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, bucketed=False):
     import torch.distributed as dist
     from acvae_b200 import parallel
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -37,6 +37,8 @@ def _worker(rank, world, port, out_dir):
     m = harness.build_model(d, SEEDS[0], device=f"cuda:{rank}")
     flat = parallel.FlatGradBuffer(m.parameters())
     m.grad_sink = flat
+    if bucketed:
+        flat.enable_bucketing(m)          # decoder.* gradients reduced behind the backward's "decoder gradients final" event
     with torch.cuda.device(rank):
         r = _run_rank(d, m, SEEDS[rank])
     local = flat.flat.clone()
@@ -82,12 +84,13 @@ def _oracle_rank(d, weight_seed, batch_seed):
     return float(terms["loss"]), {k: v.grad.detach().numpy() for k, v in p.items() if v.grad is not None}
 
 
-def test_two_rank_nccl_gradient_average_vs_oracle(tmp_path):
+@pytest.mark.parametrize("bucketed", [False, True])
+def test_two_rank_nccl_gradient_average_vs_oracle(tmp_path, bucketed):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     import torch.multiprocessing as mp
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), bucketed), nprocs=world, join=True)
     got = [dict(np.load(tmp_path / f"rank{r}.npz")) for r in range(world)]
     d = synthetic.CFG1
     ref = [_oracle_rank(d, SEEDS[0], SEEDS[r]) for r in range(world)]
