@@ -95,6 +95,12 @@ SYMBOLS = {
     "acvae_loss_combine_bwd": (C.c_int, [_i64, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
     "acvae_diversity_stats": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "acvae_set_input_event": (C.c_int, [_vp]),
+    "acvae_ipc_export": (C.c_int, [_vp, _vp, C.POINTER(C.c_int64)]),
+    "acvae_ipc_open": (C.c_int, [_vp, _i64, C.POINTER(_vp)]),
+    "acvae_dp_comm_bytes": (_sz, []),
+    "acvae_dp_workspace_bytes": (_sz, []),
+    "acvae_dp_clip_adam": (C.c_int, [_i32, _i32, _i64, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp,
+                                     _vp, _sz, _vp]),
     "acvae_set_bucket_event": (C.c_int, [_vp]),
     "acvae_mbleu_stats": (C.c_int, [_i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp]),
     "acvae_encoder_handoff_fwd": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),

@@ -3,6 +3,7 @@
 #include "../../include/acvae_b200.h"
 #include <stdlib.h>
 
+#include "dp_optim.cuh"
 #include "handoff.cuh"
 #include "optim.cuh"
 #include "sample.cuh"
@@ -296,6 +297,75 @@ int acvae_clip_adam_dev(int64_t n, float* params, float* grads, float* exp_avg, 
   ACVAE_REQUIRE(hyper, "hyper (device vector of 6 floats) is NULL");
   return clip_adam_impl(n, params, grads, exp_avg, exp_avg_sq, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, hyper, step, total_norm,
                         write_clipped_grads, workspace, workspace_bytes, stream);
+}
+
+// ---- CUDA IPC plumbing of the fused data-parallel optimizer (one process per GPU on one node) ----
+typedef CUresult (*PFN_getRange)(CUdeviceptr*, size_t*, CUdeviceptr);
+static PFN_getRange addr_range_fn() {
+  static PFN_getRange fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_getRange>(f);
+  }
+  return fn;
+}
+
+int acvae_ipc_export(const void* ptr, void* handle64, int64_t* offset) {
+  ACVAE_REQUIRE(ptr && handle64 && offset, "NULL pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  PFN_getRange fn = addr_range_fn();
+  ACVAE_REQUIRE(fn, "cuMemGetAddressRange is not available");
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (fn(&base, &size, (CUdeviceptr)ptr) != CUDA_SUCCESS) return set_error("cuMemGetAddressRange", "pointer is not a device allocation");
+  cudaIpcMemHandle_t h;
+  ACVAE_CHECK(cudaIpcGetMemHandle(&h, (void*)base));          // fails for stream-ordered / VMM allocations (expandable segments)
+  memcpy(handle64, &h, 64);
+  *offset = (int64_t)((CUdeviceptr)ptr - base);
+  return 0;
+}
+
+int acvae_ipc_open(const void* handle64, int64_t offset, void** peer_ptr) {
+  ACVAE_REQUIRE(handle64 && peer_ptr && offset >= 0, "bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* base = nullptr;
+  ACVAE_CHECK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  *peer_ptr = static_cast<char*>(base) + offset;
+  return 0;
+}
+
+size_t acvae_dp_comm_bytes(void) { return align_up(sizeof(DpComm)); }
+size_t acvae_dp_workspace_bytes(void) { return sizeof(float) * kDpBlocks + 64; }
+
+int acvae_dp_clip_adam(int32_t world, int32_t rank, int64_t n, const void* const* grads, void* const* params, void* const* comm,
+                       float* grad_shard, float* exp_avg, float* exp_avg_sq, const float* hyper, int32_t* step, float* total_norm,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  ACVAE_REQUIRE(world >= 1 && world <= kDpMaxWorld && rank >= 0 && rank < world, "bad world / rank");
+  ACVAE_REQUIRE(n > 0 && n % (4LL * world) == 0, "n must be a positive multiple of 4 * world (pad the flat buffers)");
+  ACVAE_REQUIRE(grads && params && comm && grad_shard && exp_avg && exp_avg_sq && hyper && step && workspace, "NULL pointer");
+  ACVAE_REQUIRE(workspace_bytes >= acvae_dp_workspace_bytes(), "workspace too small");
+  DpParams a{};
+  a.world = world; a.rank = rank; a.n4 = n / 4 / world;
+  for (int q = 0; q < world; ++q) {
+    ACVAE_REQUIRE(grads[q] && params[q] && comm[q] && aligned16(grads[q]) && aligned16(params[q]), "peer buffers must be non-NULL and 16-byte aligned");
+    a.grads[q] = (const float4*)grads[q]; a.params[q] = (float4*)params[q]; a.comm[q] = (DpComm*)comm[q];
+  }
+  ACVAE_REQUIRE((a.n4 * 16) % 16 == 0 && aligned16(grad_shard) && aligned16(exp_avg) && aligned16(exp_avg_sq), "shard buffers must be 16-byte aligned");
+  a.gshard = (float4*)grad_shard; a.m = (float4*)exp_avg; a.v = (float4*)exp_avg_sq;
+  a.partial = (float*)workspace; a.ticket = (unsigned*)((char*)workspace + sizeof(float) * kDpBlocks);
+  a.hyper = hyper; a.step = step; a.total_norm = total_norm;
+  int blocks = (int)((a.n4 + kDpThreads - 1) / kDpThreads);
+  blocks = blocks < 1 ? 1 : (blocks > kDpBlocks ? kDpBlocks : blocks);
+  cudaStream_t st = (cudaStream_t)stream;
+  ACVAE_LAUNCH(dp_reduce_kernel, blocks, kDpThreads, 0, st, a);
+  ACVAE_LAUNCH(dp_adam_kernel, blocks, kDpThreads, 0, st, a);
+  ACVAE_LAUNCH(step_advance_kernel, 1, 1, 0, st, step);
+  return 0;
 }
 
 int acvae_loss_combine_fwd(int64_t n, const float* q_utt, const float* p_utt, const float* ce, const float* kl, float kl_weight,

@@ -196,6 +196,15 @@ def bench_dims():
     return synthetic.STRESS if os.environ.get("ACVAE_BENCH_CONFIG", "") == "stress" else synthetic.CFG1
 
 
+def exchange_mode(world):
+    if world == 1:
+        return "none"
+    m = os.environ.get("ACVAE_BENCH_EXCHANGE", "fused")
+    if m not in ("fused", "nccl", "nccl-bucketed"):
+        raise SystemExit(f"ACVAE_BENCH_EXCHANGE={m}: expected fused | nccl | nccl-bucketed")
+    return m
+
+
 def make_train_step(dev, world, rank, use_graph=True):
     import torch.distributed as dist
     import acvae_b200 as models
@@ -209,10 +218,17 @@ def make_train_step(dev, world, rank, use_graph=True):
     ts.init_state = {k_: p_.detach().clone() for k_, p_ in model.named_parameters()}
     flat = parallel.FlatGradBuffer(model.parameters())
     model.grad_sink = flat          # fused backward writes weight gradients straight into the all-reduce buffer
-    if world > 1 and os.environ.get("ACVAE_BENCH_NO_BUCKETS") is None:
-        flat.enable_bucketing(model)    # the decoder's 12.7 MB are reduced under the tail of the backward
-    # clip_grad_norm_ + Adam (pytorch_runner_vae.py:322-324) as two launches over the flat buffers
-    opt = models.FusedClipAdam(flat, lr=LR, max_grad_norm=MAX_GRAD_NORM)
+    # gradient exchange (DDP's all-reduce, pytorch_runner_vae.py:204-207) + clip_grad_norm_ + Adam (:322-324):
+    #   "fused"  (default) reduce-scatter + clip + Adam + all-gather in two kernels over NVLink peer memory, no NCCL call
+    #   "nccl-bucketed"    NCCL all-reduce, the decoder's 12.7 MB under the tail of the backward; then clip + Adam
+    #   "nccl"             one NCCL all-reduce after the backward; then clip + Adam
+    ts.exchange = exchange_mode(world)
+    if ts.exchange == "nccl-bucketed":
+        flat.enable_bucketing(model)
+    if ts.exchange == "fused":
+        opt = models.DistributedClipAdam(flat, lr=LR, max_grad_norm=MAX_GRAD_NORM)
+    else:
+        opt = models.FusedClipAdam(flat, lr=LR, max_grad_norm=MAX_GRAD_NORM)
     crit = models.LabelSmoothingLoss(d.V, smoothing=SMOOTHING, device=dev)
     klf = models.Normal_kl_loss(device=dev)
     mse = torch.nn.MSELoss()
@@ -249,7 +265,8 @@ def make_train_step(dev, world, rank, use_graph=True):
         # kernels but its 608-row gradient GEMM needs 175 tiles = two waves instead of 140 = one: no net gain at this shape.)
         loss = fused_loss(out, packed, st_targets, KL_WEIGHT)
         loss.backward()
-        flat.all_reduce()
+        if ts.exchange != "fused":
+            flat.all_reduce()
         opt.step()
         loss_buf.copy_(loss.detach())
 
@@ -620,6 +637,11 @@ def run_ours(args):
                             "-> graph replay -> loss read back"},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
+            "gradient_exchange": {"none": "single GPU", "fused": "reduce-scatter + clip + Adam + all-gather fused over NVLink peer memory "
+                                  "(DistributedClipAdam, csrc/dp_optim.cuh; no NCCL call in the step)",
+                                  "nccl": "NCCL all-reduce (AVG) of the flat 32 MB buffer, then clip + Adam",
+                                  "nccl-bucketed": "NCCL all-reduce in two buckets (decoder gradients under the backward's tail), "
+                                  "then clip + Adam"}[ts.exchange],
             "clocks": clk,
             "roofline": roofline,
             "roofline_other": roofline_other,

@@ -265,6 +265,26 @@ int acvae_encoder_handoff_fwd(int32_t N, int32_t C, int32_t Te, int32_t F, const
 int acvae_encoder_handoff_bwd(int32_t N, int32_t C, int32_t Te, int32_t F, const float *d_audio_embeds,
                               float *d_fmap, void *stream);
 
+/* ---- data-parallel optimizer tail as one fused compute + collective over NVLink peer memory --------
+ * Replaces, for one process per GPU on one node: DistributedDataParallel's gradient all-reduce
+ * (runners/pytorch_runner_vae.py:204-207, inside loss.backward() :321) + clip_grad_norm_ (:322) +
+ * optimizer.step() (:324).  Every rank owns 1/world of the flat buffers: it averages ITS shard of the
+ * gradients reading the peers' buffers over NVLink (fixed rank order), publishes the shard's sum of
+ * squares, clips with the global norm, runs Adam on the shard and writes the new parameters into
+ * every rank's parameter buffer.  grads / params / comm: HOST arrays of `world` device pointers, entry
+ * [rank] local, the others mapped with acvae_ipc_open from the peers' acvae_ipc_export handles; comm
+ * blocks (acvae_dp_comm_bytes each) and the workspace must be zero before the first call.
+ * n = floats per flat buffer (multiple of 4*world); grad_shard / exp_avg / exp_avg_sq: local [n/world].
+ * hyper: device {max_norm, lr, beta1, beta2, eps, weight_decay}; step as in acvae_clip_adam.          */
+int acvae_ipc_export(const void *ptr, void *handle64, int64_t *offset);
+int acvae_ipc_open(const void *handle64, int64_t offset, void **peer_ptr);
+size_t acvae_dp_comm_bytes(void);
+size_t acvae_dp_workspace_bytes(void);
+int acvae_dp_clip_adam(int32_t world, int32_t rank, int64_t n, const void *const *grads,
+                       void *const *params, void *const *comm, float *grad_shard, float *exp_avg,
+                       float *exp_avg_sq, const float *hyper, int32_t *step, float *total_norm,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- loss composition (runners/pytorch_runner_vae.py:315-320) as one node ------------------
  * terms[4] = {loss, ce, kl, mse}; loss = ce + kl_weight*kl + alpha*mean((q_utt - p_utt)^2) (nn.MSELoss, :318).
  * ce / kl are the device scalars of acvae_vocab_ce_fwd / acvae_kl_fwd.  q_utt == p_utt == NULL: no global term.

@@ -103,3 +103,68 @@ def test_two_rank_nccl_gradient_average_vs_oracle(tmp_path, bucketed):
     for k in got[0]:
         if k not in ("loss", "local_norm"):
             assert np.array_equal(got[0][k], got[1][k]), ("ranks disagree after the all-reduce", k)
+
+
+# ---- fused reduce-scatter + clip + Adam + all-gather over NVLink peer memory (DistributedClipAdam) --------------------
+def _dp_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from acvae_b200 import DistributedClipAdam, parallel
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(0)                                      # identical initial parameters on every rank
+    shapes = [(4400, 256), (768, 768), (256,), (1, 7), (513, 3)]
+    params = [torch.nn.Parameter(torch.randn(s, device=dev)) for s in shapes]
+    flat = parallel.FlatGradBuffer(params)
+    opt = DistributedClipAdam(flat, lr=5e-4, max_grad_norm=1.0)
+    init = [p.detach().cpu().clone() for p in params]
+    graph = None
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)  # different gradients per rank
+    local_grads = []
+    for it, scale in enumerate((1.0, 1e-4, 3.0, 1.0)):        # clipped, not clipped, clipped; the last step replays a CUDA graph
+        gs = [torch.randn(s, device=dev, generator=gen) * scale for s in shapes]
+        local_grads.append([x.cpu() for x in gs])
+        flat.zero()
+        for p, x in zip(params, gs):
+            p.grad.copy_(x)
+        if it < 3:
+            opt.step()
+        else:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                graph.capture_begin(); opt.step(); graph.capture_end()
+            torch.cuda.current_stream().wait_stream(side)
+            graph.replay()
+        torch.cuda.synchronize()
+        dist.barrier()
+    torch.save({"init": init, "grads": local_grads, "params": [p.detach().cpu() for p in params], "norm": float(opt.total_norm)},
+               os.path.join(out_dir, f"dp{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_fused_dp_optimizer_vs_torch(tmp_path, world):
+    """DistributedClipAdam (peer-memory reduce-scatter + global-norm clip + Adam + all-gather in two kernels, no NCCL) ==
+    average of the ranks' gradients -> clip_grad_norm_ -> torch.optim.Adam on every rank; parameters bit-identical across
+    ranks; also through a captured CUDA graph."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (run with gpurun --gpus {world})")
+    import torch.multiprocessing as mp
+    mp.spawn(_dp_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = [torch.load(tmp_path / f"dp{r}.pt") for r in range(world)]
+    ref = [torch.nn.Parameter(p.clone()) for p in got[0]["init"]]
+    ropt = torch.optim.Adam(ref, lr=5e-4)
+    for it in range(4):
+        for i, r in enumerate(ref):
+            r.grad = sum(got[q]["grads"][it][i] for q in range(world)) / world
+        norm = torch.nn.utils.clip_grad_norm_(ref, 1.0)
+        ropt.step()
+    assert abs(got[0]["norm"] - float(norm)) <= 1e-5 * float(norm)
+    for i, r in enumerate(ref):
+        torch.testing.assert_close(got[0]["params"][i], r.data, rtol=1e-6, atol=1e-7)
+        for q in range(1, world):
+            assert torch.equal(got[0]["params"][i], got[q]["params"][i]), "ranks must hold bit-identical parameters"
