@@ -10,9 +10,12 @@
 
 namespace acvae {
 
-constexpr int kAuxStreams = 13;     // 0,1: posterior directions; 2: prior; 3: memory backward; 4..11: weight-gradient fan; 12: main chain
-constexpr int kAuxMain = 12;
-constexpr int kAuxFan0 = 4, kAuxFanN = 8;
+// 0,1: posterior directions; 2: prior; 3: memory backward; 4..11: weight-gradient fan of the decoder / posterior;
+// 12..19: weight-gradient fan of the prior (its own streams: stream order is FIFO, so work that becomes ready at different
+// times must not share a stream); 20: main chain
+constexpr int kAuxStreams = 21;
+constexpr int kAuxMain = 20;
+constexpr int kAuxFan0 = 4, kAuxFanN = 16, kAuxPriorFan0 = 12;
 constexpr int kAuxEvents = 128;
 
 struct Aux {

@@ -260,10 +260,13 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   return 0;
 }
 
-// k-blocks per CTA of the weight-gradient GEMMs on the fan streams (see TcThroughputScope)
+// k-blocks per CTA of the weight-gradient GEMMs on the fan streams (see TcThroughputScope).  A tc_gemm CTA owns its SM
+// (197 KB of shared memory, 62 K registers) and spends ~3 us in prologue + epilogue whatever its K range, so deep split-K
+// wastes SM time the backward is short of next to the chains, while no split leaves the K = N*Te contractions as 60 us
+// stragglers: measured step 0.912 / 0.902 / 0.938 / 0.975 ms at 6 / 12 / 24 / 64 (profiles/r2/fan_min_kblk.log).
 inline int fan_min_kblk() {
   static int v = 0;
-  if (!v) { const char* e = getenv("ACVAE_FAN_MIN_KBLK"); v = e ? atoi(e) : 6; if (v < 1) v = 1; }
+  if (!v) { const char* e = getenv("ACVAE_FAN_MIN_KBLK"); v = e ? atoi(e) : 12; if (v < 1) v = 1; }
   return v;
 }
 
@@ -356,7 +359,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     // weight / bias gradients that need only the chain's dg_p / dml_p: fanned over four streams so that they fill
     // the SMs the decoder's persistent kernel leaves free instead of queueing behind the attention backward
     {
-      cudaStream_t* f = &ax->s[kAuxFan0];
+      cudaStream_t* f = &ax->s[kAuxPriorFan0];
       TcThroughputScope throughput(fan_min_kblk());
       for (int i = 0; i < 6; ++i) ACVAE_TRY(stream_dep(sp, f[i], ax));
       ACVAE_TRY(linear_bwd_weight(4 * E, E, NT, ws.dg_p, 4 * E, ws.xp, E, gw.p_wih, 3 * E, f[0]));
@@ -367,6 +370,10 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
       ACVAE_TRY(colsum(NT, 4 * E, ws.dg_p, 4 * E, gw.p_bih, f[5]));
       ACVAE_CHECK(cudaMemcpyAsync(gw.p_bhh, gw.p_bih, sizeof(float) * 4 * E, cudaMemcpyDeviceToDevice, f[5]));
       ACVAE_TRY(colsum(NT, 2 * E, ws.dml_p, 2 * E, gw.p_head_b, f[5]));
+      // d xe_p, the half that needs only the chain (the attention-query half is added behind the attention backward)
+      ACVAE_TRY(stream_dep(sp, f[6], ax));
+      ACVAE_TRY(linear_bwd_data(NT, E, 4 * E, ws.dg_p, 4 * E, w.p_wih, 3 * E, ws.dxe_p, E, f[6]));
+      ACVAE_CHECK(zero(gw.p_emb, (size_t)V * E, f[6]));
     }
     // critical first: d ctx -> attention backward -> per-clip accumulation (the memory backward waits for it)
     ACVAE_TRY(linear_bwd_data(NT, E, 4 * E, ws.dg_p, 4 * E, w.p_wih + E, 3 * E, ws.dctx_p, E, sp));
@@ -398,14 +405,13 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     // the rest: embedding / attention-query weight gradients (need dqp_p from the attention backward); off sp, which
     // carries the prior's half of the memory backward next (the step's last dependency chain)
     {
-      cudaStream_t f3 = ax->s[kAuxFan0 + 7];
+      cudaStream_t fe = ax->s[kAuxPriorFan0 + 6], fw = ax->s[kAuxPriorFan0 + 7];
       TcThroughputScope throughput(fan_min_kblk());
-      ACVAE_TRY(stream_dep(sp, f3, ax));
-      ACVAE_TRY(linear_bwd_data(NT, E, 4 * E, ws.dg_p, 4 * E, w.p_wih, 3 * E, ws.dxe_p, E, f3));
-      ACVAE_TRY(linear_bwd_data(NT, E, E, ws.dqp_p, E, w.p_attn_w, 2 * E, ws.dxe_p, E, f3, 1));
-      ACVAE_CHECK(zero(gw.p_emb, (size_t)V * E, f3));
-      ACVAE_TRY(scatter_rows(NT, E, ws.dxe_p, E, ws.words, gw.p_emb, f3));
-      ACVAE_TRY(linear_bwd_weight(E, E, NT, ws.dqp_p, E, ws.xp, E, gw.p_attn_w, 2 * E, f3));
+      ACVAE_TRY(stream_dep(sp, fe, ax));
+      ACVAE_TRY(stream_dep(sp, fw, ax));
+      ACVAE_TRY(linear_bwd_data(NT, E, E, ws.dqp_p, E, w.p_attn_w, 2 * E, ws.dxe_p, E, fe, 1));
+      ACVAE_TRY(scatter_rows(NT, E, ws.dxe_p, E, ws.words, gw.p_emb, fe));
+      ACVAE_TRY(linear_bwd_weight(E, E, NT, ws.dqp_p, E, ws.xp, E, gw.p_attn_w, 2 * E, fw));
     }
     return 0;
   };
@@ -424,6 +430,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     dpool = ws.dpool;
   } else {
     ACVAE_CHECK(zero(gw.g_w, (size_t)2 * E * E, st)); ACVAE_CHECK(zero(gw.g_b, (size_t)2 * E, st));
+    ACVAE_TRY(stream_dep(st_user, ax->s[kAuxFan0 + 7], ax));     // every fan stream is forked before the join below
   }
   ACVAE_LAUNCH(pool_bwd_kernel, grid1d((long long)NT * E), 256, 0, st, N, T, E, dpool, ws.steplens, 0, ws.amax_d,
                gi.d_outputs, ws.dout);

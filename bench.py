@@ -429,6 +429,13 @@ def run_ours(args):
         feed_host(i); run_step()
     ms_e2e = timed_e2e(args.steps, first=3)
     clk = clocks.stop()
+    if args.train_only:      # quick A/B runs (profiles/*.sh): the two train numbers only, never the driver's line
+        if rank == 0:
+            print(json.dumps({"train_only": True, "n_gpus": world, "ms_per_step": round(ms_resident, 4),
+                              "e2e_ms_per_step": round(ms_e2e, 4), "clocks": clk}), flush=True)
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
 
     # ---- dominant kernel, timed live with CUDA events on its own launching stream (eager steps, L2 flushed) ----
     from acvae_b200 import _lib
@@ -760,6 +767,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-only", action="store_true", help="print the train step's two timings and stop (A/B runs)")
     ap.add_argument("--profile", default="", choices=["", "train", "sample"],
                     help="run ONE eager train step / sampling pass between cudaProfilerStart/Stop (for ncu) and exit")
     args = ap.parse_args()

@@ -16,6 +16,9 @@ def eager():
         return m.inference_forward({"audio_embeds": a, "audio_embeds_lens": l}, method="sample", max_length=20, n_captions=10)
 for _ in range(3): eager()
 torch.cuda.synchronize()
+if os.environ.get("PROFILE"):          # one eager call between cudaProfilerStart/Stop for `ncu --profile-from-start off`
+    torch.cuda.profiler.start(); eager(); torch.cuda.synchronize(); torch.cuda.profiler.stop()
+    print("profiled one eager call"); sys.exit(0)
 l0 = F.launch_count(); t0 = time.perf_counter()
 for _ in range(10): o = eager()
 torch.cuda.synchronize(); te = (time.perf_counter() - t0) / 10

@@ -163,7 +163,7 @@ def test_fused_dp_optimizer_vs_torch(tmp_path, world):
             r.grad = sum(got[q]["grads"][it][i] for q in range(world)) / world
         norm = torch.nn.utils.clip_grad_norm_(ref, 1.0)
         ropt.step()
-    assert abs(got[0]["norm"] - float(norm)) <= 1e-5 * float(norm)
+    assert abs(got[0]["norm"] - float(norm)) <= 1e-4 * float(norm)      # fp32 sums of 2 M squares in different orders
     for i, r in enumerate(ref):
         torch.testing.assert_close(got[0]["params"][i], r.data, rtol=1e-6, atol=1e-7)
         for q in range(1, world):
