@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libacvae_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_float_p = C.POINTER(C.c_float)
 c_void_p = C.c_void_p
@@ -56,7 +56,7 @@ class SampleIO(C.Structure):
     _fields_ = [("audio_embeds", c_void_p), ("mem_lens", c_void_p), ("eps_p", c_void_p), ("u", c_void_p),
                 ("method", C.c_int32), ("temp", C.c_float), ("start_idx", C.c_int32), ("end_idx", C.c_int32),
                 ("seqs", c_void_p), ("sampled_logprobs", c_void_p), ("p_means", c_void_p), ("p_logs", c_void_p),
-                ("p_z", c_void_p), ("outputs", c_void_p), ("n_steps", c_void_p)]
+                ("p_z", c_void_p), ("outputs", c_void_p), ("n_steps", c_void_p), ("rng_state", c_void_p)]
 
 
 # every symbol include/acvae_b200.h declares: (name, restype, argtypes)

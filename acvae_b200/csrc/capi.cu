@@ -232,7 +232,7 @@ int acvae_decode_sample(const acvae_dims* d, const acvae_weights* w, const acvae
   ACVAE_TRY(check_dims(d));
   ACVAE_REQUIRE(w && io && workspace, "NULL pointer");
   ACVAE_REQUIRE(io->audio_embeds && io->mem_lens && io->eps_p && io->seqs && io->sampled_logprobs, "NULL pointer in io");
-  ACVAE_REQUIRE(io->method == 0 || io->u, "method sample/gumbel needs uniform noise u");
+  ACVAE_REQUIRE(io->method == 0 || io->u || io->rng_state, "method sample/gumbel needs uniform noise u or an rng_state to draw it from");
   ACVAE_REQUIRE(io->method >= 0 && io->method <= 2, "unknown sampling method");
   ACVAE_REQUIRE(io->temp > 0.0f, "temp must be positive");
   ACVAE_REQUIRE(workspace_bytes >= carve_sample_ws(*d, nullptr).bytes, "workspace too small");

@@ -72,6 +72,7 @@ struct EpiParams {
   float* pmax; float* pexp; float* psum; float* pbest; int* parg;   // [M, ntiles]
   const float* noise; long long ld_noise; float inv_temp;           // optional Gumbel-max: uniform u ...
   int noise_is_gumbel;                                              // ... or the Gumbel variate itself (precomputed)
+  const unsigned long long* rng; int rng_step;                      // ... or drawn here: device {seed, call}, see philox_uniform4
   // EPI_DLOGITS
   const float* lse; const int* targets; const float* row_w; const float* gscale; // gscale: device [1] = dLoss / count
   float smooth_off, smooth_on;
@@ -87,6 +88,31 @@ struct GemmParams {
   GemmSeg seg[kMaxSeg];
   EpiParams epi;
 };
+
+// ---- counter-based sampling noise (no [T, N, V] tensor) ------------------------------------------------------------
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11), key = the 64-bit seed,
+// counter = (sequence row, word group, decode step, call number).  Word w of the vocabulary belongs to group
+// (w / 128) * 32 + w % 32 and takes output word (w % 128) / 32 of it, so the lane that owns columns lane, lane+32, lane+64,
+// lane+96 of a 128-wide tile draws all four with one call.  u = (x >> 8) * 2^-24 in [0, 1).  The same function in numpy
+// (oracle/philox_ref.py) lets the tests reproduce the device's draws exactly.
+__device__ __forceinline__ void philox4x32_10(unsigned k0, unsigned k1, unsigned c0, unsigned c1, unsigned c2, unsigned c3,
+                                              unsigned (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+    const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (unsigned)p1; c3 = (unsigned)p0; c0 = n0; c2 = n2;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ void philox_uniform4(const unsigned long long* rng, int step, int row, int group, float (&u)[4]) {
+  const unsigned long long seed = rng[0];
+  unsigned x[4];
+  philox4x32_10((unsigned)seed, (unsigned)(seed >> 32), (unsigned)row, (unsigned)group, (unsigned)step, (unsigned)rng[1], x);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) u[i] = (float)(x[i] >> 8) * 5.9604644775390625e-8f;
+}
 
 __device__ __forceinline__ float gumbel_from_u(float u) {
   // reference models/word_model.py:188-190 (eps = 1e-20)
@@ -247,6 +273,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const float* 
     const int ntiles = ntiles_x;
     for (int rb = wid * kRows; rb < BM; rb += NW * kRows) {
       float nz[kRows][kCols];
+      const bool noisy = ep.noise || ep.rng;
       if (ep.noise) {
 #pragma unroll
         for (int i = 0; i < kRows; ++i)
@@ -255,6 +282,19 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const float* 
             const int gm = m0 + rb + i, u = c0 + lane + 32 * q;
             nz[i][q] = (rb + i < BM && gm < p.M && u < U && lane + 32 * q < BN) ? ep.noise[(long long)gm * ep.ld_noise + u] : 0.5f;
           }
+      } else if (ep.rng) {
+        static_assert(BN <= 128 && 128 % BN == 0, "one Philox call per (row, lane) needs column tiles that divide 128");
+        const int w0 = (c0 & 127) >> 5;          // first output word this tile uses (0 for 128-wide tiles)
+#pragma unroll
+        for (int i = 0; i < kRows; ++i) {
+          float uu[4];
+          philox_uniform4(ep.rng, ep.rng_step, m0 + rb + i, ((c0 >> 7) << 5) + lane, uu);
+#pragma unroll
+          for (int q = 0; q < kCols; ++q) {
+            const int w = w0 + q;
+            nz[i][q] = w == 0 ? uu[0] : (w == 1 ? uu[1] : (w == 2 ? uu[2] : uu[3]));
+          }
+        }
       }
 #pragma unroll
       for (int i = 0; i < kRows; ++i) {
@@ -273,7 +313,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const float* 
             vmax = fmaxf(vmax, v);
             vsum += v;
             float key = v;
-            if (ep.noise) key = v * ep.inv_temp + (ep.noise_is_gumbel ? nz[i][q] : gumbel_from_u(nz[i][q]));
+            if (noisy) key = v * ep.inv_temp + (ep.noise_is_gumbel ? nz[i][q] : gumbel_from_u(nz[i][q]));
             if (key > best) { best = key; barg = u; bestlogit = v; }
           }
         }

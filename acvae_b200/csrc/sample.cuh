@@ -146,6 +146,9 @@ inline int sample_step_tc(const StepCtx& c, const StepBufs& b, SampleWs& ws, int
   return 0;
 }
 
+// the next call draws from a fresh counter range (also when the call is a replayed CUDA graph)
+__global__ void rng_advance_kernel(unsigned long long* rng) { rng[1] += 1ull; }
+
 // g = -log(-log(u + 1e-20) + 1e-20) (word_model.py:188-190), elementwise at full occupancy on a side stream:
 // inside the vocabulary GEMM's epilogue the two logs per logit cost more than the GEMM itself.
 __global__ void gumbel_kernel(long long n, const float* __restrict__ u, float* __restrict__ g) {
@@ -176,7 +179,8 @@ inline int decode_sample(const acvae_dims& d, const acvae_weights& w, const acva
   StepBufs b{2, ws.qp_p, ws.w_p, ws.ctx_p, ws.gates_p, ws.c_p, ws.h_p, ws.pm, ws.pl, ws.pz,
              ws.qp_d, ws.w_d, ws.ctx_d, ws.gates_d, ws.hd};
   const bool use_tc = sample_tc_ok(d);
-  Aux* ax = (use_tc && io.method != 0) ? aux() : nullptr;    // side stream: Gumbel variates one step ahead
+  const bool draw = io.method != 0 && !io.u;                 // noise drawn in the vocabulary epilogue (Philox), no u tensor
+  Aux* ax = (use_tc && io.method != 0 && io.u) ? aux() : nullptr;    // injected u: side stream, Gumbel variates one step ahead
   const long long nv = (long long)N * d.V;
   auto gumbel_ahead = [&](int t) -> int {
     cudaStream_t sg = ax->s[0];
@@ -205,9 +209,12 @@ inline int decode_sample(const acvae_dims& d, const acvae_weights& w, const acva
       if (t + 1 < T) ACVAE_TRY(gumbel_ahead(t + 1));
       v.noise = ws.gum[t & 1]; v.ld_noise = d.V; v.noise_is_gumbel = 1;
       v.inv_temp = io.method == 1 ? 1.0f / io.temp : 1.0f;
-    } else if (io.method != 0) {
+    } else if (io.method != 0 && io.u) {
       v.noise = io.u + (long long)t * N * d.V; v.ld_noise = d.V;
       v.inv_temp = io.method == 1 ? 1.0f / io.temp : 1.0f;   // word_model.py:187-198
+    } else if (draw) {
+      v.rng = reinterpret_cast<const unsigned long long*>(io.rng_state); v.rng_step = t;
+      v.inv_temp = io.method == 1 ? 1.0f / io.temp : 1.0f;
     }
     v.red.logprob = io.sampled_logprobs + t; v.red.ld_row = T;
     v.red.seqs = (long long*)io.seqs + t; v.red.ld_seqs = T;
@@ -224,6 +231,7 @@ inline int decode_sample(const acvae_dims& d, const acvae_weights& w, const acva
     ACVAE_TRY(keep(io.p_z, ws.pz)); ACVAE_TRY(keep(io.outputs, ws.hd));
   }
   if (io.n_steps) ACVAE_LAUNCH(sample_nsteps_kernel, 1, 32, 0, st, T, (const int*)ws.active, io.n_steps);
+  if (draw) ACVAE_LAUNCH(rng_advance_kernel, 1, 1, 0, st, reinterpret_cast<unsigned long long*>(io.rng_state));
   return 0;
 }
 

@@ -168,6 +168,7 @@ struct VocabStatsArgs {
   const float* cls_w; const float* cls_b;
   float *pmax, *pexp, *psum, *pbest; int* parg;       // partial buffers [M, ntiles]
   const float* noise; long long ld_noise; float inv_temp; int noise_is_gumbel;
+  const unsigned long long* rng; int rng_step;          // counter-based noise drawn in the epilogue (gemm.cuh philox_uniform4)
   const int* live;
   VocabReduceParams red;                                // outputs (M/ntiles/partials filled in here)
 };
@@ -178,6 +179,7 @@ inline int vocab_stats(VocabStatsArgs a, cudaStream_t st) {
   p.epi.bias[0] = a.cls_b;
   p.epi.pmax = a.pmax; p.epi.pexp = a.pexp; p.epi.psum = a.psum; p.epi.pbest = a.pbest; p.epi.parg = a.parg;
   p.epi.noise = a.noise; p.epi.ld_noise = a.ld_noise; p.epi.inv_temp = a.inv_temp; p.epi.noise_is_gumbel = a.noise_is_gumbel;
+  p.epi.rng = a.rng; p.epi.rng_step = a.rng_step;
   p.live = a.live; a.red.live = a.live;
   int used_tc = 0;
   ACVAE_TRY(launch_gemm<EPI_STATS>(p, st, &used_tc));

@@ -502,8 +502,10 @@ def vocab_stats(hidden, cls_w, cls_b):
 
 @_guard
 def decode_sample(dims, weights: Dict[str, torch.Tensor], audio_embeds, mem_lens, eps_p, u=None, method="greedy",
-                  temp=1.0, start_idx=1, end_idx=2, keep_latents=False):
-    """Prior-latent stepwise decoding (reference vae_model.py:880-894, 700-720)."""
+                  temp=1.0, start_idx=1, end_idx=2, keep_latents=False, rng_state=None):
+    """Prior-latent stepwise decoding (reference vae_model.py:880-894, 700-720).  The word-sampling noise (word_model.py:187-198)
+    is either injected (`u` [T,N,V] uniforms) or drawn inside the vocabulary GEMM's epilogue from `rng_state` (int64 device
+    tensor {seed, calls}; the call increments `calls`): no [T,N,V] tensor exists in that mode."""
     l = _lib.lib()
     dev = audio_embeds.device
     N, T, E = dims.N, dims.T, dims.E
@@ -512,9 +514,14 @@ def decode_sample(dims, weights: Dict[str, torch.Tensor], audio_embeds, mem_lens
     audio_embeds = audio_embeds.contiguous()
     io.audio_embeds = _dev(audio_embeds); io.mem_lens = _dev(mem_lens, torch.int32); io.eps_p = _dev(eps_p)
     if code != 0:
-        if u is None:
-            raise RuntimeError("sampling methods need uniform noise `u` [T,N,V]")
-        io.u = _dev(u)
+        if u is not None:
+            io.u = _dev(u)
+        elif rng_state is not None:
+            if rng_state.dtype != torch.int64 or rng_state.numel() != 2:
+                raise ValueError("rng_state must be an int64 tensor {seed, calls}")
+            io.rng_state = _dev(rng_state, torch.int64)
+        else:
+            raise RuntimeError("sampling methods need uniform noise `u` [T,N,V] or an `rng_state` to draw it from")
     io.method, io.temp, io.start_idx, io.end_idx = code, float(temp), int(start_idx), int(end_idx)
     out = {"seqs": torch.empty(N, T, dtype=torch.int64, device=dev),
            "sampled_logprobs": torch.empty(N, T, dtype=torch.float32, device=dev),

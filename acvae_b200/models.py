@@ -416,6 +416,25 @@ class _FusedVAEBase(CaptionModel):
         return out
 
     # ---- inference -----------------------------------------------------------------------
+    def sampling_rng(self, dev) -> torch.Tensor:
+        """Device state {seed, calls} of the word-sampling generator (Philox4x32-10, csrc/gemm.cuh).  Created on first use with a
+        seed drawn from torch's CPU generator (so `torch.manual_seed` makes sampling reproducible); every sampling call advances
+        `calls` on the device, which keeps a replayed CUDA graph (GraphSampler) drawing fresh noise."""
+        dev = torch.device(dev)
+        if dev.type == "cuda" and dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        st = getattr(self, "_sampling_rng", None)
+        if st is None or st.device != dev:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            st = torch.tensor([seed, 0], dtype=torch.int64, device=dev)
+            self._sampling_rng = st
+        return st
+
+    def seed_sampling(self, seed: int, device=None) -> None:
+        """Restart the word-sampling generator from `seed` (call 0)."""
+        dev = device if device is not None else next(self.parameters()).device
+        self._sampling_rng = torch.tensor([int(seed), 0], dtype=torch.int64, device=dev)
+
     def inference_forward(self, encoded, **kwargs):
         """vae_model.py:880-894.  Extra kwargs: `n_captions` (K sequences per clip sharing the
         clip's memory), `eps_p`, `u` (noise injection)."""
@@ -458,11 +477,12 @@ class _FusedVAEBase(CaptionModel):
         eps_p, u = kwargs.get("eps_p"), kwargs.get("u")
         if eps_p is None:
             eps_p = torch.randn(max_length, N, E, device=dev)
-        if method != "greedy" and u is None:
-            u = torch.rand(max_length, N, V, device=dev)
+        # word-sampling noise (word_model.py:187-198 draws torch.rand_like(logits) per step): injected `u` [T,N,V] for parity
+        # tests, otherwise drawn inside the vocabulary GEMM from the model's counter-based generator (no [T,N,V] tensor)
+        rng = self.sampling_rng(dev) if (method != "greedy" and u is None) else None
         out = F.decode_sample(dims, weights, audio, mem_lens, eps_p.to(dev).contiguous(),
                               None if u is None else u.to(dev).contiguous(), method, kwargs.get("temp", 1),
-                              self.start_idx, self.end_idx, keep_latents=kwargs.get("keep_latents", False))
+                              self.start_idx, self.end_idx, keep_latents=kwargs.get("keep_latents", False), rng_state=rng)
         if K > 1:
             out["seqs"] = out["seqs"].view(clips, K, max_length)
         return out

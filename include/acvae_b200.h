@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ACVAE_ABI_VERSION 1
+#define ACVAE_ABI_VERSION 2
 
 typedef struct acvae_dims {
   int32_t N;     /* sequences in the batch (clips x captions-per-clip)        */
@@ -198,12 +198,16 @@ int acvae_kl_bwd(int64_t rows, int32_t E, const float *q_mean, const float *q_lo
  * caps=None (vae_model.py:880-894, 700-720) and sample_next_word
  * (word_model.py:173-207).  N sequences, `mem_rep` consecutive sequences
  * share one clip's memory (audio_embeds is [N/mem_rep,Te,Eenc]).
- * method: 0 greedy, 1 multinomial-as-Gumbel-max (needs u), 2 gumbel (needs u). */
+ * method: 0 greedy, 1 multinomial-as-Gumbel-max, 2 gumbel (word_model.py:173-207).  The uniforms behind the Gumbel
+ * variates are either injected (`u`, what the parity tests do: the reference draws torch.rand_like(logits) per step) or
+ * drawn inside the vocabulary GEMM's epilogue from a counter-based generator (u == NULL): Philox4x32-10 keyed by
+ * rng_state[0] with counter (sequence, word group, step, rng_state[1]) -- no [T,N,V] tensor exists and every call
+ * increments rng_state[1] on the device, so a replayed CUDA graph draws fresh noise (csrc/gemm.cuh philox_uniform4). */
 typedef struct acvae_sample_io {
   const float   *audio_embeds;   /* [N/mem_rep,Te,Eenc] */
   const int32_t *mem_lens;       /* [N/mem_rep]         */
   const float   *eps_p;          /* [T,N,E] prior noise */
-  const float   *u;              /* [T,N,V] uniforms in (0,1) or NULL for greedy */
+  const float   *u;              /* [T,N,V] uniforms in [0,1), or NULL: greedy / drawn from rng_state */
   int32_t method;
   float   temp;
   int32_t start_idx, end_idx;
@@ -211,6 +215,7 @@ typedef struct acvae_sample_io {
   float   *sampled_logprobs;     /* [N,T] */
   float   *p_means, *p_logs, *p_z, *outputs;  /* [N,T,E] or NULL */
   int32_t *n_steps;              /* device scalar: steps executed before every row had finished */
+  uint64_t *rng_state;           /* device [2] = {seed, calls}; required when method != 0 and u == NULL */
 } acvae_sample_io;
 size_t acvae_sample_workspace_bytes(const acvae_dims *d);
 int acvae_decode_sample(const acvae_dims *d, const acvae_weights *w, const acvae_sample_io *io,

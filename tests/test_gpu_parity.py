@@ -280,6 +280,40 @@ def test_graph_sampler_matches_eager_and_oracle():
     assert not torch.equal(a1, a2), "two replays must not reuse the same noise"
 
 
+@pytest.mark.parametrize("clips,K,method,temp", [(3, 4, "sample", 1.0), (26, 10, "sample", 0.7), (26, 10, "gumbel", 1.0)])
+def test_sampling_device_drawn_noise_vs_host_philox_and_oracle(clips, K, method, temp):
+    """The product sampling path draws its word noise inside the vocabulary GEMM (Philox4x32-10, no [T,N,V] tensor).  The host
+    restatement of the generator (oracle/philox_ref.py, pinned on the Random123 known answers) regenerates the same uniforms;
+    fed to the ORACLE they must give the ids the device sampled -- on the SIMT step (12 sequences, 64-wide vocabulary tiles)
+    and on the tensor-core step (260 sequences, 128-wide tiles) -- and the call counter must advance."""
+    _require_cuda()
+    import acvae_oracle as oracle
+    import philox_ref
+    d, seed, ml = synthetic.Dims(N=clips, Te=62, L=20), 8, 6
+    m = harness.build_model(d, seed).eval()
+    b = synthetic.make_batch(d, seed)
+    rs = np.random.RandomState(2)
+    eps = torch.from_numpy(rs.standard_normal((ml, d.N * K, d.E)).astype(np.float32))
+    p = harness.oracle_params(d, seed)
+    m.seed_sampling(0x1234ABCD5678)
+    for call in range(2):
+        with torch.no_grad():
+            out = m(torch.from_numpy(b["audio_embeds"]).cuda(), torch.from_numpy(b["mem_lens"].copy()), method=method, temp=temp,
+                    max_length=ml, n_captions=K, eps_p=eps)
+        u = torch.from_numpy(philox_ref.sampling_uniforms(0x1234ABCD5678, call, ml, d.N * K, d.V))
+        with torch.no_grad():
+            o = oracle.inference_forward(p, torch.from_numpy(b["audio_embeds"]).repeat_interleave(K, 0),
+                                         np.repeat(b["mem_lens"], K), eps, method, ml, temp, u)
+        got = out["seqs"].cpu().numpy().reshape(d.N * K, ml)
+        assert np.array_equal(got, o["seqs"].numpy()), ("call", call)
+    assert m.sampling_rng("cuda").cpu().tolist() == [0x1234ABCD5678, 2]
+    # the injected-noise path under the same uniforms gives the same ids too
+    with torch.no_grad():
+        inj = m(torch.from_numpy(b["audio_embeds"]).cuda(), torch.from_numpy(b["mem_lens"].copy()), method=method, temp=temp,
+                max_length=ml, n_captions=K, eps_p=eps, u=u)
+    assert np.array_equal(inj["seqs"].cpu().numpy().reshape(d.N * K, ml), got)
+
+
 def test_sampling_full_size_first_and_last_clips_vs_oracle():
     """BASELINE configs[3] at full size: 1045 clips x 10 captions = 10 450 sequences, max_length 20, multinomial sampling.
     The oracle decodes the first and the last clip (20 sequences) under the SAME prior noise and the SAME uniforms (the rows

@@ -129,3 +129,20 @@ def test_bleu_oracle_hand_worked_case():
     # brevity penalty: candidate shorter than the closest reference
     t2 = dv.bleu_stats([4, 5], [[4, 5, 6, 7]])
     assert abs(dv.corpus_bleu([t2])[0] - math.exp(1 - 4 / 2)) < 1e-6
+
+
+def test_philox_reference_known_answers():
+    """oracle/philox_ref.py (the host restatement of the device's sampling-noise generator) against the Random123 known-answer
+    vectors of philox4x32-10, plus the layout properties the device relies on."""
+    import philox_ref
+    def hexes(t):
+        return [f"{int(x):08x}" for x in t]
+    assert hexes(philox_ref.philox4x32_10((0, 0), (0, 0, 0, 0))) == ["6627e8d5", "e169c58d", "bc57ac4c", "9b00dbd8"]
+    assert hexes(philox_ref.philox4x32_10((0xFFFFFFFF,) * 2, (0xFFFFFFFF,) * 4)) == ["408f276d", "41c83b0e", "a20bc7c6", "6d5451fd"]
+    assert hexes(philox_ref.philox4x32_10((0xA4093822, 0x299F31D0), (0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344))) == \
+        ["d16cfe09", "94fdcceb", "5001e420", "24126ea1"]
+    u = philox_ref.sampling_uniforms(7, 0, 3, 5, 4400)
+    assert u.shape == (3, 5, 4400) and u.dtype == np.float32 and 0.0 <= u.min() and u.max() < 1.0
+    assert abs(float(u.mean()) - 0.5) < 0.01
+    assert not np.array_equal(u, philox_ref.sampling_uniforms(7, 1, 3, 5, 4400))      # the call counter selects a fresh range
+    assert np.array_equal(u[:, :, :300], philox_ref.sampling_uniforms(7, 0, 3, 5, 300))  # a word's draw does not depend on V
