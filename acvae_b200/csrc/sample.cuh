@@ -20,6 +20,7 @@ struct SampleWs {
   float *qp_p, *w_p, *ctx_p, *gates_p, *c_p, *h_p, *pm, *pl, *pz, *qp_d, *w_d, *ctx_d, *gates_d, *hd;
   float *pmax, *pexp, *psum, *pbest; int* parg;
   float *xe_p, *xe_d, *pre, *pre_h;   // tensor-core step: gathered embeddings, gate pre-activations
+  float *pre_d, *q_tab;               // tensor-core step: the decoder's own pre-activations; prior query projection of every word [V,E]
   float* gum[2];                      // tensor-core step: Gumbel variates of the current / next step [N,V]
   size_t bytes;
 };
@@ -39,6 +40,7 @@ inline SampleWs carve_sample_ws(const acvae_dims& d, void* base) {
   w.pmax = ar.take<float>(N * nt); w.pexp = ar.take<float>(N * nt); w.psum = ar.take<float>(N * nt);
   w.pbest = ar.take<float>(N * nt * 2); w.parg = ar.take<int>(N * nt);
   w.xe_p = ar.take<float>(N * E); w.xe_d = ar.take<float>(N * E); w.pre = ar.take<float>(N * 4 * E); w.pre_h = ar.take<float>(N * 3 * E);
+  w.pre_d = ar.take<float>(N >= 256 ? N * 3 * E : 0); w.q_tab = ar.take<float>(N >= 256 ? (size_t)d.V * E : 0);
   const size_t gum = N >= 256 ? N * (size_t)d.V : 0;   // only the large-batch tensor-core step uses it
   w.gum[0] = ar.take<float>(gum); w.gum[1] = ar.take<float>(gum);
   w.bytes = ar.off;
@@ -76,29 +78,61 @@ inline int tc_linear2(int M, int Nn, const float* a0, long long lda0, const floa
   p.epi.c[0] = c; p.epi.ldc = ldc; p.epi.bias[0] = bias; p.epi.scale = 1.0f; p.epi.accumulate = accumulate;
   return launch_gemm<EPI_PLAIN>(p, st);
 }
-__global__ void gather2_kernel(int rows, int E, const float* __restrict__ t0, const float* __restrict__ t1,
-                               const int* __restrict__ idx, long long idx_stride, float* __restrict__ o0,
-                               float* __restrict__ o1, const int* __restrict__ live) {
+// rows of three tables for the step's input words: prior / decoder word embeddings and the prior's query projection
+__global__ void gather3_kernel(int rows, int E, const float* __restrict__ t0, const float* __restrict__ t1,
+                               const float* __restrict__ t2, const int* __restrict__ idx, long long idx_stride,
+                               float* __restrict__ o0, float* __restrict__ o1, float* __restrict__ o2, long long ld_o2,
+                               const int* __restrict__ live) {
   if (live && *live == 0) return;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= (long long)rows * E) return;
   const int r = (int)(i / E), e = (int)(i % E);
   const long long src = (long long)idx[r * idx_stride] * E + e;
-  o0[i] = t0[src]; o1[i] = t1[src];
+  *reinterpret_cast<float4*>(o0 + i) = *reinterpret_cast<const float4*>(t0 + src);
+  *reinterpret_cast<float4*>(o1 + i) = *reinterpret_cast<const float4*>(t1 + src);
+  *reinterpret_cast<float4*>(o2 + (long long)r * ld_o2 + e) = *reinterpret_cast<const float4*>(t2 + src);
 }
 
-inline int sample_step_tc(const StepCtx& c, const StepBufs& b, SampleWs& ws, int slot, int prev, const int* words,
+// One decode step (text_encoder.py:247-268, decoder.py:175-203, vae_model.py:808) as three concurrent branches:
+//   s2 : the recurrent half of the prior's gates, [z_{t-1} | h_{t-1}] . W^T + b_ih      (ready when the step starts)
+//   s1 : everything of the decoder that needs only h^dec_{t-1}: query projection, attention, [xe | ctx] . W_ih^T, h . W_hh^T
+//   st : word gather (the prior's query projection is a row of a per-call table: it depends on the word id only) ->
+//        prior attention -> gates += [xe | ctx] . W^T -> LSTM cell -> head -> z_t -> decoder gates += z_t . W^T -> GRU cell
+// 10 dependent kernels per step instead of 16.
+inline int sample_step_tc(const StepCtx& c, const StepBufs& b, SampleWs& ws, Aux* ax, int slot, int prev, const int* words,
                           long long words_stride, const float* eps_t) {
   const int N = c.d.N, E = c.d.E, A = c.d.A, Te = c.d.Te;
   const long long S = b.S;
   const acvae_weights& w = c.w;
-  cudaStream_t st = c.st;
+  cudaStream_t st = c.st, s1 = ax->s[1], s2 = ax->s[2];
   const int* live = c.live;
-  ACVAE_LAUNCH(gather2_kernel, grid1d((long long)N * E), 256, 0, st, N, E, w.p_emb, w.d_emb, words, words_stride, ws.xe_p,
-               ws.xe_d, live);
-  // ---- prior (text_encoder.py:247-268) ----
-  ACVAE_TRY(tc_linear2(N, E, ws.xe_p, E, w.p_attn_w, 2 * E, E, nullptr, 0, nullptr, 0, 0, nullptr,
-                       b.qp_p + (long long)slot * E, S * E, 0, live, st));
+  const float* hprev = prev >= 0 ? b.hd + (long long)prev * E : nullptr;
+  if (prev >= 0) {
+    ACVAE_TRY(stream_dep(st, s2, ax));
+    ACVAE_TRY(tc_linear2(N, 4 * E, b.pz + (long long)prev * E, S * E, w.p_wih + 2 * E, 3 * E, E, b.h_p + (long long)prev * E,
+                         S * E, w.p_whh, E, E, w.p_bih, ws.pre, 4 * E, 0, live, s2));
+  }
+  ACVAE_LAUNCH(gather3_kernel, grid1d((long long)N * E / 4), 256, 0, st, N, E, w.p_emb, w.d_emb, (const float*)ws.q_tab, words,
+               words_stride, ws.xe_p, ws.xe_d, b.qp_p + (long long)slot * E, S * E, live);
+  // ---- decoder branch ----
+  ACVAE_TRY(stream_dep(st, s1, ax));
+  if (hprev)
+    ACVAE_TRY(tc_linear2(N, A, hprev, S * E, w.d_attn_w, 2 * E, E, nullptr, 0, nullptr, 0, 0, nullptr,
+                         b.qp_d + (long long)slot * A, S * A, 0, live, s1));
+  {
+    AttnFwdParams a{};
+    a.rows = N; a.Te = Te; a.A = A; a.E = E; a.Dq = E; a.rows_per_clip = c.d.mem_rep; a.live = live;
+    a.qp_in = hprev ? b.qp_d + (long long)slot * A : nullptr; a.ld_qp_in = S * A;
+    a.P = c.Pd; a.mem = c.mem; a.v = w.d_attn_v; a.mem_lens = c.mem_lens;
+    a.ctx = b.ctx_d + (long long)slot * E; a.ld_ctx = S * E;
+    a.w_out = nullptr;
+    ACVAE_TRY(launch_attn_fwd(a, s1));
+  }
+  ACVAE_TRY(tc_linear2(N, 3 * E, ws.xe_d, E, w.d_wih, 3 * E, E, b.ctx_d + (long long)slot * E, S * E, w.d_wih + E, 3 * E, E,
+                       w.d_bih, ws.pre_d, 3 * E, 0, live, s1));
+  if (hprev)
+    ACVAE_TRY(tc_linear2(N, 3 * E, hprev, S * E, w.d_whh, E, E, nullptr, 0, nullptr, 0, 0, nullptr, ws.pre_h, 3 * E, 0, live, s1));
+  // ---- prior (critical path) ----
   {
     AttnFwdParams a{};
     a.rows = N; a.Te = Te; a.A = E; a.E = E; a.Dq = E; a.rows_per_clip = c.d.mem_rep; a.live = live;
@@ -108,11 +142,9 @@ inline int sample_step_tc(const StepCtx& c, const StepBufs& b, SampleWs& ws, int
     a.w_out = nullptr;
     ACVAE_TRY(launch_attn_fwd(a, st));
   }
+  if (prev >= 0) ACVAE_TRY(stream_dep(s2, st, ax));
   ACVAE_TRY(tc_linear2(N, 4 * E, ws.xe_p, E, w.p_wih, 3 * E, E, b.ctx_p + (long long)slot * E, S * E, w.p_wih + E, 3 * E, E,
-                       w.p_bih, ws.pre, 4 * E, 0, live, st));
-  if (prev >= 0)
-    ACVAE_TRY(tc_linear2(N, 4 * E, b.pz + (long long)prev * E, S * E, w.p_wih + 2 * E, 3 * E, E, b.h_p + (long long)prev * E,
-                         S * E, w.p_whh, E, E, nullptr, ws.pre, 4 * E, 1, live, st));
+                       prev >= 0 ? nullptr : w.p_bih, ws.pre, 4 * E, prev >= 0 ? 1 : 0, live, st));
   ACVAE_LAUNCH(lstm_cell_kernel, grid1d((long long)N * E), 256, 0, st, N, E, (const float*)ws.pre, w.p_bhh,
                prev >= 0 ? (const float*)(b.c_p + (long long)prev * E) : (const float*)nullptr, S * E,
                b.c_p + (long long)slot * E, b.h_p + (long long)slot * E, S * E, live);
@@ -120,27 +152,11 @@ inline int sample_step_tc(const StepCtx& c, const StepBufs& b, SampleWs& ws, int
                        ws.pre, 2 * E, 0, live, st));
   ACVAE_LAUNCH(head_cell_kernel, grid1d((long long)N * E), 256, 0, st, N, E, (const float*)ws.pre, eps_t,
                b.pm + (long long)slot * E, b.pl + (long long)slot * E, b.pz + (long long)slot * E, S * E, live);
-  // ---- decoder (decoder.py:175-203), fed the prior's sample (vae_model.py:808) ----
-  const float* hprev = prev >= 0 ? b.hd + (long long)prev * E : nullptr;
-  if (hprev)
-    ACVAE_TRY(tc_linear2(N, A, hprev, S * E, w.d_attn_w, 2 * E, E, nullptr, 0, nullptr, 0, 0, nullptr,
-                         b.qp_d + (long long)slot * A, S * A, 0, live, st));
-  {
-    AttnFwdParams a{};
-    a.rows = N; a.Te = Te; a.A = A; a.E = E; a.Dq = E; a.rows_per_clip = c.d.mem_rep; a.live = live;
-    a.qp_in = hprev ? b.qp_d + (long long)slot * A : nullptr; a.ld_qp_in = S * A;
-    a.P = c.Pd; a.mem = c.mem; a.v = w.d_attn_v; a.mem_lens = c.mem_lens;
-    a.ctx = b.ctx_d + (long long)slot * E; a.ld_ctx = S * E;
-    a.w_out = nullptr;
-    ACVAE_TRY(launch_attn_fwd(a, st));
-  }
-  ACVAE_TRY(tc_linear2(N, 3 * E, ws.xe_d, E, w.d_wih, 3 * E, E, b.ctx_d + (long long)slot * E, S * E, w.d_wih + E, 3 * E, E,
-                       w.d_bih, ws.pre, 3 * E, 0, live, st));
+  // ---- decoder, fed the prior's sample (vae_model.py:808) ----
+  ACVAE_TRY(stream_dep(s1, st, ax));
   ACVAE_TRY(tc_linear2(N, 3 * E, b.pz + (long long)slot * E, S * E, w.d_wih + 2 * E, 3 * E, E, nullptr, 0, nullptr, 0, 0,
-                       nullptr, ws.pre, 3 * E, 1, live, st));
-  if (hprev)
-    ACVAE_TRY(tc_linear2(N, 3 * E, hprev, S * E, w.d_whh, E, E, nullptr, 0, nullptr, 0, 0, nullptr, ws.pre_h, 3 * E, 0, live, st));
-  ACVAE_LAUNCH(gru_cell_kernel, grid1d((long long)N * E), 256, 0, st, N, E, (const float*)ws.pre,
+                       nullptr, ws.pre_d, 3 * E, 1, live, st));
+  ACVAE_LAUNCH(gru_cell_kernel, grid1d((long long)N * E), 256, 0, st, N, E, (const float*)ws.pre_d,
                hprev ? (const float*)ws.pre_h : (const float*)nullptr, w.d_bhh, hprev, S * E, b.hd + (long long)slot * E, S * E,
                live);
   return 0;
@@ -180,7 +196,12 @@ inline int decode_sample(const acvae_dims& d, const acvae_weights& w, const acva
              ws.qp_d, ws.w_d, ws.ctx_d, ws.gates_d, ws.hd};
   const bool use_tc = sample_tc_ok(d);
   const bool draw = io.method != 0 && !io.u;                 // noise drawn in the vocabulary epilogue (Philox), no u tensor
-  Aux* ax = (use_tc && io.method != 0 && io.u) ? aux() : nullptr;    // injected u: side stream, Gumbel variates one step ahead
+  Aux* axs = use_tc ? aux() : nullptr;                        // side streams of the tensor-core step's branches
+  if (use_tc && !axs) return set_error("decode_sample", "could not create the side streams");
+  Aux* ax = (use_tc && io.method != 0 && io.u) ? axs : nullptr;      // injected u: side stream, Gumbel variates one step ahead
+  // the prior's query projection depends on the input word only: one row per vocabulary entry, once per call
+  if (use_tc)
+    ACVAE_TRY(tc_linear2(d.V, E, w.p_emb, E, w.p_attn_w, 2 * E, E, nullptr, 0, nullptr, 0, 0, nullptr, ws.q_tab, E, 0, nullptr, st));
   const long long nv = (long long)N * d.V;
   auto gumbel_ahead = [&](int t) -> int {
     cudaStream_t sg = ax->s[0];
@@ -194,7 +215,7 @@ inline int decode_sample(const acvae_dims& d, const acvae_weights& w, const acva
     const int* live = t > 0 ? ws.active + (t - 1) : nullptr;
     StepCtx c{d, w, st, io.mem_lens, ws.mem, ws.Pp, ws.Pd, live};
     if (use_tc) {
-      ACVAE_TRY(sample_step_tc(c, b, ws, slot, prev, ws.words + slot, 2, io.eps_p + (long long)t * N * E));
+      ACVAE_TRY(sample_step_tc(c, b, ws, axs, slot, prev, ws.words + slot, 2, io.eps_p + (long long)t * N * E));
     } else {
       ACVAE_TRY(prior_step(c, b, slot, prev, ws.words + slot, 2, io.eps_p + (long long)t * N * E));
       // inference: the decoder consumes the prior's sample (vae_model.py:808)
