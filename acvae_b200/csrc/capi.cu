@@ -64,7 +64,7 @@ int acvae_gemm(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, int
   p.epi.c[0] = C; p.epi.ldc = ldc; p.epi.bias[0] = bias; p.epi.scale = 1.0f; p.epi.accumulate = accumulate;
   int tc = 0;
   ACVAE_TRY(launch_gemm<EPI_PLAIN>(p, (cudaStream_t)stream, &tc));
-  if (used_tc) *used_tc = tc;
+  if (used_tc) *used_tc = tc ? 1 : 0;
   return 0;
 }
 

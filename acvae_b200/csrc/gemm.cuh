@@ -92,8 +92,10 @@ struct GemmParams {
 // ---- counter-based sampling noise (no [T, N, V] tensor) ------------------------------------------------------------
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11), key = the 64-bit seed,
 // counter = (sequence row, word group, decode step, call number).  Word w of the vocabulary belongs to group
-// (w / 128) * 32 + w % 32 and takes output word (w % 128) / 32 of it, so the lane that owns columns lane, lane+32, lane+64,
-// lane+96 of a 128-wide tile draws all four with one call.  u = (x >> 8) * 2^-24 in [0, 1).  The same function in numpy
+// (w / 128) * 32 + ((w % 128) / 64) * 16 + w % 16 and takes output word (w % 64) / 16 of it: the four outputs of one call
+// are four columns of the SAME 64-column half tile, 16 apart, so the thread-per-row epilogue of the persistent tcgen05
+// kernel (one thread = one row x 64 columns) uses every output it computes, and the lane-per-column epilogues get theirs
+// with one call per lane and a shuffle.  u = (x >> 8) * 2^-24 in [0, 1).  The same function in numpy
 // (oracle/philox_ref.py) lets the tests reproduce the device's draws exactly.
 __device__ __forceinline__ void philox4x32_10(unsigned k0, unsigned k1, unsigned c0, unsigned c1, unsigned c2, unsigned c3,
                                               unsigned (&out)[4]) {
@@ -117,6 +119,12 @@ __device__ __forceinline__ void philox_uniform4(const unsigned long long* rng, i
 __device__ __forceinline__ float gumbel_from_u(float u) {
   // reference models/word_model.py:188-190 (eps = 1e-20)
   return -logf(-logf(u + 1e-20f) + 1e-20f);
+}
+// the same variate for device-drawn noise, with the hardware logarithm (lg2.approx, 2^-21 absolute error on the inner log):
+// the two exact logf cost ~50 instructions per logit, more than the vocabulary GEMM itself; the injected-noise path, which is
+// what is pinned against the reference token by token, keeps the exact form
+__device__ __forceinline__ float gumbel_from_u_fast(float u) {
+  return -__logf(-__logf(u + 1e-20f) + 1e-20f);
 }
 
 
@@ -283,16 +291,27 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const float* 
             nz[i][q] = (rb + i < BM && gm < p.M && u < U && lane + 32 * q < BN) ? ep.noise[(long long)gm * ep.ld_noise + u] : 0.5f;
           }
       } else if (ep.rng) {
-        static_assert(BN <= 128 && 128 % BN == 0, "one Philox call per (row, lane) needs column tiles that divide 128");
-        const int w0 = (c0 & 127) >> 5;          // first output word this tile uses (0 for 128-wide tiles)
+        // the Philox word layout is defined on 64-column half tiles: EPI_STATS only ever runs with 128- or 64-wide tiles
 #pragma unroll
         for (int i = 0; i < kRows; ++i) {
           float uu[4];
-          philox_uniform4(ep.rng, ep.rng_step, m0 + rb + i, ((c0 >> 7) << 5) + lane, uu);
+          if constexpr (BN == 128) {
+            // lane L draws group 32 * tile + L (half L / 16, columns L % 16 + {0, 16, 32, 48} of it); column lane + 32 q lives
+            // in half q / 2 at offset lane + 32 (q % 2): group of lane (q / 2) * 16 + lane % 16, output word lane / 16 + 2 (q % 2)
+            philox_uniform4(ep.rng, ep.rng_step, m0 + rb + i, ((c0 >> 7) << 5) + lane, uu);
 #pragma unroll
-          for (int q = 0; q < kCols; ++q) {
-            const int w = w0 + q;
-            nz[i][q] = w == 0 ? uu[0] : (w == 1 ? uu[1] : (w == 2 ? uu[2] : uu[3]));
+            for (int q = 0; q < kCols; ++q) {
+              const int src = (q >> 1) * 16 + (lane & 15);
+              const float u0 = __shfl_sync(0xffffffffu, uu[2 * (q & 1)], src), u1 = __shfl_sync(0xffffffffu, uu[2 * (q & 1) + 1], src);
+              nz[i][q] = lane < 16 ? u0 : u1;
+            }
+          } else if constexpr (BN == 64) {
+            philox_uniform4(ep.rng, ep.rng_step, m0 + rb + i, ((c0 >> 7) << 5) + ((c0 & 64) >> 2) + (lane & 15), uu);
+#pragma unroll
+            for (int q = 0; q < kCols; ++q) nz[i][q] = lane < 16 ? uu[2 * q] : uu[2 * q + 1];
+          } else {
+#pragma unroll
+            for (int q = 0; q < kCols; ++q) nz[i][q] = 0.5f;
           }
         }
       }
@@ -313,7 +332,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const float* 
             vmax = fmaxf(vmax, v);
             vsum += v;
             float key = v;
-            if (noisy) key = v * ep.inv_temp + (ep.noise_is_gumbel ? nz[i][q] : gumbel_from_u(nz[i][q]));
+            if (noisy) key = v * ep.inv_temp + (ep.noise_is_gumbel ? nz[i][q] : (ep.rng ? gumbel_from_u_fast(nz[i][q]) : gumbel_from_u(nz[i][q])));
             if (key > best) { best = key; barg = u; bestlogit = v; }
           }
         }

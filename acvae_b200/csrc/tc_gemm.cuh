@@ -175,6 +175,12 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_ld4_nowait(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
 // x = hi + lo.  kind::tf32 reads 32-bit words and ignores the 13 low mantissa bits, so the RAW fp32 word already
 // acts as hi = trunc_tf32(x) and needs no rewrite; only lo = x - trunc_tf32(x) (exact in fp32, same sign,
 // |lo| < 2^-10 |x|) is written, rounded to nearest tf32 so that its own representation error (2^-21 |x|) is
@@ -433,6 +439,272 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
   }
 }
 
+// =====================================================================================================
+// Persistent variant for the many-tile forward GEMMs (sampling: M = 10 450 sequences, 656 .. 2870 output tiles).
+// One CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the operand ring, the split workers and the MMA
+// issuer run straight through the tile boundaries, and the accumulator lives in TMEM for the WHOLE K range of a tile
+// (K <= 512 on this path: the tensor core's truncating accumulation costs 7e-9 * K relative, profiles/prec_probe.py),
+// in one of FOUR 128-column buffers (all 512 TMEM columns).  When a tile's last MMA retires, the eight epilogue warps
+// work on it (thread = one output row x 64 columns) while the next tiles are being multiplied -- the one-tile kernel above
+// pays prologue + main loop + epilogue serially per tile (23 us per vocabulary tile of which 6 are MMAs).
+//   EPI_PLAIN: the 64 values go to registers, the buffer is handed back at once, the stores follow.
+//   EPI_STATS: row statistics are thread-local in this layout (no staging tile, no shuffles): a SMALL loop walks the row
+//   eight columns at a time straight from TMEM (an unrolled 64-column body with its 32 inlined Philox calls does not fit
+//   the instruction cache: ncu stall_no_instruction 6.1 per issue, profiles/r2), keeps an online max / sum-exp, and each
+//   thread emits the partial of a 64-column half tile (same partial layout as the 64-wide SIMT tiles).
+// =====================================================================================================
+template <int EPI>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_gemm_persist_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcParams tp,
+                       const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
+                       const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
+                       int tiles_n, int total_tiles) {
+  if (p.live && *p.live == 0) return;
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcStages * kTcStageBytes);
+  uint64_t* full = bars;
+  uint64_t* ready = bars + kTcStages;
+  uint64_t* empty = bars + 2 * kTcStages;
+  uint64_t* afull = bars + 3 * kTcStages;      // [4] accumulator buffer complete (tcgen05.commit)
+  uint64_t* aempty = afull + 4;                // [4] accumulator buffer consumed (count 8: one per epilogue warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 4);
+
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 4); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 4; ++b) { mbar_init(&afull[b], 1); mbar_init(&aempty[b], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (wid == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  const int nblk0 = (tp.seg[0].K + kTcBK - 1) / kTcBK;
+  const int nblk1 = tp.nseg > 1 ? (tp.seg[1].K + kTcBK - 1) / kTcBK : 0;
+  const int total = nblk0 + nblk1;             // k-blocks per tile
+
+  if (wid == 0) {
+    // ===== TMA producer =====
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * kTcBM, c0 = (tile % tiles_n) * kTcBN;
+      for (int i = 0; i < total; ++i, ++it) {
+        const int st = it % kTcStages;
+        if (it >= kTcStages) mbar_wait(&empty[st], (it / kTcStages - 1) & 1);
+        const bool s1 = i >= nblk0;
+        const int kb = (s1 ? i - nblk0 : i) * kTcBK;
+        const CUtensorMap* ma = s1 ? &mapA1 : &mapA0;
+        const CUtensorMap* mb = s1 ? &mapB1 : &mapB0;
+        uint8_t* sa = smem + st * kTcStageBytes;
+        uint8_t* sb = sa + 2 * kTcTileBytes;
+        if (elect_one()) {
+          mbar_expect_tx(&full[st], 2 * kTcTileBytes);
+          tma_load_2d(sa, ma, &full[st], kb, m0);
+          tma_load_2d(sb, mb, &full[st], kb, c0);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (wid == 1) {
+    // ===== MMA issuer =====
+    const uint64_t tmpl = tc_smem_desc(0, 16u, 1024u, 2u);          // K-major operands only on this path
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+    const uint32_t ring = smem_u32(smem) >> 4;
+    int it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 3;
+      if (lt >= 4) mbar_wait(&aempty[buf], ((lt >> 2) - 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_c = tmem_d + (uint32_t)buf * kTcBN;
+      for (int i = 0; i < total; ++i, ++it) {
+        const int st = it % kTcStages;
+        mbar_wait(&ready[st], (it / kTcStages) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t dah = tmpl + (uint64_t)(ring + (uint32_t)(st * (kTcStageBytes >> 4)));
+          const uint64_t dal = dah + (kTcTileBytes >> 4);
+          const uint64_t dbh = dah + 2 * (kTcTileBytes >> 4);
+          const uint64_t dbl = dbh + (kTcTileBytes >> 4);
+          if (tp.single_pass) {
+            tc_mma_tf32(tmem_c, dah, dbh, idesc, i > 0 ? 1u : 0u);
+#pragma unroll
+            for (int j = 1; j < kTcBK / 8; ++j) tc_mma_tf32_c<1>(tmem_c, dah + j * 2, dbh + j * 2, idesc);
+          } else {
+            tc_mma_tf32(tmem_c, dal, dbh, idesc, i > 0 ? 1u : 0u);
+            tc_mma_tf32_c<1>(tmem_c, dah, dbl, idesc);
+            tc_mma_tf32_c<1>(tmem_c, dah, dbh, idesc);
+#pragma unroll
+            for (int j = 1; j < kTcBK / 8; ++j) {
+              tc_mma_tf32_c<1>(tmem_c, dal + j * 2, dbh + j * 2, idesc);
+              tc_mma_tf32_c<1>(tmem_c, dah + j * 2, dbl + j * 2, idesc);
+              tc_mma_tf32_c<1>(tmem_c, dah + j * 2, dbh + j * 2, idesc);
+            }
+          }
+          tc_commit(&empty[st]);
+          if (i == total - 1) tc_commit(&afull[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (wid >= 8) {
+    // ===== epilogue warps =====
+    const int q = wid & 3, ch = (wid - 8) >> 2;
+    const EpiParams& ep = p.epi;
+    const int U = p.U;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 3;
+      const int tile_x = tile % tiles_n;
+      const int m0 = (tile / tiles_n) * kTcBM, c0 = tile_x * kTcBN + ch * (kTcBN / 2);
+      const int gm = m0 + q * 32 + lane;
+      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kTcBN + ch * (kTcBN / 2));
+      mbar_wait_backoff(&afull[buf], (lt >> 2) & 1);
+      tc_fence_after();
+      if constexpr (EPI == EPI_PLAIN) {
+        float acc[kTcBN / 2];
+#pragma unroll
+        for (int cc = 0; cc < kTcBN / 2; cc += 32) {
+          uint32_t v[32];
+          tc_ld32(taddr + cc, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[cc + j] = __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&aempty[buf]);          // the values are in registers: the buffer is free again
+        if (gm >= p.M || c0 >= U) continue;
+        float* __restrict__ dst = ep.c[0] + (long long)gm * ep.ldc + c0;
+        const float* __restrict__ bias = ep.bias[0];
+        const bool vec = (ep.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.c[0]) & 15) == 0 && c0 + kTcBN / 2 <= U;
+        if (vec) {
+#pragma unroll
+          for (int j = 0; j < kTcBN / 2; j += 4) {
+            float4 v = make_float4(acc[j] * ep.scale, acc[j + 1] * ep.scale, acc[j + 2] * ep.scale, acc[j + 3] * ep.scale);
+            if (bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
+              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            if (ep.accumulate) {
+              const float4 o = *reinterpret_cast<const float4*>(dst + j);
+              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            *reinterpret_cast<float4*>(dst + j) = v;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < kTcBN / 2; ++j) {
+            if (c0 + j < U) {
+              float v = acc[j] * ep.scale;
+              if (bias) v += __ldg(bias + c0 + j);
+              if (ep.accumulate) v += dst[j];
+              dst[j] = v;
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_STATS) {
+        float m = -INFINITY, sexp = 0.0f, vsum = 0.0f, best = -INFINITY, bestlogit = 0.0f;
+        int barg = 0x7fffffff;
+        const bool row_ok = gm < p.M && c0 < U;
+        const bool noisy = ep.noise || ep.rng;
+        const float* __restrict__ nrow = ep.noise ? ep.noise + (long long)gm * ep.ld_noise + c0 : nullptr;
+        const float* __restrict__ bias = ep.bias[0];
+#pragma unroll 1
+        for (int g0 = 0; g0 < 16; g0 += 4) {
+          // sixteen columns per pass: g0 + k + 16 h (k, h = 0..3).  Philox group (tile, half, g0 + k) yields the four
+          // variates of columns g0 + k + {0, 16, 32, 48} (gemm.cuh philox_uniform4): every output word is used.
+          uint32_t a[4][4];
+          __syncwarp();                                // the TMEM loads are warp-collective (.sync.aligned)
+#pragma unroll
+          for (int h = 0; h < 4; ++h) tc_ld4_nowait(taddr + 16 * h + g0, a[h]);
+          tc_ld_wait();
+          if (row_ok) {
+          float v[16];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float uu[4];
+            if (ep.rng) philox_uniform4(ep.rng, ep.rng_step, gm, ((c0 >> 7) << 5) + ch * 16 + g0 + k, uu);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int jj = g0 + k + 16 * h, u = c0 + jj, e = k * 4 + h;
+              if (u < U) {
+                v[e] = __uint_as_float(a[h][k]) + (bias ? __ldg(bias + u) : 0.0f);
+                float key = v[e];
+                if (ep.rng) key = v[e] * ep.inv_temp + gumbel_from_u_fast(uu[h]);
+                else if (noisy) key = v[e] * ep.inv_temp + (ep.noise_is_gumbel ? nrow[jj] : gumbel_from_u(nrow[jj]));
+                vsum += v[e];
+                if (key > best || (key == best && u < barg)) { best = key; barg = u; bestlogit = v[e]; }
+              } else {
+                v[e] = -INFINITY;
+              }
+            }
+          }
+          // online log-sum-exp: one rescale per sixteen columns (column c0 is always valid, so the maximum is finite)
+          float gmax = v[0];
+#pragma unroll
+          for (int e = 1; e < 16; ++e) gmax = fmaxf(gmax, v[e]);
+          const float nm = fmaxf(m, gmax);
+          float add = 0.0f;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) add += expf(v[e] - nm);
+          sexp = sexp * expf(m - nm) + add;
+          m = nm;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&aempty[buf]);
+        if (row_ok) {
+          const int ntiles = (U + kTcBN / 2 - 1) / (kTcBN / 2);
+          const long long o = (long long)gm * ntiles + tile_x * 2 + ch;
+          ep.pmax[o] = m; ep.pexp[o] = sexp; ep.psum[o] = vsum; ep.pbest[o * 2] = best; ep.pbest[o * 2 + 1] = bestlogit;
+          ep.parg[o] = barg;
+        }
+      }
+    }
+  } else if (wid >= 4) {
+    // ===== split workers =====
+    const int wt = tid - 128;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int i = 0; i < total; ++i, ++it) {
+        const int st = it % kTcStages;
+        mbar_wait(&full[st], (it / kTcStages) & 1);
+        if (!tp.single_pass) {
+          uint4* hiA = reinterpret_cast<uint4*>(smem + st * kTcStageBytes);
+          uint4* loA = hiA + kTcTileBytes / 16;
+          uint4* hiB = loA + kTcTileBytes / 16;
+          uint4* loB = hiB + kTcTileBytes / 16;
+#pragma unroll
+          for (int q0 = 0; q0 < kTcTileBytes / 16; q0 += 128 * 4) {
+            uint4 x[4], y[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { x[u] = hiA[q0 + u * 128 + wt]; y[u] = hiB[q0 + u * 128 + wt]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              loA[q0 + u * 128 + wt] = make_uint4(tc_lo(x[u].x), tc_lo(x[u].y), tc_lo(x[u].z), tc_lo(x[u].w));
+              loB[q0 + u * 128 + wt] = make_uint4(tc_lo(y[u].x), tc_lo(y[u].y), tc_lo(y[u].z), tc_lo(y[u].w));
+            }
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[st]);
+      }
+    }
+  }
+  __syncthreads();
+  if (wid == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(512));
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -517,6 +789,29 @@ inline int try_launch_tc(const GemmParams& p, cudaStream_t st) {
   }
   dim3 grid((NC + kTcBN - 1) / kTcBN, (p.M + kTcBM - 1) / kTcBM);
   GemmParams pl = p;
+  if constexpr (EPI == EPI_PLAIN || EPI == EPI_STATS) {
+    // many-tile forward GEMMs: the persistent kernel (accumulator in TMEM for the whole K range, epilogue overlapped)
+    static int persist = -1;
+    if (persist < 0) { const char* e = getenv("ACVAE_TC_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
+    int nblk = 0;
+    bool kmajor = true;
+    for (int s = 0; s < p.nseg; ++s) {
+      nblk += (p.seg[s].K + kTcBK - 1) / kTcBK;
+      kmajor = kmajor && !p.seg[s].a_trans && !p.seg[s].w_trans && !p.seg[s].k_zero_period;
+    }
+    const int tiles = (int)(grid.x * grid.y);
+    if (persist && kmajor && !tp.trace && !p.epi.atomic && nblk <= 16 && tiles > 148) {
+      static bool configured_p[kMaxDevices] = {false};
+      bool& cfg = configured_p[current_device()];
+      if (!cfg) {
+        ACVAE_CHECK(cudaFuncSetAttribute(tc_gemm_persist_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+        cfg = true;
+      }
+      ACVAE_LAUNCH((tc_gemm_persist_kernel<EPI>), dim3(148), kTcThreads, kTcSmemBytes, st, pl, tp, maps[0], maps[1], maps[2], maps[3],
+                   (int)grid.x, tiles);
+      return EPI == EPI_STATS ? 2 : 1;
+    }
+  }
   if constexpr (EPI == EPI_PLAIN) {
     int nblk = 0;
     for (int s = 0; s < p.nseg; ++s) nblk += (p.seg[s].K + kTcBK - 1) / kTcBK;
@@ -549,7 +844,7 @@ inline int launch_gemm(const GemmParams& p, cudaStream_t st, int* used_tc = null
   if constexpr (EPI == EPI_PLAIN || EPI == EPI_STATS || EPI == EPI_DLOGITS) {
     const int r = try_launch_tc<EPI>(p, st);
     if (r < 0) return r;
-    if (r == 1) { if (used_tc) *used_tc = 1; return 0; }
+    if (r >= 1) { if (used_tc) *used_tc = r; return 0; }   // 2: EPI_STATS partials are per 64-column half tile
   }
   return launch_gemm_simt<EPI>(p, st);
 }

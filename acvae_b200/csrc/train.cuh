@@ -183,7 +183,7 @@ inline int vocab_stats(VocabStatsArgs a, cudaStream_t st) {
   p.live = a.live; a.red.live = a.live;
   int used_tc = 0;
   ACVAE_TRY(launch_gemm<EPI_STATS>(p, st, &used_tc));
-  const int tile = used_tc ? kTcBN : kVocabTile;      // column-tile width of the kernel that ran
+  const int tile = used_tc == 1 ? kTcBN : kVocabTile;  // column width of one partial of the kernel that ran (persistent tcgen05: half tiles)
   a.red.M = a.M; a.red.ntiles = (a.V + tile - 1) / tile;
   a.red.pmax = a.pmax; a.red.pexp = a.pexp; a.red.psum = a.psum; a.red.pbest = a.pbest; a.red.parg = a.parg;
   ACVAE_LAUNCH(vocab_reduce_kernel, (a.M + 3) / 4, 128, 0, st, a.red);

@@ -42,3 +42,19 @@ for (M, N, K, at, bt, what) in shapes:
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / n * 1e3
     print(f"{what:34s} M={M:5d} N={N:5d} K={K:5d} tc={int(used)} {us:8.1f} us  {2*M*N*K/us/1e6:8.2f} TFLOP/s")
+
+# the vocabulary GEMM with its statistics epilogue (EPI_STATS: logits never reach HBM)
+for M in (608, 1310, 10450):
+    hid = torch.randn(M, 256, device="cuda"); cw = torch.randn(4400, 256, device="cuda") * 0.05; cb = torch.randn(4400, device="cuda")
+    for _ in range(3):
+        F.vocab_stats(hid, cw, cb)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph(); side = torch.cuda.Stream()
+    with torch.cuda.graph(g, stream=side):
+        for _ in range(reps):
+            F.vocab_stats(hid, cw, cb)
+    g.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / reps * 1e3
+    print(f"{'vocab_stats (GEMM + reduce)':34s} M={M:5d} N= 4400 K=  256      {us:8.1f} us  {2*M*4400*256/us/1e6:8.2f} TFLOP/s")
