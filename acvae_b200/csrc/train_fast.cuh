@@ -44,6 +44,12 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
                ws.words);
   ACVAE_TRY(stream_dep(st, sq0, ax));
   ACVAE_TRY(stream_dep(st, sq1, ax));
+  // the prior's word-only inputs (embedding rows, query projection) need no memory: ahead of everything on the prior's stream,
+  // so that its batched word attention runs UNDER the posterior chain instead of across its end (attention CTAs fill every
+  // SM for 40 us; the posterior head GEMM behind the chain then waits ~20 us for a free SM)
+  ACVAE_TRY(stream_dep(st, sp, ax));
+  ACVAE_TRY(gather_rows(NT, E, w.p_emb, ws.words, ws.xp, sp));
+  ACVAE_TRY(linear_fwd(NT, E, E, ws.xp, E, w.p_attn_w, 2 * E, nullptr, ws.qp_p, E, sp));
 
   // ---- posterior (text_encoder.py:182-216): the two directions are independent chains --------------
   ACVAE_TRY(gather_rows(NT, E, w.q_emb, ws.qids, ws.xq, sq0));
@@ -73,6 +79,7 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     }
   }
   ACVAE_TRY(stream_dep(sq1, sq0, ax));
+  cudaEvent_t ev_qz = ax->ev();
   if (post_chain) {
     PostChainFwd pc{};
     pc.N = N; pc.T = T; pc.lens = ws.steplens; pc.ho = ws.ho; pc.bar = ws.bars + 0 * 128;
@@ -98,6 +105,7 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     } else {
       ACVAE_TRY(launch_gemm<EPI_HEAD>(h, sq0));
     }
+    ACVAE_CHECK(cudaEventRecord(ev_qz, sq0));      // q_z is final: the decoder does not wait for the pooling below
     ACVAE_LAUNCH(pool_fwd_kernel, grid1d((long long)N * 2 * E), 256, 0, sq0, N, T, 2 * E, ws.ho, ws.steplens, 0,
                  io.q_means_utt, ws.amax_q);
   }
@@ -107,12 +115,15 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   ACVAE_TRY(memory_prepare(d, w, io.audio_embeds, ws.mem, ws.Pp, ws.Pd, st));
   ACVAE_TRY(stream_dep(st, sp, ax));
   // cluster decoder chain: the context's share of the gate pre-activations per FRAME, Mg = mem . W_ih[:, E:2E]^T, so that
-  // the chain needs neither the K = E context product nor an exchange of the context (cluster_chain.cuh)
-  if (cl) ACVAE_TRY(linear_fwd(N * Te, 3 * E, E, ws.mem, E, w.d_wih + E, 3 * E, nullptr, ws.Mg, 3 * E, st));
+  // the chain needs neither the K = E context product nor an exchange of the context (cluster_chain.cuh).  96 exclusive CTAs
+  // that nothing needs before the decoder chain starts: on a low-priority stream, behind the prior's attention
+  cudaStream_t s_mg = ax->s[kAuxFan0];
+  if (cl) {
+    ACVAE_TRY(stream_dep(st, s_mg, ax));
+    ACVAE_TRY(linear_fwd(N * Te, 3 * E, E, ws.mem, E, w.d_wih + E, 3 * E, nullptr, ws.Mg, 3 * E, s_mg));
+  }
 
   // ---- prior (text_encoder.py:247-268): word attention and input-side gates batched over (n,t) ---------
-  ACVAE_TRY(gather_rows(NT, E, w.p_emb, ws.words, ws.xp, sp));
-  ACVAE_TRY(linear_fwd(NT, E, E, ws.xp, E, w.p_attn_w, 2 * E, nullptr, ws.qp_p, E, sp));
   {
     AttnFwdParams a{};
     a.rows = NT; a.Te = Te; a.A = E; a.E = E; a.Dq = E; a.rows_per_clip = T;
@@ -165,7 +176,7 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
 
   // ---- decoder (decoder.py:175-203): needs q_z from the posterior -------------------------------------------
   ACVAE_TRY(gather_rows(NT, E, w.d_emb, ws.words, ws.xd, st));
-  ACVAE_TRY(stream_dep(sq0, st, ax));
+  ACVAE_CHECK(cudaStreamWaitEvent(st, ev_qz, 0));
   {
     // gx_d = [emb | q_z] . W_ih[:, {0:E, 2E:3E}]^T + b_ih  (3E columns), kept in dgi_d until the backward overwrites it
     GemmParams g{};
@@ -185,6 +196,7 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     // each and the decoder's clusters trickle in two at a time on the 20 SMs left (214 instead of 108 us); when the
     // decoder's 8 clusters come first they take 64 SMs and the prior packs two CTAs per SM onto the other 84.  So the
     // prior waits for the decoder's inputs and is held back a few microseconds behind the decoder's launch.
+    ACVAE_TRY(stream_dep(s_mg, st, ax));
     if (prior_chain) ACVAE_TRY(stream_dep(st, sp, ax));
     ACVAE_TRY(launch_cluster_chain(dec_cl_fwd_kernel, dec_cl_clusters(N), dec_cl_fwd_smem(Te), st, "dec_cl_fwd_kernel", dc));
     if (prior_chain) {
@@ -249,12 +261,14 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     v.red.seqs = (long long*)io.seqs; v.red.ld_seqs = 1;
     ACVAE_TRY(vocab_stats(v, st));
   }
-  // global-constraint head (vae_model.py:722-729)
-  ACVAE_LAUNCH(pool_fwd_kernel, grid1d((long long)N * E), 256, 0, st, N, T, E, io.outputs, ws.steplens, 0, ws.pool_d,
+  // global-constraint head (vae_model.py:722-729): needs only the decoder's outputs -- next to the vocabulary GEMM, not behind it
+  cudaStream_t s_g = cl ? sq1 : st;
+  ACVAE_LAUNCH(pool_fwd_kernel, grid1d((long long)N * E), 256, 0, s_g, N, T, E, io.outputs, ws.steplens, 0, ws.pool_d,
                ws.amax_d);
-  ACVAE_TRY(linear_fwd(N, 2 * E, E, ws.pool_d, E, w.g_w, E, w.g_b, io.p_means_utt, 2 * E, st));
+  ACVAE_TRY(linear_fwd(N, 2 * E, E, ws.pool_d, E, w.g_w, E, w.g_b, io.p_means_utt, 2 * E, s_g));
   if (io.logits) ACVAE_TRY(linear_fwd(NT, d.V, E, io.outputs, E, w.cls_w, E, w.cls_b, io.logits, d.V, st));
   ACVAE_TRY(stream_dep(sp, st, ax));
+  ACVAE_TRY(stream_dep(sq0, st, ax));            // the posterior's pooling
   if (cl) ACVAE_TRY(stream_dep(sq1, st, ax));
   ACVAE_TRY(stream_dep(st, st_user, ax));
   return 0;
