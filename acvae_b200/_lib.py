@@ -75,6 +75,8 @@ SYMBOLS = {
     "acvae_train_fwd": (C.c_int, [_DP, _WP, C.POINTER(TrainIO), _vp, _sz, _vp]),
     "acvae_train_bwd": (C.c_int, [_DP, _WP, C.POINTER(TrainIO), C.POINTER(TrainGradsIn),
                                   C.POINTER(WeightGrads), _vp, _vp, _sz, _vp]),
+    "acvae_defer_classifier_grads": (C.c_int, [_i32]),
+    "acvae_join_deferred": (C.c_int, [_vp]),
     "acvae_vocab_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "acvae_vocab_logits": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "acvae_vocab_logits_bwd": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -106,8 +106,11 @@ int acvae_train_bwd(const acvae_dims* d, const acvae_weights* w, const acvae_tra
   ACVAE_REQUIRE(w && io && gin && gw && workspace, "NULL pointer");
   ACVAE_REQUIRE(workspace_bytes >= carve_train_ws(*d, nullptr).bytes, "workspace too small");
   ACVAE_REQUIRE(io->tf_flags && io->dis_flags, "tf_flags / dis_flags are required");
-  if (!getenv("ACVAE_DISABLE_FAST") && fast_path_ok(*d, *io))
-    return train_bwd_fast(*d, *w, *io, *gin, *gw, d_audio_embeds, workspace, (cudaStream_t)stream);
+  if (!getenv("ACVAE_DISABLE_FAST") && fast_path_ok(*d, *io)) {
+    ACVAE_TRY(train_bwd_fast(*d, *w, *io, *gin, *gw, d_audio_embeds, workspace, (cudaStream_t)stream));
+    return join_deferred_cls_grads((cudaStream_t)stream);     // (already joined through the fan: clears the pending mark)
+  }
+  ACVAE_TRY(join_deferred_cls_grads((cudaStream_t)stream));
   ACVAE_TRY(train_bwd(*d, *w, *io, *gin, *gw, d_audio_embeds, workspace, (cudaStream_t)stream));
   if (bucket_event()) ACVAE_CHECK(cudaEventRecord(bucket_event(), (cudaStream_t)stream));
   return 0;
@@ -191,11 +194,24 @@ int acvae_vocab_ce_bwd(int32_t M, int32_t V, int32_t E, const float* hidden, con
   p.epi.lse = row_lse; p.epi.targets = targets; p.epi.row_w = row_w; p.epi.gscale = ws.scal;
   p.epi.smooth_on = 1.0f - smoothing; p.epi.smooth_off = smoothing / (float)(V - 1);
   ACVAE_TRY(launch_gemm<EPI_DLOGITS>(p, st));
+  cudaStream_t sw = st;
+  if (cls_defer_flag() && (d_cls_w || d_cls_b)) {
+    // the weight / bias gradients feed nothing before the optimizer: off the caller's stream (which carries the step's critical
+    // path into acvae_train_bwd), joined back by acvae_train_bwd / the optimizer entries
+    Aux* ax = aux();
+    ACVAE_REQUIRE(ax, "no side streams");
+    sw = ax->s[kAuxFan0 + 7];
+    ACVAE_TRY(stream_dep(st, sw, ax));
+    *cls_defer_pending() = true;
+  }
   if (d_hidden) ACVAE_TRY(linear_bwd_data(M, E, V, ws.dlogits, V, cls_w, E, d_hidden, E, st));
-  if (d_cls_w) ACVAE_TRY(linear_bwd_weight(V, E, M, ws.dlogits, V, hidden, E, d_cls_w, E, st));
-  if (d_cls_b) ACVAE_TRY(colsum(M, V, ws.dlogits, V, d_cls_b, st));
+  if (d_cls_w) ACVAE_TRY(linear_bwd_weight(V, E, M, ws.dlogits, V, hidden, E, d_cls_w, E, sw));
+  if (d_cls_b) ACVAE_TRY(colsum(M, V, ws.dlogits, V, d_cls_b, sw));
   return 0;
 }
+
+int acvae_defer_classifier_grads(int32_t on) { cls_defer_flag() = on != 0; return 0; }
+int acvae_join_deferred(void* stream) { return join_deferred_cls_grads((cudaStream_t)stream); }
 
 int acvae_kl_fwd(int64_t rows, int32_t E, const float* q_mean, const float* q_log, const float* p_mean,
                  const float* p_log, float* kl_out, void* workspace, size_t workspace_bytes, void* stream) {
@@ -264,6 +280,7 @@ static int clip_adam_impl(int64_t n, float* params, float* grads, float* exp_avg
   ACVAE_REQUIRE(params && grads && exp_avg && exp_avg_sq && step && workspace, "NULL pointer");
   ACVAE_REQUIRE(aligned16(params) && aligned16(grads) && aligned16(exp_avg) && aligned16(exp_avg_sq), "flat buffers must be 16-byte aligned");
   ACVAE_REQUIRE(workspace_bytes >= sizeof(float) * kOptBlocks, "workspace too small");
+  ACVAE_TRY(join_deferred_cls_grads((cudaStream_t)stream));
   const long long n4 = n / 4;
   int blocks = (int)((n4 + kOptThreads - 1) / kOptThreads);
   blocks = blocks < 1 ? 1 : (blocks > kOptBlocks ? kOptBlocks : blocks);
@@ -349,6 +366,7 @@ int acvae_dp_clip_adam(int32_t world, int32_t rank, int64_t n, const void* const
   ACVAE_REQUIRE(n > 0 && n % (4LL * world) == 0, "n must be a positive multiple of 4 * world (pad the flat buffers)");
   ACVAE_REQUIRE(grads && params && comm && grad_shard && exp_avg && exp_avg_sq && hyper && step && workspace, "NULL pointer");
   ACVAE_REQUIRE(workspace_bytes >= acvae_dp_workspace_bytes(), "workspace too small");
+  ACVAE_TRY(join_deferred_cls_grads((cudaStream_t)stream));
   DpParams a{};
   a.world = world; a.rank = rank; a.n4 = n / 4 / world;
   for (int q = 0; q < world; ++q) {

@@ -62,6 +62,13 @@ inline cudaEvent_t& input_ready_event() { static cudaEvent_t e = nullptr; return
 // the backward.  A data-parallel caller starts the all-reduce of that bucket behind it, under the rest of the backward.
 inline cudaEvent_t& bucket_event() { static cudaEvent_t e = nullptr; return e; }
 
+// Deferred classifier gradients (acvae_defer_classifier_grads): the loss backward produces d hidden on the caller's stream and
+// d W_cls / d b_cls -- which nothing in the step reads before the optimizer -- on fan stream 7; every later entry point that
+// could consume them (acvae_train_bwd, the optimizer entries) joins that stream back into the caller's.
+inline bool& cls_defer_flag() { static bool f = false; return f; }
+inline bool* cls_defer_pending() { static bool p[kMaxDevices] = {false}; return &p[current_device()]; }
+inline int join_deferred_cls_grads(cudaStream_t user);
+
 // Make `st` wait for the caller's "inputs ready" event, if one is set: called by EVERY entry point right before its first
 // kernel that reads audio_embeds (both training schedules, the sampling / beam / diverse-beam loops, acvae_memory_prepare).
 inline int wait_input_event(cudaStream_t st) {
@@ -79,6 +86,16 @@ inline int stream_dep(cudaStream_t from, cudaStream_t to, Aux* a) {
   cudaEvent_t e = a->ev();
   ACVAE_CHECK(cudaEventRecord(e, from));
   ACVAE_CHECK(cudaStreamWaitEvent(to, e, 0));
+  return 0;
+}
+
+inline int join_deferred_cls_grads(cudaStream_t user) {
+  bool* pending = cls_defer_pending();
+  if (!*pending) return 0;
+  Aux* ax = aux();
+  if (!ax) return set_error("join_deferred_cls_grads", "no side streams");
+  ACVAE_TRY(stream_dep(ax->s[kAuxFan0 + 7], user, ax));
+  *pending = false;
   return 0;
 }
 

@@ -118,10 +118,6 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   // the chain needs neither the K = E context product nor an exchange of the context (cluster_chain.cuh).  96 exclusive CTAs
   // that nothing needs before the decoder chain starts: on a low-priority stream, behind the prior's attention
   cudaStream_t s_mg = ax->s[kAuxFan0];
-  if (cl) {
-    ACVAE_TRY(stream_dep(st, s_mg, ax));
-    ACVAE_TRY(linear_fwd(N * Te, 3 * E, E, ws.mem, E, w.d_wih + E, 3 * E, nullptr, ws.Mg, 3 * E, s_mg));
-  }
 
   // ---- prior (text_encoder.py:247-268): word attention and input-side gates batched over (n,t) ---------
   {
@@ -131,6 +127,10 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     a.P = ws.Pp; a.mem = ws.mem; a.v = w.p_attn_v; a.mem_lens = io.mem_lens;
     a.ctx = ws.ctx_p; a.ld_ctx = E; a.w_out = ws.w_p; a.ld_w = Te;
     ACVAE_TRY(launch_attn_fwd(a, sp));
+    if (cl) {     // behind the attention (which must not be slowed down: it has to be gone when the posterior chain ends)
+      ACVAE_TRY(stream_dep(sp, s_mg, ax));
+      ACVAE_TRY(linear_fwd(N * Te, 3 * E, E, ws.mem, E, w.d_wih + E, 3 * E, nullptr, ws.Mg, 3 * E, s_mg));
+    }
     // gx_p = [xe | ctx] . W_ih[:, :2E]^T + b_ih   (4E columns, gate-major), written into the gate buffer
     GemmParams g{};
     g.M = NT; g.U = 4 * E; g.G = 1; g.nseg = 2;
@@ -601,9 +601,10 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     ACVAE_TRY(colsum(NT, 3 * E, ws.dgi_d, 3 * E, gw.d_bih, f[5]));
     ACVAE_TRY(colsum(NT, 3 * E, ws.dgh_d, 3 * E, gw.d_bhh, f[4]));
     if (bucket_event()) {
-      // every decoder.* gradient is final once fan streams 0..6 and sx (attention v / bias / memory-side weights) get here;
-      // fan 7 also carries late prior work and must not hold the bucket back
+      // every decoder.* gradient is final once fan streams 0..7 (7: deferred classifier gradients, acvae_defer_classifier_grads)
+      // and sx (attention v / bias / memory-side weights) get here
       for (int i = 0; i < 6; ++i) ACVAE_TRY(stream_dep(f[i], f[6], ax));
+      ACVAE_TRY(stream_dep(f[7], f[6], ax));
       ACVAE_TRY(stream_dep(sx, f[6], ax));
       ACVAE_TRY(stream_dep(st_user, f[6], ax));       // the classifier's gradients (loss backward, caller's stream)
       ACVAE_CHECK(cudaEventRecord(bucket_event(), f[6]));

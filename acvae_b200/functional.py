@@ -444,10 +444,16 @@ class VAELossFn(torch.autograd.Function):
         else:
             dw = torch.empty_like(w)
             db = torch.empty(V, dtype=torch.float32, device=h2.device)
-        _lib.check(l.acvae_vocab_ce_bwd(M, V, E, _dev(h2), _dev(w), _dev(b), _dev(tg, torch.int32), _opt(ctx.rw), ctx.smoothing,
-                                        _dev(row_lse), scal.data_ptr() + 8, _dev(dh), _dev(dw), _dev(db),
-                                        ctx.ws.data_ptr(), ctx.ws.numel(), _stream()), "acvae_vocab_ce_bwd")
         sink = ctx.grad_sink is not None
+        # sink mode: the classifier's weight / bias gradients land in the flat buffer and nothing reads them before the optimizer
+        # (or the all-reduce, behind acvae_train_bwd's join) -- off the critical stream
+        l.acvae_defer_classifier_grads(1 if sink else 0)
+        try:
+            _lib.check(l.acvae_vocab_ce_bwd(M, V, E, _dev(h2), _dev(w), _dev(b), _dev(tg, torch.int32), _opt(ctx.rw), ctx.smoothing,
+                                            _dev(row_lse), scal.data_ptr() + 8, _dev(dh), _dev(dw), _dev(db),
+                                            ctx.ws.data_ptr(), ctx.ws.numel(), _stream()), "acvae_vocab_ce_bwd")
+        finally:
+            l.acvae_defer_classifier_grads(0)
         return (dh, None if sink else dw, None if sink else db, None, None, None, None, None,
                 dk[0], dk[1], dk[2], dk[3], dqu, dpu, None, None, None)
 

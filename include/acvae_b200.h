@@ -229,6 +229,15 @@ int acvae_beam_search(const acvae_dims *d, const acvae_weights *w, const float *
                       const int32_t *mem_lens, const float *eps_b, int32_t beam, int32_t start_idx,
                       int64_t *seqs, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Deferred classifier gradients.  With the switch on, acvae_vocab_ce_bwd produces d_hidden on the caller's stream and
+ * d_cls_w / d_cls_b -- which nothing in the step reads before the optimizer -- on a side stream, so the ~20 us they take no
+ * longer sit between the loss and acvae_train_bwd on the step's critical path.  acvae_train_bwd, acvae_clip_adam*,
+ * acvae_dp_clip_adam and acvae_join_deferred join that stream back into the stream they are given; a caller that reads the
+ * two gradients any other way calls acvae_join_deferred(stream) first.  (The reference has no counterpart: autograd
+ * computes the three gradients of the classifier back to back, decoder.py:199.)                                           */
+int acvae_defer_classifier_grads(int32_t on);
+int acvae_join_deferred(void *stream);
+
 /* ---- fused optimizer tail --------------------------------
  * Global-norm gradient clipping (runners/pytorch_runner_vae.py:322, clip_grad_norm_ semantics:
  * coef = min(1, max_norm / (||g||_2 + 1e-6)); max_norm <= 0 disables it) chained with the Adam
