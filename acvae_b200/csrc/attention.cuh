@@ -492,7 +492,7 @@ inline int launch_attn_bwd_acc(const AttnBwdAccParams& p, cudaStream_t st) {
 // 608 rows at CFG1, on the critical tail of the backward.  Here a clip's rows are handled together, in two launches:
 //   attn_dalpha_kernel    d alpha[t,j] = d ctx[t,:] . mem[n,j,:]        grid (Te/8, clips), a warp per frame
 //                         (skipped when `ds_in` is given: the decoder's chain kernels have produced d s and d qp already)
-//   attn_bwd_clip_kernel  grid (4, clips); CTA (s, n) owns attention columns / memory columns [s*A/4, (s+1)*A/4):
+//   attn_bwd_clip_kernel  grid (8, clips); CTA (s, n) owns attention columns / memory columns [s*A/8, (s+1)*A/8):
 //     softmax backward d s[t,j] = w (d alpha - sum w d alpha) (every CTA of the clip, redundantly: T x Te values);
 //     ONE evaluation of g = 1 - tanh^2 per (t, j, a) feeds d qp[t,a] = v_a sum_j d s g, d P[j,a] = v_a sum_t d s g and
 //     d v[a] = sum d s tanh;   d mem[n,j,e] (+)= sum_t w[t,j] d ctx[t,e]
@@ -510,11 +510,11 @@ struct AttnBwdClipParams {
   float* dmem; int dmem_accumulate;   // [clips,Te,E]
   float* dv;                // [A], atomically accumulated (zeroed by the caller)
 };
-constexpr int kAbcSplit = 4;
-constexpr int kAbcMaxFr = 24;             // frames per thread in the tanh pass: Te <= 4 * 24
+constexpr int kAbcSplit = 8;              // CTAs per clip: 256 CTAs of 30 K registers / 60 KB, two per SM (4 -> 8: 41 -> ~22 us, profiles/r2)
+constexpr int kAbcMaxFr = 12;             // frames per thread in the tanh pass: Te <= (256 / AS) * 12
 inline size_t attn_bwd_clip_smem(int T, int Te, int A, int E) {
   const int ld = Te + 1, AS = A / kAbcSplit;
-  return ((size_t)2 * T * ld + (size_t)T * E + (size_t)T * AS + (size_t)4 * T * AS + (size_t)Te * AS + 64) * sizeof(float);
+  return ((size_t)2 * T * ld + (size_t)T * E + (size_t)T * AS + (size_t)256 * T + (size_t)Te * AS + 64) * sizeof(float);
 }
 
 // d alpha[t, j] for one clip and 8 frames: warp = frame, lanes over E (E <= 256), four rows' shuffle trees in flight at once
@@ -559,8 +559,8 @@ __global__ void __launch_bounds__(256) attn_bwd_clip_kernel(const __grid_constan
   float* ws = dss + T * ld;               // [T][ld]  softmax weights
   float* dcs = ws + T * ld;               // [T][E]   d ctx rows of the clip
   float* qs = dcs + T * E;                // [T][AS]  2 log2 e * q[t, my columns]
-  float* red = qs + T * AS;               // [4][T][AS] partial d qp per frame group
-  float* Pss = red + 4 * T * AS;          // [Te][AS] 2 log2 e * P[n, :, my columns]
+  float* red = qs + T * AS;               // [G][T][AS] partial d qp per frame group (G = 256 / AS)
+  float* Pss = red + 256 * T;             // [Te][AS] 2 log2 e * P[n, :, my columns]
   const int s = blockIdx.x, n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int len = max(1, min(p.mem_lens[n], Te));
   const long long r0 = (long long)n * T;
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(256) attn_bwd_clip_kernel(const __grid_constan
           dvacc = fmaf(d, fmaf(-2.0f, r, 1.0f), dvacc);
         }
       }
-      if (!p.ds_in && jq < 4) red[(jq * T + t) * AS + a] = dq;
+      if (!p.ds_in) red[(jq * T + t) * AS + a] = dq;
     }
 #pragma unroll
     for (int f = 0; f < kAbcMaxFr; ++f) {
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(256) attn_bwd_clip_kernel(const __grid_constan
 inline int launch_attn_bwd_clip(const AttnBwdClipParams& p, cudaStream_t st) {
   if (p.clips <= 0) return 1;
   const int AS = p.A / kAbcSplit, ES = p.E / kAbcSplit;
-  if (p.A % (4 * kAbcSplit) || p.E % (4 * kAbcSplit) || AS > 256 || ES > 256 || 256 % AS || 256 % ES || 256 / AS > 4 || p.E > 256 ||
+  if (p.A % (4 * kAbcSplit) || p.E % (4 * kAbcSplit) || AS > 256 || ES > 256 || 256 % AS || 256 % ES || 256 / AS > 8 || p.E > 256 ||
       p.Te > (256 / AS) * kAbcMaxFr)
     return 0;
   const size_t smem = attn_bwd_clip_smem(p.T, p.Te, p.A, p.E);

@@ -453,8 +453,12 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
 //   the instruction cache: ncu stall_no_instruction 6.1 per issue, profiles/r2), keeps an online max / sum-exp, and each
 //   thread emits the partial of a 64-column half tile (same partial layout as the 64-wide SIMT tiles).
 // =====================================================================================================
+// EPI_STATS runs TWO epilogue groups of eight warps (24 warps, 80 registers): with the sampling noise drawn in place the
+// epilogue of a tile (Philox + two logarithms + exp per logit: ~18 us) is twice its main loop (8.7 us); the groups take
+// alternate tiles (buffers 0, 2 / 1, 3), so a tile leaves the SM every ~9 us.  EPI_PLAIN keeps one group (128 registers).
+template <int EPI> __host__ __device__ constexpr int tc_persist_threads() { return EPI == EPI_STATS ? 768 : kTcThreads; }
 template <int EPI>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(tc_persist_threads<EPI>(), 1)
 tc_gemm_persist_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcParams tp,
                        const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
                        const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
@@ -554,11 +558,13 @@ tc_gemm_persist_kernel(const __grid_constant__ GemmParams p, const __grid_consta
     }
   } else if (wid >= 8) {
     // ===== epilogue warps =====
-    const int q = wid & 3, ch = (wid - 8) >> 2;
+    const int q = wid & 3, ch = ((wid - 8) >> 2) & 1, grp = (wid - 8) >> 3;
+    constexpr int kGroups = tc_persist_threads<EPI>() / 256 - 1;      // 1 or 2 groups of eight warps
     const EpiParams& ep = p.epi;
     const int U = p.U;
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      if (kGroups == 2 && (lt & 1) != grp) continue;                  // the other group's tile
       const int buf = lt & 3;
       const int tile_x = tile % tiles_n;
       const int m0 = (tile / tiles_n) * kTcBM, c0 = tile_x * kTcBN + ch * (kTcBN / 2);
@@ -807,8 +813,8 @@ inline int try_launch_tc(const GemmParams& p, cudaStream_t st) {
         ACVAE_CHECK(cudaFuncSetAttribute(tc_gemm_persist_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
         cfg = true;
       }
-      ACVAE_LAUNCH((tc_gemm_persist_kernel<EPI>), dim3(148), kTcThreads, kTcSmemBytes, st, pl, tp, maps[0], maps[1], maps[2], maps[3],
-                   (int)grid.x, tiles);
+      ACVAE_LAUNCH((tc_gemm_persist_kernel<EPI>), dim3(148), tc_persist_threads<EPI>(), kTcSmemBytes, st, pl, tp, maps[0], maps[1], maps[2],
+                   maps[3], (int)grid.x, tiles);
       return EPI == EPI_STATS ? 2 : 1;
     }
   }
