@@ -350,6 +350,8 @@ struct DecClFwd {
   float *qp, *w, *gates, *out;   // saved: [N,T,A], [N,T,Te], [N,T,4E], [N,T,E]
   float* aw;              // [N,Te,T] user-visible attention weights or NULL
   long long* trace;       // optional [T][16] clock64 stamps of thread 0 of CTA 0 (profiles/cluster_trace.py) or NULL
+  int t0, t1;             // steps [t0, t1) of the chain (t1 == 0: T); t0 > 0 resumes from the saved state of step t0 - 1 --
+                          // scheduled sampling cuts the chain at every free step, whose input word is the previous step's arg-max
 };
 inline int dec_cl_slice(int Te) { return (kDecR * Te + kClC - 1) / kClC; }          // (row, frame) pairs owned per CTA in the score reduction
 inline size_t dec_cl_fwd_smem(int Te) {
@@ -425,15 +427,24 @@ __global__ void __cluster_dims__(kClC, 1, 1) __launch_bounds__(kClThreads, 1) de
   const int mycount = max(0, min(SL, R * Te - rank * SL));           // pairs of my score slice
   ClHop hopR{{cl_smem(RSb), cl_smem(RSb + kClC * SL)}, {cl_smem(&bars[2]), cl_smem(&bars[3])}, (uint32_t)(kClC * mycount * 4)};
   ClHop hopG{{cl_smem(SC), cl_smem(SC + kClC * SL)}, {cl_smem(&bars[4]), cl_smem(&bars[5])}, (uint32_t)(R * Te * 4)};
+  const int t0 = p.t0, nsteps = (p.t1 > 0 ? p.t1 : T) - p.t0;
+  float hprev = 0.0f;
+  if (t0 > 0) {
+    // resume: h_{t0-1} of my rows from the saved outputs, into the buffer the first step's query projection reads
+    hprev = live ? p.out[((long long)n * T + t0 - 1) * E + u] : 0.0f;
+    for (int i = tid; i < R * E; i += kClThreads) {
+      const int r = i / E, k = i - r * E;
+      Hb[R * E + i] = n0 + r < N ? p.out[((long long)(n0 + r) * T + t0 - 1) * E + k] : 0.0f;
+    }
+  }
   __syncthreads();
   cl_sync_all();
-  float hprev = 0.0f;
-  for (int t = 0; t < T; ++t) {
-    const int par = t & 1;
+  for (int s = 0; s < nsteps; ++s) {
+    const int t = t0 + s, par = s & 1;       // the hop protocol counts the steps of THIS launch
     long long* tr = (p.trace && blockIdx.x == 0 && tid == 0) ? p.trace + t * 16 : nullptr;   // profiling only
     CL_STAMP(0);
     if (tid == 0) {
-      if (t + 1 < T) hopA.arm(par);
+      if (s + 1 < nsteps) hopA.arm(par);
       hopR.arm(par); hopG.arm(par);
     }
     float gxr = 0.f, gxz = 0.f, gxn = 0.f;
@@ -444,7 +455,7 @@ __global__ void __cluster_dims__(kClC, 1, 1) __launch_bounds__(kClThreads, 1) de
     // ---- A: h_{t-1} gathered -> query projection of my 32 columns (zero query at t = 0, decoder.py:94-98) ----
     float4 a[4][2];
     if (t > 0) {
-      hopA.wait(par ^ 1, (t - 1) >> 1);
+      if (s > 0) hopA.wait(par ^ 1, (s - 1) >> 1);
       CL_STAMP(1);
       ldrows4(Hb + (par ^ 1) * R * E, 0, lane, a);
       float v[16][1];
@@ -502,7 +513,7 @@ __global__ void __cluster_dims__(kClC, 1, 1) __launch_bounds__(kClThreads, 1) de
     }
     // ---- RS landed: sum the eight partials of my slice and send the sums to every CTA ----
     CL_STAMP(4);
-    hopR.wait(par, t >> 1);
+    hopR.wait(par, s >> 1);
     CL_STAMP(5);
     for (int i = tid; i < kClC * mycount; i += kClThreads) {
       const int dst = i / mycount, k = i - dst * mycount;
@@ -513,7 +524,7 @@ __global__ void __cluster_dims__(kClC, 1, 1) __launch_bounds__(kClThreads, 1) de
       cl_st_async_f32(cl_mapa(hopG.buf[par] + (uint32_t)((rank * SL + k) * 4), (uint32_t)dst), sum, cl_mapa(hopG.bar[par], (uint32_t)dst));
     }
     // ---- AG landed: masked softmax of every row (warp r = row r) ----
-    hopG.wait(par, t >> 1);
+    hopG.wait(par, s >> 1);
     CL_STAMP(6);
     if (w < R) {
       const int nr = n0 + w;
@@ -577,7 +588,7 @@ __global__ void __cluster_dims__(kClC, 1, 1) __launch_bounds__(kClThreads, 1) de
       const float ng = tanhf(x2 + gxn + rg * hn);
       const float hnew = (1.0f - zg) * ng + zg * hprev;
       hprev = hnew;
-      if (t + 1 < T) {
+      if (s + 1 < nsteps) {
         // all-gather h_t: the eight lanes of a row group hold the row's four units; lane l8 sends the float4 to CTA l8
         const float4 hv = gather4(hnew, lane);
         const uint32_t dst = (uint32_t)(lane & 7);

@@ -17,7 +17,8 @@ __global__ void words_init_kernel(int N, int T, int L, const int* __restrict__ c
   if (i >= N * T) return;
   const int n = i / T, t = i % T;
   if ((tf_mask >> t) & 1ull) words[i] = caps[(long long)n * L + t];
-  else if (t == 0) words[i] = start_idx;
+  else words[i] = start_idx;      // t == 0: the start token; free steps: a VALID placeholder (the batched gathers of the hoisted
+                                  // schedule read every entry) until the previous step's arg-max overwrites it
 }
 
 // ---- vocabulary statistics: combine per-tile partials -------------------------

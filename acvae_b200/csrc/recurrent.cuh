@@ -301,6 +301,7 @@ struct PriorChainFwd {
   float *gates, *c, *h;  // [N,T,4E], [N,T,E], [N,T,E]
   float *pm, *pl, *pz;   // [N,T,E]
   unsigned* bar;
+  int t0, t1;            // steps [t0, t1) (t1 == 0: T); t0 > 0 resumes from the saved state of step t0 - 1 (stand-alone kernel only)
 };
 // The prior chain as phase functions: used by the stand-alone kernel below and, merged phase by phase, by the
 // decoder kernel (the two chains are independent and have the same barrier structure, and two cooperative
@@ -412,11 +413,13 @@ __global__ void __launch_bounds__(kChainThreads, 2) prior_chain_fwd_kernel(const
   prior_fwd_setup(p, Wl, Wh, r, u0, q.u);
   __syncthreads();
   GridBar gb{p.bar, 0u, gridDim.x};
-  for (int t = 0; t < p.T; ++t) {
+  const int t1 = p.t1 > 0 ? p.t1 : p.T;
+  if (p.t0 > 0 && q.epi) r.c_prev = p.c[((long long)q.n * p.T + p.t0 - 1) * kChainE + q.u];    // resume (h, z are read from global)
+  for (int t = p.t0; t < t1; ++t) {
     prior_fwd_lstm(p, Wl, r, t, q);
     grid_sync(gb);
     prior_fwd_head(p, Wh, r, t, q);
-    if (t + 1 < p.T) grid_sync(gb);
+    if (t + 1 < t1) grid_sync(gb);
   }
 }
 

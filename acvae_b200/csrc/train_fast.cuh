@@ -13,11 +13,28 @@
 
 namespace acvae {
 
+// The hoisted multi-stream schedule covers the hybrid variant without prior-z replacement (dis_ratio == 0).  Scheduled sampling
+// (some tf_flags false: vae_model.py:826-832 feeds the previous step's arg-max word instead of the caption's) is covered where the
+// decoder chain runs on clusters next to the stand-alone prior chain: both chains are cut at every free step (see train_fwd_fast).
 inline bool fast_path_ok(const acvae_dims& d, const acvae_train_io& io) {
   if (d.variant != 0 || d.mem_rep != 1) return false;
-  for (int t = 0; t < d.T; ++t)
-    if (!io.tf_flags[t] || io.dis_flags[t]) return false;
+  bool all_tf = true;
+  for (int t = 0; t < d.T; ++t) {
+    if (io.dis_flags[t]) return false;
+    if (t > 0 && !io.tf_flags[t]) all_tf = false;       // step 0 always starts from <start>
+  }
+  if (!all_tf && !(cluster_chain_supported(d.N, d.T, d.Te, d.E, d.A) && chain_supported(d.N, d.T, d.Te, d.E, d.A))) return false;
   return aux() != nullptr;
+}
+
+// rows of two embedding tables for ONE step's words: out[n, t, :] = table[words[n, t], :]  (buffers are [N, T, E])
+__global__ void gather_step2_kernel(int N, int T, int t, int E, const float* __restrict__ t0, const float* __restrict__ t1,
+                                    const int* __restrict__ words, float* __restrict__ o0, float* __restrict__ o1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * E) return;
+  const int n = i / E, e = i - n * E;
+  const long long src = (long long)words[n * T + t] * E + e, dst = ((long long)n * T + t) * E + e;
+  o0[dst] = t0[src]; o1[dst] = t1[src];
 }
 
 inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acvae_train_io& io, void* workspace,
@@ -197,11 +214,61 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     // decoder's 8 clusters come first they take 64 SMs and the prior packs two CTAs per SM onto the other 84.  So the
     // prior waits for the decoder's inputs and is held back a few microseconds behind the decoder's launch.
     ACVAE_TRY(stream_dep(s_mg, st, ax));
-    if (prior_chain) ACVAE_TRY(stream_dep(st, sp, ax));
-    ACVAE_TRY(launch_cluster_chain(dec_cl_fwd_kernel, dec_cl_clusters(N), dec_cl_fwd_smem(Te), st, "dec_cl_fwd_kernel", dc));
-    if (prior_chain) {
-      ACVAE_LAUNCH(stream_delay_kernel, 1, 1, 0, sp, 8000u);
-      ACVAE_TRY(launch_chain(prior_chain_fwd_kernel, 0, sp, "prior_chain_fwd_kernel", ppc));
+    // Scheduled sampling: a free step t (tf_flags[t] == 0) is fed the arg-max word of step t-1 (vae_model.py:826-832), which
+    // exists only once the decoder has produced step t-1.  Both chains are cut there: vocabulary arg-max of the N rows of step
+    // t-1, then the word-dependent hoisted inputs of step t alone (embedding rows, the prior's query projection / attention /
+    // input gates, the decoder's input gates), then the chains resume from their saved state.  Teacher-forced steps keep the
+    // batched inputs computed above; with every step teacher-forced this is one segment = the schedule of the benchmark.
+    int seg_begin = 0;
+    for (int seg_end = 1; seg_end <= T; ++seg_end) {
+      if (seg_end < T && io.tf_flags[seg_end]) continue;
+      const int a = seg_begin;
+      if (a > 0) {
+        VocabStatsArgs v{};
+        v.M = N; v.V = d.V; v.E = E; v.hidden = io.outputs + (long long)(a - 1) * E; v.ld_h = (long long)T * E;
+        v.cls_w = w.cls_w; v.cls_b = w.cls_b;
+        v.pmax = ws.pmax; v.pexp = ws.pexp; v.psum = ws.psum; v.pbest = ws.pbest; v.parg = ws.parg;
+        v.red.lse = io.logit_lse + (a - 1); v.red.lsum = io.logit_sum + (a - 1); v.red.logprob = io.sampled_logprobs + (a - 1);
+        v.red.ld_row = T; v.red.seqs = (long long*)io.seqs + (a - 1); v.red.ld_seqs = T;
+        v.red.next_word = ws.words + a; v.red.ld_next = T;
+        ACVAE_TRY(vocab_stats(v, st));
+        ACVAE_LAUNCH(gather_step2_kernel, grid1d((long long)N * E), 256, 0, st, N, T, a, E, w.d_emb, w.p_emb, (const int*)ws.words,
+                     ws.xd, ws.xp);
+        ACVAE_TRY(stream_dep(st, sp, ax));
+        {   // decoder input gates of step a
+          GemmParams g{};
+          g.M = N; g.U = 3 * E; g.G = 1; g.nseg = 2;
+          g.seg[0] = seg_plain(ws.xd + (long long)a * E, s1 * E, w.d_wih, 3 * E, E);
+          g.seg[1] = seg_plain(io.q_z + (long long)a * E, s1 * E, w.d_wih + 2 * E, 3 * E, E);
+          g.epi.c[0] = ws.dgi_d + (long long)a * 3 * E; g.epi.ldc = s1 * 3 * E; g.epi.bias[0] = w.d_bih; g.epi.scale = 1.0f;
+          ACVAE_TRY(launch_gemm<EPI_PLAIN>(g, st));
+        }
+        {   // prior: query projection, word attention, input gates of step a
+          ACVAE_TRY(linear_fwd(N, E, E, ws.xp + (long long)a * E, s1 * E, w.p_attn_w, 2 * E, nullptr, ws.qp_p + (long long)a * E, s1 * E, sp));
+          AttnFwdParams at{};
+          at.rows = N; at.Te = Te; at.A = E; at.E = E; at.Dq = E; at.rows_per_clip = 1;
+          at.qp_in = ws.qp_p + (long long)a * E; at.ld_qp_in = s1 * E;
+          at.P = ws.Pp; at.mem = ws.mem; at.v = w.p_attn_v; at.mem_lens = io.mem_lens;
+          at.ctx = ws.ctx_p + (long long)a * E; at.ld_ctx = s1 * E; at.w_out = ws.w_p + (long long)a * Te; at.ld_w = s1 * Te;
+          ACVAE_TRY(launch_attn_fwd(at, sp));
+          GemmParams g{};
+          g.M = N; g.U = 4 * E; g.G = 1; g.nseg = 2;
+          g.seg[0] = seg_plain(ws.xp + (long long)a * E, s1 * E, w.p_wih, 3 * E, E);
+          g.seg[1] = seg_plain(ws.ctx_p + (long long)a * E, s1 * E, w.p_wih + E, 3 * E, E);
+          g.epi.c[0] = ws.dg_p + (long long)a * 4 * E; g.epi.ldc = s1 * 4 * E; g.epi.bias[0] = w.p_bih; g.epi.scale = 1.0f;
+          ACVAE_TRY(launch_gemm<EPI_PLAIN>(g, sp));
+        }
+      }
+      dc.t0 = a; dc.t1 = seg_end;
+      if (prior_chain) ACVAE_TRY(stream_dep(st, sp, ax));
+      ACVAE_TRY(launch_cluster_chain(dec_cl_fwd_kernel, dec_cl_clusters(N), dec_cl_fwd_smem(Te), st, "dec_cl_fwd_kernel", dc));
+      if (prior_chain) {
+        ppc.t0 = a; ppc.t1 = seg_end;
+        if (a > 0) ACVAE_CHECK(cudaMemsetAsync(ppc.bar, 0, 128 * sizeof(unsigned), sp));     // the grid barrier counts from zero
+        ACVAE_LAUNCH(stream_delay_kernel, 1, 1, 0, sp, 8000u);
+        ACVAE_TRY(launch_chain(prior_chain_fwd_kernel, 0, sp, "prior_chain_fwd_kernel", ppc));
+      }
+      seg_begin = seg_end;
     }
     // the context itself (weight gradients, rnn_input) from the saved weights, off the critical stream
     ACVAE_TRY(stream_dep(st, sq1, ax));

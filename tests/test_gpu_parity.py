@@ -86,6 +86,28 @@ def test_train_cfg1_vs_oracle():
         harness.assert_close(r["grads"][k], ref, TOL, ("grad", k))      # norm-wise, element-wise and row-wise
 
 
+@pytest.mark.parametrize("ss_ratio", [0.8, 0.5])
+def test_train_cfg1_scheduled_sampling_vs_oracle(ss_ratio, monkeypatch):
+    """Scheduled sampling at BASELINE configs[1] (vae_model.py:826-832: a free step is fed the previous step's arg-max word): the
+    hoisted schedule cuts the cluster decoder chain and the prior chain at every free step (train_fast.cuh) -- loss terms, greedy ids
+    and EVERY gradient against oracle autograd, and the same numbers as the general launch-per-step schedule."""
+    _require_cuda()
+    d = synthetic.CFG1
+    r = harness.run_cuda_train(d, 17, ss_ratio=ss_ratio)
+    o = harness.run_oracle_train(d, 17, ss_ratio=ss_ratio)
+    for k in ("loss", "ce", "kl", "global"):
+        assert abs(float(r["terms"][k]) - float(o["terms"][k])) <= TOL * max(1.0, abs(float(o["terms"][k]))), k
+    assert np.array_equal(r["out"]["seqs"].cpu().numpy(), o["out"]["seqs"].numpy())
+    for k in ("q_means", "p_means", "p_logs", "outputs", "attn_weights", "p_means_utt"):
+        assert harness.rel_err(r["out"][k], o["out"][k]) < TOL, k
+    for k, ref in o["grads"].items():
+        harness.assert_close(r["grads"][k], ref, TOL, ("grad", k))
+    monkeypatch.setenv("ACVAE_DISABLE_FAST", "1")
+    g = harness.run_cuda_train(d, 17, ss_ratio=ss_ratio)
+    assert np.array_equal(r["out"]["seqs"].cpu().numpy(), g["out"]["seqs"].cpu().numpy())
+    assert abs(float(r["terms"]["loss"]) - float(g["terms"]["loss"])) <= 1e-5 * abs(float(g["terms"]["loss"]))
+
+
 def test_train_stress_vs_oracle():
     """BASELINE configs[4] shape (N=128, Te=187, L=30, V=5000, E=256): loss, KL and EVERY gradient against oracle
     autograd at 1e-4 -- a different kernel mix from configs[1] (row tiling for N > 32, streamed memory for Te > 83)."""
