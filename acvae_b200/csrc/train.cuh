@@ -37,6 +37,7 @@ struct TrainWs {
   float *dml_p, *dg_p, *dhp_carry, *dcp_carry, *dzp_carry, *dxe_p, *dctx_p, *ds_p, *dqp_p;
   float *dml_q, *dho, *dgi_q[2], *dgh_q[2], *dhq_carry, *dxq, *dzq_carry;
   float *dPp, *dPd, *dmem, *dmem2, *dpool;
+  float *zsel, *dpz;  // [N,T,E] hoisted schedule with dis flags: the z each decoder step consumed; d p_z incl. the decoder's share
   unsigned* bars;   // grid-barrier counters of the persistent chain kernels (recurrent.cuh)
   size_t bytes;
 };
@@ -70,6 +71,7 @@ inline TrainWs carve_train_ws(const acvae_dims& d, void* base) {
   w.dml_q = ar.take<float>(NT * 2 * E); w.dho = ar.take<float>(NT * 2 * E);
   for (int k = 0; k < 2; ++k) { w.dgi_q[k] = ar.take<float>(NT * 3 * E); w.dgh_q[k] = ar.take<float>(NT * 3 * E); }
   w.dhq_carry = ar.take<float>(N * E); w.dxq = ar.take<float>(NT * E); w.dzq_carry = ar.take<float>(N * E);
+  w.zsel = ar.take<float>(NT * E); w.dpz = ar.take<float>(NT * E);
   w.dPp = ar.take<float>(N * Te * E); w.dPd = ar.take<float>(N * Te * A); w.dmem = ar.take<float>(N * Te * E);
   w.dmem2 = ar.take<float>(N * Te * E);
   w.dpool = ar.take<float>(N * 2 * E);

@@ -13,18 +13,36 @@
 
 namespace acvae {
 
-// The hoisted multi-stream schedule covers the hybrid variant without prior-z replacement (dis_ratio == 0).  Scheduled sampling
-// (some tf_flags false: vae_model.py:826-832 feeds the previous step's arg-max word instead of the caption's) is covered where the
-// decoder chain runs on clusters next to the stand-alone prior chain: both chains are cut at every free step (see train_fwd_fast).
+// The hoisted multi-stream schedule covers the hybrid variant.  Scheduled sampling (some tf_flags false: vae_model.py:826-832 feeds
+// the previous step's arg-max word instead of the caption's) and prior-z replacement (dis_flags: vae_model.py:800-806, the decoder
+// consumes the prior's sample at that step) are covered where the decoder chain runs on clusters next to the stand-alone prior chain:
+// both chains are cut at every free step, and a segment with dis steps runs the prior first (see train_fwd_fast / train_bwd_fast).
 inline bool fast_path_ok(const acvae_dims& d, const acvae_train_io& io) {
   if (d.variant != 0 || d.mem_rep != 1) return false;
   bool all_tf = true;
   for (int t = 0; t < d.T; ++t) {
-    if (io.dis_flags[t]) return false;
+    if (io.dis_flags[t]) all_tf = false;                // (either kind of flag needs the segmented chains)
     if (t > 0 && !io.tf_flags[t]) all_tf = false;       // step 0 always starts from <start>
   }
   if (!all_tf && !(cluster_chain_supported(d.N, d.T, d.Te, d.E, d.A) && chain_supported(d.N, d.T, d.Te, d.E, d.A))) return false;
   return aux() != nullptr;
+}
+
+// z each decoder step consumed: the posterior's sample, or the prior's where dis_flags[t] (vae_model.py:800-806)
+__global__ void zsel_kernel(long long n, int T, int E, unsigned long long dis_mask, const float* __restrict__ q_z,
+                            const float* __restrict__ p_z, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = (int)((i / E) % T);
+  out[i] = ((dis_mask >> t) & 1ull) ? p_z[i] : q_z[i];
+}
+// d p_z = upstream gradient (or 0) + the decoder's d z at the steps where it consumed the prior's sample
+__global__ void dpz_kernel(long long n, int T, int E, unsigned long long dis_mask, const float* __restrict__ up,
+                           const float* __restrict__ dxz, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = (int)((i / E) % T);
+  out[i] = (up ? up[i] : 0.0f) + (((dis_mask >> t) & 1ull) ? dxz[i] : 0.0f);
 }
 
 // rows of two embedding tables for ONE step's words: out[n, t, :] = table[words[n, t], :]  (buffers are [N, T, E])
@@ -260,6 +278,28 @@ inline int train_fwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
         }
       }
       dc.t0 = a; dc.t1 = seg_end;
+      bool seg_dis = false;
+      for (int t = a; t < seg_end; ++t) seg_dis = seg_dis || io.dis_flags[t];
+      if (seg_dis) {
+        // the decoder consumes the prior's sample at some step of this segment (vae_model.py:800-806): the prior's segment
+        // first, then the decoder's input gates of those steps from p_z, then the decoder's segment
+        ppc.t0 = a; ppc.t1 = seg_end;
+        if (a > 0) ACVAE_CHECK(cudaMemsetAsync(ppc.bar, 0, 128 * sizeof(unsigned), sp));
+        ACVAE_TRY(launch_chain(prior_chain_fwd_kernel, 0, sp, "prior_chain_fwd_kernel", ppc));
+        ACVAE_TRY(stream_dep(sp, st, ax));
+        for (int t = a; t < seg_end; ++t) {
+          if (!io.dis_flags[t]) continue;
+          GemmParams g{};
+          g.M = N; g.U = 3 * E; g.G = 1; g.nseg = 2;
+          g.seg[0] = seg_plain(ws.xd + (long long)t * E, s1 * E, w.d_wih, 3 * E, E);
+          g.seg[1] = seg_plain(io.p_z + (long long)t * E, s1 * E, w.d_wih + 2 * E, 3 * E, E);
+          g.epi.c[0] = ws.dgi_d + (long long)t * 3 * E; g.epi.ldc = s1 * 3 * E; g.epi.bias[0] = w.d_bih; g.epi.scale = 1.0f;
+          ACVAE_TRY(launch_gemm<EPI_PLAIN>(g, st));
+        }
+        ACVAE_TRY(launch_cluster_chain(dec_cl_fwd_kernel, dec_cl_clusters(N), dec_cl_fwd_smem(Te), st, "dec_cl_fwd_kernel", dc));
+        seg_begin = seg_end;
+        continue;
+      }
       if (prior_chain) ACVAE_TRY(stream_dep(st, sp, ax));
       ACVAE_TRY(launch_cluster_chain(dec_cl_fwd_kernel, dec_cl_clusters(N), dec_cl_fwd_smem(Te), st, "dec_cl_fwd_kernel", dc));
       if (prior_chain) {
@@ -373,6 +413,16 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   if (merge_env < 0) { const char* e = getenv("ACVAE_MERGE_BWD"); merge_env = (e && e[0] == '0') ? 0 : 1; }
   const bool merge_bwd = !cl && coop && merge_env == 1;
   if (coop) ACVAE_CHECK(cudaMemsetAsync(ws.bars + 4 * 128, 0, 4 * 128 * sizeof(unsigned), st));
+  // prior-z replacement (dis_flags, vae_model.py:800-806): the decoder's d z goes to the prior at those steps, so the prior's
+  // backward chain waits for the decoder's; zin = the z each decoder step consumed (operand of the z block of d W_ih)
+  bool any_dis = false;
+  for (int t = 0; t < T; ++t) any_dis = any_dis || io.dis_flags[t];
+  const unsigned long long dis_mask = flag_mask(io.dis_flags, T);
+  const float* zin = io.q_z;
+  if (any_dis) {
+    ACVAE_LAUNCH(zsel_kernel, grid1d((long long)NT * E), 256, 0, st, (long long)NT * E, T, E, dis_mask, io.q_z, io.p_z, ws.zsel);
+    zin = ws.zsel;
+  }
   // (Starting the prior's backward chain earlier -- right behind the KL gradients, under the cross-entropy gradient GEMMs --
   // was tried: the cooperative kernel holds all 148 SMs, the GEMMs it overlaps take 130 instead of 27 us and the step gets
   // 30 us longer, gpurun_out r2f timeline.)
@@ -523,11 +573,11 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     // decoder first, the prior's cooperative chain a few microseconds behind it on its own stream (see train_fwd_fast)
     if (coop) ACVAE_TRY(stream_dep(st, sp, ax));
     ACVAE_TRY(launch_cluster_chain(dec_cl_bwd_kernel, dec_cl_clusters(N), dec_cl_bwd_smem(Te), st, "dec_cl_bwd_kernel", dc));
-    if (coop) {
+    if (coop && !any_dis) {
       ACVAE_LAUNCH(stream_delay_kernel, 1, 1, 0, sp, 8000u);
       ACVAE_TRY(launch_chain(prior_chain_bwd_kernel, 0, sp, "prior_chain_bwd_kernel", ppc));
     }
-    ACVAE_TRY(prior_remainders());
+    if (!any_dis) ACVAE_TRY(prior_remainders());
   } else if (coop) {
     DecChainBwd dc{};
     dc.N = N; dc.T = T; dc.Te = Te; dc.dout = ws.dout; dc.attn_w = w.d_attn_w; dc.attn_v = w.d_attn_v; dc.wih = w.d_wih;
@@ -588,6 +638,15 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
   }
   // d z fed to the decoder -> d q_z (needed by the posterior backward): first thing after the chain
   ACVAE_TRY(linear_bwd_data(NT, E, 3 * E, ws.dgi_d, 3 * E, w.d_wih + 2 * E, 3 * E, ws.dxz_d, E, st));
+  if (cl && any_dis) {
+    // the prior's backward chain behind the decoder's: d p_z = upstream + the decoder's d z at the dis steps
+    ACVAE_TRY(stream_dep(st, sp, ax));
+    ACVAE_LAUNCH(dpz_kernel, grid1d((long long)NT * E), 256, 0, sp, (long long)NT * E, T, E, dis_mask, gi.d_p_z, (const float*)ws.dxz_d,
+                 ws.dpz);
+    ppc.d_pz = ws.dpz;
+    ACVAE_TRY(launch_chain(prior_chain_bwd_kernel, 0, sp, "prior_chain_bwd_kernel", ppc));
+    ACVAE_TRY(prior_remainders());
+  }
   ACVAE_TRY(stream_dep(st, sx, ax));
   // ---- side stream sx (overlaps the posterior chains) ----
   // critical first: the decoder's per-clip attention accumulation (into its own buffer: no ordering against the
@@ -662,7 +721,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     ACVAE_TRY(scatter_rows(NT, E, ws.dxe_d, E, ws.words, gw.d_emb, f[0]));
     ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_d, 3 * E, ws.xd, E, gw.d_wih, 3 * E, f[1]));
     ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_d, 3 * E, ws.ctx_d, E, gw.d_wih + E, 3 * E, f[2]));
-    ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_d, 3 * E, io.q_z, E, gw.d_wih + 2 * E, 3 * E, f[3]));
+    ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgi_d, 3 * E, zin, E, gw.d_wih + 2 * E, 3 * E, f[3]));
     ACVAE_TRY(linear_bwd_weight(3 * E, E, NT, ws.dgh_d, 3 * E, io.outputs - E, E, gw.d_whh, E, f[4], T, 0, -1));
     ACVAE_TRY(linear_bwd_weight(A, E, NT, ws.dqp_d, A, io.outputs - E, E, gw.d_attn_w, 2 * E, f[5], T, 0, -1));
     ACVAE_TRY(colsum(NT, 3 * E, ws.dgi_d, 3 * E, gw.d_bih, f[5]));
@@ -685,6 +744,7 @@ inline int train_bwd_fast(const acvae_dims& d, const acvae_weights& w, const acv
     h.rows = NT; h.U = E;
     if (gi.d_q_z) { h.dz0 = gi.d_q_z; h.ld_dz0 = E; }
     h.dz1 = ws.dxz_d; h.ld_dz1 = E;
+    if (any_dis) { h.flag_mask = dis_mask; h.period = T; h.want = 0; h.use_flags = 1; }   // d z of the decoder: the non-dis steps only
     if (gi.d_q_means) { h.dmean = gi.d_q_means; h.ld_dmean = E; }
     if (gi.d_q_logs) { h.dlog = gi.d_q_logs; h.ld_dlog = E; }
     h.eps = io.eps_q; h.ld_eps = E; h.logv = io.q_logs; h.ld_logv = E;

@@ -259,11 +259,13 @@ def make_train_step(dev, world, rank, use_graph=True):
     # fed the previous step's arg-max word), which cuts the chains there (train_fast.cuh)
     free = [int(x) for x in os.environ.get("ACVAE_BENCH_SS_FREE", "").split(",") if x.strip()]
     tf_flags = [t not in free for t in range(st_prep.T)]
+    dis_steps = [int(x) for x in os.environ.get("ACVAE_BENCH_DIS", "").split(",") if x.strip()]     # steps fed the prior's z
+    dis_flags = [t in dis_steps for t in range(st_prep.T)]
 
     def step_body():
         flat.zero()
         out = model.train_forward({"audio_embeds": st_audio, "audio_embeds_lens": st_mem_lens}, st_prep, None,
-                                  ss_ratio=1.0, dis_ratio=0.0, tf_flags=tf_flags, dis_flags=[False] * st_prep.T)
+                                  ss_ratio=1.0, dis_ratio=0.0, tf_flags=tf_flags, dis_flags=dis_flags)
         packed = torch.nn.utils.rnn.pack_padded_sequence(out["logits"], lens1, batch_first=True).data
         # criterion(packed, targets) + kl_w * kl_loss(...) + alpha * MSE(...) (pytorch_runner_vae.py:315-320) as one node.
         # (FusedVAELoss.forward_padded -- all N*T rows with row weights instead of packing -- saves the five pack / un-pack

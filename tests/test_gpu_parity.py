@@ -86,15 +86,17 @@ def test_train_cfg1_vs_oracle():
         harness.assert_close(r["grads"][k], ref, TOL, ("grad", k))      # norm-wise, element-wise and row-wise
 
 
-@pytest.mark.parametrize("ss_ratio", [0.8, 0.5])
-def test_train_cfg1_scheduled_sampling_vs_oracle(ss_ratio, monkeypatch):
-    """Scheduled sampling at BASELINE configs[1] (vae_model.py:826-832: a free step is fed the previous step's arg-max word): the
-    hoisted schedule cuts the cluster decoder chain and the prior chain at every free step (train_fast.cuh) -- loss terms, greedy ids
-    and EVERY gradient against oracle autograd, and the same numbers as the general launch-per-step schedule."""
+@pytest.mark.parametrize("ss_ratio,dis_ratio", [(0.8, 0.0), (0.5, 0.0), (1.0, 0.3), (0.8, 0.3)])
+def test_train_cfg1_scheduled_sampling_vs_oracle(ss_ratio, dis_ratio, monkeypatch):
+    """Scheduled sampling (vae_model.py:826-832: a free step is fed the previous step's arg-max word) and prior-z replacement
+    (vae_model.py:800-806: at a dis step the decoder consumes the prior's sample) at BASELINE configs[1]: the hoisted schedule cuts
+    the cluster decoder chain and the prior chain at every free step and runs the prior first in a segment with dis steps
+    (train_fast.cuh) -- loss terms, greedy ids and EVERY gradient against oracle autograd, and the same numbers as the general
+    launch-per-step schedule."""
     _require_cuda()
     d = synthetic.CFG1
-    r = harness.run_cuda_train(d, 17, ss_ratio=ss_ratio)
-    o = harness.run_oracle_train(d, 17, ss_ratio=ss_ratio)
+    r = harness.run_cuda_train(d, 17, ss_ratio=ss_ratio, dis_ratio=dis_ratio)
+    o = harness.run_oracle_train(d, 17, ss_ratio=ss_ratio, dis_ratio=dis_ratio)
     for k in ("loss", "ce", "kl", "global"):
         assert abs(float(r["terms"][k]) - float(o["terms"][k])) <= TOL * max(1.0, abs(float(o["terms"][k]))), k
     assert np.array_equal(r["out"]["seqs"].cpu().numpy(), o["out"]["seqs"].numpy())
@@ -103,7 +105,7 @@ def test_train_cfg1_scheduled_sampling_vs_oracle(ss_ratio, monkeypatch):
     for k, ref in o["grads"].items():
         harness.assert_close(r["grads"][k], ref, TOL, ("grad", k))
     monkeypatch.setenv("ACVAE_DISABLE_FAST", "1")
-    g = harness.run_cuda_train(d, 17, ss_ratio=ss_ratio)
+    g = harness.run_cuda_train(d, 17, ss_ratio=ss_ratio, dis_ratio=dis_ratio)
     assert np.array_equal(r["out"]["seqs"].cpu().numpy(), g["out"]["seqs"].cpu().numpy())
     assert abs(float(r["terms"]["loss"]) - float(g["terms"]["loss"])) <= 1e-5 * abs(float(g["terms"]["loss"]))
 
