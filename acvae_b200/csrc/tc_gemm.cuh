@@ -440,7 +440,7 @@ tc_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcP
 }
 
 // =====================================================================================================
-// Persistent variant for the many-tile forward GEMMs (sampling: M = 10 450 sequences, 656 .. 2870 output tiles).
+// Persistent variant for the forward GEMMs with >= 75 output tiles (sampling: M = 10 450 sequences, 656 .. 2870 tiles).
 // One CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the operand ring, the split workers and the MMA
 // issuer run straight through the tile boundaries, and the accumulator lives in TMEM for the WHOLE K range of a tile
 // (K <= 512 on this path: the tensor core's truncating accumulation costs 7e-9 * K relative, profiles/prec_probe.py),
@@ -797,8 +797,11 @@ inline int try_launch_tc(const GemmParams& p, cudaStream_t st) {
   GemmParams pl = p;
   if constexpr (EPI == EPI_PLAIN || EPI == EPI_STATS) {
     // many-tile forward GEMMs: the persistent kernel (accumulator in TMEM for the whole K range, epilogue overlapped)
-    static int persist = -1;
-    if (persist < 0) { const char* e = getenv("ACVAE_TC_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
+    static int persist = -1, min_tiles = 75;   // measured: sampling at 1310 sequences 3.74 -> 3.63 ms from 149 -> 75, nothing below; the train step is indifferent
+    if (persist < 0) {
+      const char* e = getenv("ACVAE_TC_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1;
+      const char* m = getenv("ACVAE_TC_PERSIST_MIN_TILES"); if (m) min_tiles = atoi(m);
+    }
     int nblk = 0;
     bool kmajor = true;
     for (int s = 0; s < p.nseg; ++s) {
@@ -806,15 +809,15 @@ inline int try_launch_tc(const GemmParams& p, cudaStream_t st) {
       kmajor = kmajor && !p.seg[s].a_trans && !p.seg[s].w_trans && !p.seg[s].k_zero_period;
     }
     const int tiles = (int)(grid.x * grid.y);
-    if (persist && kmajor && !tp.trace && !p.epi.atomic && nblk <= 16 && tiles > 148) {
+    if (persist && kmajor && !tp.trace && !p.epi.atomic && nblk <= 16 && tiles >= min_tiles) {
       static bool configured_p[kMaxDevices] = {false};
       bool& cfg = configured_p[current_device()];
       if (!cfg) {
         ACVAE_CHECK(cudaFuncSetAttribute(tc_gemm_persist_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
         cfg = true;
       }
-      ACVAE_LAUNCH((tc_gemm_persist_kernel<EPI>), dim3(148), tc_persist_threads<EPI>(), kTcSmemBytes, st, pl, tp, maps[0], maps[1], maps[2],
-                   maps[3], (int)grid.x, tiles);
+      ACVAE_LAUNCH((tc_gemm_persist_kernel<EPI>), dim3(tiles < 148 ? tiles : 148), tc_persist_threads<EPI>(), kTcSmemBytes, st, pl, tp,
+                   maps[0], maps[1], maps[2], maps[3], (int)grid.x, tiles);
       return EPI == EPI_STATS ? 2 : 1;
     }
   }
