@@ -205,7 +205,7 @@ def exchange_mode(world):
     return m
 
 
-def make_train_step(dev, world, rank, use_graph=True):
+def make_train_step(dev, world, rank, use_graph=True, free_steps=None, dis_steps=None):
     import torch.distributed as dist
     import acvae_b200 as models
     from acvae_b200 import functional as F, parallel, synthetic
@@ -257,9 +257,10 @@ def make_train_step(dev, world, rank, use_graph=True):
 
     # profiles only (never the driver's line): ACVAE_BENCH_SS_FREE="4,9,15" makes those decode steps free (scheduled sampling:
     # fed the previous step's arg-max word), which cuts the chains there (train_fast.cuh)
-    free = [int(x) for x in os.environ.get("ACVAE_BENCH_SS_FREE", "").split(",") if x.strip()]
+    free = free_steps if free_steps is not None else [int(x) for x in os.environ.get("ACVAE_BENCH_SS_FREE", "").split(",") if x.strip()]
     tf_flags = [t not in free for t in range(st_prep.T)]
-    dis_steps = [int(x) for x in os.environ.get("ACVAE_BENCH_DIS", "").split(",") if x.strip()]     # steps fed the prior's z
+    if dis_steps is None:
+        dis_steps = [int(x) for x in os.environ.get("ACVAE_BENCH_DIS", "").split(",") if x.strip()]     # steps fed the prior's z
     dis_flags = [t in dis_steps for t in range(st_prep.T)]
 
     def step_body():
@@ -468,6 +469,28 @@ def run_ours(args):
         if world > 1:
             dist.barrier(); dist.destroy_process_group()
         return
+
+    # ---- the same step with scheduled sampling and prior-z replacement (the reference decays ss_ratio every iteration and raises
+    #      dis_ratio after its freeze epoch, pytorch_runner_vae.py:110-122): six free decode steps (ss_ratio ~0.7 of T = 19) and two
+    #      dis steps, one flag pattern captured as a graph; side line, one GPU only ----
+    ss_line = None
+    if world == 1 and not os.environ.get("ACVAE_BENCH_SS_FREE") and not os.environ.get("ACVAE_BENCH_DIS"):
+        SS_FREE, SS_DIS = [2, 5, 8, 11, 14, 17], [6, 12]
+        ts2 = make_train_step(dev, world, rank, use_graph=not args.no_graph, free_steps=SS_FREE, dis_steps=SS_DIS)
+        for i in range(3):
+            ts2.load_resident(i); ts2.run_step()
+        evs = []
+        for i in range(20):
+            flush.fill_(float(i))
+            ts2.load_resident(i)
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(); ts2.run_step(); b_.record(); evs.append((a_, b_))
+        torch.cuda.synchronize()
+        ms_ss = sum(a_.elapsed_time(b_) for a_, b_ in evs) / len(evs)
+        ss_line = {"free_steps": SS_FREE, "dis_steps": SS_DIS, "ms_per_step": round(ms_ss, 4), "value": round(d.N / (ms_ss * 1e-3), 1),
+                   "unit": "clips/s", "note": "chains cut at the free steps and resumed from saved state (train_fast.cuh); the general "
+                   "launch-per-step schedule takes 4.6 ms on the same flags (profiles/r2/ss_bench.log)"}
+        del ts2
 
     # ---- dominant kernel, timed live with CUDA events on its own launching stream (eager steps, L2 flushed) ----
     from acvae_b200 import _lib
@@ -678,6 +701,7 @@ def run_ours(args):
                             "fills, which are timed alone"},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
+            "scheduled_sampling": ss_line,
             "gradient_exchange": {"none": "single GPU", "fused": "reduce-scatter + clip + Adam + all-gather fused over NVLink peer memory "
                                   "(DistributedClipAdam, csrc/dp_optim.cuh; no NCCL call in the step)",
                                   "nccl": "NCCL all-reduce (AVG) of the flat 32 MB buffer, then clip + Adam",
