@@ -99,6 +99,7 @@ SYMBOLS = {
     "acvae_set_input_event": (C.c_int, [_vp]),
     "acvae_ipc_export": (C.c_int, [_vp, _vp, C.POINTER(C.c_int64)]),
     "acvae_ipc_open": (C.c_int, [_vp, _i64, C.POINTER(_vp)]),
+    "acvae_ipc_close_all": (C.c_int, []),
     "acvae_dp_comm_bytes": (_sz, []),
     "acvae_dp_workspace_bytes": (_sz, []),
     "acvae_dp_clip_adam": (C.c_int, [_i32, _i32, _i64, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp,

@@ -3,6 +3,10 @@
 #include "../../include/acvae_b200.h"
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <string>
+
 #include "dp_optim.cuh"
 #include "handoff.cuh"
 #include "optim.cuh"
@@ -346,13 +350,40 @@ int acvae_ipc_export(const void* ptr, void* handle64, int64_t* offset) {
   return 0;
 }
 
+// A handle names a whole allocation and may be opened once per process: two tensors of a peer that live in the same allocation
+// (torch's caching allocator carves many tensors out of one cudaMalloc block) share the mapping.
+namespace {
+struct IpcCache {
+  std::mutex mu;
+  std::map<std::string, void*> open;      // 64-byte handle -> mapped base
+};
+IpcCache& ipc_cache() { static IpcCache c; return c; }
+}  // namespace
+
 int acvae_ipc_open(const void* handle64, int64_t offset, void** peer_ptr) {
   ACVAE_REQUIRE(handle64 && peer_ptr && offset >= 0, "bad argument");
-  cudaIpcMemHandle_t h;
-  memcpy(&h, handle64, 64);
+  IpcCache& c = ipc_cache();
+  std::lock_guard<std::mutex> g(c.mu);
+  const std::string key(static_cast<const char*>(handle64), 64);
+  auto it = c.open.find(key);
   void* base = nullptr;
-  ACVAE_CHECK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  if (it != c.open.end()) {
+    base = it->second;
+  } else {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    ACVAE_CHECK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    c.open.emplace(key, base);
+  }
   *peer_ptr = static_cast<char*>(base) + offset;
+  return 0;
+}
+
+int acvae_ipc_close_all(void) {
+  IpcCache& c = ipc_cache();
+  std::lock_guard<std::mutex> g(c.mu);
+  for (auto& kv : c.open) cudaIpcCloseMemHandle(kv.second);
+  c.open.clear();
   return 0;
 }
 

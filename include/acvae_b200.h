@@ -292,6 +292,9 @@ int acvae_encoder_handoff_bwd(int32_t N, int32_t C, int32_t Te, int32_t F, const
  * hyper: device {max_norm, lr, beta1, beta2, eps, weight_decay}; step as in acvae_clip_adam.          */
 int acvae_ipc_export(const void *ptr, void *handle64, int64_t *offset);
 int acvae_ipc_open(const void *handle64, int64_t offset, void **peer_ptr);
+/* Unmaps every peer allocation acvae_ipc_open has mapped in this process (mappings are cached per handle: a handle names a
+ * whole allocation and two tensors of a peer may share one).  Call after the last step, before the peers free their buffers. */
+int acvae_ipc_close_all(void);
 size_t acvae_dp_comm_bytes(void);
 size_t acvae_dp_workspace_bytes(void);
 int acvae_dp_clip_adam(int32_t world, int32_t rank, int64_t n, const void *const *grads,

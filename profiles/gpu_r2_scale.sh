@@ -4,7 +4,7 @@ N=${1:-8}; O=gpurun_out/r2scale; mkdir -p $O
 run() { ACVAE_BENCH_EXCHANGE=$1 timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
   bench.py --gpus $N --steps 100 --warmup 10 > $O/bench_n${N}_$1.json 2> $O/bench_n${N}_$1.err; echo "N=$N $1 rc=$?"; }
 run fused
-[ "$N" = "8" ] && run nccl
+[ "$N" = "8" ] && [ -z "$SKIP_NCCL" ] && run nccl
 python - <<PY
 import json, glob
 for f in sorted(glob.glob("$O/bench_n${N}_*.json")):
