@@ -110,6 +110,53 @@ def test_train_cfg1_scheduled_sampling_vs_oracle(ss_ratio, dis_ratio, monkeypatc
     assert abs(float(r["terms"]["loss"]) - float(g["terms"]["loss"])) <= 1e-5 * abs(float(g["terms"]["loss"]))
 
 
+@pytest.mark.parametrize("mode", ["chain_schedule_ss", "general_schedule_ss", "sampling"])
+def test_input_event_is_honoured_by_every_entry_point(mode, monkeypatch):
+    """`set_input_event` (acvae_set_input_event): the step's audio embeddings arrive through an asynchronous copy on a SIDE stream,
+    the caller records an event behind it, and every entry point must wait for that event before its first read of the audio --
+    the hoisted schedule (here with scheduled sampling), the general launch-per-step schedule and the sampling loop.  The copy is
+    held back ~20 ms behind a spin kernel and the destination starts as zeros, so an entry point that does not wait computes on
+    zeros and cannot match the run on resident data."""
+    _require_cuda()
+    from acvae_b200 import functional as F
+    d = synthetic.CFG0
+    m = harness.build_model(d, 4)
+    b = synthetic.make_batch(d, 4)
+    T = int(b["cap_lens"].max()) - 1
+    tf, dis = harness.flags_for(b, T, 0.7, 0.0)
+    host = torch.from_numpy(b["audio_embeds"]).pin_memory()
+    lens = torch.from_numpy(b["mem_lens"].copy())
+    caps, cap_lens = torch.from_numpy(b["caps"]), b["cap_lens"].copy()
+    eq, ep = torch.from_numpy(b["eps_q"][:, :T].copy()), torch.from_numpy(b["eps_p"][:T].copy())
+    eps_s = torch.from_numpy(np.random.RandomState(5).standard_normal((8, d.N, d.E)).astype(np.float32))    # sampling: injected prior noise
+    if mode == "general_schedule_ss":
+        monkeypatch.setenv("ACVAE_DISABLE_FAST", "1")
+
+    def run(audio):
+        with torch.no_grad():
+            if mode == "sampling":
+                m.eval()
+                return m(audio, lens, method="greedy", max_length=8, eps_p=eps_s)["seqs"].cpu()
+            m.train()
+            o = m(audio, lens, caps, cap_lens, ss_ratio=0.7, dis_ratio=0.0, eps_q=eq, eps_p=ep, tf_flags=tf, dis_flags=dis)
+            return torch.cat([o["seqs"].float().cpu().reshape(-1), o["outputs"].cpu().reshape(-1), o["p_means"].cpu().reshape(-1)])
+
+    ref = run(host.cuda())
+    dev = torch.zeros_like(host, device="cuda")
+    side, ev = torch.cuda.Stream(), torch.cuda.Event()
+    torch.cuda.synchronize()
+    try:
+        F.set_input_event(ev)
+        with torch.cuda.stream(side):
+            torch.cuda._sleep(40_000_000)                  # ~20 ms at 1.9 GHz: the copy lands long after the call below is enqueued
+            dev.copy_(host, non_blocking=True)
+            ev.record(side)
+        got = run(dev)
+    finally:
+        F.set_input_event(None)
+    assert torch.equal(got, ref), "the entry point read the audio embeddings before the caller's input event"
+
+
 def test_train_stress_vs_oracle():
     """BASELINE configs[4] shape (N=128, Te=187, L=30, V=5000, E=256): loss, KL and EVERY gradient against oracle
     autograd at 1e-4 -- a different kernel mix from configs[1] (row tiling for N > 32, streamed memory for Te > 83)."""
