@@ -826,9 +826,15 @@ inline int try_launch_tc(const GemmParams& p, cudaStream_t st) {
     for (int s = 0; s < p.nseg; ++s) nblk += (p.seg[s].K + kTcBK - 1) / kTcBK;
     const int tiles = (int)(grid.x * grid.y);
     int splits = 148 / tiles;                       // fill the machine once
-    static int min_blk = 0;                         // k-blocks per CTA below which splitting stops paying (profiles/r1/gemm_split.log: 16 -> 11 us at 2)
-    if (!min_blk) { const char* e = getenv("ACVAE_TC_MIN_KBLK"); min_blk = e ? atoi(e) : 2; if (min_blk < 1) min_blk = 1; }
-    const int mb = tc_min_kblk_override() > 0 ? tc_min_kblk_override() : min_blk;
+    // k-blocks per CTA below which splitting stops.  Alone, a launch is fastest split down to 2 k-blocks per CTA
+    // (profiles/r1/gemm_split.log: 16 -> 11 us); inside the step every split CTA owns an SM the chains and the other GEMMs are
+    // short of, and the optimum moves to ~6 (profiles/r2/tc_min_kblk.log: 0.871 / 0.848 / 0.844 ms per step at 2 / 4 / 6).
+    static int min_blk = 0, min_blk_bwd = 0;
+    if (!min_blk) {
+      const char* e = getenv("ACVAE_TC_MIN_KBLK"); min_blk = e ? atoi(e) : 6; if (min_blk < 1) min_blk = 1;
+      const char* b = getenv("ACVAE_TC_MIN_KBLK_BWD"); min_blk_bwd = b ? atoi(b) : min_blk; if (min_blk_bwd < 1) min_blk_bwd = 1;
+    }
+    const int mb = tc_min_kblk_override() > 0 ? tc_min_kblk_override() : (p.epi.free_order ? min_blk_bwd : min_blk);
     if (splits > nblk / mb) splits = nblk / mb;
     if (!p.epi.free_order) splits = p.epi.accumulate ? 1 : (splits > 2 ? 2 : splits);   // forward / sampling: reproducible
     if (splits >= 2) {
