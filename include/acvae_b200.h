@@ -142,7 +142,12 @@ int acvae_memory_prepare(const acvae_dims *d, const acvae_weights *w, const floa
 /* Full training forward: H1 + H2 (posterior) + T x {H3 prior, H4 z choice,
  * H5 decoder, H6 greedy word, H7 bookkeeping} + H8 global head + vocab
  * statistics (argmax / lse / sum) without storing logits.
- * Replaces Hybrid_VAEModel.forward (vae_model.py:732-750) / VAEModel.forward. */
+ * Replaces Hybrid_VAEModel.forward (vae_model.py:732-750) / VAEModel.forward.
+ * Two schedules behind this one entry (same results, chosen per call from dims and flags):
+ *   - hoisted (csrc/train_fast.cuh): everything that does not depend on a recurrent state batched over all N*T rows, each
+ *     recurrent chain one persistent kernel (clusters / cooperative grids); hybrid variant, E == A == 256, Te <= 96, N <= 32.
+ *     Free steps (tf_flags[t] == 0) and dis steps cut the chains and resume them from saved state.
+ *   - general (csrc/train.cuh): one launch sequence per step; every variant and shape. */
 int acvae_train_fwd(const acvae_dims *d, const acvae_weights *w, const acvae_train_io *io,
                     void *workspace, size_t workspace_bytes, void *stream);
 
