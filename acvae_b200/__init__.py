@@ -19,7 +19,7 @@ from .models import (CaptionModel, Hybrid_VAEModel, PosteriorRNN, PosteriorRNN_h
                      PreparedBatch, PriorRNN, Seq2SeqAttention, VAEModel, VAERNNBahdanauAttnDecoder)
 from .train_util import CrossEntropyLoss, FusedVAELoss, LabelSmoothingLoss, Normal_kl_loss  # noqa: F401
 from .lazy import LazyLogits  # noqa: F401
-from .optim import DistributedClipAdam, FusedClipAdam  # noqa: F401
+from .optim import DistributedClipAdam, FusedClipAdam, PeerMemoryUnavailable  # noqa: F401
 from .metrics import diversity_stats, ids_to_sentences, mbleu, predictions_json  # noqa: F401
 from .sampler import GraphSampler, gather_captions  # noqa: F401
 from .functional import encoder_handoff, get_precision, set_input_event, set_precision  # noqa: F401

@@ -171,6 +171,12 @@ class FusedClipAdam(torch.optim.Optimizer):
         self._bind_state()
 
 
+class PeerMemoryUnavailable(RuntimeError):
+    """Raised by DistributedClipAdam ON EVERY RANK when some rank cannot export or map the flat buffers through CUDA IPC (e.g. the
+    caching allocator runs with expandable segments, or the GPUs have no peer access): the caller falls back to
+    `FlatGradBuffer.all_reduce()` + `FusedClipAdam` on all ranks together."""
+
+
 class DistributedClipAdam(FusedClipAdam):
     """Data-parallel optimizer tail as ONE fused compute + collective over NVLink peer memory (one process per GPU, one
     node): replaces DDP's gradient all-reduce (`pytorch_runner_vae.py:204-207, 321`) + `clip_grad_norm_` (`:322`) +
@@ -216,22 +222,37 @@ class DistributedClipAdam(FusedClipAdam):
                 off = C.c_int64(0)
                 _lib.check(l.acvae_ipc_export(t.data_ptr(), h, C.byref(off)), "acvae_ipc_export")
                 return bytes(h), int(off.value)
-            mine = {"grads": export(g), "params": export(self.flat_params), "comm": export(self._comm), "rank": self.rank}
+            # Both phases (export, map) are agreed on by all ranks: a failure anywhere raises PeerMemoryUnavailable everywhere.
+            try:
+                mine = {"grads": export(g), "params": export(self.flat_params), "comm": export(self._comm), "rank": self.rank}
+            except Exception as e:                   # noqa: BLE001 -- reported to the peers below
+                mine = {"error": f"rank {self.rank}: {e}"}
             everyone = [None] * self.world
             dist.all_gather_object(everyone, mine, group=process_group)
+            errors = [x["error"] for x in everyone if "error" in x]
+            if errors:
+                raise PeerMemoryUnavailable("CUDA IPC export failed: " + "; ".join(errors))
             self._peer_ptrs = {}
-            for key, local in (("grads", g), ("params", self.flat_params), ("comm", self._comm)):
-                arr = (C.c_void_p * self.world)()
-                for q, info in enumerate(everyone):
-                    if q == self.rank:
-                        arr[q] = local.data_ptr()
-                    else:
-                        hb, off = info[key]
-                        out = C.c_void_p()
-                        _lib.check(l.acvae_ipc_open((C.c_ubyte * 64).from_buffer_copy(hb), off, C.byref(out)), "acvae_ipc_open")
-                        arr[q] = out.value
-                self._peer_ptrs[key] = arr
-            dist.barrier(group=process_group)       # every rank has mapped every buffer before anyone steps
+            err = None
+            try:
+                for key, local in (("grads", g), ("params", self.flat_params), ("comm", self._comm)):
+                    arr = (C.c_void_p * self.world)()
+                    for q, info in enumerate(everyone):
+                        if q == self.rank:
+                            arr[q] = local.data_ptr()
+                        else:
+                            hb, off = info[key]
+                            out = C.c_void_p()
+                            _lib.check(l.acvae_ipc_open((C.c_ubyte * 64).from_buffer_copy(hb), off, C.byref(out)), "acvae_ipc_open")
+                            arr[q] = out.value
+                    self._peer_ptrs[key] = arr
+            except Exception as e:                   # noqa: BLE001
+                err = f"rank {self.rank}: {e}"
+            outcome = [None] * self.world
+            dist.all_gather_object(outcome, err, group=process_group)     # also the barrier: every rank has mapped every buffer
+            errors = [x for x in outcome if x]
+            if errors:
+                raise PeerMemoryUnavailable("CUDA IPC mapping failed: " + "; ".join(errors))
         self.state.clear()                          # moments are sharded: no per-parameter views
 
     @torch.no_grad()

@@ -225,9 +225,15 @@ def make_train_step(dev, world, rank, use_graph=True, free_steps=None, dis_steps
     ts.exchange = exchange_mode(world)
     if ts.exchange == "nccl-bucketed":
         flat.enable_bucketing(model)
+    opt = None
     if ts.exchange == "fused":
-        opt = models.DistributedClipAdam(flat, lr=LR, max_grad_norm=MAX_GRAD_NORM)
-    else:
+        try:
+            opt = models.DistributedClipAdam(flat, lr=LR, max_grad_norm=MAX_GRAD_NORM)
+        except models.PeerMemoryUnavailable as e:      # raised on every rank together: all fall back to the NCCL exchange
+            if rank == 0:
+                print(f"[bench] peer-memory exchange unavailable ({e}); falling back to one NCCL all-reduce", file=sys.stderr)
+            ts.exchange = "nccl"
+    if opt is None:
         opt = models.FusedClipAdam(flat, lr=LR, max_grad_norm=MAX_GRAD_NORM)
     crit = models.LabelSmoothingLoss(d.V, smoothing=SMOOTHING, device=dev)
     klf = models.Normal_kl_loss(device=dev)
